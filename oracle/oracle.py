@@ -1,0 +1,192 @@
+"""ctypes front-end of the CPU ORACLE (oracle/fedd_oracle.c).
+
+Test infrastructure only: tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+`--impl reference` legs may import this module.  The product package (feddlib_b200) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libfedd_oracle.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(os.path.join(_HERE, "fedd_oracle.c")):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+_I32P = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_I64P = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+_F64P = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build())
+        L.fo_matrix_new.restype = C.c_void_p
+        L.fo_matrix_new.argtypes = [C.c_int64, C.c_int32]
+        L.fo_matrix_free.argtypes = [C.c_void_p]
+        L.fo_fill_complete.restype = C.c_int64
+        L.fo_fill_complete.argtypes = [C.c_void_p]
+        L.fo_matrix_nnz.restype = C.c_int64
+        L.fo_matrix_nnz.argtypes = [C.c_void_p]
+        L.fo_get_csr.argtypes = [C.c_void_p, _I64P, _I64P, _F64P]
+        L.fo_matrix_scale.argtypes = [C.c_void_p, C.c_double]
+        L.fo_insert.argtypes = [C.c_void_p, C.c_int64, C.c_int32, _I64P, _F64P]
+        common = [C.c_int, C.c_char_p, C.c_int64, _I32P, _F64P, _I64P]
+        L.fo_assembly_laplace.argtypes = common + [C.c_void_p]
+        L.fo_assembly_laplace_vecfield.argtypes = common + [C.c_void_p]
+        L.fo_assembly_linelas.argtypes = common + [C.c_double, C.c_double, C.c_void_p]
+        L.fo_assembly_advection.argtypes = common + [_F64P, C.c_void_p]
+        L.fo_assembly_advection_in_u.argtypes = common + [_F64P, C.c_void_p]
+        L.fo_assembly_div_divT.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.c_int64, _I32P, _F64P, _I64P,
+                                           _I32P, _I64P, C.c_void_p, C.c_void_p, C.c_int]
+        L.fo_quadrature.argtypes = [C.c_int, C.c_int, _F64P, _F64P]
+        L.fo_get_phi.argtypes = [C.c_int, C.c_char_p, C.c_int, _F64P, _F64P]
+        L.fo_get_dphi.argtypes = [C.c_int, C.c_char_p, C.c_int, _F64P, _F64P]
+        L.fo_determine_degree2.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int]
+        L.fo_determine_degree1.argtypes = [C.c_int, C.c_char_p, C.c_int]
+        L.fo_nloc.argtypes = [C.c_int, C.c_char_p]
+        _lib = L
+    return _lib
+
+
+STD, GRAD = 0, 1
+
+
+class Matrix:
+    """Emulation of FEDD::Matrix(map, numEntries) on a dense global row-id range [0, nrows)."""
+
+    def __init__(self, nrows: int, cap_hint: int = 32):
+        self.nrows = int(nrows)
+        self._h = lib().fo_matrix_new(self.nrows, int(cap_hint))
+        self.filled = False
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().fo_matrix_free(self._h)
+            self._h = None
+
+    def insertGlobalValues(self, row, cols, vals):
+        cols = np.ascontiguousarray(cols, dtype=np.int64)
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
+        if lib().fo_insert(self._h, int(row), cols.size, cols, vals) != 0:
+            raise IndexError("row out of range")
+
+    def fillComplete(self):
+        lib().fo_fill_complete(self._h)
+        self.filled = True
+
+    def scale(self, s: float):
+        lib().fo_matrix_scale(self._h, float(s))
+
+    def csr(self):
+        """(rowptr int64[nrows+1], col_gid int64[nnz], values float64[nnz])"""
+        if not self.filled:
+            self.fillComplete()
+        nnz = lib().fo_matrix_nnz(self._h)
+        rowptr = np.empty(self.nrows + 1, dtype=np.int64)
+        col = np.empty(nnz, dtype=np.int64)
+        val = np.empty(nnz, dtype=np.float64)
+        lib().fo_get_csr(self._h, rowptr, col, val)
+        return rowptr, col, val
+
+    def scipy(self, ncols=None):
+        import scipy.sparse as sp
+        rowptr, col, val = self.csr()
+        return sp.csr_matrix((val, col, rowptr), shape=(self.nrows, ncols or self.nrows))
+
+
+def _chk(rc, what):
+    if rc != 0:
+        raise ValueError(f"oracle: {what} failed (unsupported dim / FE type?)")
+
+
+def _prep(conn, coords, gid):
+    conn = np.ascontiguousarray(conn, dtype=np.int32)
+    coords = np.ascontiguousarray(coords, dtype=np.float64)
+    gid = np.ascontiguousarray(gid, dtype=np.int64)
+    return conn, coords, gid
+
+
+def assembly_laplace(dim, fe, conn, coords, gid, A: Matrix):
+    conn, coords, gid = _prep(conn, coords, gid)
+    _chk(lib().fo_assembly_laplace(dim, fe.encode(), conn.shape[0], conn, coords, gid, A._h), "assemblyLaplace")
+
+
+def assembly_laplace_vecfield(dim, fe, conn, coords, gid, A: Matrix):
+    conn, coords, gid = _prep(conn, coords, gid)
+    _chk(lib().fo_assembly_laplace_vecfield(dim, fe.encode(), conn.shape[0], conn, coords, gid, A._h),
+         "assemblyLaplaceVecField")
+
+
+def assembly_linelas(dim, fe, conn, coords, gid, lam, mu, A: Matrix):
+    conn, coords, gid = _prep(conn, coords, gid)
+    _chk(lib().fo_assembly_linelas(dim, fe.encode(), conn.shape[0], conn, coords, gid, lam, mu, A._h),
+         "assemblyLinElasXDim")
+
+
+def assembly_advection(dim, fe, conn, coords, gid, u, A: Matrix):
+    conn, coords, gid = _prep(conn, coords, gid)
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    assert u.size == dim * coords.shape[0]
+    _chk(lib().fo_assembly_advection(dim, fe.encode(), conn.shape[0], conn, coords, gid, u, A._h),
+         "assemblyAdvectionVecField")
+
+
+def assembly_advection_in_u(dim, fe, conn, coords, gid, u, A: Matrix):
+    conn, coords, gid = _prep(conn, coords, gid)
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    assert u.size == dim * coords.shape[0]
+    _chk(lib().fo_assembly_advection_in_u(dim, fe.encode(), conn.shape[0], conn, coords, gid, u, A._h),
+         "assemblyAdvectionInUVecField")
+
+
+def assembly_div_divT(dim, fe1, fe2, conn1, coords1, gid1, conn2, gid2, B: Matrix, BT: Matrix, fast=False):
+    conn1, coords1, gid1 = _prep(conn1, coords1, gid1)
+    conn2 = np.ascontiguousarray(conn2, dtype=np.int32)
+    gid2 = np.ascontiguousarray(gid2, dtype=np.int64)
+    assert conn1.shape[0] == conn2.shape[0]
+    _chk(lib().fo_assembly_div_divT(dim, fe1.encode(), fe2.encode(), conn1.shape[0], conn1, coords1, gid1,
+                                    conn2, gid2, B._h, BT._h, int(bool(fast))), "assemblyDivAndDivT")
+
+
+def quadrature(dim, deg):
+    pts = np.zeros(16 * 3)
+    w = np.zeros(16)
+    n = lib().fo_quadrature(dim, deg, pts, w)
+    if n < 0:
+        raise ValueError("no such rule on this path")
+    return pts[: n * dim].reshape(n, dim).copy(), w[:n].copy()
+
+
+def get_phi(dim, fe, deg):
+    n = lib().fo_nloc(dim, fe.encode())
+    phi = np.zeros(16 * 10)
+    w = np.zeros(16)
+    nq = lib().fo_get_phi(dim, fe.encode(), deg, phi, w)
+    return phi[: nq * n].reshape(nq, n).copy(), w[:nq].copy()
+
+
+def get_dphi(dim, fe, deg):
+    n = lib().fo_nloc(dim, fe.encode())
+    dphi = np.zeros(16 * 10 * 3)
+    w = np.zeros(16)
+    nq = lib().fo_get_dphi(dim, fe.encode(), deg, dphi, w)
+    return dphi[: nq * n * dim].reshape(nq, n, dim).copy(), w[:nq].copy()
+
+
+def determine_degree(dim, fe1, fe2, t1, t2, extra=0):
+    return lib().fo_determine_degree2(dim, fe1.encode(), fe2.encode(), t1, t2, extra)
+
+
+def determine_degree1(dim, fe, t):
+    return lib().fo_determine_degree1(dim, fe.encode(), t)
