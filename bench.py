@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py -- FE assembly throughput (P2 tet elasticity) on B200, the metric of BASELINE.json.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--M m] [--mode gather|coloured|atomic]
+
+A "step" is one full assembly of the linear-elasticity matrix (FE::assemblyLinElasXDim,
+reference feddlib/core/FE/FE_def.hpp:2739-3040) on the built-in structured cube with P2 tetrahedra
+(config 3 of BASELINE.json: H/h = 70 -> 2 058 000 tets, 716 110 929 CSR values).  Prints ONE JSON line.
+
+ * value       elements/s, device-resident inputs and outputs, CUDA events, max over ranks
+ * e2e         the same metric through the host-buffer path of the C ABI: coordinates H2D from pinned
+               memory and the CSR values D2H into pinned memory inside the timed region
+ * roofline    algorithmic bytes (conn + vertex coords + values) / device time of the pass
+ * cpu_baseline  the CPU oracle (a restatement of the reference loops, kind "port") on a bounded sample
+ * --impl reference : the same oracle on all host cores (the reference itself needs Trilinos, absent here)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+LAM, MU = 8.0e6, 2.0e6  # nu = 0.4, mu = 2e6 (steadyLinElas_Perf/parametersProblem.xml:10-11, LinElas_def.hpp:76-77)
+METRIC = "fe_assembly_p2_tet_elasticity_elements_per_s"
+UNIT = "elements/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def oracle_elasticity_time(M, repeat=1):
+    """Seconds for one CPU assembly (oracle: per-entry inserts + fillComplete sort/merge) of the M^3 cube."""
+    from oracle import mesh as OM
+    from oracle import oracle as O
+    conn, co, gid = OM.structured(3, "P2", 1, M)
+    best = 1e30
+    for _ in range(repeat):
+        t0 = time.perf_counter()
+        A = O.Matrix(3 * co.shape[0], 240)            # LinElas_def.hpp:80 capacity hint dim*80
+        O.assembly_linelas(3, "P2", conn, co, gid, LAM, MU, A)
+        A.fillComplete()
+        best = min(best, time.perf_counter() - t0)
+        del A
+    return best, conn.shape[0]
+
+
+def _worker(M):
+    return oracle_elasticity_time(M)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; FEDDLib itself needs Trilinos/MPI, not in
+    this image) on all host cores, one independent element partition (sub-cube) per core."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    M = args.ref_M
+    oracle_elasticity_time(2)  # build/load
+    times = []
+    with mp.get_context("fork").Pool(cores) as pool:
+        for _ in range(args.warmup):
+            pool.map(_worker, [M] * cores)
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            res = pool.map(_worker, [M] * cores)
+            times.append(time.perf_counter() - t0)
+    ne = res[0][1] * cores
+    dt = float(np.mean(times))
+    value = ne / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"P2 tet linear elasticity, structured cube, {cores} partitions of 6*{M}^3 tets "
+                                   "(bounded sample of config 3)", "lambda": LAM, "mu": MU},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{cores} x (6*{M}^3 = {res[0][1]}) tets per step, one process per core, "
+                                       "per-entry insert + per-row sort/merge; ghost-row merge not included"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--M", type=int, default=70, help="H/h of the cube per GPU (70 = config 3)")
+    ap.add_argument("--mode", default="gather", choices=["gather", "coloured", "atomic"])
+    ap.add_argument("--ref-M", dest="ref_M", type=int, default=14)
+    ap.add_argument("--cpu-M", dest="cpu_M", type=int, default=16)
+    ap.add_argument("--e2e-steps", dest="e2e_steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--all-modes", action="store_true", help="also time the other scatter modes (extra keys)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+
+    from feddlib_b200 import BLOCK_FULL, Context, Mesh, Pattern
+    from feddlib_b200 import mesh as PM
+
+    dim, fe, M = 3, "P2", args.M
+    ctx = Context(local_rank)
+    ctx.set_scatter_mode(args.mode)
+    if world == 1:
+        conn, coords, gid = PM.build_structured(dim, fe, 1, M)
+        t0 = time.perf_counter()
+        mesh = Mesh(ctx, dim, conn, coords)
+        pat = Pattern(ctx, mesh)
+        ctx.synchronize()
+        t_pattern = time.perf_counter() - t0
+        runner = None
+    else:
+        from feddlib_b200 import dist as fdist
+        t0 = time.perf_counter()
+        runner = fdist.DistributedElasticity(ctx, dim, fe, M, rank, world)
+        mesh, pat, conn, coords = runner.mesh, runner.pat, runner.conn, runner.coords
+        ctx.synchronize()
+        t_pattern = time.perf_counter() - t0
+    ne = conn.shape[0]
+    nnz = pat.nnz(dim, dim, BLOCK_FULL)
+    values = ctx.empty_values(nnz)
+
+    def step():
+        pat.assemble_linelas_d(values, LAM, MU)
+        if runner is not None:
+            runner.exchange(values)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launches
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1) / steps
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, (ctx.launches - l0) // steps
+
+    with ClockSampler(local_rank) as clk:
+        ms, launches = timed(step, args.steps, args.warmup)
+    clocks = clk.summary()
+
+    ne_total = ne * world
+    value = ne_total / (ms * 1e-3)
+
+    # roofline of the assembly pass (all launches of one step on this rank): algorithmic bytes of SURVEY.md 8(d)
+    n_vertices = (M + 1) ** 3
+    alg_bytes = ne * conn.shape[1] * 4 + n_vertices * dim * 8 + nnz * 8
+    peak, peak_src = peaks()
+    achieved = alg_bytes / (ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_step": alg_bytes,
+                "kernel": f"assembly pass = k_geom + k_gather bucket launches ({launches} launches/step)"
+                if args.mode == "gather" else f"{args.mode} scatter pass ({launches} launches/step)"}
+
+    extra = {}
+    if args.all_modes and world == 1:
+        for m in ("gather", "coloured", "atomic"):
+            if m == args.mode:
+                continue
+            ctx.set_scatter_mode(m)
+            ms_m, l_m = timed(step, max(2, args.steps // 3), 3)
+            extra[m] = {"ms_per_step": ms_m, "value": ne / (ms_m * 1e-3), "launches": l_m,
+                        "hbm_frac": alg_bytes / (ms_m * 1e-3) / 1e9 / peak}
+        ctx.set_scatter_mode(args.mode)
+
+    # e2e: host buffers through the C ABI's host-pointer entry points; H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        pinned_vals = torch.empty(nnz, dtype=torch.float64, pin_memory=True)
+        pinned_xyz = torch.from_numpy(coords).pin_memory()
+        out_np, xyz_np = pinned_vals.numpy(), pinned_xyz.numpy()
+
+        def e2e_step():
+            mesh.update_coords(xyz_np)                      # H2D of this step's points (pinned)
+            pat.assemble_linelas(LAM, MU, out=out_np)       # assemble + D2H of the CSR values (pinned)
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": ne_total / dt, "unit": UNIT, "h2d_bytes_per_step": int(coords.nbytes),
+               "d2h_bytes_per_step": int(nnz * 8), "ms_per_step": dt * 1e3, "steps": args.e2e_steps}
+        checksum = float(out_np[: min(nnz, 1 << 20)].sum())
+        del pinned_vals
+    else:
+        checksum = float(values[: min(nnz, 1 << 20)].sum().item())
+
+    cpu_baseline = None
+    if rank == 0:
+        t_cpu, ne_cpu = oracle_elasticity_time(args.cpu_M)
+        cpu_baseline = {"value": ne_cpu / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
+                        "sample": f"6*{args.cpu_M}^3 = {ne_cpu} P2 tets of the same cube workload, oracle restatement "
+                                  f"(per-entry insert + per-row sort/merge), {t_cpu:.1f} s on 1 core"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"config 3: linear elasticity P2 3D cube H/h={M} per GPU, {ne} tets/GPU, "
+                                       f"{nnz} CSR values/GPU (30x30 local blocks)",
+                           "lambda": LAM, "mu": MU, "scatter_mode": args.mode,
+                           "l2_policy": "outputs (5.7 GB at M=70) exceed the 126 MB L2; no flush needed",
+                           "parallelism": f"element partition over {world} GPU(s)",
+                           "pattern_build_s": t_pattern},
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
+                "clocks": clocks, "checksum_first_1Mi_values": checksum}
+        if extra:
+            line["other_scatter_modes"] = extra
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

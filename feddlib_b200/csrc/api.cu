@@ -1,0 +1,442 @@
+// C-ABI assembly entry points of libfeddb200.so: operator dispatch, scatter-mode selection and
+// kernel launches.  See include/feddb200.h for the reference interfaces each call replaces.
+#include <algorithm>
+#include <cstring>
+
+#include "kernels.cuh"
+
+using namespace fb;
+
+namespace {
+
+int elem_index(int dim, int nloc)
+{
+    if (dim == 2) return nloc == 3 ? 0 : (nloc == 6 ? 1 : -1);
+    if (dim == 3) return nloc == 4 ? 2 : (nloc == 10 ? 3 : -1);
+    return -1;
+}
+
+// device copy of the operator tables, cached per context slot
+int get_tables(feddb200_ctx *c, int op, int dim, int nv, int np, const OpTables **out_d, OpTables *out_h = nullptr)
+{
+    OpTables t;
+    if (build_tables(t, op, dim, nv, np) != 0) {
+        set_error("no quadrature/basis tables for this combination of dimension and FE types");
+        return FEDDB200_ELOGIC;
+    }
+    const int key = 1 + dim * 10000 + nv * 100 + np;
+    OpTables *slot = c->tab_d + op;
+    if (c->tab_key[op] != key) {
+        FB_CUDA(cudaMemcpyAsync(slot, &t, sizeof(OpTables), cudaMemcpyHostToDevice, c->stream));
+        FB_CUDA(cudaStreamSynchronize(c->stream));
+        c->tab_key[op] = key;
+    }
+    *out_d = slot;
+    if (out_h) *out_h = t;
+    return FEDDB200_OK;
+}
+
+template <int OP, int DIM, int NR, int NC>
+int launch_elem_t(feddb200_ctx *c, ElemArgs &A, bool atomic)
+{
+    constexpr int RD = RowDofs<OP, DIM>::value;
+    const int64_t nthreads = A.n_items * NR * RD;
+    if (nthreads == 0) return FEDDB200_OK;
+    const int64_t blocks = (nthreads + 127) / 128;
+    FB_LOGIC(blocks >= (int64_t(1) << 31), "launch too large");
+    if (atomic) k_elem<OP, DIM, NR, NC, true><<<(unsigned)blocks, 128, 0, c->stream>>>(A);
+    else k_elem<OP, DIM, NR, NC, false><<<(unsigned)blocks, 128, 0, c->stream>>>(A);
+    c->launches++;
+    FB_CUDA(cudaGetLastError());
+    return FEDDB200_OK;
+}
+
+template <int OP>
+int launch_elem(feddb200_ctx *c, int dim, int nr, int nc, ElemArgs &A, bool atomic)
+{
+    if constexpr (OP == OP_B) {
+        if (dim == 2 && nr == 3 && nc == 3) return launch_elem_t<OP, 2, 3, 3>(c, A, atomic);
+        if (dim == 2 && nr == 3 && nc == 6) return launch_elem_t<OP, 2, 3, 6>(c, A, atomic);
+        if (dim == 3 && nr == 4 && nc == 4) return launch_elem_t<OP, 3, 4, 4>(c, A, atomic);
+        if (dim == 3 && nr == 4 && nc == 10) return launch_elem_t<OP, 3, 4, 10>(c, A, atomic);
+    } else if constexpr (OP == OP_BT) {
+        if (dim == 2 && nr == 3 && nc == 3) return launch_elem_t<OP, 2, 3, 3>(c, A, atomic);
+        if (dim == 2 && nr == 6 && nc == 3) return launch_elem_t<OP, 2, 6, 3>(c, A, atomic);
+        if (dim == 3 && nr == 4 && nc == 4) return launch_elem_t<OP, 3, 4, 4>(c, A, atomic);
+        if (dim == 3 && nr == 10 && nc == 4) return launch_elem_t<OP, 3, 10, 4>(c, A, atomic);
+    } else {
+        if (nr == nc) {
+            if (dim == 2 && nr == 3) return launch_elem_t<OP, 2, 3, 3>(c, A, atomic);
+            if (dim == 2 && nr == 6) return launch_elem_t<OP, 2, 6, 6>(c, A, atomic);
+            if (dim == 3 && nr == 4) return launch_elem_t<OP, 3, 4, 4>(c, A, atomic);
+            if (dim == 3 && nr == 10) return launch_elem_t<OP, 3, 10, 10>(c, A, atomic);
+        }
+    }
+    set_error("this operator is not implemented for the given combination of FE types");
+    return FEDDB200_ELOGIC;
+}
+
+int launch_elem_op(feddb200_ctx *c, int op, int dim, int nr, int nc, ElemArgs &A, bool atomic)
+{
+    switch (op) {
+    case OP_LAP:  return launch_elem<OP_LAP>(c, dim, nr, nc, A, atomic);
+    case OP_ELAS: return launch_elem<OP_ELAS>(c, dim, nr, nc, A, atomic);
+    case OP_ADV:  return launch_elem<OP_ADV>(c, dim, nr, nc, A, atomic);
+    case OP_ADVU: return launch_elem<OP_ADVU>(c, dim, nr, nc, A, atomic);
+    case OP_NSJ:  return launch_elem<OP_NSJ>(c, dim, nr, nc, A, atomic);
+    case OP_B:    return launch_elem<OP_B>(c, dim, nr, nc, A, atomic);
+    case OP_BT:   return launch_elem<OP_BT>(c, dim, nr, nc, A, atomic);
+    }
+    set_error("unknown operator");
+    return FEDDB200_ELOGIC;
+}
+
+// ---------------------------------------------------------------------------------------
+// gather path preparation (lazy, once per pattern): canonical position map, row types,
+// (type, length) buckets
+// ---------------------------------------------------------------------------------------
+int ensure_gather(feddb200_pat *p)
+{
+    if (p->gather_ready) return FEDDB200_OK;
+    feddb200_ctx *c = p->ctx;
+    const int dim = p->rm->dim, nl = p->rm->nloc;
+    FB_LOGIC(p->rm->nloc != p->cm->nloc, "gather path needs a square pattern");
+    const int64_t n_rows = p->n_rows;
+    p->posc_stride = (nl + 1) & ~1;
+    FB_CUDA(cudaMalloc(&p->posc_d, sizeof(uint16_t) * std::max<int64_t>(p->n_inc * p->posc_stride, 1)));
+    int8_t *rtype_d = nullptr;
+    FB_CUDA(cudaMalloc(&rtype_d, std::max<int64_t>(n_rows, 1)));
+    if (n_rows > 0) {
+        const int grid = (int)std::min<int64_t>((n_rows + 127) / 128, 148 * 64);
+        switch (elem_index(dim, nl)) {
+        case 0: k_canon_pos<2, 3><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->pos_d, p->pos_stride, p->posc_d, p->posc_stride, rtype_d); break;
+        case 1: k_canon_pos<2, 6><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->pos_d, p->pos_stride, p->posc_d, p->posc_stride, rtype_d); break;
+        case 2: k_canon_pos<3, 4><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->pos_d, p->pos_stride, p->posc_d, p->posc_stride, rtype_d); break;
+        case 3: k_canon_pos<3, 10><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->pos_d, p->pos_stride, p->posc_d, p->posc_stride, rtype_d); break;
+        default: set_error("unsupported element"); return FEDDB200_ELOGIC;
+        }
+        c->launches++;
+        FB_CUDA(cudaGetLastError());
+    }
+    std::vector<int8_t> rtype(n_rows);
+    FB_CUDA(cudaMemcpyAsync(rtype.data(), rtype_d, n_rows, cudaMemcpyDeviceToHost, c->stream));
+    FB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(rtype_d);
+    std::vector<int32_t> perm(n_rows);
+    for (int64_t r = 0; r < n_rows; r++) perm[r] = (int32_t)r;
+    auto cap = [&](int64_t r) { const int l = (int)(p->rowptr_h[r + 1] - p->rowptr_h[r]); return std::max(8, (l + 7) & ~7); };
+    auto key = [&](int32_t r) { return (int64_t)rtype[r] * 100000 + cap(r); };
+    std::stable_sort(perm.begin(), perm.end(), [&](int32_t a, int32_t b) { return key(a) < key(b); });
+    p->buckets.clear();
+    for (int64_t s = 0; s < n_rows;) {
+        int64_t e = s;
+        while (e < n_rows && key(perm[e]) == key(perm[s])) e++;
+        p->buckets.push_back({(int)rtype[perm[s]], cap(perm[s]), s, e - s});
+        s = e;
+    }
+    FB_CUDA(cudaMalloc(&p->row_perm_d, sizeof(int32_t) * std::max<int64_t>(n_rows, 1)));
+    FB_CUDA(cudaMemcpy(p->row_perm_d, perm.data(), sizeof(int32_t) * n_rows, cudaMemcpyHostToDevice));
+    const int gs = dim == 3 ? 14 : 8;
+    FB_CUDA(cudaMalloc(&p->geom_d, sizeof(double) * std::max<int64_t>(p->rm->ne * gs, 1)));
+    p->gather_ready = true;
+    return FEDDB200_OK;
+}
+
+// canonical coefficient table from the operator's own quadrature rule (Laplace / elasticity use the
+// Grad-Grad degree): r[type][jc][s][t] = sum_q w_q c_row,s(q) c_col,t(q), where c are the
+// coefficients of grad(lambda_v) in the basis gradients:  vertex v: 4 lambda_v - 1 on v;
+// edge (p,q): 4 lambda_q on p, 4 lambda_p on q;  P1: 1.
+void canon_table(const OpTables &t, int dim, int nl, CanonR &R)
+{
+    std::memset(&R, 0, sizeof(R));
+    const int nv = dim + 1;
+    const bool p2 = nl > nv;
+    static const int E2[3][2] = {{0, 1}, {1, 2}, {0, 2}};
+    static const int E3[6][2] = {{0, 1}, {1, 2}, {0, 2}, {0, 3}, {1, 3}, {2, 3}};
+    auto edge = [&](int j, int k) { return dim == 2 ? E2[j - nv][k] : E3[j - nv][k]; };
+    for (int type = 0; type < (p2 ? 2 : 1); type++)
+        for (int jc = 0; jc < nl; jc++)
+            for (int s = 0; s < (type == 0 ? 1 : 2); s++)
+                for (int tt = 0; tt < (jc < nv ? 1 : 2); tt++) {
+                    double sum = 0.0;
+                    for (int q = 0; q < t.nq; q++) {
+                        const double *lam = &t.lam[q * 4];
+                        double crow, ccol;
+                        if (!p2) { crow = 1.0; ccol = 1.0; }
+                        else {
+                            crow = type == 0 ? 4.0 * lam[0] - 1.0 : 4.0 * lam[1 - s];
+                            ccol = jc < nv ? 4.0 * lam[jc] - 1.0 : 4.0 * lam[edge(jc, 1 - tt)];
+                        }
+                        sum += t.w[q] * crow * ccol;
+                    }
+                    R.r[type][jc][s][tt] = sum;
+                }
+}
+
+template <int OPG, int DIM, int NL>
+int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
+{
+    constexpr int TPR = OPG == 1 ? DIM * DIM : 1;
+    const int64_t blocks_geom = (p->rm->ne + 255) / 256;
+    if (p->rm->ne > 0) {
+        k_geom<DIM, NL><<<(unsigned)blocks_geom, 256, 0, c->stream>>>(p->rm->ne, p->rm->conn_d, p->rm->coords_d, p->geom_d);
+        c->launches++;
+    }
+    for (const Bucket &b : p->buckets) {
+        // block size: multiple of 16 (lane-private 8-byte banks) and of TPR (a node's threads stay
+        // in one block); shrink until the accumulators fit the opt-in shared memory
+        const int unit = (OPG == 1 && DIM == 3) ? 144 : 32;
+        int nt = (OPG == 1 && DIM == 3) ? 288 : 256;
+        const size_t budget = c->smem_optin - 1024;
+        while (nt > unit && (size_t)b.lcap * nt * 8 > budget) nt -= unit;
+        if ((size_t)b.lcap * nt * 8 > budget) {
+            set_error("row too long for the gather path's shared-memory accumulators; use the coloured or atomic mode");
+            return FEDDB200_ELOGIC;
+        }
+        const size_t smem = (size_t)b.lcap * nt * 8;
+        G.start = b.start; G.count = b.count; G.lcap = b.lcap;
+        const int64_t nthreads = b.count * TPR;
+        const int64_t blocks = (nthreads + nt - 1) / nt;
+        auto launch = [&](auto kernel) -> int {
+            FB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+            kernel<<<(unsigned)blocks, nt, smem, c->stream>>>(G);
+            c->launches++;
+            FB_CUDA(cudaGetLastError());
+            return FEDDB200_OK;
+        };
+        int rc;
+        if (b.type == 0) rc = launch(k_gather<OPG, DIM, NL, 0>);
+        else {
+            if constexpr (NL > DIM + 1) rc = launch(k_gather<OPG, DIM, NL, 1>);
+            else { set_error("edge-node row in a P1 pattern"); rc = FEDDB200_ELOGIC; }
+        }
+        if (rc != FEDDB200_OK) return rc;
+    }
+    return FEDDB200_OK;
+}
+
+template <int OPG>
+int launch_gather(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
+{
+    switch (elem_index(p->rm->dim, p->rm->nloc)) {
+    case 0: return launch_gather_t<OPG, 2, 3>(c, p, G);
+    case 1: return launch_gather_t<OPG, 2, 6>(c, p, G);
+    case 2: return launch_gather_t<OPG, 3, 4>(c, p, G);
+    case 3: return launch_gather_t<OPG, 3, 10>(c, p, G);
+    }
+    set_error("unsupported element");
+    return FEDDB200_ELOGIC;
+}
+
+// common driver of every assembly call
+int run_op(feddb200_ctx *c, const feddb200_pat *pc, int op, const double *u_d, double c0, double c1, double c2,
+           int vec_field, double *values_d)
+{
+    FB_LOGIC(!c || !pc || !values_d, "assembly: null argument");
+    FB_LOGIC(pc->ctx != c, "assembly: pattern belongs to another context");
+    feddb200_pat *p = const_cast<feddb200_pat *>(pc);
+    FB_CUDA(cudaSetDevice(c->device));
+    const feddb200_mesh *rm = p->rm, *cm = p->cm;
+    const int dim = rm->dim, nr = rm->nloc, nc = cm->nloc;
+    const bool square = (op != OP_B && op != OP_BT);
+    FB_LOGIC(square && nr != nc, "assembly: this operator needs the same FE space for rows and columns");
+    FB_LOGIC((op == OP_ADV || op == OP_ADVU || op == OP_NSJ) && !u_d, "assembly: velocity vector is null");
+    const feddb200_mesh *vm = (op == OP_B) ? cm : rm; // velocity / geometry mesh
+    const int nv = vm->nloc, np = (op == OP_B) ? nr : nc;
+    const OpTables *tab_d = nullptr;
+    OpTables tab_h;
+    int rc = get_tables(c, op, dim, nv, np, &tab_d, &tab_h);
+    if (rc != FEDDB200_OK) return rc;
+
+    int64_t factor;
+    switch (op) {
+    case OP_LAP:  factor = vec_field ? dim : 1; break;
+    case OP_ADV:  factor = dim; break;
+    case OP_B: case OP_BT: factor = dim; break;
+    default:      factor = (int64_t)dim * dim; break;
+    }
+    const int64_t nnz = factor * p->nnz;
+
+    int mode = c->mode;
+    if (mode == FEDDB200_SCATTER_GATHER && !(op == OP_LAP || op == OP_ELAS)) mode = FEDDB200_SCATTER_COLOURED;
+
+    if (mode == FEDDB200_SCATTER_GATHER) {
+        rc = ensure_gather(p);
+        if (rc != FEDDB200_OK) return rc;
+        GatherArgs G;
+        G.row_perm = p->row_perm_d; G.rowptr = p->rowptr_d; G.inc_ptr = p->inc_ptr_d; G.inc = p->inc_d;
+        G.posc = p->posc_d; G.posc_stride = p->posc_stride; G.geom = p->geom_d;
+        G.c0 = c0; G.c1 = c1; G.values = values_d; G.vec_dim = (op == OP_LAP && vec_field) ? dim : 0;
+        canon_table(tab_h, dim, nr, G.R);
+        return op == OP_LAP ? launch_gather<0>(c, p, G) : launch_gather<1>(c, p, G);
+    }
+
+    ElemArgs A;
+    A.conn_r = rm->conn_d; A.conn_c = cm->conn_d; A.conn_v = vm->conn_d; A.coords = vm->coords_d;
+    A.row_lid = p->row_lid_d; A.rowptr = p->rowptr_d; A.pos = p->pos_d; A.pos_stride = p->pos_stride;
+    A.elems = nullptr; A.n_items = rm->ne; A.u = u_d; A.c0 = c0; A.c1 = c1; A.c2 = c2; A.tab = tab_d;
+    A.values = values_d; A.vec_dim = (op == OP_LAP && vec_field) ? dim : 0;
+    if (nnz > 0) FB_CUDA(cudaMemsetAsync(values_d, 0, sizeof(double) * nnz, c->stream));
+    if (mode == FEDDB200_SCATTER_ATOMIC) return launch_elem_op(c, op, dim, nr, nc, A, true);
+    rc = ensure_colouring(p);
+    if (rc != FEDDB200_OK) return rc;
+    for (int k = 0; k < p->n_colours; k++) {
+        A.elems = p->colour_perm_d + p->colour_ptr[k];
+        A.n_items = p->colour_ptr[k + 1] - p->colour_ptr[k];
+        rc = launch_elem_op(c, op, dim, nr, nc, A, false);
+        if (rc != FEDDB200_OK) return rc;
+    }
+    return FEDDB200_OK;
+}
+
+__global__ void k_unpack_add(double *__restrict__ values, const double *__restrict__ recv, const int64_t *__restrict__ slot, int64_t n)
+{
+    // slots of one exchange are distinct per sender but two senders may hit the same slot
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(values + slot[t], recv[t]);
+}
+
+__global__ void k_scale(double *__restrict__ v, int64_t n, double a)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) v[t] *= a;
+}
+
+// host-pointer wrapper: grow-only device scratch owned by the context, H2D of u, D2H of the values
+int scratch(feddb200_ctx *c, int which, int64_t bytes, double **out)
+{
+    if ((int64_t)c->scratch_bytes[which] < bytes) {
+        if (c->scratch_d[which]) FB_CUDA(cudaFree(c->scratch_d[which]));
+        c->scratch_d[which] = nullptr;
+        c->scratch_bytes[which] = 0;
+        FB_CUDA(cudaMalloc(&c->scratch_d[which], (size_t)std::max<int64_t>(bytes, 8)));
+        c->scratch_bytes[which] = (size_t)bytes;
+    }
+    *out = (double *)c->scratch_d[which];
+    return FEDDB200_OK;
+}
+
+template <class F>
+int with_host_buffers(feddb200_ctx *c, const feddb200_pat *p, int64_t nnz, const double *u, int64_t nu, double *values, F &&run)
+{
+    FB_LOGIC(!c || !p || !values, "assembly: null argument");
+    FB_CUDA(cudaSetDevice(c->device));
+    double *v_d = nullptr, *u_d = nullptr;
+    int rc = scratch(c, 0, sizeof(double) * nnz, &v_d);
+    if (rc != FEDDB200_OK) return rc;
+    if (u) {
+        rc = scratch(c, 1, sizeof(double) * nu, &u_d);
+        if (rc != FEDDB200_OK) return rc;
+        FB_CUDA(cudaMemcpyAsync(u_d, u, sizeof(double) * nu, cudaMemcpyHostToDevice, c->stream));
+    }
+    rc = run(u_d, v_d);
+    if (rc == FEDDB200_OK && nnz > 0) {
+        FB_CUDA(cudaMemcpyAsync(values, v_d, sizeof(double) * nnz, cudaMemcpyDeviceToHost, c->stream));
+        FB_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return rc;
+}
+
+} // namespace
+
+extern "C" int feddb200_assemble_laplace_d(feddb200_ctx *c, const feddb200_pat *p, int vec_field, double *v)
+{
+    return run_op(c, p, OP_LAP, nullptr, 0, 0, 0, vec_field, v);
+}
+extern "C" int feddb200_assemble_linelas_d(feddb200_ctx *c, const feddb200_pat *p, double lambda, double mu, double *v)
+{
+    return run_op(c, p, OP_ELAS, nullptr, lambda, mu, 0, 0, v);
+}
+extern "C" int feddb200_assemble_advection_d(feddb200_ctx *c, const feddb200_pat *p, const double *u, double *v)
+{
+    return run_op(c, p, OP_ADV, u, 0, 0, 0, 0, v);
+}
+extern "C" int feddb200_assemble_advection_in_u_d(feddb200_ctx *c, const feddb200_pat *p, const double *u, double *v)
+{
+    return run_op(c, p, OP_ADVU, u, 0, 0, 0, 0, v);
+}
+extern "C" int feddb200_assemble_div_divT_d(feddb200_ctx *c, const feddb200_pat *pB, const feddb200_pat *pBT, double *vB, double *vBT)
+{
+    FB_LOGIC((vB && !pB) || (vBT && !pBT), "assemble_div_divT: output given without its pattern");
+    if (vB) { const int rc = run_op(c, pB, OP_B, nullptr, 0, 0, 0, 0, vB); if (rc) return rc; }
+    if (vBT) { const int rc = run_op(c, pBT, OP_BT, nullptr, 0, 0, 0, 0, vBT); if (rc) return rc; }
+    return FEDDB200_OK;
+}
+extern "C" int feddb200_assemble_ns_jacobian_d(feddb200_ctx *c, const feddb200_pat *p, double rho, double nu,
+                                               const double *u, int newton, double *v)
+{
+    return run_op(c, p, OP_NSJ, u, rho * nu, rho, newton ? rho : 0.0, 0, v);
+}
+
+extern "C" int feddb200_assemble_laplace(feddb200_ctx *c, const feddb200_pat *p, int vec_field, double *values)
+{
+    FB_LOGIC(!p, "null pattern");
+    const int64_t nnz = (vec_field ? p->rm->dim : 1) * p->nnz;
+    return with_host_buffers(c, p, nnz, nullptr, 0, values,
+                             [&](double *, double *v_d) { return feddb200_assemble_laplace_d(c, p, vec_field, v_d); });
+}
+extern "C" int feddb200_assemble_linelas(feddb200_ctx *c, const feddb200_pat *p, double lambda, double mu, double *values)
+{
+    FB_LOGIC(!p, "null pattern");
+    const int64_t nnz = (int64_t)p->rm->dim * p->rm->dim * p->nnz;
+    return with_host_buffers(c, p, nnz, nullptr, 0, values,
+                             [&](double *, double *v_d) { return feddb200_assemble_linelas_d(c, p, lambda, mu, v_d); });
+}
+extern "C" int feddb200_assemble_advection(feddb200_ctx *c, const feddb200_pat *p, const double *u, double *values)
+{
+    FB_LOGIC(!p || !u, "null argument");
+    return with_host_buffers(c, p, (int64_t)p->rm->dim * p->nnz, u, (int64_t)p->rm->dim * p->rm->nn, values,
+                             [&](double *u_d, double *v_d) { return feddb200_assemble_advection_d(c, p, u_d, v_d); });
+}
+extern "C" int feddb200_assemble_advection_in_u(feddb200_ctx *c, const feddb200_pat *p, const double *u, double *values)
+{
+    FB_LOGIC(!p || !u, "null argument");
+    return with_host_buffers(c, p, (int64_t)p->rm->dim * p->rm->dim * p->nnz, u, (int64_t)p->rm->dim * p->rm->nn, values,
+                             [&](double *u_d, double *v_d) { return feddb200_assemble_advection_in_u_d(c, p, u_d, v_d); });
+}
+extern "C" int feddb200_assemble_div_divT(feddb200_ctx *c, const feddb200_pat *pB, const feddb200_pat *pBT, double *vB, double *vBT)
+{
+    if (vB) {
+        FB_LOGIC(!pB, "null pattern");
+        const int rc = with_host_buffers(c, pB, (int64_t)pB->rm->dim * pB->nnz, nullptr, 0, vB, [&](double *, double *v_d) {
+            return feddb200_assemble_div_divT_d(c, pB, nullptr, v_d, nullptr);
+        });
+        if (rc) return rc;
+    }
+    if (vBT) {
+        FB_LOGIC(!pBT, "null pattern");
+        const int rc = with_host_buffers(c, pBT, (int64_t)pBT->rm->dim * pBT->nnz, nullptr, 0, vBT, [&](double *, double *v_d) {
+            return feddb200_assemble_div_divT_d(c, nullptr, pBT, nullptr, v_d);
+        });
+        if (rc) return rc;
+    }
+    return FEDDB200_OK;
+}
+extern "C" int feddb200_assemble_ns_jacobian(feddb200_ctx *c, const feddb200_pat *p, double rho, double nu, const double *u,
+                                             int newton, double *values)
+{
+    FB_LOGIC(!p || !u, "null argument");
+    return with_host_buffers(c, p, (int64_t)p->rm->dim * p->rm->dim * p->nnz, u, (int64_t)p->rm->dim * p->rm->nn, values,
+                             [&](double *u_d, double *v_d) { return feddb200_assemble_ns_jacobian_d(c, p, rho, nu, u_d, newton, v_d); });
+}
+
+extern "C" int feddb200_unpack_add_d(feddb200_ctx *c, double *values_d, const double *recv_d, const int64_t *slot_d, int64_t n)
+{
+    FB_LOGIC(!c || (n > 0 && (!values_d || !recv_d || !slot_d)) || n < 0, "unpack_add: bad arguments");
+    if (n == 0) return FEDDB200_OK;
+    FB_CUDA(cudaSetDevice(c->device));
+    k_unpack_add<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16), 256, 0, c->stream>>>(values_d, recv_d, slot_d, n);
+    c->launches++;
+    FB_CUDA(cudaGetLastError());
+    return FEDDB200_OK;
+}
+
+extern "C" int feddb200_scale_d(feddb200_ctx *c, double *values_d, int64_t n, double alpha)
+{
+    FB_LOGIC(!c || (n > 0 && !values_d) || n < 0, "scale: bad arguments");
+    if (n == 0) return FEDDB200_OK;
+    FB_CUDA(cudaSetDevice(c->device));
+    k_scale<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16), 256, 0, c->stream>>>(values_d, n, alpha);
+    c->launches++;
+    FB_CUDA(cudaGetLastError());
+    return FEDDB200_OK;
+}

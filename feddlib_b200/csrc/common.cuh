@@ -1,0 +1,109 @@
+// Internal definitions shared by the translation units of libfeddb200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/feddb200.h"
+
+namespace fb {
+
+void set_error(const std::string &msg);
+
+#define FB_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            fb::set_error(std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ +   \
+                          ":" + std::to_string(__LINE__) + ")");                                   \
+            return FEDDB200_ERUNTIME;                                                              \
+        }                                                                                          \
+    } while (0)
+
+#define FB_LOGIC(cond, msg)                                                                        \
+    do {                                                                                           \
+        if (cond) {                                                                                \
+            fb::set_error(msg);                                                                    \
+            return FEDDB200_ELOGIC;                                                                \
+        }                                                                                          \
+    } while (0)
+
+// operators of the hot path
+enum Op { OP_LAP = 0, OP_ELAS = 1, OP_ADV = 2, OP_ADVU = 3, OP_B = 4, OP_BT = 5, OP_NSJ = 6 };
+
+// Reference-element tables of one operator (restated from the FE type and quadrature degree,
+// see tables.cu): weights, gradients of the "velocity" space, values of the "value" space.
+constexpr int MAXQ = 15;
+constexpr int MAXN = 10;
+struct OpTables {
+    int nq, nv, np, dim;
+    double w[MAXQ];
+    double dphi[MAXQ * MAXN * 3]; // [q][i][c], stride nv*dim
+    double phi[MAXQ * MAXN];      // [q][i],   stride np
+    double lam[MAXQ * 4];         // barycentric coordinates of the quadrature points
+};
+
+struct Bucket {            // rows of one type with node-row length <= lcap, processed by one gather launch
+    int type;              // 0 vertex-node rows, 1 edge-node rows
+    int lcap;
+    int64_t start, count;  // range in row_perm
+};
+
+} // namespace fb
+
+struct feddb200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    int mode = FEDDB200_SCATTER_GATHER;
+    int64_t launches = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    fb::OpTables *tab_d = nullptr; // device copies of the operator tables, one slot per operator
+    int tab_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    void *scratch_d[2] = {nullptr, nullptr}; // grow-only device scratch of the host-pointer entry points
+    size_t scratch_bytes[2] = {0, 0};
+};
+
+struct feddb200_mesh {
+    feddb200_ctx *ctx = nullptr;
+    int dim = 0, nloc = 0;
+    int64_t ne = 0, nn = 0;
+    int32_t *conn_d = nullptr;
+    double *coords_d = nullptr;
+    std::vector<int32_t> conn_h; // kept for the host-side greedy element colouring
+};
+
+struct feddb200_pat {
+    feddb200_ctx *ctx = nullptr;
+    const feddb200_mesh *rm = nullptr, *cm = nullptr;
+    int64_t n_rows = 0, n_owned = 0, n_cols = 0, nnz = 0, nnz_owned = 0;
+    int max_len = 0;
+    int pos_stride = 0;
+    int64_t *rowptr_d = nullptr;  // [n_rows+1]  node-level
+    int32_t *colind_d = nullptr;  // [nnz]
+    int32_t *row_lid_d = nullptr; // [rm->nn] or null (identity)
+    uint16_t *pos_d = nullptr;    // [ne*nr][pos_stride] position of col node j in the row of node i
+    // row -> (element, local index) incidences, rows ascending, elements ascending within a row
+    int64_t n_inc = 0;
+    int64_t *inc_ptr_d = nullptr; // [n_rows+1]
+    int32_t *inc_d = nullptr;     // [n_inc]  (e << 4) | i
+    int32_t *row_perm_d = nullptr; // rows ordered by bucket (built lazily with the gather maps)
+    uint16_t *posc_d = nullptr;    // [n_inc][posc_stride] canonical position map
+    int posc_stride = 0;
+    double *geom_d = nullptr;      // [ne][GS] per-element geometry cache, recomputed by every assembly
+    bool gather_ready = false;
+    std::vector<fb::Bucket> buckets;
+    // element colouring (lazy)
+    int n_colours = 0;
+    std::vector<int64_t> colour_ptr;
+    int32_t *colour_perm_d = nullptr;
+    std::vector<int64_t> rowptr_h;
+};
+
+namespace fb {
+int build_tables(OpTables &t, int op, int dim, int nloc_v, int nloc_p);
+int ensure_colouring(feddb200_pat *pat);
+} // namespace fb

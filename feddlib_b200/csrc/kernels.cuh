@@ -1,0 +1,593 @@
+// Device code of the assembly hot path (sm_100a).  Three scatter strategies share the math:
+//
+//  * element-row kernels (k_elem): one thread per (element, local row[, row dof]).  The thread
+//    evaluates its row of the local matrix by quadrature exactly as the reference loops do
+//    (FE_def.hpp:637-661 etc.) and adds it to the CSR values either with RED.ADD.F64 atomics
+//    (FEDDB200_SCATTER_ATOMIC) or, launched once per element colour, with plain
+//    read-modify-write (FEDDB200_SCATTER_COLOURED, deterministic).
+//  * row-gather kernels (k_gather): output-stationary.  One thread per CSR row component walks
+//    the elements incident to its row node in a fixed order, accumulates in lane-private
+//    shared-memory banks and writes every CSR value exactly once with vector stores -- no
+//    atomics, no memset, bitwise reproducible.  (FEDDB200_SCATTER_GATHER)
+#pragma once
+#include "common.cuh"
+
+namespace fb {
+
+// -----------------------------------------------------------------------------------------
+// affine map of an element: B[i][j] = x_{j+1}[i] - x_0[i], Binv = adj(B)/det, |det|
+// (reference: FE_def.hpp:5342-5357 buildTransformation, SmallMatrix.hpp:306-358)
+// -----------------------------------------------------------------------------------------
+template <int DIM>
+__device__ __forceinline__ void affine_map(const int32_t *__restrict__ el, const double *__restrict__ coords,
+                                           double (&Binv)[DIM][DIM], double &adet)
+{
+    double B[DIM][DIM], x0[DIM];
+    const int64_t n0 = el[0];
+#pragma unroll
+    for (int i = 0; i < DIM; i++) x0[i] = coords[n0 * DIM + i];
+#pragma unroll
+    for (int j = 0; j < DIM; j++) {
+        const int64_t nj = el[j + 1];
+#pragma unroll
+        for (int i = 0; i < DIM; i++) B[i][j] = coords[nj * DIM + i] - x0[i];
+    }
+    if constexpr (DIM == 2) {
+        const double det = B[0][0] * B[1][1] - B[1][0] * B[0][1];
+        const double r = 1.0 / det;
+        Binv[0][0] = B[1][1] * r;
+        Binv[0][1] = -B[0][1] * r;
+        Binv[1][0] = -B[1][0] * r;
+        Binv[1][1] = B[0][0] * r;
+        adet = fabs(det);
+    } else {
+        const double det = B[0][0] * B[1][1] * B[2][2] + B[0][1] * B[1][2] * B[2][0] + B[0][2] * B[1][0] * B[2][1] -
+                           B[2][0] * B[1][1] * B[0][2] - B[2][1] * B[1][2] * B[0][0] - B[2][2] * B[1][0] * B[0][1];
+        const double r = 1.0 / det;
+        Binv[0][0] = (B[1][1] * B[2][2] - B[1][2] * B[2][1]) * r;
+        Binv[0][1] = (B[0][2] * B[2][1] - B[0][1] * B[2][2]) * r;
+        Binv[0][2] = (B[0][1] * B[1][2] - B[0][2] * B[1][1]) * r;
+        Binv[1][0] = (B[1][2] * B[2][0] - B[1][0] * B[2][2]) * r;
+        Binv[1][1] = (B[0][0] * B[2][2] - B[0][2] * B[2][0]) * r;
+        Binv[1][2] = (B[0][2] * B[1][0] - B[0][0] * B[1][2]) * r;
+        Binv[2][0] = (B[1][0] * B[2][1] - B[1][1] * B[2][0]) * r;
+        Binv[2][1] = (B[0][1] * B[2][0] - B[0][0] * B[2][1]) * r;
+        Binv[2][2] = (B[0][0] * B[1][1] - B[0][1] * B[1][0]) * r;
+        adet = fabs(det);
+    }
+}
+
+// physical gradient g[d] = sum_c ghat[c] * Binv[c][d]   (FE_def.hpp:83-96 applyBTinv)
+template <int DIM>
+__device__ __forceinline__ void push_grad(const double *__restrict__ ghat, const double (&Binv)[DIM][DIM], double (&g)[DIM])
+{
+#pragma unroll
+    for (int d = 0; d < DIM; d++) {
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < DIM; c++) s += ghat[c] * Binv[c][d];
+        g[d] = s;
+    }
+}
+
+struct ElemArgs {
+    const int32_t *conn_r, *conn_c, *conn_v; // row / column / velocity(geometry) connectivity
+    const double *coords;                    // points of the velocity mesh
+    const int32_t *row_lid;                  // nullable
+    const int64_t *rowptr;
+    const uint16_t *pos;
+    int pos_stride;
+    const int32_t *elems;                    // nullable: element list of this launch (one colour)
+    int64_t n_items;
+    const double *u;
+    double c0, c1, c2;                       // lambda,mu | rho*nu, rho, rho(newton)
+    const OpTables *tab;
+    double *values;
+    int vec_dim;                             // LAP: 0 scalar, dim = block-diagonal copies
+    int atomic;
+};
+
+template <bool ATOMIC>
+__device__ __forceinline__ void add_to(double *p, double v)
+{
+    if constexpr (ATOMIC) atomicAdd(p, v);
+    else *p += v;
+}
+
+// threads per row node
+template <int OP, int DIM> struct RowDofs { static constexpr int value = (OP == OP_ELAS || OP == OP_ADVU || OP == OP_BT || OP == OP_NSJ) ? DIM : 1; };
+
+template <int OP, int DIM, int NR, int NC, bool ATOMIC>
+__global__ void __launch_bounds__(128) k_elem(const ElemArgs A)
+{
+    constexpr int RD = RowDofs<OP, DIM>::value;
+    constexpr int NV = (OP == OP_B) ? NC : NR;  // nodes of the velocity (gradient) space
+    constexpr int NP = (OP == OP_B) ? NR : NC;  // nodes of the value space (pressure for B/BT)
+    __shared__ OpTables T;
+    {
+        const double *src = reinterpret_cast<const double *>(A.tab);
+        double *dst = reinterpret_cast<double *>(&T);
+        for (int k = threadIdx.x; k < (int)(sizeof(OpTables) / sizeof(double)); k += blockDim.x) dst[k] = src[k];
+    }
+    __syncthreads();
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= A.n_items * (NR * RD)) return;
+    const int64_t item = t / (NR * RD);
+    const int rem = (int)(t - item * (NR * RD));
+    const int i = rem / RD;
+    const int a = rem - i * RD; // row dof handled by this thread (0 when RD == 1)
+    const int64_t e = A.elems ? A.elems[item] : item;
+
+    int32_t I = A.conn_r[e * NR + i];
+    if (A.row_lid) I = A.row_lid[I];
+    if (I < 0) return;
+
+    const int32_t *cv = A.conn_v + e * NV;
+    double Binv[DIM][DIM], adet;
+    affine_map<DIM>(cv, A.coords, Binv, adet);
+
+    const int nq = T.nq;
+    const int64_t base = A.rowptr[I];
+    const int64_t L = A.rowptr[I + 1] - base;
+    const uint16_t *pos = A.pos + (e * NR + i) * A.pos_stride;
+
+    if constexpr (OP == OP_LAP) {
+        double acc[NC];
+#pragma unroll
+        for (int j = 0; j < NC; j++) acc[j] = 0.0;
+        for (int q = 0; q < nq; q++) {
+            double gi[DIM];
+            push_grad<DIM>(&T.dphi[(q * NV + i) * DIM], Binv, gi);
+            const double w = T.w[q];
+#pragma unroll
+            for (int j = 0; j < NC; j++) {
+                double gj[DIM];
+                push_grad<DIM>(&T.dphi[(q * NV + j) * DIM], Binv, gj);
+                double s = 0.0;
+#pragma unroll
+                for (int d = 0; d < DIM; d++) s += w * gi[d] * gj[d];
+                acc[j] += s;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NC; j++) {
+            const double v = acc[j] * adet;
+            const int64_t p = pos[j];
+            if (A.vec_dim == 0) add_to<ATOMIC>(A.values + base + p, v);
+            else for (int d = 0; d < DIM; d++) add_to<ATOMIC>(A.values + DIM * base + d * L + p, v);
+        }
+    } else if constexpr (OP == OP_ELAS) {
+        const double lambda = A.c0, mu = A.c1;
+        double acc[NC][DIM];
+#pragma unroll
+        for (int j = 0; j < NC; j++)
+#pragma unroll
+            for (int b = 0; b < DIM; b++) acc[j][b] = 0.0;
+        for (int q = 0; q < nq; q++) {
+            double gi[DIM];
+            push_grad<DIM>(&T.dphi[(q * NV + i) * DIM], Binv, gi);
+            const double w = T.w[q];
+            double gia = 0.0;
+#pragma unroll
+            for (int d = 0; d < DIM; d++) gia = (d == a) ? gi[d] : gia;
+#pragma unroll
+            for (int j = 0; j < NC; j++) {
+                double gj[DIM];
+                push_grad<DIM>(&T.dphi[(q * NV + j) * DIM], Binv, gj);
+                double dot = 0.0, gja = 0.0;
+#pragma unroll
+                for (int d = 0; d < DIM; d++) { dot += gi[d] * gj[d]; gja = (d == a) ? gj[d] : gja; }
+#pragma unroll
+                for (int b = 0; b < DIM; b++) {
+                    // K^{ab}_ij = mu (delta_ab g_i.g_j + g_i[b] g_j[a]) + lambda g_i[a] g_j[b]  (SURVEY A.4,
+                    // algebraically equal to the epsilon-tensor form of FE_def.hpp:2939-2993)
+                    const double k = mu * ((b == a ? dot : 0.0) + gi[b] * gja) + lambda * gia * gj[b];
+                    acc[j][b] += w * k;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NC; j++) {
+            const int64_t p = pos[j];
+#pragma unroll
+            for (int b = 0; b < DIM; b++)
+                add_to<ATOMIC>(A.values + (int64_t)DIM * DIM * base + (int64_t)a * DIM * L + DIM * p + b, adet * acc[j][b]);
+        }
+    } else if constexpr (OP == OP_ADV) {
+        double ul[NV][DIM];
+#pragma unroll
+        for (int m = 0; m < NV; m++)
+#pragma unroll
+            for (int d = 0; d < DIM; d++) ul[m][d] = A.u[(int64_t)DIM * cv[m] + d];
+        double acc[NC];
+#pragma unroll
+        for (int j = 0; j < NC; j++) acc[j] = 0.0;
+        for (int q = 0; q < nq; q++) {
+            double uq[DIM];
+#pragma unroll
+            for (int d = 0; d < DIM; d++) uq[d] = 0.0;
+#pragma unroll
+            for (int m = 0; m < NV; m++) {
+                const double ph = T.phi[q * NP + m];
+#pragma unroll
+                for (int d = 0; d < DIM; d++) uq[d] += ul[m][d] * ph;
+            }
+            const double f = T.w[q] * T.phi[q * NP + i];
+#pragma unroll
+            for (int j = 0; j < NC; j++) {
+                double gj[DIM];
+                push_grad<DIM>(&T.dphi[(q * NV + j) * DIM], Binv, gj);
+                double s = 0.0;
+#pragma unroll
+                for (int d = 0; d < DIM; d++) s += uq[d] * gj[d];
+                acc[j] += f * s;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NC; j++) {
+            const double v = acc[j] * adet;
+            const int64_t p = pos[j];
+            for (int d = 0; d < DIM; d++) add_to<ATOMIC>(A.values + DIM * base + d * L + p, v);
+        }
+    } else if constexpr (OP == OP_ADVU || OP == OP_NSJ) {
+        // thread handles row dof d1 = a.  W^{d1 d2}_ij = |det| sum_q w_q D_q[d2][d1] phi_i phi_j with
+        // D_q[d2][d1] = sum_m u_{m,d1} g_m(q)[d2]  (FE_def.hpp:1887-1912)
+        double ua[NV];
+#pragma unroll
+        for (int m = 0; m < NV; m++) ua[m] = A.u[(int64_t)DIM * cv[m] + a];
+        double acc[NC][DIM];
+#pragma unroll
+        for (int j = 0; j < NC; j++)
+#pragma unroll
+            for (int b = 0; b < DIM; b++) acc[j][b] = 0.0;
+        for (int q = 0; q < nq; q++) {
+            double Dh[DIM], D[DIM];
+#pragma unroll
+            for (int c = 0; c < DIM; c++) Dh[c] = 0.0;
+#pragma unroll
+            for (int m = 0; m < NV; m++)
+#pragma unroll
+                for (int c = 0; c < DIM; c++) Dh[c] += ua[m] * T.dphi[(q * NV + m) * DIM + c];
+            push_grad<DIM>(Dh, Binv, D);
+            const double wq = T.w[q];
+            const double phi_i = T.phi[q * NP + i];
+            if constexpr (OP == OP_ADVU) {
+                const double f = wq * phi_i;
+#pragma unroll
+                for (int j = 0; j < NC; j++) {
+                    const double fj = f * T.phi[q * NP + j];
+#pragma unroll
+                    for (int b = 0; b < DIM; b++) acc[j][b] += fj * D[b];
+                }
+            } else {
+                // fused (0,0) block: c0*Laplace (diag) + c1*N(u) (diag) + c2*W(u) (full)
+                double gi[DIM], uq[DIM];
+                push_grad<DIM>(&T.dphi[(q * NV + i) * DIM], Binv, gi);
+#pragma unroll
+                for (int d = 0; d < DIM; d++) uq[d] = 0.0;
+#pragma unroll
+                for (int m = 0; m < NV; m++) {
+                    const double ph = T.phi[q * NP + m];
+#pragma unroll
+                    for (int d = 0; d < DIM; d++) uq[d] += A.u[(int64_t)DIM * cv[m] + d] * ph;
+                }
+#pragma unroll
+                for (int j = 0; j < NC; j++) {
+                    double gj[DIM];
+                    push_grad<DIM>(&T.dphi[(q * NV + j) * DIM], Binv, gj);
+                    double lap = 0.0, adv = 0.0;
+#pragma unroll
+                    for (int d = 0; d < DIM; d++) { lap += gi[d] * gj[d]; adv += uq[d] * gj[d]; }
+                    const double diag = wq * (A.c0 * lap + A.c1 * phi_i * adv);
+                    const double fj = A.c2 * wq * phi_i * T.phi[q * NP + j];
+#pragma unroll
+                    for (int b = 0; b < DIM; b++) acc[j][b] += (b == a ? diag : 0.0) + fj * D[b];
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NC; j++) {
+            const int64_t p = pos[j];
+#pragma unroll
+            for (int b = 0; b < DIM; b++)
+                add_to<ATOMIC>(A.values + (int64_t)DIM * DIM * base + (int64_t)a * DIM * L + DIM * p + b, adet * acc[j][b]);
+        }
+    } else if constexpr (OP == OP_B) {
+        // row = pressure node i, cols = (velocity node j, d)   (FE_def.hpp:1991-2017)
+        double acc[NC][DIM];
+#pragma unroll
+        for (int j = 0; j < NC; j++)
+#pragma unroll
+            for (int d = 0; d < DIM; d++) acc[j][d] = 0.0;
+        for (int q = 0; q < nq; q++) {
+            const double f = T.w[q] * T.phi[q * NP + i];
+#pragma unroll
+            for (int j = 0; j < NC; j++) {
+                double gj[DIM];
+                push_grad<DIM>(&T.dphi[(q * NV + j) * DIM], Binv, gj);
+#pragma unroll
+                for (int d = 0; d < DIM; d++) acc[j][d] += f * gj[d];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NC; j++) {
+            const int64_t p = pos[j];
+#pragma unroll
+            for (int d = 0; d < DIM; d++) add_to<ATOMIC>(A.values + (int64_t)DIM * base + DIM * p + d, adet * acc[j][d]);
+        }
+    } else if constexpr (OP == OP_BT) {
+        // row = (velocity node i, dof a), cols = pressure nodes j   (FE_def.hpp:2021-2047)
+        double acc[NC];
+#pragma unroll
+        for (int j = 0; j < NC; j++) acc[j] = 0.0;
+        for (int q = 0; q < nq; q++) {
+            double gi[DIM];
+            push_grad<DIM>(&T.dphi[(q * NV + i) * DIM], Binv, gi);
+            double gia = 0.0;
+#pragma unroll
+            for (int d = 0; d < DIM; d++) gia = (d == a) ? gi[d] : gia;
+            const double f = T.w[q] * gia;
+#pragma unroll
+            for (int j = 0; j < NC; j++) acc[j] += f * T.phi[q * NP + j];
+        }
+#pragma unroll
+        for (int j = 0; j < NC; j++)
+            add_to<ATOMIC>(A.values + (int64_t)DIM * base + (int64_t)a * L + pos[j], adet * acc[j]);
+    }
+}
+
+// -----------------------------------------------------------------------------------------
+// row-gather path
+// -----------------------------------------------------------------------------------------
+// per-element geometry cache: gradients of the barycentric coordinates G_v = grad lambda_v
+// (v = 0..DIM) and |det B|.  Layout [e][GS] doubles, G_v at 3*v (DIM*v), |det| at GS-2.
+template <int DIM> struct GeomStride { static constexpr int value = DIM == 3 ? 14 : 8; };
+
+template <int DIM, int NL>
+__global__ void __launch_bounds__(256) k_geom(int64_t ne, const int32_t *__restrict__ conn,
+                                              const double *__restrict__ coords, double *__restrict__ geom)
+{
+    constexpr int GS = GeomStride<DIM>::value;
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    double Binv[DIM][DIM], adet;
+    affine_map<DIM>(conn + e * NL, coords, Binv, adet);
+    double *g = geom + e * GS;
+    // grad lambda_k = row k-1 of Binv (k >= 1), grad lambda_0 = -(sum of the others)
+#pragma unroll
+    for (int d = 0; d < DIM; d++) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < DIM; k++) { g[DIM * (k + 1) + d] = Binv[k][d]; s -= Binv[k][d]; }
+        g[d] = s;
+    }
+    g[GS - 2] = adet;
+    g[GS - 1] = 0.0;
+}
+
+// canonical relabelling of an element seen from local node i: the vertex permutation pi puts
+// node i at canonical vertex 0 (vertex nodes) or on canonical edge (0,1) (edge nodes)
+template <int DIM>
+__host__ __device__ inline void canon_perm(int i, int (&pi)[DIM + 1])
+{
+    constexpr int NVTX = DIM + 1;
+    int first = i, second = -1;
+    if (i >= NVTX) {
+        const int e = i - NVTX;
+        if constexpr (DIM == 2) { const int E[3][2] = {{0, 1}, {1, 2}, {0, 2}}; first = E[e][0]; second = E[e][1]; }
+        else { const int E[6][2] = {{0, 1}, {1, 2}, {0, 2}, {0, 3}, {1, 3}, {2, 3}}; first = E[e][0]; second = E[e][1]; }
+    }
+    int n = 0;
+    pi[n++] = first;
+    if (second >= 0) pi[n++] = second;
+    for (int v = 0; v < NVTX; v++)
+        if (v != first && v != second) pi[n++] = v;
+}
+
+// actual local node index of canonical local node jc under permutation pi
+template <int DIM>
+__host__ __device__ inline int canon_node(const int (&pi)[DIM + 1], int jc)
+{
+    constexpr int NVTX = DIM + 1;
+    if (jc < NVTX) return pi[jc];
+    const int e = jc - NVTX;
+    int a, b;
+    if constexpr (DIM == 2) { const int E[3][2] = {{0, 1}, {1, 2}, {0, 2}}; a = pi[E[e][0]]; b = pi[E[e][1]]; }
+    else { const int E[6][2] = {{0, 1}, {1, 2}, {0, 2}, {0, 3}, {1, 3}, {2, 3}}; a = pi[E[e][0]]; b = pi[E[e][1]]; }
+    if (a > b) { const int t = a; a = b; b = t; }
+    if constexpr (DIM == 2) return NVTX + (a == 0 ? (b == 1 ? 0 : 2) : 1);
+    else return NVTX + (a == 0 ? (b == 1 ? 0 : (b == 2 ? 2 : 3)) : (a == 1 ? (b == 2 ? 1 : 4) : 5));
+}
+
+// per-incidence canonical position map: posc[k][jc] = position (in the row of the incidence's
+// row node) of canonical local node jc; rtype[row] = 0 vertex node / 1 edge node
+template <int DIM, int NL>
+__global__ void k_canon_pos(int64_t n_rows, const int64_t *__restrict__ inc_ptr, const int32_t *__restrict__ inc,
+                            const uint16_t *__restrict__ pos, int pos_stride, uint16_t *__restrict__ posc,
+                            int posc_stride, int8_t *__restrict__ rtype)
+{
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x) {
+        int8_t ty = 0;
+        for (int64_t k = inc_ptr[r]; k < inc_ptr[r + 1]; k++) {
+            const int32_t code = inc[k];
+            const int64_t e = code >> 4;
+            const int i = code & 15;
+            ty = i > DIM ? 1 : 0;
+            int pi[DIM + 1];
+            canon_perm<DIM>(i, pi);
+            for (int jc = 0; jc < NL; jc++)
+                posc[k * posc_stride + jc] = pos[(e * NL + i) * pos_stride + canon_node<DIM>(pi, jc)];
+        }
+        rtype[r] = ty;
+    }
+}
+
+// Canonical coefficient table: K_{i',j'} = sum_{s,t} r[type][j'][s][t] * E(pi(s_i'), sv(j',t)) where
+// s runs over the canonical support of the row function (vertex 0 | edge (0,1)) and t over the
+// support of column function j' (a vertex function uses t = 0 only).
+struct CanonR {
+    double r[2][MAXN][2][2];
+};
+
+struct GatherArgs {
+    const int32_t *row_perm;  // rows of this launch: row_perm[start .. start+count)
+    int64_t start, count;
+    const int64_t *rowptr;
+    const int64_t *inc_ptr;
+    const int32_t *inc;
+    const uint16_t *posc;
+    int posc_stride;
+    const double *geom;
+    double c0, c1;            // lambda, mu
+    double *values;
+    int lcap;
+    int vec_dim;              // LAP: 0 scalar, DIM = replicate to the DIM block-diagonal dof rows
+    CanonR R;
+};
+
+__device__ __forceinline__ void st_v2(double *p, double a, double b)
+{
+    asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ void st_v4(double *p, double a, double b, double c, double d)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
+// support (canonical vertices) of canonical local node jc
+template <int DIM>
+__device__ __forceinline__ constexpr int canon_sv(int jc, int t)
+{
+    constexpr int NVTX = DIM + 1;
+    if (jc < NVTX) return jc;
+    if constexpr (DIM == 2) { constexpr int E[3][2] = {{0, 1}, {1, 2}, {0, 2}}; return E[jc - NVTX][t]; }
+    else { constexpr int E[6][2] = {{0, 1}, {1, 2}, {0, 2}, {0, 3}, {1, 3}, {2, 3}}; return E[jc - NVTX][t]; }
+}
+
+// OPG: 0 Laplace (one thread per row node), 1 elasticity (DIM*DIM threads per row node)
+// TYPE: 0 vertex rows, 1 edge rows
+template <int OPG, int DIM, int NL, int TYPE>
+__global__ void __launch_bounds__(288) k_gather(const GatherArgs A)
+{
+    constexpr int NVTX = DIM + 1;
+    constexpr int GS = GeomStride<DIM>::value;
+    constexpr int TPR = OPG == 1 ? DIM * DIM : 1; // threads per row node
+    constexpr int NS = TYPE == 0 ? 1 : 2;          // canonical support size of the row function
+    extern __shared__ double acc[];                // [lcap][blockDim.x], lane-private banks
+    const int NT = blockDim.x;
+    const int tid = threadIdx.x;
+    const int64_t t = blockIdx.x * (int64_t)NT + tid;
+    const bool active = t < A.count * TPR;
+    const int64_t rloc = active ? t / TPR : 0;
+    const int comp = (int)(t - rloc * TPR);
+    const int a = comp / DIM, b = comp - a * DIM;
+    const int32_t row = active ? A.row_perm[A.start + rloc] : 0;
+    const int64_t base = active ? A.rowptr[row] : 0;
+    const int L = active ? (int)(A.rowptr[row + 1] - base) : 0;
+
+    for (int p = 0; p < L; p++) acc[p * NT + tid] = 0.0;
+
+    if (active) {
+        const int64_t k1 = A.inc_ptr[row + 1];
+        for (int64_t k = A.inc_ptr[row]; k < k1; k++) {
+            const int32_t code = A.inc[k];
+            const int64_t e = code >> 4;
+            int pi[NVTX];
+            canon_perm<DIM>(code & 15, pi);
+            const double *g = A.geom + e * GS;
+            const double adet = g[GS - 2];
+            // E[s][w] for canonical row-support vertex s and canonical vertex w
+            double E[NS][NVTX];
+            if constexpr (OPG == 0) {
+                double Gs[NS][DIM];
+#pragma unroll
+                for (int s = 0; s < NS; s++)
+#pragma unroll
+                    for (int d = 0; d < DIM; d++) Gs[s][d] = g[DIM * pi[s] + d] * adet;
+#pragma unroll
+                for (int w = 0; w < NVTX; w++) {
+                    double Gw[DIM];
+#pragma unroll
+                    for (int d = 0; d < DIM; d++) Gw[d] = g[DIM * pi[w] + d];
+#pragma unroll
+                    for (int s = 0; s < NS; s++) {
+                        double dot = 0.0;
+#pragma unroll
+                        for (int d = 0; d < DIM; d++) dot += Gs[s][d] * Gw[d];
+                        E[s][w] = dot;
+                    }
+                }
+            } else {
+                const double mu = A.c1 * adet, lam = A.c0 * adet;
+                double Gs[NS][DIM], Gsa[NS], Gsb[NS];
+#pragma unroll
+                for (int s = 0; s < NS; s++) {
+#pragma unroll
+                    for (int d = 0; d < DIM; d++) Gs[s][d] = g[DIM * pi[s] + d];
+                    Gsa[s] = g[DIM * pi[s] + a];
+                    Gsb[s] = g[DIM * pi[s] + b];
+                }
+#pragma unroll
+                for (int w = 0; w < NVTX; w++) {
+                    double Gw[DIM];
+#pragma unroll
+                    for (int d = 0; d < DIM; d++) Gw[d] = g[DIM * pi[w] + d];
+                    const double Gwa = g[DIM * pi[w] + a], Gwb = g[DIM * pi[w] + b];
+#pragma unroll
+                    for (int s = 0; s < NS; s++) {
+                        double dot = 0.0;
+#pragma unroll
+                        for (int d = 0; d < DIM; d++) dot += Gs[s][d] * Gw[d];
+                        // E^{ab}_{sw} = mu (delta_ab G_s.G_w + G_s[b] G_w[a]) + lambda G_s[a] G_w[b]
+                        E[s][w] = mu * ((a == b ? dot : 0.0) + Gsb[s] * Gwa) + lam * Gsa[s] * Gwb;
+                    }
+                }
+            }
+            const uint16_t *pc = A.posc + k * A.posc_stride;
+#pragma unroll
+            for (int jc = 0; jc < NL; jc++) {
+                double v = 0.0;
+#pragma unroll
+                for (int s = 0; s < NS; s++) {
+                    v += A.R.r[TYPE][jc][s][0] * E[s][canon_sv<DIM>(jc, 0)];
+                    if (jc >= NVTX) v += A.R.r[TYPE][jc][s][1] * E[s][canon_sv<DIM>(jc, 1)];
+                }
+                const int p = pc[jc];
+                acc[p * NT + tid] += v;
+            }
+        }
+    }
+
+    if constexpr (OPG == 0) {
+        // thread owns node row `row`; scalar: one CSR row of L values; vec field: DIM dof rows
+        if (active) {
+            const int nrep = A.vec_dim == 0 ? 1 : A.vec_dim;
+            for (int d = 0; d < nrep; d++) {
+                double *out = A.values + (int64_t)nrep * base + (int64_t)d * L;
+                int p = 0;
+                while (p < L && (reinterpret_cast<uintptr_t>(out + p) & 31)) { out[p] = acc[p * NT + tid]; p++; }
+                for (; p + 4 <= L; p += 4)
+                    st_v4(out + p, acc[p * NT + tid], acc[(p + 1) * NT + tid], acc[(p + 2) * NT + tid], acc[(p + 3) * NT + tid]);
+                for (; p < L; p++) out[p] = acc[p * NT + tid];
+            }
+        }
+    } else {
+        // threads (a, b = 0..DIM-1) of a node hold interleaved parts of dof row (I, a): entry
+        // (p, b') lives in the accumulator of thread (a, b').  Thread (a, b) writes the b-th
+        // third of the dof row as one contiguous run.  The DIM threads are adjacent lanes of the
+        // same warp unless the group straddles a warp boundary, hence the block barrier.
+        __syncthreads();
+        if (active) {
+            const int tid0 = tid - b; // thread (a, 0); may lie in the previous warp
+            double *out = A.values + (int64_t)DIM * DIM * base + (int64_t)a * DIM * L;
+            const int x0 = b * L, x1 = x0 + L;
+            auto val = [&](int x) { const int p = x / DIM; return acc[p * NT + tid0 + (x - p * DIM)]; };
+            int x = x0;
+            while (x < x1 && (reinterpret_cast<uintptr_t>(out + x) & 31)) { out[x] = val(x); x++; }
+            for (; x + 4 <= x1; x += 4) st_v4(out + x, val(x), val(x + 1), val(x + 2), val(x + 3));
+            for (; x < x1; x++) out[x] = val(x);
+        }
+    }
+}
+
+} // namespace fb

@@ -1,0 +1,230 @@
+"""Thin object layer over the C ABI (include/feddb200.h): Context, Mesh, Pattern.
+
+PyTorch appears only as plumbing (device buffers, streams); every computation is in
+libfeddb200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import (BLOCK_DIAG, BLOCK_FULL, BLOCK_SCALAR, SCATTER_ATOMIC, SCATTER_COLOURED, SCATTER_GATHER, check,
+                   ptr)
+
+_MODES = {"atomic": SCATTER_ATOMIC, "coloured": SCATTER_COLOURED, "colored": SCATTER_COLOURED,
+          "gather": SCATTER_GATHER}
+
+
+class Context:
+    """One engine context per GPU / rank (feddb200_create)."""
+
+    def __init__(self, device: int = 0, use_torch_stream: bool = True):
+        self._L = _lib.load()
+        h = C.c_void_p()
+        check(self._L.feddb200_create(C.byref(h), int(device)))
+        self._h = h
+        self.device = int(device)
+        if use_torch_stream:
+            self.bind_torch_stream()
+
+    def bind_torch_stream(self):
+        """Run the engine's kernels on torch's current CUDA stream so torch events time them."""
+        import torch
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        check(self._L.feddb200_set_stream(self._h, C.c_void_p(s)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.feddb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_scatter_mode(self, mode):
+        check(self._L.feddb200_set_scatter_mode(self._h, _MODES[mode] if isinstance(mode, str) else int(mode)))
+
+    @property
+    def scatter_mode(self) -> int:
+        return self._L.feddb200_get_scatter_mode(self._h)
+
+    def synchronize(self):
+        check(self._L.feddb200_synchronize(self._h))
+
+    @property
+    def launches(self) -> int:
+        return int(self._L.feddb200_launch_count(self._h))
+
+    def empty_values(self, n: int):
+        import torch
+        return torch.empty(int(n), dtype=torch.float64, device=f"cuda:{self.device}")
+
+    def scale_d(self, values, alpha: float):
+        check(self._L.feddb200_scale_d(self._h, ptr(values), values.numel(), float(alpha)))
+
+    def unpack_add_d(self, values, recv, slots):
+        check(self._L.feddb200_unpack_add_d(self._h, ptr(values), ptr(recv), ptr(slots), recv.numel()))
+
+
+class Mesh:
+    """Uploaded connectivity + repeated points (feddb200_mesh_upload)."""
+
+    def __init__(self, ctx: Context, dim: int, conn: np.ndarray, coords: np.ndarray):
+        self.ctx = ctx
+        conn = np.ascontiguousarray(conn, dtype=np.int32)
+        coords = np.ascontiguousarray(coords, dtype=np.float64)
+        if conn.ndim != 2 or coords.ndim != 2 or coords.shape[1] != dim:
+            raise _lib.LogicError("Mesh: conn must be [ne, nloc] and coords [nn, dim]")
+        self.dim, self.nloc = int(dim), int(conn.shape[1])
+        self.ne, self.nn = int(conn.shape[0]), int(coords.shape[0])
+        h = C.c_void_p()
+        check(ctx._L.feddb200_mesh_upload(ctx._h, C.byref(h), self.dim, self.nloc, self.ne, ptr(conn), self.nn,
+                                          ptr(coords)))
+        self._h = h
+
+    def update_coords(self, coords: np.ndarray):
+        coords = np.ascontiguousarray(coords, dtype=np.float64)
+        assert coords.shape == (self.nn, self.dim)
+        check(self.ctx._L.feddb200_mesh_update_coords(self.ctx._h, self._h, ptr(coords)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.ctx._L.feddb200_mesh_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Pattern:
+    """Node-level CSR pattern + scatter/gather maps (feddb200_pattern_build)."""
+
+    def __init__(self, ctx: Context, row_mesh: Mesh, col_mesh: Mesh | None = None, row_lid=None, n_rows=0,
+                 n_owned_rows=0, col_lid=None, n_cols=0, extra_row=None, extra_col=None):
+        self.ctx = ctx
+        self.row_mesh = row_mesh
+        self.col_mesh = col_mesh or row_mesh
+        as32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+        row_lid, col_lid, extra_row, extra_col = as32(row_lid), as32(col_lid), as32(extra_row), as32(extra_col)
+        n_extra = 0 if extra_row is None else int(extra_row.size)
+        h = C.c_void_p()
+        check(ctx._L.feddb200_pattern_build(ctx._h, C.byref(h), row_mesh._h, self.col_mesh._h, int(n_rows),
+                                            int(n_owned_rows), ptr(row_lid), int(n_cols), ptr(col_lid), n_extra,
+                                            ptr(extra_row), ptr(extra_col)))
+        self._h = h
+        v = [C.c_int64() for _ in range(5)]
+        ml = C.c_int32()
+        check(ctx._L.feddb200_pattern_info(h, *[C.byref(x) for x in v], C.byref(ml), None))
+        self.n_rows, self.n_owned_rows, self.n_cols, self.nnz_nodes, self.nnz_owned_nodes = [int(x.value) for x in v]
+        self.max_row_len = int(ml.value)
+        self.dim = row_mesh.dim
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.ctx._L.feddb200_pat_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def n_colours(self) -> int:
+        nc = C.c_int32()
+        check(self.ctx._L.feddb200_pattern_info(self._h, None, None, None, None, None, None, C.byref(nc)))
+        return int(nc.value)
+
+    def nodes(self):
+        rowptr = np.empty(self.n_rows + 1, dtype=np.int64)
+        colind = np.empty(self.nnz_nodes, dtype=np.int32)
+        check(self.ctx._L.feddb200_pattern_get_nodes(self.ctx._h, self._h, ptr(rowptr), ptr(colind)))
+        return rowptr, colind
+
+    def nnz(self, row_dofs=1, col_dofs=1, mode=BLOCK_SCALAR) -> int:
+        n = int(self.ctx._L.feddb200_pattern_nnz(self._h, row_dofs, col_dofs, mode))
+        if n < 0:
+            raise _lib.LogicError("unsupported dof layout")
+        return n
+
+    def nnz_owned(self, row_dofs=1, col_dofs=1, mode=BLOCK_SCALAR) -> int:
+        return int(self.ctx._L.feddb200_pattern_nnz_owned(self._h, row_dofs, col_dofs, mode))
+
+    def expand(self, row_dofs=1, col_dofs=1, mode=BLOCK_SCALAR):
+        """dof-level CSR (rowptr int64, colind int32) of owned + ghost rows."""
+        nnz = self.nnz(row_dofs, col_dofs, mode)
+        rowptr = np.empty(self.n_rows * row_dofs + 1, dtype=np.int64)
+        colind = np.empty(nnz, dtype=np.int32)
+        check(self.ctx._L.feddb200_pattern_expand(self.ctx._h, self._h, row_dofs, col_dofs, mode, ptr(rowptr),
+                                                  ptr(colind)))
+        return rowptr, colind
+
+    # ---- device-resident assembly (values: CUDA float64 tensor, fully overwritten) ----
+    def assemble_laplace_d(self, values, vec_field=False):
+        check(self.ctx._L.feddb200_assemble_laplace_d(self.ctx._h, self._h, int(bool(vec_field)), ptr(values)))
+
+    def assemble_linelas_d(self, values, lam, mu):
+        check(self.ctx._L.feddb200_assemble_linelas_d(self.ctx._h, self._h, float(lam), float(mu), ptr(values)))
+
+    def assemble_advection_d(self, values, u):
+        check(self.ctx._L.feddb200_assemble_advection_d(self.ctx._h, self._h, ptr(u), ptr(values)))
+
+    def assemble_advection_in_u_d(self, values, u):
+        check(self.ctx._L.feddb200_assemble_advection_in_u_d(self.ctx._h, self._h, ptr(u), ptr(values)))
+
+    def assemble_ns_jacobian_d(self, values, u, rho, nu, newton=True):
+        check(self.ctx._L.feddb200_assemble_ns_jacobian_d(self.ctx._h, self._h, float(rho), float(nu), ptr(u),
+                                                          int(bool(newton)), ptr(values)))
+
+    # ---- host-buffer forms (H2D / D2H inside the call) ----
+    def assemble_laplace(self, vec_field=False):
+        out = np.empty(self.nnz(self.dim, self.dim, BLOCK_DIAG) if vec_field else self.nnz(), dtype=np.float64)
+        check(self.ctx._L.feddb200_assemble_laplace(self.ctx._h, self._h, int(bool(vec_field)), ptr(out)))
+        return out
+
+    def assemble_linelas(self, lam, mu, out=None):
+        if out is None:
+            out = np.empty(self.nnz(self.dim, self.dim, BLOCK_FULL), dtype=np.float64)
+        check(self.ctx._L.feddb200_assemble_linelas(self.ctx._h, self._h, float(lam), float(mu), ptr(out)))
+        return out
+
+    def assemble_advection(self, u):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        out = np.empty(self.nnz(self.dim, self.dim, BLOCK_DIAG), dtype=np.float64)
+        check(self.ctx._L.feddb200_assemble_advection(self.ctx._h, self._h, ptr(u), ptr(out)))
+        return out
+
+    def assemble_advection_in_u(self, u):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        out = np.empty(self.nnz(self.dim, self.dim, BLOCK_FULL), dtype=np.float64)
+        check(self.ctx._L.feddb200_assemble_advection_in_u(self.ctx._h, self._h, ptr(u), ptr(out)))
+        return out
+
+    def assemble_ns_jacobian(self, u, rho, nu, newton=True):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        out = np.empty(self.nnz(self.dim, self.dim, BLOCK_FULL), dtype=np.float64)
+        check(self.ctx._L.feddb200_assemble_ns_jacobian(self.ctx._h, self._h, float(rho), float(nu), ptr(u),
+                                                        int(bool(newton)), ptr(out)))
+        return out
+
+
+def assemble_div_divT_d(ctx: Context, patB: Pattern | None, patBT: Pattern | None, valuesB=None, valuesBT=None):
+    check(ctx._L.feddb200_assemble_div_divT_d(ctx._h, patB._h if patB else None, patBT._h if patBT else None,
+                                              ptr(valuesB), ptr(valuesBT)))
+
+
+def assemble_div_divT(ctx: Context, patB: Pattern, patBT: Pattern):
+    dim = patB.dim
+    vB = np.empty(patB.nnz(1, dim, BLOCK_FULL), dtype=np.float64)
+    vBT = np.empty(patBT.nnz(dim, 1, BLOCK_FULL), dtype=np.float64)
+    check(ctx._L.feddb200_assemble_div_divT(ctx._h, patB._h, patBT._h, ptr(vB), ptr(vBT)))
+    return vB, vBT

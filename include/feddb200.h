@@ -1,0 +1,171 @@
+/*
+ * feddb200.h -- C ABI of the B200-native finite-element assembly engine (libfeddb200.so).
+ *
+ * Drop-in boundary for FEDDLib's element-wise matrix assembly hot path.  Every entry point
+ * cites the reference interface it replaces (paths under /root/reference/feddlib).  The
+ * reference's host side (class FE<SC,LO,GO,NO>) keeps its C++ signatures; a glue header
+ * (feddlib_b200/csrc/host/FE_b200.hpp) extracts flat arrays from
+ * `Domain`, calls the functions below and wraps the returned CSR arrays in a Tpetra
+ * CrsMatrix on the same row/column maps.
+ *
+ * Conventions
+ *  - return 0 on success, <0 on error; feddb200_last_error() gives the text (thread-local).
+ *    This mirrors the reference's TEUCHOS_TEST_FOR_EXCEPTION(std::logic_error|runtime_error)
+ *    convention (core/FE/FE_def.hpp:610,676,1691,2746,6950): FEDDB200_ELOGIC for argument /
+ *    "not implemented for this FE type" errors, FEDDB200_ERUNTIME for CUDA/runtime failures.
+ *  - plain pointers and sizes only.  Pointers are HOST pointers unless the name ends in _d
+ *    (device pointer on the context's device).  The library never frees caller memory.
+ *  - there is no CPU fallback: every call fails loudly if no CUDA device is usable.
+ *  - local ids are int32 (reference LO = int, core/General/DefaultTypeDefs.hpp:7), global ids
+ *    int64 (GO = long long), scalars double (SC = double).
+ */
+#ifndef FEDDB200_H
+#define FEDDB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FEDDB200_OK        0
+#define FEDDB200_ELOGIC   (-1)   /* std::logic_error in the reference   */
+#define FEDDB200_ERUNTIME (-2)   /* std::runtime_error in the reference */
+
+typedef struct feddb200_ctx  feddb200_ctx;   /* one per GPU / rank                                  */
+typedef struct feddb200_mesh feddb200_mesh;  /* uploaded connectivity + repeated points              */
+typedef struct feddb200_pat  feddb200_pat;   /* node-level CSR pattern + scatter/gather maps         */
+
+/* scatter modes (north_star: coloured-deterministic with an atomic variant alongside; the
+ * row-gather mode is the B200-first default: every CSR value is written exactly once) */
+#define FEDDB200_SCATTER_ATOMIC   0
+#define FEDDB200_SCATTER_COLOURED 1
+#define FEDDB200_SCATTER_GATHER   2
+
+/* dof layouts of a matrix on a node-level pattern (node-wise numbering dim*g+d,
+ * core/LinearAlgebra/Map_def.hpp:95-108) */
+#define FEDDB200_BLOCK_SCALAR 0  /* 1 dof per row node, 1 per col node   (assemblyLaplace)            */
+#define FEDDB200_BLOCK_DIAG   1  /* dim x dim, only (d,d) stored         (LaplaceVecField, Advection) */
+#define FEDDB200_BLOCK_FULL   2  /* row_dofs x col_dofs full blocks      (LinElas, AdvectionInU, B, BT) */
+
+const char *feddb200_last_error(void);
+int  feddb200_device_count(void);
+
+/* ---- context ------------------------------------------------------------------------- */
+int  feddb200_create(feddb200_ctx **ctx, int device);
+void feddb200_destroy(feddb200_ctx *ctx);
+/* run all work of this context on an existing CUDA stream (cudaStream_t as void*); NULL = the
+ * context's own stream */
+int  feddb200_set_stream(feddb200_ctx *ctx, void *cuda_stream);
+int  feddb200_set_scatter_mode(feddb200_ctx *ctx, int mode);
+int  feddb200_get_scatter_mode(const feddb200_ctx *ctx);
+int  feddb200_synchronize(feddb200_ctx *ctx);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+int64_t feddb200_launch_count(const feddb200_ctx *ctx);
+
+/* ---- device memory helpers (so a pure C/C++ host can keep values resident) ------------- */
+int  feddb200_dev_alloc(feddb200_ctx *ctx, void **ptr_d, int64_t bytes);
+int  feddb200_dev_free(feddb200_ctx *ctx, void *ptr_d);
+int  feddb200_copy_h2d(feddb200_ctx *ctx, void *dst_d, const void *src, int64_t bytes);
+int  feddb200_copy_d2h(feddb200_ctx *ctx, void *dst, const void *src_d, int64_t bytes);
+
+/* ---- mesh ------------------------------------------------------------------------------
+ * Replaces the per-call reads of Domain::getElementsC / getPointsRepeated
+ * (core/FE/FE_def.hpp:617-621, core/FE/Domain_def.hpp:421-508) with a one-time upload; the
+ * natural call site is FE::addFE (core/FE/FE_def.hpp:64-72).
+ *   dim   2|3;  nloc 3,6 (P1/P2 triangle) or 4,10 (P1/P2 tetrahedron)
+ *   conn  [ne][nloc]  local (repeated-map) node ids, reference local ordering
+ *   coords[nn_rep][dim] repeated points, AoS like vec2D_dbl_Type */
+int  feddb200_mesh_upload(feddb200_ctx *ctx, feddb200_mesh **mesh, int dim, int nloc, int64_t ne,
+                          const int32_t *conn, int64_t nn_rep, const double *coords);
+/* replace the point coordinates (moving meshes / per-step e2e upload) */
+int  feddb200_mesh_update_coords(feddb200_ctx *ctx, feddb200_mesh *mesh, const double *coords);
+void feddb200_mesh_free(feddb200_mesh *mesh);
+
+/* ---- pattern ---------------------------------------------------------------------------
+ * One-time sparsity builder.  Replaces what Matrix(map,numEntries) + insertGlobalValues +
+ * fillComplete build dynamically inside Tpetra (core/LinearAlgebra/Matrix_def.hpp:46-51,
+ * 88-92, 192-199): the CSR graph over (row node, col node) pairs of every element, rows in
+ * row-map order, columns ascending by column-map local index.
+ *   row_mesh/col_mesh   share the element index (same ne); identical for square operators,
+ *                       pressure/velocity for B and B^T (core/FE/FE_def.hpp:1982-2016)
+ *   row_lid[nn_rep(row_mesh)]  row index of each repeated node: 0..n_owned-1 = position in the
+ *                       unique (row) map, n_owned..n_rows-1 = ghost rows (nodes owned by another
+ *                       rank; their values are shipped to the owner, the Tpetra Export/ADD
+ *                       step), -1 = node produces no row.  NULL = identity (one rank: the
+ *                       unique map lists the repeated nodes in order, Map_def.hpp:201-206).
+ *   col_lid[nn_rep(col_mesh)]  column-map local index of each repeated node; NULL = identity.
+ *   extra_row/extra_col [n_extra]  additional (row, col) node entries that other ranks
+ *                       contribute to owned rows (received ghost-row structure); may be NULL. */
+int  feddb200_pattern_build(feddb200_ctx *ctx, feddb200_pat **pat,
+                            const feddb200_mesh *row_mesh, const feddb200_mesh *col_mesh,
+                            int64_t n_rows, int64_t n_owned_rows, const int32_t *row_lid,
+                            int64_t n_cols, const int32_t *col_lid,
+                            int64_t n_extra, const int32_t *extra_row, const int32_t *extra_col);
+void feddb200_pat_free(feddb200_pat *pat);
+
+/* sizes: node rows (owned+ghost), owned node rows, node cols, node nnz (all rows), node nnz of
+ * owned rows, longest node row, number of element colours */
+int  feddb200_pattern_info(const feddb200_pat *pat, int64_t *n_rows, int64_t *n_owned_rows, int64_t *n_cols,
+                           int64_t *nnz_nodes, int64_t *nnz_owned_nodes, int32_t *max_row_len, int32_t *n_colours);
+/* node-level CSR to host: rowptr[n_rows+1], colind[nnz_nodes] */
+int  feddb200_pattern_get_nodes(feddb200_ctx *ctx, const feddb200_pat *pat, int64_t *rowptr, int32_t *colind);
+/* number of values of the dof-level matrix (owned + ghost rows) for a layout */
+int64_t feddb200_pattern_nnz(const feddb200_pat *pat, int row_dofs, int col_dofs, int block_mode);
+/* dof-level CSR (what the Tpetra::CrsMatrix is built from): rowptr[row_dofs*n_rows+1],
+ * colind[nnz] (column-map local dof indices, col_dofs*col_node+d) */
+int  feddb200_pattern_expand(feddb200_ctx *ctx, const feddb200_pat *pat, int row_dofs, int col_dofs, int block_mode,
+                             int64_t *rowptr, int32_t *colind);
+
+/* ---- assembly (values only; the pattern is fixed) ---------------------------------------
+ * `values_d` is a device array of feddb200_pattern_nnz(...) doubles in dof-level CSR order;
+ * it is fully overwritten.  Each function computes exactly what the cited reference routine
+ * inserts, before any scaling the problem classes apply afterwards. */
+
+/* FE::assemblyLaplace (core/FE/FE_def.hpp:604-667) [vec_field=0, BLOCK_SCALAR] and
+ * FE::assemblyLaplaceVecField (:670-734) [vec_field=1, BLOCK_DIAG with dim dofs] */
+int  feddb200_assemble_laplace_d(feddb200_ctx *ctx, const feddb200_pat *pat, int vec_field, double *values_d);
+/* FE::assemblyLinElasXDim (core/FE/FE_def.hpp:2739-3040) [BLOCK_FULL, dim x dim] */
+int  feddb200_assemble_linelas_d(feddb200_ctx *ctx, const feddb200_pat *pat, double lambda, double mu, double *values_d);
+/* FE::assemblyAdvectionVecField (core/FE/FE_def.hpp:1685-1836) [BLOCK_DIAG]; u_rep_d is the
+ * repeated, node-wise interleaved velocity u[dim*LID+d] (:1785,1800) */
+int  feddb200_assemble_advection_d(feddb200_ctx *ctx, const feddb200_pat *pat, const double *u_rep_d, double *values_d);
+/* FE::assemblyAdvectionInUVecField (core/FE/FE_def.hpp:1839-1929) [BLOCK_FULL, dim x dim] */
+int  feddb200_assemble_advection_in_u_d(feddb200_ctx *ctx, const feddb200_pat *pat, const double *u_rep_d, double *values_d);
+/* FE::assemblyDivAndDivT / assemblyDivAndDivTFast (core/FE/FE_def.hpp:1932-2057, 2061-2148):
+ * patB has pressure rows x velocity cols [BLOCK_FULL 1 x dim], patBT velocity rows x pressure
+ * cols [BLOCK_FULL dim x 1]; positive sign, callers scale by -1 (NavierStokes_def.hpp:217-218).
+ * Either output may be NULL. */
+int  feddb200_assemble_div_divT_d(feddb200_ctx *ctx, const feddb200_pat *patB, const feddb200_pat *patBT,
+                                  double *valuesB_d, double *valuesBT_d);
+/* Fused (0,0) block of the Navier-Stokes system, the three calls of
+ * NavierStokes::reAssemble + assembleConstantMatrices (problems/specific/NavierStokes_def.hpp:
+ * 140-152, 297-313) in one pass on the union (BLOCK_FULL) pattern:
+ *   values = rho*nu*LaplaceVecField + rho*N(u) [+ rho*W(u) if newton] */
+int  feddb200_assemble_ns_jacobian_d(feddb200_ctx *ctx, const feddb200_pat *pat, double rho, double nu,
+                                     const double *u_rep_d, int newton, double *values_d);
+
+/* host-pointer forms of the same calls (what the glue uses when the matrix lives on the
+ * host): H2D of u, D2H of the values inside the call */
+int  feddb200_assemble_laplace(feddb200_ctx *ctx, const feddb200_pat *pat, int vec_field, double *values);
+int  feddb200_assemble_linelas(feddb200_ctx *ctx, const feddb200_pat *pat, double lambda, double mu, double *values);
+int  feddb200_assemble_advection(feddb200_ctx *ctx, const feddb200_pat *pat, const double *u_rep, double *values);
+int  feddb200_assemble_advection_in_u(feddb200_ctx *ctx, const feddb200_pat *pat, const double *u_rep, double *values);
+int  feddb200_assemble_div_divT(feddb200_ctx *ctx, const feddb200_pat *patB, const feddb200_pat *patBT,
+                                double *valuesB, double *valuesBT);
+int  feddb200_assemble_ns_jacobian(feddb200_ctx *ctx, const feddb200_pat *pat, double rho, double nu,
+                                   const double *u_rep, int newton, double *values);
+
+/* ---- ghost-row exchange helpers (the Tpetra Export/ADD step of fillComplete) -------------
+ * After an assembly the values of ghost rows sit behind the owned rows in `values_d`
+ * (offset feddb200_pattern_nnz of the owned part).  The host ships them to the owners
+ * (NCCL) and calls unpack_add on the receiving side:  values_d[slot[k]] += recv_d[k]. */
+int64_t feddb200_pattern_nnz_owned(const feddb200_pat *pat, int row_dofs, int col_dofs, int block_mode);
+int  feddb200_unpack_add_d(feddb200_ctx *ctx, double *values_d, const double *recv_d, const int64_t *slot_d, int64_t n);
+/* Matrix::scale (core/LinearAlgebra/Matrix_def.hpp:257) on resident values */
+int  feddb200_scale_d(feddb200_ctx *ctx, double *values_d, int64_t n, double alpha);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEDDB200_H */

@@ -1,0 +1,155 @@
+"""GPU tests of the reference-facing interface mirror (FE / Domain / Matrix) and of the C ABI's error
+behaviour, edge cases included (empty mesh, wrong FE type, mismatched maps)."""
+import numpy as np
+import pytest
+
+from util import TOL, oracle_csr, random_u, rel_frobenius
+
+pytestmark = pytest.mark.gpu
+
+
+def test_fe_interface_laplace_like_reference_driver(engine_ctx):
+    """Reads like feddlib/core/FE/tests/fe.cpp:60-101 + Laplace::assemble (Laplace_def.hpp:36-60)."""
+    from feddlib_b200 import FE, Domain, Matrix
+    dim, FEType, M = 2, "P1", 16
+    domain = Domain.buildMesh(dim, FEType, 1, M)
+    fe = FE(ctx=engine_ctx)
+    fe.addFE(domain)
+    A = Matrix(domain.getMapUnique(), domain.getApproxEntriesPerRow())
+    fe.assemblyLaplace(dim, FEType, 2, A)
+    assert A.isFillComplete()
+    rp, ci, v = oracle_csr("laplace", dim, FEType, domain.getElementsC(), domain.getPointsRepeated())
+    assert np.array_equal(A.rowptr, rp) and np.array_equal(A.colind, ci)
+    assert rel_frobenius(A.numpy_values(), v) <= TOL
+    S = A.toScipy()
+    assert abs(S @ np.ones(S.shape[1])).max() < 1e-12
+    # post-assembly contract of the problem classes: resumeFill -> scale -> fillComplete(dom, rng)
+    A.resumeFill(); A.scale(0.5); A.fillComplete(domain.getMapUnique(), domain.getMapUnique())
+    assert rel_frobenius(A.numpy_values(), 0.5 * v) <= TOL
+
+
+def test_fe_interface_all_entry_points(engine_ctx):
+    from feddlib_b200 import FE, Domain, Map, Matrix
+    from feddlib_b200 import mesh as PM
+    dim, M = 3, 2
+    dv = Domain.buildMesh(dim, "P2", 1, M)
+    conn_p = PM.vertex_connectivity(dv.getElementsC(), dim)
+    # pressure domain on the vertex nodes: keep only referenced nodes, renumbered 0..n_p-1
+    used = np.unique(conn_p)
+    renum = -np.ones(dv.getPointsRepeated().shape[0], dtype=np.int64); renum[used] = np.arange(used.size)
+    dp = Domain(dim, "P1", renum[conn_p].astype(np.int32), dv.getPointsRepeated()[used], Map(np.arange(used.size)))
+    fe = FE(ctx=engine_ctx)
+    fe.addFE(dv); fe.addFE(dp)
+    n = dv.getMapUnique().getNodeNumElements()
+    u = random_u(dim, n)
+    conn, co = dv.getElementsC(), dv.getPointsRepeated()
+
+    K = Matrix(dv.getMapVecFieldUnique(), dim * dv.getApproxEntriesPerRow())
+    fe.assemblyLinElasXDim(dim, "P2", K, 8e6, 2e6, True)
+    assert rel_frobenius(K.numpy_values(), oracle_csr("linelas", dim, "P2", conn, co, lam=8e6, mu=2e6)[2]) <= TOL
+
+    A = Matrix(dv.getMapVecFieldUnique(), dim * dv.getApproxEntriesPerRow())
+    fe.assemblyLaplaceVecField(dim, "P2", 2, A, True)
+    assert rel_frobenius(A.numpy_values(), oracle_csr("laplace_vec", dim, "P2", conn, co)[2]) <= TOL
+
+    N = Matrix(dv.getMapVecFieldUnique(), dim * dv.getApproxEntriesPerRow())
+    fe.assemblyAdvectionVecField(dim, "P2", N, u, True)
+    assert rel_frobenius(N.numpy_values(), oracle_csr("advection", dim, "P2", conn, co, u=u)[2]) <= TOL
+
+    W = Matrix(dv.getMapVecFieldUnique(), dim * dv.getApproxEntriesPerRow())
+    fe.assemblyAdvectionInUVecField(dim, "P2", W, u, True)
+    assert rel_frobenius(W.numpy_values(), oracle_csr("advection_in_u", dim, "P2", conn, co, u=u)[2]) <= TOL
+
+    B = Matrix(dp.getMapUnique(), dim * dv.getApproxEntriesPerRow())
+    BT = Matrix(dv.getMapVecFieldUnique(), dp.getApproxEntriesPerRow())
+    fe.assemblyDivAndDivTFast(dim, "P2", "P1", 2, B, BT, dv.getMapVecFieldUnique(), dp.getMapUnique(), True)
+    conn_p_local = dp.getElementsC()
+    ro = oracle_csr("div", dim, "P2", conn, co, fe2="P1", conn2=conn_p_local)
+    assert np.array_equal(B.rowptr, ro[0]) and np.array_equal(B.colind, ro[1])
+    assert rel_frobenius(B.numpy_values(), ro[2]) <= TOL
+    assert B.domainMap.isSameAs(dv.getMapVecFieldUnique()) and B.rangeMap.isSameAs(dp.getMapUnique())
+    B.resumeFill(); B.scale(-1.0); B.fillComplete(dv.getMapVecFieldUnique(), dp.getMapUnique())   # NavierStokes_def.hpp:217-221
+    assert rel_frobenius(B.numpy_values(), -ro[2]) <= TOL
+
+
+def test_error_behaviour_matches_reference(engine_ctx):
+    from feddlib_b200 import FE, Domain, LogicError, Matrix
+    d = Domain.buildMesh(2, "P1", 1, 3)
+    fe = FE(ctx=engine_ctx)
+    A = Matrix(d.getMapUnique(), 20)
+    with pytest.raises(LogicError, match="Use addFE"):          # FE_def.hpp:6950
+        fe.assemblyLaplace(2, "P1", 2, A)
+    fe.addFE(d)
+    with pytest.raises(LogicError, match="Not implemented for P0"):   # FE_def.hpp:610
+        fe.assemblyLaplace(2, "P0", 2, A)
+    with pytest.raises(LogicError, match="Use addFE"):
+        fe.assemblyLaplace(3, "P1", 2, A)
+    with pytest.raises(LogicError):                              # wrong row map (vector field on a scalar map)
+        fe.assemblyLaplaceVecField(2, "P1", 2, A)
+    with pytest.raises(LogicError, match="numberMV"):            # FE_def.hpp:1691
+        fe.assemblyAdvectionVecField(2, "P1", Matrix(d.getMapVecFieldUnique(), 40), np.zeros((32, 2)))
+
+
+def test_c_abi_argument_errors(engine_ctx):
+    from feddlib_b200 import LogicError, Mesh, Pattern
+    co = np.zeros((4, 3))
+    with pytest.raises(LogicError, match="only P1/P2"):
+        Mesh(engine_ctx, 3, np.zeros((1, 8), dtype=np.int32), co)            # Q1 hexahedron: not implemented
+    with pytest.raises(LogicError, match="out of range"):
+        Mesh(engine_ctx, 3, np.array([[0, 1, 2, 9]], dtype=np.int32), co)
+    m3 = Mesh(engine_ctx, 3, np.array([[0, 1, 2, 3]], dtype=np.int32), np.eye(4, 3))
+    m2 = Mesh(engine_ctx, 2, np.array([[0, 1, 2]], dtype=np.int32), np.eye(3, 2))
+    with pytest.raises(LogicError, match="share the element list"):
+        Pattern(engine_ctx, m3, m2)
+    p = Pattern(engine_ctx, m3)
+    with pytest.raises(LogicError, match="unsupported dof layout"):
+        p.nnz(4, 4, 2)
+
+
+def test_empty_and_single_element_meshes(engine_ctx):
+    from feddlib_b200 import Mesh, Pattern
+    empty = Mesh(engine_ctx, 3, np.zeros((0, 4), dtype=np.int32), np.zeros((5, 3)))
+    p = Pattern(engine_ctx, empty)
+    assert p.nnz_nodes == 0 and p.n_rows == 5
+    for mode in ("gather", "coloured", "atomic"):
+        engine_ctx.set_scatter_mode(mode)
+        assert p.assemble_laplace().size == 0
+    # a single P2 tetrahedron with random vertices
+    from oracle import mesh as OM
+    rng = np.random.default_rng(11)
+    conn, co, _ = OM.p2_of_p1(np.array([[0, 1, 2, 3]], dtype=np.int32), rng.uniform(0, 1, (4, 3)))
+    pat = Pattern(engine_ctx, Mesh(engine_ctx, 3, conn, co))
+    for mode in ("gather", "coloured", "atomic"):
+        engine_ctx.set_scatter_mode(mode)
+        got = pat.assemble_linelas(3.0, 1.5)
+        assert rel_frobenius(got, oracle_csr("linelas", 3, "P2", conn, co, lam=3.0, mu=1.5)[2]) <= TOL
+
+
+def test_ragged_mesh_with_unused_nodes(engine_ctx):
+    """Nodes that no element references still get (empty) rows, like an owned node without local elements."""
+    from feddlib_b200 import BLOCK_SCALAR, Mesh, Pattern
+    conn = np.array([[0, 2, 5], [2, 5, 6]], dtype=np.int32)
+    co = np.array([[0, 0], [9, 9], [1, 0], [9, 9], [9, 9], [0, 1], [1, 1.0]])
+    pat = Pattern(engine_ctx, Mesh(engine_ctx, 2, conn, co))
+    rp, ci = pat.expand(1, 1, BLOCK_SCALAR)
+    rpo, cio, vo = oracle_csr("laplace", 2, "P1", conn, co)
+    assert np.array_equal(rp, rpo) and np.array_equal(ci, cio)
+    for mode in ("gather", "coloured", "atomic"):
+        engine_ctx.set_scatter_mode(mode)
+        assert rel_frobenius(pat.assemble_laplace(), vo) <= TOL
+
+
+def test_device_resident_path_and_launch_counter(engine_ctx):
+    import torch
+    from feddlib_b200 import BLOCK_FULL, Mesh, Pattern
+    from util import mesh_structured
+    conn, co = mesh_structured(3, "P2", 3)
+    pat = Pattern(engine_ctx, Mesh(engine_ctx, 3, conn, co))
+    engine_ctx.set_scatter_mode("gather")
+    vals = engine_ctx.empty_values(pat.nnz(3, 3, BLOCK_FULL))
+    before = engine_ctx.launches
+    pat.assemble_linelas_d(vals, 8e6, 2e6)
+    engine_ctx.synchronize()
+    assert engine_ctx.launches > before
+    assert rel_frobenius(vals.cpu().numpy(), oracle_csr("linelas", 3, "P2", conn, co, lam=8e6, mu=2e6)[2]) <= TOL
+    assert torch.isfinite(vals).all()
