@@ -39,6 +39,7 @@ SIGNATURES = {
     "feddb200_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
     "feddb200_destroy": (None, [_vp]),
     "feddb200_set_stream": (C.c_int, [_vp, _vp]),
+    "feddb200_use_own_stream": (C.c_int, [_vp]),
     "feddb200_set_scatter_mode": (C.c_int, [_vp, C.c_int]),
     "feddb200_get_scatter_mode": (C.c_int, [_vp]),
     "feddb200_synchronize": (C.c_int, [_vp]),

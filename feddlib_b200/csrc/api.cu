@@ -232,7 +232,7 @@ int launch_gather(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
 int run_op(feddb200_ctx *c, const feddb200_pat *pc, int op, const double *u_d, double c0, double c1, double c2,
            int vec_field, double *values_d)
 {
-    FB_LOGIC(!c || !pc || !values_d, "assembly: null argument");
+    FB_LOGIC(!c || !pc, "assembly: null argument");
     FB_LOGIC(pc->ctx != c, "assembly: pattern belongs to another context");
     feddb200_pat *p = const_cast<feddb200_pat *>(pc);
     FB_CUDA(cudaSetDevice(c->device));
@@ -256,6 +256,8 @@ int run_op(feddb200_ctx *c, const feddb200_pat *pc, int op, const double *u_d, d
     default:      factor = (int64_t)dim * dim; break;
     }
     const int64_t nnz = factor * p->nnz;
+    FB_LOGIC(nnz > 0 && !values_d, "assembly: values pointer is null");
+    if (nnz == 0) return FEDDB200_OK;
 
     int mode = c->mode;
     if (mode == FEDDB200_SCATTER_GATHER && !(op == OP_LAP || op == OP_ELAS)) mode = FEDDB200_SCATTER_COLOURED;
@@ -318,7 +320,7 @@ int scratch(feddb200_ctx *c, int which, int64_t bytes, double **out)
 template <class F>
 int with_host_buffers(feddb200_ctx *c, const feddb200_pat *p, int64_t nnz, const double *u, int64_t nu, double *values, F &&run)
 {
-    FB_LOGIC(!c || !p || !values, "assembly: null argument");
+    FB_LOGIC(!c || !p || (nnz > 0 && !values), "assembly: null argument");
     FB_CUDA(cudaSetDevice(c->device));
     double *v_d = nullptr, *u_d = nullptr;
     int rc = scratch(c, 0, sizeof(double) * nnz, &v_d);

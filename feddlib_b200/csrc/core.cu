@@ -75,7 +75,14 @@ extern "C" void feddb200_destroy(feddb200_ctx *c)
 extern "C" int feddb200_set_stream(feddb200_ctx *c, void *s)
 {
     FB_LOGIC(!c, "null context");
-    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    c->stream = (cudaStream_t)s; // NULL selects the legacy default stream, as in the CUDA runtime
+    return FEDDB200_OK;
+}
+
+extern "C" int feddb200_use_own_stream(feddb200_ctx *c)
+{
+    FB_LOGIC(!c, "null context");
+    c->stream = c->own_stream;
     return FEDDB200_OK;
 }
 

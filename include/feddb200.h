@@ -54,9 +54,11 @@ int  feddb200_device_count(void);
 /* ---- context ------------------------------------------------------------------------- */
 int  feddb200_create(feddb200_ctx **ctx, int device);
 void feddb200_destroy(feddb200_ctx *ctx);
-/* run all work of this context on an existing CUDA stream (cudaStream_t as void*); NULL = the
- * context's own stream */
+/* run all work of this context on an existing CUDA stream (cudaStream_t as void*; NULL = the
+ * legacy default stream, as in the CUDA runtime).  A new context runs on its own non-blocking
+ * stream; feddb200_use_own_stream switches back to it. */
 int  feddb200_set_stream(feddb200_ctx *ctx, void *cuda_stream);
+int  feddb200_use_own_stream(feddb200_ctx *ctx);
 int  feddb200_set_scatter_mode(feddb200_ctx *ctx, int mode);
 int  feddb200_get_scatter_mode(const feddb200_ctx *ctx);
 int  feddb200_synchronize(feddb200_ctx *ctx);
