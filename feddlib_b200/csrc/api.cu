@@ -102,17 +102,19 @@ int ensure_gather(feddb200_pat *p)
     const int dim = p->rm->dim, nl = p->rm->nloc;
     FB_LOGIC(p->rm->nloc != p->cm->nloc, "gather path needs a square pattern");
     const int64_t n_rows = p->n_rows;
-    p->posc_stride = (nl + 1) & ~1;
+    p->posc_stride = nl <= 4 ? 4 : (nl <= 8 ? 8 : 16);
+    FB_LOGIC(p->rm->ne >= (int64_t(1) << 24), "gather path supports up to 2^24 elements per GPU");
+    FB_CUDA(cudaMalloc(&p->incp_d, sizeof(uint32_t) * std::max<int64_t>(p->n_inc, 1)));
     FB_CUDA(cudaMalloc(&p->posc_d, sizeof(uint16_t) * std::max<int64_t>(p->n_inc * p->posc_stride, 1)));
     int8_t *rtype_d = nullptr;
     FB_CUDA(cudaMalloc(&rtype_d, std::max<int64_t>(n_rows, 1)));
     if (n_rows > 0) {
         const int grid = (int)std::min<int64_t>((n_rows + 127) / 128, 148 * 64);
         switch (elem_index(dim, nl)) {
-        case 0: k_canon_pos<2, 3><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->pos_d, p->pos_stride, p->posc_d, p->posc_stride, rtype_d); break;
-        case 1: k_canon_pos<2, 6><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->pos_d, p->pos_stride, p->posc_d, p->posc_stride, rtype_d); break;
-        case 2: k_canon_pos<3, 4><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->pos_d, p->pos_stride, p->posc_d, p->posc_stride, rtype_d); break;
-        case 3: k_canon_pos<3, 10><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->pos_d, p->pos_stride, p->posc_d, p->posc_stride, rtype_d); break;
+        case 0: k_canon_pos<2, 3><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->pos_d, p->pos_stride, p->posc_d, p->incp_d, rtype_d); break;
+        case 1: k_canon_pos<2, 6><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->pos_d, p->pos_stride, p->posc_d, p->incp_d, rtype_d); break;
+        case 2: k_canon_pos<3, 4><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->pos_d, p->pos_stride, p->posc_d, p->incp_d, rtype_d); break;
+        case 3: k_canon_pos<3, 10><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->pos_d, p->pos_stride, p->posc_d, p->incp_d, rtype_d); break;
         default: set_error("unsupported element"); return FEDDB200_ELOGIC;
         }
         c->launches++;
@@ -124,7 +126,7 @@ int ensure_gather(feddb200_pat *p)
     cudaFree(rtype_d);
     std::vector<int32_t> perm(n_rows);
     for (int64_t r = 0; r < n_rows; r++) perm[r] = (int32_t)r;
-    auto cap = [&](int64_t r) { const int l = (int)(p->rowptr_h[r + 1] - p->rowptr_h[r]); return std::max(8, (l + 7) & ~7); };
+    auto cap = [&](int64_t r) { const int l = (int)(p->rowptr_h[r + 1] - p->rowptr_h[r]); return std::max(4, (l + 3) & ~3); };
     auto key = [&](int32_t r) { return (int64_t)rtype[r] * 100000 + cap(r); };
     std::stable_sort(perm.begin(), perm.end(), [&](int32_t a, int32_t b) { return key(a) < key(b); });
     p->buckets.clear();
@@ -136,7 +138,7 @@ int ensure_gather(feddb200_pat *p)
     }
     FB_CUDA(cudaMalloc(&p->row_perm_d, sizeof(int32_t) * std::max<int64_t>(n_rows, 1)));
     FB_CUDA(cudaMemcpy(p->row_perm_d, perm.data(), sizeof(int32_t) * n_rows, cudaMemcpyHostToDevice));
-    const int gs = dim == 3 ? 14 : 8;
+    const int gs = dim == 3 ? 16 : 8;
     FB_CUDA(cudaMalloc(&p->geom_d, sizeof(double) * std::max<int64_t>(p->rm->ne * gs, 1)));
     p->gather_ready = true;
     return FEDDB200_OK;
@@ -176,24 +178,26 @@ void canon_table(const OpTables &t, int dim, int nl, CanonR &R)
 template <int OPG, int DIM, int NL>
 int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
 {
-    constexpr int TPR = OPG == 1 ? DIM * DIM : 1;
+    constexpr int TPR = OPG == 1 ? DIM : 1;
     const int64_t blocks_geom = (p->rm->ne + 255) / 256;
     if (p->rm->ne > 0) {
         k_geom<DIM, NL><<<(unsigned)blocks_geom, 256, 0, c->stream>>>(p->rm->ne, p->rm->conn_d, p->rm->coords_d, p->geom_d);
         c->launches++;
     }
     for (const Bucket &b : p->buckets) {
-        // block size: multiple of 16 (lane-private 8-byte banks) and of TPR (a node's threads stay
-        // in one block); shrink until the accumulators fit the opt-in shared memory
-        const int unit = (OPG == 1 && DIM == 3) ? 144 : 32;
-        int nt = (OPG == 1 && DIM == 3) ? 288 : 256;
+        // accumulators: NB doubles per (thread, column node), interleaved over the block's threads
+        // (lane-private 8-byte banks need a block size that is a multiple of 16).  Prefer >= 2 resident
+        // blocks per SM; shrink the block until the accumulators fit the opt-in shared memory.
+        constexpr int NB = OPG == 1 ? DIM : 1;
         const size_t budget = c->smem_optin - 1024;
-        while (nt > unit && (size_t)b.lcap * nt * 8 > budget) nt -= unit;
-        if ((size_t)b.lcap * nt * 8 > budget) {
+        const size_t per_thread = (size_t)NB * b.lcap * 8;
+        int nt = 256;
+        while (nt > 32 && per_thread * nt * 2 > budget + 1024) nt -= 32;
+        if (per_thread * nt > budget) {
             set_error("row too long for the gather path's shared-memory accumulators; use the coloured or atomic mode");
             return FEDDB200_ELOGIC;
         }
-        const size_t smem = (size_t)b.lcap * nt * 8;
+        const size_t smem = per_thread * nt;
         G.start = b.start; G.count = b.count; G.lcap = b.lcap;
         const int64_t nthreads = b.count * TPR;
         const int64_t blocks = (nthreads + nt - 1) / nt;
@@ -266,8 +270,8 @@ int run_op(feddb200_ctx *c, const feddb200_pat *pc, int op, const double *u_d, d
         rc = ensure_gather(p);
         if (rc != FEDDB200_OK) return rc;
         GatherArgs G;
-        G.row_perm = p->row_perm_d; G.rowptr = p->rowptr_d; G.inc_ptr = p->inc_ptr_d; G.inc = p->inc_d;
-        G.posc = p->posc_d; G.posc_stride = p->posc_stride; G.geom = p->geom_d;
+        G.row_perm = p->row_perm_d; G.rowptr = p->rowptr_d; G.inc_ptr = p->inc_ptr_d; G.incp = p->incp_d;
+        G.posc = p->posc_d; G.geom = p->geom_d;
         G.c0 = c0; G.c1 = c1; G.values = values_d; G.vec_dim = (op == OP_LAP && vec_field) ? dim : 0;
         canon_table(tab_h, dim, nr, G.R);
         return op == OP_LAP ? launch_gather<0>(c, p, G) : launch_gather<1>(c, p, G);

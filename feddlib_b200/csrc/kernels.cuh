@@ -339,9 +339,11 @@ __global__ void __launch_bounds__(128) k_elem(const ElemArgs A)
 // -----------------------------------------------------------------------------------------
 // row-gather path
 // -----------------------------------------------------------------------------------------
-// per-element geometry cache: gradients of the barycentric coordinates G_v = grad lambda_v
-// (v = 0..DIM) and |det B|.  Layout [e][GS] doubles, G_v at 3*v (DIM*v), |det| at GS-2.
-template <int DIM> struct GeomStride { static constexpr int value = DIM == 3 ? 14 : 8; };
+// per-element geometry cache, one aligned line per element:
+//   3D: [e][v = 0..3] = (G_v.x, G_v.y, G_v.z, |det B|)   32 B per vertex, 128 B per element
+//   2D: [e] = (G_0.x, G_0.y, G_1.x, G_1.y, G_2.x, G_2.y, |det B|, |det B|)   64 B per element
+// with G_v = grad lambda_v, the gradients of the barycentric coordinates.
+template <int DIM> struct GeomStride { static constexpr int value = DIM == 3 ? 16 : 8; };
 
 template <int DIM, int NL>
 __global__ void __launch_bounds__(256) k_geom(int64_t ne, const int32_t *__restrict__ conn,
@@ -354,15 +356,24 @@ __global__ void __launch_bounds__(256) k_geom(int64_t ne, const int32_t *__restr
     affine_map<DIM>(conn + e * NL, coords, Binv, adet);
     double *g = geom + e * GS;
     // grad lambda_k = row k-1 of Binv (k >= 1), grad lambda_0 = -(sum of the others)
+    double G[DIM + 1][DIM];
 #pragma unroll
     for (int d = 0; d < DIM; d++) {
         double s = 0.0;
 #pragma unroll
-        for (int k = 0; k < DIM; k++) { g[DIM * (k + 1) + d] = Binv[k][d]; s -= Binv[k][d]; }
-        g[d] = s;
+        for (int k = 0; k < DIM; k++) { G[k + 1][d] = Binv[k][d]; s -= Binv[k][d]; }
+        G[0][d] = s;
     }
-    g[GS - 2] = adet;
-    g[GS - 1] = 0.0;
+    if constexpr (DIM == 3) {
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            g[4 * v + 0] = G[v][0]; g[4 * v + 1] = G[v][1]; g[4 * v + 2] = G[v][2]; g[4 * v + 3] = adet;
+        }
+    } else {
+#pragma unroll
+        for (int v = 0; v < 3; v++) { g[2 * v] = G[v][0]; g[2 * v + 1] = G[v][1]; }
+        g[6] = adet; g[7] = adet;
+    }
 }
 
 // canonical relabelling of an element seen from local node i: the vertex permutation pi puts
@@ -399,13 +410,19 @@ __host__ __device__ inline int canon_node(const int (&pi)[DIM + 1], int jc)
     else return NVTX + (a == 0 ? (b == 1 ? 0 : (b == 2 ? 2 : 3)) : (a == 1 ? (b == 2 ? 1 : 4) : 5));
 }
 
-// per-incidence canonical position map: posc[k][jc] = position (in the row of the incidence's
-// row node) of canonical local node jc; rtype[row] = 0 vertex node / 1 edge node
+// position words per incidence: 16 bit per canonical local node, padded to a 16-byte multiple
+template <int NL> struct PoscStride { static constexpr int value = NL <= 4 ? 4 : (NL <= 8 ? 8 : 16); };
+
+// Per-incidence gather records (one-time, pattern build):
+//   incp[k]  = (element << 8) | (pi(3)<<6 | pi(2)<<4 | pi(1)<<2 | pi(0))   canonical vertex permutation
+//   posc[k][jc] = position, in the row of the incidence's row node, of canonical local node jc
+//   rtype[row]  = 0 vertex node / 1 edge node
 template <int DIM, int NL>
 __global__ void k_canon_pos(int64_t n_rows, const int64_t *__restrict__ inc_ptr, const int32_t *__restrict__ inc,
                             const uint16_t *__restrict__ pos, int pos_stride, uint16_t *__restrict__ posc,
-                            int posc_stride, int8_t *__restrict__ rtype)
+                            uint32_t *__restrict__ incp, int8_t *__restrict__ rtype)
 {
+    constexpr int PS = PoscStride<NL>::value;
     for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x) {
         int8_t ty = 0;
         for (int64_t k = inc_ptr[r]; k < inc_ptr[r + 1]; k++) {
@@ -415,14 +432,17 @@ __global__ void k_canon_pos(int64_t n_rows, const int64_t *__restrict__ inc_ptr,
             ty = i > DIM ? 1 : 0;
             int pi[DIM + 1];
             canon_perm<DIM>(i, pi);
-            for (int jc = 0; jc < NL; jc++)
-                posc[k * posc_stride + jc] = pos[(e * NL + i) * pos_stride + canon_node<DIM>(pi, jc)];
+            uint32_t bits = 0;
+            for (int v = 0; v <= DIM; v++) bits |= (uint32_t)pi[v] << (2 * v);
+            incp[k] = ((uint32_t)e << 8) | bits;
+            for (int jc = 0; jc < PS; jc++)
+                posc[k * PS + jc] = jc < NL ? pos[(e * NL + i) * pos_stride + canon_node<DIM>(pi, jc)] : 0;
         }
         rtype[r] = ty;
     }
 }
 
-// Canonical coefficient table: K_{i',j'} = sum_{s,t} r[type][j'][s][t] * E(pi(s_i'), sv(j',t)) where
+// Canonical coefficient table: K_{i',j'} = sum_{s,t} r[type][j'][s][t] * E(s, sv(j',t)) where
 // s runs over the canonical support of the row function (vertex 0 | edge (0,1)) and t over the
 // support of column function j' (a vertex function uses t = 0 only).
 struct CanonR {
@@ -434,9 +454,8 @@ struct GatherArgs {
     int64_t start, count;
     const int64_t *rowptr;
     const int64_t *inc_ptr;
-    const int32_t *inc;
+    const uint32_t *incp;
     const uint16_t *posc;
-    int posc_stride;
     const double *geom;
     double c0, c1;            // lambda, mu
     double *values;
@@ -445,13 +464,13 @@ struct GatherArgs {
     CanonR R;
 };
 
-__device__ __forceinline__ void st_v2(double *p, double a, double b)
-{
-    asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(a), "d"(b) : "memory");
-}
 __device__ __forceinline__ void st_v4(double *p, double a, double b, double c, double d)
 {
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void ld_v4(const double *p, double (&v)[4])
+{
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
 }
 
 // support (canonical vertices) of canonical local node jc
@@ -464,129 +483,175 @@ __device__ __forceinline__ constexpr int canon_sv(int jc, int t)
     else { constexpr int E[6][2] = {{0, 1}, {1, 2}, {0, 2}, {0, 3}, {1, 3}, {2, 3}}; return E[jc - NVTX][t]; }
 }
 
-// OPG: 0 Laplace (one thread per row node), 1 elasticity (DIM*DIM threads per row node)
-// TYPE: 0 vertex rows, 1 edge rows
+// one incidence's operands, as loaded from global memory
+template <int DIM, int NL>
+struct IncData {
+    double G[DIM + 1][4];                       // canonical vertex v: (Gx, Gy[, Gz], |det|) -- 2D uses [0],[1] and [3]
+    uint32_t P[PoscStride<NL>::value / 2];      // packed 16-bit positions
+};
+
+template <int DIM, int NL>
+__device__ __forceinline__ void load_inc(const GatherArgs &A, int64_t k, uint32_t code, IncData<DIM, NL> &D)
+{
+    constexpr int GS = GeomStride<DIM>::value;
+    constexpr int PW = PoscStride<NL>::value / 2;
+    const double *g = A.geom + (int64_t)(code >> 8) * GS;
+    if constexpr (DIM == 3) {
+#pragma unroll
+        for (int v = 0; v < 4; v++) ld_v4(g + 4 * ((code >> (2 * v)) & 3), D.G[v]);
+    } else {
+        const double ad = __ldg(g + 6);
+#pragma unroll
+        for (int v = 0; v < 3; v++) {
+            const double2 t = __ldg(reinterpret_cast<const double2 *>(g) + ((code >> (2 * v)) & 3));
+            D.G[v][0] = t.x; D.G[v][1] = t.y; D.G[v][2] = 0.0; D.G[v][3] = ad;
+        }
+    }
+    const uint32_t *pw = reinterpret_cast<const uint32_t *>(A.posc) + k * PW;
+    if constexpr (PW == 8) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(pw)), b = __ldg(reinterpret_cast<const uint4 *>(pw) + 1);
+        D.P[0] = a.x; D.P[1] = a.y; D.P[2] = a.z; D.P[3] = a.w; D.P[4] = b.x; D.P[5] = b.y; D.P[6] = b.z; D.P[7] = b.w;
+    } else if constexpr (PW == 4) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(pw));
+        D.P[0] = a.x; D.P[1] = a.y; D.P[2] = a.z; D.P[3] = a.w;
+    } else {
+        const uint2 a = __ldg(reinterpret_cast<const uint2 *>(pw));
+        D.P[0] = a.x; D.P[1] = a.y;
+    }
+}
+
+__device__ __forceinline__ double sel3(const double (&v)[4], int c) { return c == 0 ? v[0] : (c == 1 ? v[1] : v[2]); }
+
+// One incidence of one thread: evaluate the thread's part of local row i' (canonical) and add it to the
+// lane-private accumulators.  OPG 0: Laplace, 1 value per column node.  OPG 1: elasticity, the thread
+// owns row dof `a` and produces the DIM column dofs b of every column node.
 template <int OPG, int DIM, int NL, int TYPE>
-__global__ void __launch_bounds__(288) k_gather(const GatherArgs A)
+__device__ __forceinline__ void gather_incidence(const GatherArgs &A, const IncData<DIM, NL> &D, int a, double *my, int NT)
 {
     constexpr int NVTX = DIM + 1;
-    constexpr int GS = GeomStride<DIM>::value;
-    constexpr int TPR = OPG == 1 ? DIM * DIM : 1; // threads per row node
-    constexpr int NS = TYPE == 0 ? 1 : 2;          // canonical support size of the row function
-    extern __shared__ double acc[];                // [lcap][blockDim.x], lane-private banks
+    constexpr int NS = TYPE == 0 ? 1 : 2;   // canonical support size of the row function
+    constexpr int NB = OPG == 1 ? DIM : 1;  // values per column node
+    const double adet = D.G[0][3];
+    // E[s][w][b] for canonical row-support vertex s and canonical vertex w
+    double E[NS][NVTX][NB];
+    if constexpr (OPG == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; s++)
+#pragma unroll
+            for (int w = 0; w < NVTX; w++) {
+                double dot = 0.0;
+#pragma unroll
+                for (int d = 0; d < DIM; d++) dot += D.G[s][d] * D.G[w][d];
+                E[s][w][0] = dot * adet;
+            }
+    } else {
+        const double mu = A.c1 * adet, lam = A.c0 * adet;
+        double Ga[NVTX];
+#pragma unroll
+        for (int w = 0; w < NVTX; w++) Ga[w] = sel3(D.G[w], a);
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            const double ls = lam * Ga[s];
+#pragma unroll
+            for (int w = 0; w < NVTX; w++) {
+                double dot = 0.0;
+#pragma unroll
+                for (int d = 0; d < DIM; d++) dot += D.G[s][d] * D.G[w][d];
+                const double mdot = mu * dot, mga = mu * Ga[w];
+                // E^{ab}_{sw} = mu (delta_ab G_s.G_w + G_s[b] G_w[a]) + lambda G_s[a] G_w[b]
+#pragma unroll
+                for (int b = 0; b < DIM; b++) E[s][w][b] = (a == b ? mdot : 0.0) + mga * D.G[s][b] + ls * D.G[w][b];
+            }
+        }
+    }
+    // distinct canonical nodes hit distinct row positions: per chunk of column nodes load all
+    // accumulators, add, store all (keeps the shared-memory round trips independent)
+    constexpr int JB = NL <= 6 ? NL : 5;
+#pragma unroll
+    for (int j0 = 0; j0 < NL; j0 += JB) {
+        int idx[JB];
+        double old[JB][NB];
+#pragma unroll
+        for (int jj = 0; jj < JB; jj++) {
+            const int jc = j0 + jj;
+            const uint32_t p = (D.P[jc >> 1] >> (16 * (jc & 1))) & 0xffffu;
+            idx[jj] = (int)p * (NB * NT);
+#pragma unroll
+            for (int b = 0; b < NB; b++) old[jj][b] = my[idx[jj] + b * NT];
+        }
+#pragma unroll
+        for (int jj = 0; jj < JB; jj++) {
+            const int jc = j0 + jj;
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                double v = old[jj][b];
+#pragma unroll
+                for (int s = 0; s < NS; s++) {
+                    v += A.R.r[TYPE][jc][s][0] * E[s][canon_sv<DIM>(jc, 0)][b];
+                    if (jc >= NVTX) v += A.R.r[TYPE][jc][s][1] * E[s][canon_sv<DIM>(jc, 1)][b];
+                }
+                my[idx[jj] + b * NT] = v;
+            }
+        }
+    }
+}
+
+// OPG: 0 Laplace (one thread per row node), 1 elasticity (DIM threads per row node: one per row dof)
+// TYPE: 0 vertex rows, 1 edge rows
+template <int OPG, int DIM, int NL, int TYPE>
+__global__ void __launch_bounds__(256, 1) k_gather(const GatherArgs A)
+{
+    constexpr int TPR = OPG == 1 ? DIM : 1; // threads per row node
+    constexpr int NB = OPG == 1 ? DIM : 1;  // accumulators per (thread, column node)
+    extern __shared__ double acc[];         // [NB*lcap][blockDim.x], lane-private banks
     const int NT = blockDim.x;
     const int tid = threadIdx.x;
     const int64_t t = blockIdx.x * (int64_t)NT + tid;
-    const bool active = t < A.count * TPR;
-    const int64_t rloc = active ? t / TPR : 0;
-    const int comp = (int)(t - rloc * TPR);
-    const int a = comp / DIM, b = comp - a * DIM;
-    const int32_t row = active ? A.row_perm[A.start + rloc] : 0;
-    const int64_t base = active ? A.rowptr[row] : 0;
-    const int L = active ? (int)(A.rowptr[row + 1] - base) : 0;
+    if (t >= A.count * TPR) return;
+    const int64_t rloc = t / TPR;
+    const int a = (int)(t - rloc * TPR);
+    const int32_t row = A.row_perm[A.start + rloc];
+    const int64_t base = A.rowptr[row];
+    const int L = (int)(A.rowptr[row + 1] - base);
+    double *my = acc + tid;
 
-    for (int p = 0; p < L; p++) acc[p * NT + tid] = 0.0;
+    for (int p = 0; p < NB * L; p++) my[p * NT] = 0.0;
 
-    if (active) {
-        const int64_t k1 = A.inc_ptr[row + 1];
-        for (int64_t k = A.inc_ptr[row]; k < k1; k++) {
-            const int32_t code = A.inc[k];
-            const int64_t e = code >> 4;
-            int pi[NVTX];
-            canon_perm<DIM>(code & 15, pi);
-            const double *g = A.geom + e * GS;
-            const double adet = g[GS - 2];
-            // E[s][w] for canonical row-support vertex s and canonical vertex w
-            double E[NS][NVTX];
-            if constexpr (OPG == 0) {
-                double Gs[NS][DIM];
-#pragma unroll
-                for (int s = 0; s < NS; s++)
-#pragma unroll
-                    for (int d = 0; d < DIM; d++) Gs[s][d] = g[DIM * pi[s] + d] * adet;
-#pragma unroll
-                for (int w = 0; w < NVTX; w++) {
-                    double Gw[DIM];
-#pragma unroll
-                    for (int d = 0; d < DIM; d++) Gw[d] = g[DIM * pi[w] + d];
-#pragma unroll
-                    for (int s = 0; s < NS; s++) {
-                        double dot = 0.0;
-#pragma unroll
-                        for (int d = 0; d < DIM; d++) dot += Gs[s][d] * Gw[d];
-                        E[s][w] = dot;
-                    }
+    {
+        const int64_t k0 = A.inc_ptr[row], k1 = A.inc_ptr[row + 1];
+        if (k0 < k1) {
+            // two-deep software pipeline on ping-pong register buffers; prefetch indices are clamped to
+            // the row's last incidence so the loads are unconditional
+            IncData<DIM, NL> bufA, bufB;
+            const int64_t kl = k1 - 1;
+            load_inc<DIM, NL>(A, k0, A.incp[k0], bufA);
+            uint32_t code_n = A.incp[k0 + 1 < kl ? k0 + 1 : kl];
+            for (int64_t k = k0; k < k1; k += 2) {
+                const int64_t kb = k + 1 < kl ? k + 1 : kl;
+                load_inc<DIM, NL>(A, kb, code_n, bufB);
+                code_n = A.incp[k + 2 < kl ? k + 2 : kl];
+                gather_incidence<OPG, DIM, NL, TYPE>(A, bufA, a, my, NT);
+                if (k + 1 < k1) {
+                    const int64_t ka = k + 2 < kl ? k + 2 : kl;
+                    load_inc<DIM, NL>(A, ka, code_n, bufA);
+                    code_n = A.incp[k + 3 < kl ? k + 3 : kl];
+                    gather_incidence<OPG, DIM, NL, TYPE>(A, bufB, a, my, NT);
                 }
-            } else {
-                const double mu = A.c1 * adet, lam = A.c0 * adet;
-                double Gs[NS][DIM], Gsa[NS], Gsb[NS];
-#pragma unroll
-                for (int s = 0; s < NS; s++) {
-#pragma unroll
-                    for (int d = 0; d < DIM; d++) Gs[s][d] = g[DIM * pi[s] + d];
-                    Gsa[s] = g[DIM * pi[s] + a];
-                    Gsb[s] = g[DIM * pi[s] + b];
-                }
-#pragma unroll
-                for (int w = 0; w < NVTX; w++) {
-                    double Gw[DIM];
-#pragma unroll
-                    for (int d = 0; d < DIM; d++) Gw[d] = g[DIM * pi[w] + d];
-                    const double Gwa = g[DIM * pi[w] + a], Gwb = g[DIM * pi[w] + b];
-#pragma unroll
-                    for (int s = 0; s < NS; s++) {
-                        double dot = 0.0;
-#pragma unroll
-                        for (int d = 0; d < DIM; d++) dot += Gs[s][d] * Gw[d];
-                        // E^{ab}_{sw} = mu (delta_ab G_s.G_w + G_s[b] G_w[a]) + lambda G_s[a] G_w[b]
-                        E[s][w] = mu * ((a == b ? dot : 0.0) + Gsb[s] * Gwa) + lam * Gsa[s] * Gwb;
-                    }
-                }
-            }
-            const uint16_t *pc = A.posc + k * A.posc_stride;
-#pragma unroll
-            for (int jc = 0; jc < NL; jc++) {
-                double v = 0.0;
-#pragma unroll
-                for (int s = 0; s < NS; s++) {
-                    v += A.R.r[TYPE][jc][s][0] * E[s][canon_sv<DIM>(jc, 0)];
-                    if (jc >= NVTX) v += A.R.r[TYPE][jc][s][1] * E[s][canon_sv<DIM>(jc, 1)];
-                }
-                const int p = pc[jc];
-                acc[p * NT + tid] += v;
             }
         }
     }
 
-    if constexpr (OPG == 0) {
-        // thread owns node row `row`; scalar: one CSR row of L values; vec field: DIM dof rows
-        if (active) {
-            const int nrep = A.vec_dim == 0 ? 1 : A.vec_dim;
-            for (int d = 0; d < nrep; d++) {
-                double *out = A.values + (int64_t)nrep * base + (int64_t)d * L;
-                int p = 0;
-                while (p < L && (reinterpret_cast<uintptr_t>(out + p) & 31)) { out[p] = acc[p * NT + tid]; p++; }
-                for (; p + 4 <= L; p += 4)
-                    st_v4(out + p, acc[p * NT + tid], acc[(p + 1) * NT + tid], acc[(p + 2) * NT + tid], acc[(p + 3) * NT + tid]);
-                for (; p < L; p++) out[p] = acc[p * NT + tid];
-            }
-        }
-    } else {
-        // threads (a, b = 0..DIM-1) of a node hold interleaved parts of dof row (I, a): entry
-        // (p, b') lives in the accumulator of thread (a, b').  Thread (a, b) writes the b-th
-        // third of the dof row as one contiguous run.  The DIM threads are adjacent lanes of the
-        // same warp unless the group straddles a warp boundary, hence the block barrier.
-        __syncthreads();
-        if (active) {
-            const int tid0 = tid - b; // thread (a, 0); may lie in the previous warp
-            double *out = A.values + (int64_t)DIM * DIM * base + (int64_t)a * DIM * L;
-            const int x0 = b * L, x1 = x0 + L;
-            auto val = [&](int x) { const int p = x / DIM; return acc[p * NT + tid0 + (x - p * DIM)]; };
-            int x = x0;
-            while (x < x1 && (reinterpret_cast<uintptr_t>(out + x) & 31)) { out[x] = val(x); x++; }
-            for (; x + 4 <= x1; x += 4) st_v4(out + x, val(x), val(x + 1), val(x + 2), val(x + 3));
-            for (; x < x1; x++) out[x] = val(x);
-        }
+    // write-out: the thread's accumulators are exactly one CSR row (scalar / elasticity dof row (I, a)),
+    // contiguous in the values array; the block-diagonal vector Laplacian replicates it DIM times
+    const int nrep = (OPG == 0 && A.vec_dim != 0) ? A.vec_dim : 1;
+    const int n = NB * L;
+    for (int d = 0; d < nrep; d++) {
+        double *out = OPG == 1 ? A.values + (int64_t)DIM * DIM * base + (int64_t)a * n
+                               : A.values + (int64_t)nrep * base + (int64_t)d * L;
+        int p = 0;
+        while (p < n && (reinterpret_cast<uintptr_t>(out + p) & 31)) { out[p] = my[p * NT]; p++; }
+        for (; p + 4 <= n; p += 4) st_v4(out + p, my[p * NT], my[(p + 1) * NT], my[(p + 2) * NT], my[(p + 3) * NT]);
+        for (; p < n; p++) out[p] = my[p * NT];
     }
 }
 
