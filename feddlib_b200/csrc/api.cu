@@ -136,8 +136,21 @@ int ensure_gather(feddb200_pat *p)
         p->buckets.push_back({(int)rtype[perm[s]], cap(perm[s]), s, e - s});
         s = e;
     }
-    FB_CUDA(cudaMalloc(&p->row_perm_d, sizeof(int32_t) * std::max<int64_t>(n_rows, 1)));
-    FB_CUDA(cudaMemcpy(p->row_perm_d, perm.data(), sizeof(int32_t) * n_rows, cudaMemcpyHostToDevice));
+    {
+        std::vector<int64_t> inc_ptr(n_rows + 1);
+        FB_CUDA(cudaMemcpy(inc_ptr.data(), p->inc_ptr_d, sizeof(int64_t) * (n_rows + 1), cudaMemcpyDeviceToHost));
+        std::vector<RowInfo> info(n_rows);
+        for (int64_t q = 0; q < n_rows; q++) {
+            const int32_t r = perm[q];
+            info[q].base = p->rowptr_h[r];
+            info[q].k0 = inc_ptr[r];
+            info[q].len = (int32_t)(p->rowptr_h[r + 1] - p->rowptr_h[r]);
+            info[q].ninc = (int32_t)(inc_ptr[r + 1] - inc_ptr[r]);
+            info[q].pad = r;
+        }
+        FB_CUDA(cudaMalloc(&p->rowinfo_d, sizeof(RowInfo) * std::max<int64_t>(n_rows, 1)));
+        FB_CUDA(cudaMemcpy(p->rowinfo_d, info.data(), sizeof(RowInfo) * n_rows, cudaMemcpyHostToDevice));
+    }
     const int gs = dim == 3 ? 16 : 8;
     FB_CUDA(cudaMalloc(&p->geom_d, sizeof(double) * std::max<int64_t>(p->rm->ne * gs, 1)));
     p->gather_ready = true;
@@ -191,9 +204,16 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
         constexpr int NB = OPG == 1 ? DIM : 1;
         const size_t budget = c->smem_optin - 1024;
         const size_t per_thread = (size_t)NB * b.lcap * 8;
-        int nt = 256;
-        while (nt > 32 && per_thread * nt * 2 > budget + 1024) nt -= 32;
-        if (per_thread * nt > budget) {
+        // block size <= 128 (the kernel is compiled for 3 resident blocks of 128 threads): pick the size that
+        // keeps the most threads resident, preferring more (smaller) blocks so phases of different blocks overlap
+        int nt = 0;
+        size_t best = 0;
+        for (int cand = 128; cand >= 32; cand -= 32) {
+            const size_t fit = budget / (per_thread * cand);
+            const size_t resident = std::min<size_t>(fit, 16) * cand;
+            if (fit >= 1 && (resident > best || (resident == best && fit >= 2))) { best = resident; nt = cand; }
+        }
+        if (nt == 0) {
             set_error("row too long for the gather path's shared-memory accumulators; use the coloured or atomic mode");
             return FEDDB200_ELOGIC;
         }
@@ -270,7 +290,7 @@ int run_op(feddb200_ctx *c, const feddb200_pat *pc, int op, const double *u_d, d
         rc = ensure_gather(p);
         if (rc != FEDDB200_OK) return rc;
         GatherArgs G;
-        G.row_perm = p->row_perm_d; G.rowptr = p->rowptr_d; G.inc_ptr = p->inc_ptr_d; G.incp = p->incp_d;
+        G.rowinfo = (const RowInfo *)p->rowinfo_d; G.incp = p->incp_d;
         G.posc = p->posc_d; G.geom = p->geom_d;
         G.c0 = c0; G.c1 = c1; G.values = values_d; G.vec_dim = (op == OP_LAP && vec_field) ? dim : 0;
         canon_table(tab_h, dim, nr, G.R);

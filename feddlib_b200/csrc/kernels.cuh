@@ -449,11 +449,18 @@ struct CanonR {
     double r[2][MAXN][2][2];
 };
 
+// per-row record of the gather path (bucket order): one aligned 32-byte load per thread
+struct RowInfo {
+    int64_t base;   // rowptr[row]   (node level)
+    int64_t k0;     // first incidence
+    int32_t len;    // node-row length
+    int32_t ninc;   // number of incidences
+    int64_t pad;
+};
+
 struct GatherArgs {
-    const int32_t *row_perm;  // rows of this launch: row_perm[start .. start+count)
+    const RowInfo *rowinfo;   // rows of this launch: rowinfo[start .. start+count), bucket order
     int64_t start, count;
-    const int64_t *rowptr;
-    const int64_t *inc_ptr;
     const uint32_t *incp;
     const uint16_t *posc;
     const double *geom;
@@ -468,6 +475,7 @@ __device__ __forceinline__ void st_v4(double *p, double a, double b, double c, d
 {
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void ld_v4(const double *p, double (&v)[4])
 {
     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
@@ -599,7 +607,7 @@ __device__ __forceinline__ void gather_incidence(const GatherArgs &A, const IncD
 // OPG: 0 Laplace (one thread per row node), 1 elasticity (DIM threads per row node: one per row dof)
 // TYPE: 0 vertex rows, 1 edge rows
 template <int OPG, int DIM, int NL, int TYPE>
-__global__ void __launch_bounds__(256, 1) k_gather(const GatherArgs A)
+__global__ void __launch_bounds__(128, 3) k_gather(const GatherArgs A)
 {
     constexpr int TPR = OPG == 1 ? DIM : 1; // threads per row node
     constexpr int NB = OPG == 1 ? DIM : 1;  // accumulators per (thread, column node)
@@ -610,35 +618,51 @@ __global__ void __launch_bounds__(256, 1) k_gather(const GatherArgs A)
     if (t >= A.count * TPR) return;
     const int64_t rloc = t / TPR;
     const int a = (int)(t - rloc * TPR);
-    const int32_t row = A.row_perm[A.start + rloc];
-    const int64_t base = A.rowptr[row];
-    const int L = (int)(A.rowptr[row + 1] - base);
-    double *my = acc + tid;
-
-    for (int p = 0; p < NB * L; p++) my[p * NT] = 0.0;
-
+    int64_t base, k0;
+    int L, ninc;
     {
-        const int64_t k0 = A.inc_ptr[row], k1 = A.inc_ptr[row + 1];
-        if (k0 < k1) {
-            // two-deep software pipeline on ping-pong register buffers; prefetch indices are clamped to
-            // the row's last incidence so the loads are unconditional
-            IncData<DIM, NL> bufA, bufB;
-            const int64_t kl = k1 - 1;
-            load_inc<DIM, NL>(A, k0, A.incp[k0], bufA);
-            uint32_t code_n = A.incp[k0 + 1 < kl ? k0 + 1 : kl];
-            for (int64_t k = k0; k < k1; k += 2) {
-                const int64_t kb = k + 1 < kl ? k + 1 : kl;
-                load_inc<DIM, NL>(A, kb, code_n, bufB);
-                code_n = A.incp[k + 2 < kl ? k + 2 : kl];
-                gather_incidence<OPG, DIM, NL, TYPE>(A, bufA, a, my, NT);
-                if (k + 1 < k1) {
-                    const int64_t ka = k + 2 < kl ? k + 2 : kl;
-                    load_inc<DIM, NL>(A, ka, code_n, bufA);
-                    code_n = A.incp[k + 3 < kl ? k + 3 : kl];
-                    gather_incidence<OPG, DIM, NL, TYPE>(A, bufB, a, my, NT);
-                }
+        double raw[4];
+        ld_v4(reinterpret_cast<const double *>(A.rowinfo + A.start + rloc), raw);
+        base = __double_as_longlong(raw[0]);
+        k0 = __double_as_longlong(raw[1]);
+        const int64_t ln = __double_as_longlong(raw[2]);
+        L = (int)(ln & 0xffffffff);
+        ninc = (int)(ln >> 32);
+    }
+    double *my = acc + tid;
+    constexpr int GS = GeomStride<DIM>::value;
+    constexpr int PW = PoscStride<NL>::value / 2;
+
+    if (ninc > 0) {
+        // two-deep software pipeline on ping-pong register buffers plus an L2 prefetch three incidences
+        // ahead; prefetch indices are clamped to the row's last incidence so the loads are unconditional
+        IncData<DIM, NL> bufA, bufB;
+        const int64_t k1 = k0 + ninc, kl = k1 - 1;
+        const uint32_t c0 = A.incp[k0];
+        uint32_t code_n = A.incp[k0 + 1 < kl ? k0 + 1 : kl];
+        uint32_t code_f = A.incp[k0 + 3 < kl ? k0 + 3 : kl];
+        load_inc<DIM, NL>(A, k0, c0, bufA);
+        for (int p = 0; p < NB * L; p++) my[p * NT] = 0.0;
+        for (int64_t k = k0; k < k1; k += 2) {
+            const int64_t kb = k + 1 < kl ? k + 1 : kl;
+            load_inc<DIM, NL>(A, kb, code_n, bufB);
+            code_n = A.incp[k + 2 < kl ? k + 2 : kl];
+            prefetch_l2(A.geom + (int64_t)(code_f >> 8) * GS);
+            prefetch_l2(reinterpret_cast<const uint32_t *>(A.posc) + (k + 3 < kl ? k + 3 : kl) * PW);
+            code_f = A.incp[k + 4 < kl ? k + 4 : kl];
+            gather_incidence<OPG, DIM, NL, TYPE>(A, bufA, a, my, NT);
+            if (k + 1 < k1) {
+                const int64_t ka = k + 2 < kl ? k + 2 : kl;
+                load_inc<DIM, NL>(A, ka, code_n, bufA);
+                code_n = A.incp[k + 3 < kl ? k + 3 : kl];
+                prefetch_l2(A.geom + (int64_t)(code_f >> 8) * GS);
+                prefetch_l2(reinterpret_cast<const uint32_t *>(A.posc) + (k + 4 < kl ? k + 4 : kl) * PW);
+                code_f = A.incp[k + 5 < kl ? k + 5 : kl];
+                gather_incidence<OPG, DIM, NL, TYPE>(A, bufB, a, my, NT);
             }
         }
+    } else {
+        for (int p = 0; p < NB * L; p++) my[p * NT] = 0.0;
     }
 
     // write-out: the thread's accumulators are exactly one CSR row (scalar / elasticity dof row (I, a)),
