@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfeddb200.so")
+LIB_PATH = os.environ.get("FEDDB200_LIB") or os.path.join(_HERE, "libfeddb200.so")
 
 OK, ELOGIC, ERUNTIME = 0, -1, -2
 SCATTER_ATOMIC, SCATTER_COLOURED, SCATTER_GATHER = 0, 1, 2

@@ -2,6 +2,7 @@
 // kernel launches.  See include/feddb200.h for the reference interfaces each call replaces.
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 
 #include "kernels.cuh"
 
@@ -104,6 +105,7 @@ int ensure_gather(feddb200_pat *p)
     const int64_t n_rows = p->n_rows;
     p->posc_stride = nl <= 4 ? 4 : (nl <= 8 ? 8 : 16);
     FB_LOGIC(p->rm->ne >= (int64_t(1) << 24), "gather path supports up to 2^24 elements per GPU");
+    FB_LOGIC(p->max_len >= 0x8000, "gather path supports node rows of up to 32767 entries");
     FB_CUDA(cudaMalloc(&p->incp_d, sizeof(uint32_t) * std::max<int64_t>(p->n_inc, 1)));
     FB_CUDA(cudaMalloc(&p->posc_d, sizeof(uint16_t) * std::max<int64_t>(p->n_inc * p->posc_stride, 1)));
     int8_t *rtype_d = nullptr;
@@ -111,10 +113,10 @@ int ensure_gather(feddb200_pat *p)
     if (n_rows > 0) {
         const int grid = (int)std::min<int64_t>((n_rows + 127) / 128, 148 * 64);
         switch (elem_index(dim, nl)) {
-        case 0: k_canon_pos<2, 3><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->pos_d, p->pos_stride, p->posc_d, p->incp_d, rtype_d); break;
-        case 1: k_canon_pos<2, 6><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->pos_d, p->pos_stride, p->posc_d, p->incp_d, rtype_d); break;
-        case 2: k_canon_pos<3, 4><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->pos_d, p->pos_stride, p->posc_d, p->incp_d, rtype_d); break;
-        case 3: k_canon_pos<3, 10><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->pos_d, p->pos_stride, p->posc_d, p->incp_d, rtype_d); break;
+        case 0: k_canon_pos<2, 3><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->rowptr_d, p->pos_d, p->pos_stride, p->posc_d, p->incp_d, rtype_d); break;
+        case 1: k_canon_pos<2, 6><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->rowptr_d, p->pos_d, p->pos_stride, p->posc_d, p->incp_d, rtype_d); break;
+        case 2: k_canon_pos<3, 4><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->rowptr_d, p->pos_d, p->pos_stride, p->posc_d, p->incp_d, rtype_d); break;
+        case 3: k_canon_pos<3, 10><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->rowptr_d, p->pos_d, p->pos_stride, p->posc_d, p->incp_d, rtype_d); break;
         default: set_error("unsupported element"); return FEDDB200_ELOGIC;
         }
         c->launches++;
@@ -127,13 +129,13 @@ int ensure_gather(feddb200_pat *p)
     std::vector<int32_t> perm(n_rows);
     for (int64_t r = 0; r < n_rows; r++) perm[r] = (int32_t)r;
     auto cap = [&](int64_t r) { const int l = (int)(p->rowptr_h[r + 1] - p->rowptr_h[r]); return std::max(4, (l + 3) & ~3); };
-    auto key = [&](int32_t r) { return (int64_t)rtype[r] * 100000 + cap(r); };
+    auto key = [&](int32_t r) { return (int64_t)(rtype[r] & 1) * 100000 + cap(r); };
     std::stable_sort(perm.begin(), perm.end(), [&](int32_t a, int32_t b) { return key(a) < key(b); });
     p->buckets.clear();
     for (int64_t s = 0; s < n_rows;) {
         int64_t e = s;
         while (e < n_rows && key(perm[e]) == key(perm[s])) e++;
-        p->buckets.push_back({(int)rtype[perm[s]], cap(perm[s]), s, e - s});
+        p->buckets.push_back({(int)(rtype[perm[s]] & 1), cap(perm[s]), s, e - s});
         s = e;
     }
     {
@@ -146,7 +148,7 @@ int ensure_gather(feddb200_pat *p)
             info[q].k0 = inc_ptr[r];
             info[q].len = (int32_t)(p->rowptr_h[r + 1] - p->rowptr_h[r]);
             info[q].ninc = (int32_t)(inc_ptr[r + 1] - inc_ptr[r]);
-            info[q].pad = r;
+            info[q].pad = rtype[r]; // bit 1: accumulators need zero-init
         }
         FB_CUDA(cudaMalloc(&p->rowinfo_d, sizeof(RowInfo) * std::max<int64_t>(n_rows, 1)));
         FB_CUDA(cudaMemcpy(p->rowinfo_d, info.data(), sizeof(RowInfo) * n_rows, cudaMemcpyHostToDevice));
@@ -208,7 +210,9 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
         // keeps the most threads resident, preferring more (smaller) blocks so phases of different blocks overlap
         int nt = 0;
         size_t best = 0;
+        const char *force_nt = getenv("FEDDB200_GATHER_NT"); // tuning aid
         for (int cand = 128; cand >= 32; cand -= 32) {
+            if (force_nt && atoi(force_nt) != cand) continue;
             const size_t fit = budget / (per_thread * cand);
             const size_t resident = std::min<size_t>(fit, 16) * cand;
             if (fit >= 1 && (resident > best || (resident == best && fit >= 2))) { best = resident; nt = cand; }

@@ -419,12 +419,18 @@ template <int NL> struct PoscStride { static constexpr int value = NL <= 4 ? 4 :
 //   rtype[row]  = 0 vertex node / 1 edge node
 template <int DIM, int NL>
 __global__ void k_canon_pos(int64_t n_rows, const int64_t *__restrict__ inc_ptr, const int32_t *__restrict__ inc,
-                            const uint16_t *__restrict__ pos, int pos_stride, uint16_t *__restrict__ posc,
-                            uint32_t *__restrict__ incp, int8_t *__restrict__ rtype)
+                            const int64_t *__restrict__ rowptr, const uint16_t *__restrict__ pos, int pos_stride,
+                            uint16_t *__restrict__ posc, uint32_t *__restrict__ incp, int8_t *__restrict__ rtype)
 {
     constexpr int PS = PoscStride<NL>::value;
     for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x) {
         int8_t ty = 0;
+        // first-touch bitmap of the row's positions (rows longer than 1024 nodes are zero-initialised instead)
+        uint64_t seen[16];
+        for (int w = 0; w < 16; w++) seen[w] = 0;
+        const int len = (int)(rowptr[r + 1] - rowptr[r]);
+        const bool track = len <= 1024;
+        int ntouched = 0;
         for (int64_t k = inc_ptr[r]; k < inc_ptr[r + 1]; k++) {
             const int32_t code = inc[k];
             const int64_t e = code >> 4;
@@ -435,10 +441,21 @@ __global__ void k_canon_pos(int64_t n_rows, const int64_t *__restrict__ inc_ptr,
             uint32_t bits = 0;
             for (int v = 0; v <= DIM; v++) bits |= (uint32_t)pi[v] << (2 * v);
             incp[k] = ((uint32_t)e << 8) | bits;
-            for (int jc = 0; jc < PS; jc++)
-                posc[k * PS + jc] = jc < NL ? pos[(e * NL + i) * pos_stride + canon_node<DIM>(pi, jc)] : 0;
+            for (int jc = 0; jc < PS; jc++) {
+                uint16_t w = 0;
+                if (jc < NL) {
+                    w = pos[(e * NL + i) * pos_stride + canon_node<DIM>(pi, jc)];
+                    if (track && !((seen[w >> 6] >> (w & 63)) & 1)) {
+                        seen[w >> 6] |= uint64_t(1) << (w & 63);
+                        ntouched++;
+                        w |= 0x8000; // first contribution to this position: store instead of add
+                    }
+                }
+                posc[k * PS + jc] = w;
+            }
         }
-        rtype[r] = ty;
+        // bit 0: row type; bit 1: some position gets no local contribution -> accumulators need zero-init
+        rtype[r] = ty | ((!track || ntouched < len) ? 2 : 0);
     }
 }
 
@@ -534,7 +551,8 @@ __device__ __forceinline__ double sel3(const double (&v)[4], int c) { return c =
 // lane-private accumulators.  OPG 0: Laplace, 1 value per column node.  OPG 1: elasticity, the thread
 // owns row dof `a` and produces the DIM column dofs b of every column node.
 template <int OPG, int DIM, int NL, int TYPE>
-__device__ __forceinline__ void gather_incidence(const GatherArgs &A, const IncData<DIM, NL> &D, int a, double *my, int NT)
+__device__ __forceinline__ void gather_incidence(const GatherArgs &A, const IncData<DIM, NL> &D, int a, double *my, int NT,
+                                                 double (&dacc)[OPG == 1 ? DIM : 1])
 {
     constexpr int NVTX = DIM + 1;
     constexpr int NS = TYPE == 0 ? 1 : 2;   // canonical support size of the row function
@@ -572,33 +590,57 @@ __device__ __forceinline__ void gather_incidence(const GatherArgs &A, const IncD
             }
         }
     }
-    // distinct canonical nodes hit distinct row positions: per chunk of column nodes load all
-    // accumulators, add, store all (keeps the shared-memory round trips independent)
-    constexpr int JB = NL <= 6 ? NL : 5;
+    // the row node itself (canonical node 0 of a vertex row, canonical edge (0,1) of an edge row) receives a
+    // contribution from every incidence: it is accumulated in registers
+    constexpr int JD = TYPE == 0 ? 0 : NVTX;
 #pragma unroll
-    for (int j0 = 0; j0 < NL; j0 += JB) {
+    for (int b = 0; b < NB; b++) {
+        double v = dacc[b];
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            v += A.R.r[TYPE][JD][s][0] * E[s][canon_sv<DIM>(JD, 0)][b];
+            if (JD >= NVTX) v += A.R.r[TYPE][JD][s][1] * E[s][canon_sv<DIM>(JD, 1)][b];
+        }
+        dacc[b] = v;
+    }
+    // distinct canonical nodes hit distinct row positions: per chunk of column nodes load all
+    // accumulators, add, store all (keeps the shared-memory round trips independent).  Bit 15 of a
+    // position word marks the first contribution to that position: it is stored, not added.
+    constexpr int NO = NL - 1;               // off-diagonal column nodes
+    constexpr int JB = NO <= 5 ? NO : (NO == 9 ? 5 : 3);
+#pragma unroll
+    for (int j0 = 0; j0 < NO; j0 += JB) {
         int idx[JB];
         double old[JB][NB];
 #pragma unroll
         for (int jj = 0; jj < JB; jj++) {
-            const int jc = j0 + jj;
-            const uint32_t p = (D.P[jc >> 1] >> (16 * (jc & 1))) & 0xffffu;
-            idx[jj] = (int)p * (NB * NT);
+            if (j0 + jj < NO) {
+                const int jc = (j0 + jj) + ((j0 + jj) >= JD ? 1 : 0);
+                const uint32_t w = (D.P[jc >> 1] >> (16 * (jc & 1))) & 0xffffu;
+                idx[jj] = (int)(w & 0x7fffu) * (NB * NT);
+#ifdef FB_FIRST_TOUCH
+                const bool first = (w & 0x8000u) != 0;
+#else
+                const bool first = false;
+#endif
 #pragma unroll
-            for (int b = 0; b < NB; b++) old[jj][b] = my[idx[jj] + b * NT];
+                for (int b = 0; b < NB; b++) old[jj][b] = first ? 0.0 : my[idx[jj] + b * NT];
+            }
         }
 #pragma unroll
         for (int jj = 0; jj < JB; jj++) {
-            const int jc = j0 + jj;
+            if (j0 + jj < NO) {
+                const int jc = (j0 + jj) + ((j0 + jj) >= JD ? 1 : 0);
 #pragma unroll
-            for (int b = 0; b < NB; b++) {
-                double v = old[jj][b];
+                for (int b = 0; b < NB; b++) {
+                    double v = old[jj][b];
 #pragma unroll
-                for (int s = 0; s < NS; s++) {
-                    v += A.R.r[TYPE][jc][s][0] * E[s][canon_sv<DIM>(jc, 0)][b];
-                    if (jc >= NVTX) v += A.R.r[TYPE][jc][s][1] * E[s][canon_sv<DIM>(jc, 1)][b];
+                    for (int s = 0; s < NS; s++) {
+                        v += A.R.r[TYPE][jc][s][0] * E[s][canon_sv<DIM>(jc, 0)][b];
+                        if (jc >= NVTX) v += A.R.r[TYPE][jc][s][1] * E[s][canon_sv<DIM>(jc, 1)][b];
+                    }
+                    my[idx[jj] + b * NT] = v;
                 }
-                my[idx[jj] + b * NT] = v;
             }
         }
     }
@@ -606,8 +648,11 @@ __device__ __forceinline__ void gather_incidence(const GatherArgs &A, const IncD
 
 // OPG: 0 Laplace (one thread per row node), 1 elasticity (DIM threads per row node: one per row dof)
 // TYPE: 0 vertex rows, 1 edge rows
+#ifndef FB_GATHER_MINBLOCKS
+#define FB_GATHER_MINBLOCKS 3
+#endif
 template <int OPG, int DIM, int NL, int TYPE>
-__global__ void __launch_bounds__(128, 3) k_gather(const GatherArgs A)
+__global__ void __launch_bounds__(128, FB_GATHER_MINBLOCKS) k_gather(const GatherArgs A)
 {
     constexpr int TPR = OPG == 1 ? DIM : 1; // threads per row node
     constexpr int NB = OPG == 1 ? DIM : 1;  // accumulators per (thread, column node)
@@ -619,7 +664,7 @@ __global__ void __launch_bounds__(128, 3) k_gather(const GatherArgs A)
     const int64_t rloc = t / TPR;
     const int a = (int)(t - rloc * TPR);
     int64_t base, k0;
-    int L, ninc;
+    int L, ninc, flags;
     {
         double raw[4];
         ld_v4(reinterpret_cast<const double *>(A.rowinfo + A.start + rloc), raw);
@@ -628,6 +673,7 @@ __global__ void __launch_bounds__(128, 3) k_gather(const GatherArgs A)
         const int64_t ln = __double_as_longlong(raw[2]);
         L = (int)(ln & 0xffffffff);
         ninc = (int)(ln >> 32);
+        flags = (int)__double_as_longlong(raw[3]);
     }
     double *my = acc + tid;
     constexpr int GS = GeomStride<DIM>::value;
@@ -642,7 +688,16 @@ __global__ void __launch_bounds__(128, 3) k_gather(const GatherArgs A)
         uint32_t code_n = A.incp[k0 + 1 < kl ? k0 + 1 : kl];
         uint32_t code_f = A.incp[k0 + 3 < kl ? k0 + 3 : kl];
         load_inc<DIM, NL>(A, k0, c0, bufA);
-        for (int p = 0; p < NB * L; p++) my[p * NT] = 0.0;
+#ifdef FB_FIRST_TOUCH
+        if (flags & 2)
+#endif
+            for (int p = 0; p < NB * L; p++) my[p * NT] = 0.0;
+        double dacc[NB];
+#pragma unroll
+        for (int b = 0; b < NB; b++) dacc[b] = 0.0;
+        // position of the row node in its own row (same in every incidence)
+        constexpr int JD = TYPE == 0 ? 0 : DIM + 1;
+        const int pdiag = (int)((bufA.P[JD >> 1] >> (16 * (JD & 1))) & 0x7fffu) * (NB * NT);
         for (int64_t k = k0; k < k1; k += 2) {
             const int64_t kb = k + 1 < kl ? k + 1 : kl;
             load_inc<DIM, NL>(A, kb, code_n, bufB);
@@ -650,7 +705,7 @@ __global__ void __launch_bounds__(128, 3) k_gather(const GatherArgs A)
             prefetch_l2(A.geom + (int64_t)(code_f >> 8) * GS);
             prefetch_l2(reinterpret_cast<const uint32_t *>(A.posc) + (k + 3 < kl ? k + 3 : kl) * PW);
             code_f = A.incp[k + 4 < kl ? k + 4 : kl];
-            gather_incidence<OPG, DIM, NL, TYPE>(A, bufA, a, my, NT);
+            gather_incidence<OPG, DIM, NL, TYPE>(A, bufA, a, my, NT, dacc);
             if (k + 1 < k1) {
                 const int64_t ka = k + 2 < kl ? k + 2 : kl;
                 load_inc<DIM, NL>(A, ka, code_n, bufA);
@@ -658,9 +713,11 @@ __global__ void __launch_bounds__(128, 3) k_gather(const GatherArgs A)
                 prefetch_l2(A.geom + (int64_t)(code_f >> 8) * GS);
                 prefetch_l2(reinterpret_cast<const uint32_t *>(A.posc) + (k + 4 < kl ? k + 4 : kl) * PW);
                 code_f = A.incp[k + 5 < kl ? k + 5 : kl];
-                gather_incidence<OPG, DIM, NL, TYPE>(A, bufB, a, my, NT);
+                gather_incidence<OPG, DIM, NL, TYPE>(A, bufB, a, my, NT, dacc);
             }
         }
+#pragma unroll
+        for (int b = 0; b < NB; b++) my[pdiag + b * NT] = dacc[b];
     } else {
         for (int p = 0; p < NB * L; p++) my[p * NT] = 0.0;
     }
