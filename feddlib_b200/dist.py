@@ -1,0 +1,335 @@
+"""Multi-GPU element partition: ownership, column maps and the ghost-row exchange plan.
+
+What this replaces in the reference: every rank assembles its own elements; contributions to rows
+owned by another rank are shipped to the owner and ADDed inside `Matrix::fillComplete`
+(core/LinearAlgebra/Matrix_def.hpp:192-199 -> Tpetra globalAssemble), and the
+column map is rebuilt as "owned GIDs in domain-map order, then remote GIDs grouped by owning rank,
+ascending GID".  Here the same happens with one process per GPU:
+
+  one-time (host, torch.distributed for the plumbing; NCCL on GPUs, gloo in the CPU tests)
+    1. rows: owned nodes in repeated order (= Map::buildUniqueMap order, Map_def.hpp:201-206), then
+       ghost nodes grouped by owner -> the ghost values of one destination are one contiguous segment
+    2. preliminary node pattern -> ghost-row structure (row gid, col gid, col owner) -> owners
+    3. column index space = Tpetra column map (owned, then remotes by (owner, gid)) followed by
+       ghost-only columns that never reach the owned rows
+    4. final device pattern with the received entries as extra entries
+    5. senders publish their ghost rows in final CSR order; receivers resolve them to value slots
+  per assembly (device)
+    values[ghost part] --all_to_all_single (NCCL over NVLink)--> owners --unpack-add kernel--> CSR
+
+The plan builder takes the node-pattern builder as a callable so the identical host logic runs in
+the CPU tests (world_size 2, gloo) with a numpy pattern builder.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from ._lib import BLOCK_DIAG, BLOCK_FULL, BLOCK_SCALAR
+
+
+# ------------------------------------------------------------------------------------------------
+# small collective helpers on numpy int64 / float64 arrays
+# ------------------------------------------------------------------------------------------------
+class Comm:
+    """torch.distributed wrapper; device=None -> CPU tensors (gloo), else CUDA tensors (nccl)."""
+
+    def __init__(self, rank: int, size: int, device=None):
+        self.rank, self.size, self.device = rank, size, device
+
+    def _t(self, a, dtype):
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(a)).to(dtype)
+        return t.to(self.device) if self.device is not None else t
+
+    def alltoallv(self, chunks, np_dtype=np.int64):
+        """chunks[d] = 1-D array for rank d.  Returns list of arrays received from every rank."""
+        import torch
+        import torch.distributed as dist
+        tdt = torch.int64 if np_dtype == np.int64 else torch.float64
+        if self.size == 1:
+            return [np.ascontiguousarray(chunks[0], dtype=np_dtype)]
+        counts = torch.tensor([len(c) for c in chunks], dtype=torch.int64)
+        if self.device is not None:
+            counts = counts.to(self.device)
+        rcounts = torch.empty_like(counts)
+        dist.all_to_all_single(rcounts, counts)
+        rc = rcounts.cpu().tolist()
+        send = self._t(np.concatenate([np.asarray(c, dtype=np_dtype) for c in chunks]) if sum(len(c) for c in chunks)
+                       else np.zeros(0, dtype=np_dtype), tdt)
+        recv = torch.empty(int(sum(rc)), dtype=tdt, device=send.device)
+        dist.all_to_all_single(recv, send, rc, [len(c) for c in chunks])
+        out = recv.cpu().numpy()
+        offs = np.concatenate([[0], np.cumsum(rc)]).astype(np.int64)
+        return [out[offs[i]:offs[i + 1]] for i in range(self.size)]
+
+
+def numpy_node_pattern(conn_r, conn_c, row_lid, n_rows, col_lid, extra_row=None, extra_col=None):
+    """Reference (host) node-pattern builder with the semantics of feddb200_pattern_build."""
+    nr, nc = conn_r.shape[1], conn_c.shape[1]
+    r = row_lid[conn_r] if row_lid is not None else conn_r
+    c = col_lid[conn_c] if col_lid is not None else conn_c
+    rows = np.repeat(r, nc, axis=1).ravel().astype(np.int64)
+    cols = np.tile(c, (1, nr)).ravel().astype(np.int64)
+    keep = rows >= 0
+    rows, cols = rows[keep], cols[keep]
+    if extra_row is not None and len(extra_row):
+        rows = np.concatenate([rows, np.asarray(extra_row, dtype=np.int64)])
+        cols = np.concatenate([cols, np.asarray(extra_col, dtype=np.int64)])
+    key = np.unique(rows << 32 | cols)
+    rows_u, cols_u = key >> 32, key & 0xffffffff
+    rowptr = np.searchsorted(rows_u, np.arange(n_rows + 1)).astype(np.int64)
+    return rowptr, cols_u.astype(np.int32)
+
+
+# ------------------------------------------------------------------------------------------------
+# the plan
+# ------------------------------------------------------------------------------------------------
+class HaloPlan:
+    """Ownership, index spaces and ghost-row exchange plan of one rank (square node pattern)."""
+
+    def __init__(self, comm: Comm, gid_rep, owner, pattern_fn):
+        """
+        gid_rep [nn]  global id of every repeated node;  owner [nn]  owning rank of every repeated node
+        pattern_fn(row_lid, n_rows, n_owned, col_lid, n_cols, extra_row, extra_col) -> (rowptr, colind)
+                      builds the node pattern of this rank's elements (device builder or numpy_node_pattern)
+        """
+        self.comm = comm
+        rank, size = comm.rank, comm.size
+        gid_rep = np.ascontiguousarray(gid_rep, dtype=np.int64)
+        owner = np.ascontiguousarray(owner, dtype=np.int64)
+        nn = gid_rep.size
+        self.gid_rep, self.owner = gid_rep, owner
+
+        # 1. rows
+        owned = owner == rank
+        owned_ids = np.flatnonzero(owned)                       # repeated order -> unique-map order
+        ghost_ids = np.flatnonzero(~owned)
+        ghost_ids = ghost_ids[np.lexsort((gid_rep[ghost_ids], owner[ghost_ids]))]   # by (owner, gid)
+        self.n_owned, self.n_ghost = owned_ids.size, ghost_ids.size
+        self.n_rows = self.n_owned + self.n_ghost
+        row_lid = np.empty(nn, dtype=np.int32)
+        row_lid[owned_ids] = np.arange(self.n_owned, dtype=np.int32)
+        row_lid[ghost_ids] = self.n_owned + np.arange(self.n_ghost, dtype=np.int32)
+        self.row_lid = row_lid
+        self.unique_gids = gid_rep[owned_ids]
+        self.ghost_row_gids = gid_rep[ghost_ids]
+        self.ghost_row_owner = owner[ghost_ids]
+        rep_of_row = np.empty(self.n_rows, dtype=np.int64)
+        rep_of_row[row_lid] = np.arange(nn)
+
+        # 2. preliminary pattern (columns = repeated local ids) -> ghost-row structure to the owners
+        rp0, ci0 = pattern_fn(row_lid, self.n_rows, self.n_owned, None, nn, None, None)
+        g0, g1 = rp0[self.n_owned], rp0[self.n_rows]
+        grow = np.repeat(np.arange(self.n_owned, self.n_rows), np.diff(rp0[self.n_owned:]))  # row lid per ghost entry
+        gcol_rep = ci0[g0:g1].astype(np.int64)
+        dest = owner[rep_of_row[grow]]
+        send = []
+        for d in range(size):
+            m = dest == d
+            send.append(np.stack([gid_rep[rep_of_row[grow[m]]], gid_rep[gcol_rep[m]], owner[gcol_rep[m]]], axis=1).ravel()
+                        if m.any() else np.zeros(0, dtype=np.int64))
+        recv = [x.reshape(-1, 3) for x in comm.alltoallv(send)]
+        rec = np.concatenate(recv, axis=0) if len(recv) else np.zeros((0, 3), dtype=np.int64)
+
+        # 3. column index space
+        rep_sorted = np.argsort(gid_rep, kind="stable")
+        gid_sorted = gid_rep[rep_sorted]
+
+        def rep_of_gid(g):      # repeated local id of a gid, -1 if this rank does not have the node
+            pos = np.searchsorted(gid_sorted, g)
+            pos = np.minimum(pos, max(nn - 1, 0))
+            hit = (gid_sorted[pos] == g) if nn else np.zeros(g.shape, dtype=bool)
+            return np.where(hit, rep_sorted[pos], -1)
+
+        owned_cols_in_owned_rows = np.zeros(nn, dtype=bool)
+        owned_cols_in_owned_rows[ci0[:g0]] = True               # repeated nodes appearing in owned rows
+        remote_gid = gid_rep[~owned & owned_cols_in_owned_rows]
+        remote_own = owner[~owned & owned_cols_in_owned_rows]
+        if rec.size:
+            m = rec[:, 2] != rank                               # received columns owned elsewhere
+            remote_gid = np.concatenate([remote_gid, rec[m, 1]])
+            remote_own = np.concatenate([remote_own, rec[m, 2]])
+        if remote_gid.size:
+            rg, idx = np.unique(remote_gid, return_index=True)
+            ro = remote_own[idx]
+            order = np.lexsort((rg, ro))
+            remote_gid, remote_own = rg[order], ro[order]
+        self.colmap_gids = np.concatenate([self.unique_gids, remote_gid])      # the Tpetra column map
+        self.n_colmap = self.colmap_gids.size
+        # ghost-only columns (appear only in ghost rows): appended behind the column map
+        col_lid = np.full(nn, -1, dtype=np.int64)
+        col_lid[owned_ids] = np.arange(self.n_owned)
+        if remote_gid.size:
+            r_rep = rep_of_gid(remote_gid)
+            has = r_rep >= 0
+            col_lid[r_rep[has]] = self.n_owned + np.flatnonzero(has)
+        rest = np.flatnonzero(col_lid < 0)
+        col_lid[rest] = self.n_colmap + np.arange(rest.size)
+        self.n_cols = self.n_colmap + rest.size
+        self.col_lid = col_lid.astype(np.int32)
+
+        # 4. extra entries in owned rows
+        if rec.size:
+            colmap_sorted = np.argsort(self.colmap_gids, kind="stable")
+            cm_gid_sorted = self.colmap_gids[colmap_sorted]
+            er = row_lid[rep_of_gid(rec[:, 0])]
+            ec = colmap_sorted[np.searchsorted(cm_gid_sorted, rec[:, 1])]
+            assert np.all(er >= 0) and np.all(er < self.n_owned), "ghost row sent to a rank that does not own it"
+            self.extra_row, self.extra_col = er.astype(np.int32), ec.astype(np.int32)
+        else:
+            self.extra_row = self.extra_col = np.zeros(0, dtype=np.int32)
+        self.rowptr, self.colind = pattern_fn(row_lid, self.n_rows, self.n_owned, self.col_lid, self.n_cols,
+                                              self.extra_row, self.extra_col)
+        rp, ci = self.rowptr, self.colind
+        self.nnz_owned_nodes, self.nnz_nodes = int(rp[self.n_owned]), int(rp[self.n_rows])
+
+        # 5. ghost rows in final CSR order -> owners resolve them to node-level (row, position)
+        gid_of_col = np.empty(self.n_cols, dtype=np.int64)
+        gid_of_col[self.col_lid] = gid_rep
+        gid_of_col[: self.n_colmap] = self.colmap_gids
+        glen = np.diff(rp[self.n_owned:])
+        grow = np.repeat(np.arange(self.n_owned, self.n_rows), glen)
+        gq = np.arange(rp[self.n_owned], rp[self.n_rows]) - np.repeat(rp[self.n_owned:-1], glen)  # position in ghost row
+        gcol_gid = gid_of_col[ci[rp[self.n_owned]:rp[self.n_rows]]]
+        dest = owner[rep_of_row[grow]]
+        self.send_counts_nodes = np.array([(dest == d).sum() for d in range(size)], dtype=np.int64)
+        assert np.all(np.diff(dest) >= 0), "ghost rows are not grouped by owner"
+        send = []
+        for d in range(size):
+            m = dest == d
+            send.append(np.stack([gid_rep[rep_of_row[grow[m]]], gcol_gid[m], np.repeat(glen, glen)[m], gq[m]], axis=1).ravel()
+                        if m.any() else np.zeros(0, dtype=np.int64))
+        recv = [x.reshape(-1, 4) for x in comm.alltoallv(send)]
+        self.recv_counts_nodes = np.array([x.shape[0] for x in recv], dtype=np.int64)
+        rec = np.concatenate(recv, axis=0) if len(recv) else np.zeros((0, 4), dtype=np.int64)
+        if rec.size:
+            I = row_lid[rep_of_gid(rec[:, 0])].astype(np.int64)
+            colmap_sorted = np.argsort(self.colmap_gids, kind="stable")
+            c = colmap_sorted[np.searchsorted(self.colmap_gids[colmap_sorted], rec[:, 1])]
+            # position of column c in owned row I (rows are sorted by column index)
+            key_all = (np.repeat(np.arange(self.n_rows), np.diff(rp)).astype(np.int64) << 32) | ci.astype(np.int64)
+            slot = np.searchsorted(key_all, (I << 32) | c)
+            assert np.array_equal(key_all[slot], (I << 32) | c), "received entry missing from the owner's pattern"
+            self.recv_row, self.recv_pos = I, slot - rp[I]
+            self.recv_len_sender, self.recv_q = rec[:, 2], rec[:, 3]
+        else:
+            z = np.zeros(0, dtype=np.int64)
+            self.recv_row = self.recv_pos = self.recv_len_sender = self.recv_q = z
+        self._slots = {}
+
+    # -- dof-level helpers ---------------------------------------------------------------------
+    @staticmethod
+    def _factor(rd, cd, mode):
+        return 1 if mode == BLOCK_SCALAR else (rd if mode == BLOCK_DIAG else rd * cd)
+
+    def split_sizes(self, rd, cd, mode):
+        f = self._factor(rd, cd, mode)
+        return (self.send_counts_nodes * f).tolist(), (self.recv_counts_nodes * f).tolist()
+
+    def recv_slots(self, rd, cd, mode):
+        """Value slots (into this rank's dof-level CSR values) of every received value, in arrival order.
+
+        A sender ships each ghost node row as one block of f*len values in its own CSR order
+        (a, q, b); the receiver adds element (a, q, b) to rd*cd*base_I + a*cd*L_I + cd*p + b."""
+        key = (rd, cd, mode)
+        if key in self._slots:
+            return self._slots[key]
+        f = self._factor(rd, cd, mode)
+        rp = self.rowptr
+        I, p = self.recv_row, self.recv_pos
+        n = I.size
+        per = 1 if mode != BLOCK_FULL else cd
+        nrow_dofs = 1 if mode == BLOCK_SCALAR else rd
+        base, L = rp[I], rp[I + 1] - rp[I]
+        # arrival order within one sender: ghost rows in order, within a row (a, q, b).  Build the arrival index
+        # of every (entry, a, b) and scatter.
+        out = np.empty(n * f, dtype=np.int64)
+        # start offset (in values) of each received entry's row block within the stream
+        # entries of one ghost row are consecutive (q = 0..len-1); block start = cumulative f*len of earlier rows
+        first = self.recv_q == 0
+        row_block_start = np.cumsum(np.where(first, self.recv_len_sender * f, 0)) - np.where(first, self.recv_len_sender * f, 0)
+        row_block_start = np.maximum.accumulate(np.where(first, row_block_start, 0))
+        Ls, q = self.recv_len_sender, self.recv_q
+        for a in range(nrow_dofs):
+            for b in range(per):
+                arrival = row_block_start + a * per * Ls + per * q + b
+                out[arrival] = f * base + a * per * L + per * p + b
+        self._slots[key] = out
+        return out
+
+
+class DistributedMatrixAssembler:
+    """Device-side driver: per-rank mesh + pattern from a HaloPlan, assembly + ghost exchange."""
+
+    def __init__(self, ctx, dim, conn, coords, gid_rep, owner, rank, size):
+        import torch
+        from .engine import Mesh, Pattern
+        self.ctx, self.dim, self.rank, self.size = ctx, dim, rank, size
+        self.conn, self.coords = conn, coords
+        self.mesh = Mesh(ctx, dim, conn, coords)
+        self._pats = []
+
+        def pattern_fn(row_lid, n_rows, n_owned, col_lid, n_cols, er, ec):
+            pat = Pattern(ctx, self.mesh, None, row_lid, n_rows, n_owned, col_lid, n_cols, er, ec)
+            self._pats.append(pat)
+            return pat.nodes()
+
+        dev = torch.device(f"cuda:{ctx.device}")
+        self.plan = HaloPlan(Comm(rank, size, dev), gid_rep, owner, pattern_fn)
+        self.pat = self._pats[-1]
+        for p in self._pats[:-1]:
+            p.close()
+        self._dev = dev
+        self._slot_t = {}
+        self._recv_buf = {}
+
+    def exchange(self, values, rd, cd, mode):
+        """Ship ghost-row values to their owners (NCCL all-to-all-v) and add them into the owned CSR."""
+        import torch
+        import torch.distributed as dist
+        if self.size == 1:
+            return
+        key = (rd, cd, mode)
+        if key not in self._slot_t:
+            self._slot_t[key] = torch.from_numpy(self.plan.recv_slots(rd, cd, mode)).to(self._dev)
+            self._recv_buf[key] = torch.empty(self._slot_t[key].numel(), dtype=torch.float64, device=self._dev)
+        ssz, rsz = self.plan.split_sizes(rd, cd, mode)
+        n_owned_vals = self.pat.nnz_owned(rd, cd, mode)
+        send = values[n_owned_vals:]
+        recv = self._recv_buf[key]
+        dist.all_to_all_single(recv, send, rsz, ssz)
+        # one unpack launch per sender: slots are distinct within a sender, launches are stream ordered,
+        # so the summation order is fixed (deterministic)
+        off = 0
+        slots = self._slot_t[key]
+        for n in rsz:
+            if n:
+                self.ctx.unpack_add_d(values, recv[off:off + n], slots[off:off + n])
+            off += n
+
+
+def box_dims(world: int):
+    """Sub-domain grid for `world` ranks: cubes first (reference: N^3 ranks), else near-cubic boxes."""
+    best = (world, 1, 1)
+    for nx in range(1, world + 1):
+        for ny in range(1, world // nx + 1):
+            if world % (nx * ny) == 0:
+                nz = world // (nx * ny)
+                cand = tuple(sorted((nx, ny, nz), reverse=True))
+                if max(cand) - min(cand) < max(best) - min(best):
+                    best = cand
+    return best
+
+
+class DistributedElasticity(DistributedMatrixAssembler):
+    """bench.py's multi-GPU workload: P2 elasticity on a box of `world` structured sub-cubes (H/h = M each)."""
+
+    def __init__(self, ctx, dim, fe, M, rank, world):
+        from . import mesh as PM
+        dims = box_dims(world)
+        conn, coords, gid, owner = PM.build_structured_box(dim, fe, dims, M, rank)
+        super().__init__(ctx, dim, conn, coords, gid, owner, rank, world)
+        self.dims = dims
+
+    def exchange(self, values):
+        super().exchange(values, self.dim, self.dim, BLOCK_FULL)

@@ -72,3 +72,33 @@ def warp_coords(coords: np.ndarray, amp: float = 0.08) -> np.ndarray:
         o = coords[:, (d + 1) % dim]
         x[:, d] = coords[:, d] + amp * np.sin(np.pi * coords[:, d]) * np.cos(np.pi * o) * 0.5
     return x
+
+
+def build_structured_box(dim: int, fe: str, dims, M: int, rank: int):
+    """Weak-scaling workload: a box of dims[0] x dims[1] (x dims[2]) unit sub-cubes, one per rank, each
+    meshed like build_structured(N=1, M) (same cell split, same local numbering).  Returns
+    (conn, coords, gid, owner): gid on the global node lattice, owner = lowest rank holding the node
+    (the standalone ownership rule; the reference leaves it to Tpetra's directory, Map_def.hpp:194-199)."""
+    dims = tuple(int(d) for d in dims)[:dim] + (1,) * (3 - dim)
+    nranks = dims[0] * dims[1] * dims[2]
+    if not 0 <= rank < nranks:
+        raise ValueError("rank outside the box of sub-domains")
+    conn, coords, _ = build_structured(dim, fe, 1, M, 0)
+    k = 2 if fe == "P2" else 1
+    n = k * M + 1
+    off = (rank % dims[0], (rank // dims[0]) % dims[1], rank // (dims[0] * dims[1]))
+    ng = [dims[d] * (n - 1) + 1 for d in range(3)]
+    lat = np.indices((n,) * dim, dtype=np.int64)[::-1].reshape(dim, -1)
+    gid = np.zeros(lat.shape[1], dtype=np.int64)
+    owner = np.zeros(lat.shape[1], dtype=np.int64)
+    stride_g, stride_r = 1, 1
+    coords = coords.copy()
+    for d in range(dim):
+        X = lat[d] + off[d] * (n - 1)                       # global lattice coordinate
+        gid += X * stride_g
+        stride_g *= ng[d]
+        ob = np.where(X == 0, 0, np.minimum((X - 1) // (n - 1), dims[d] - 1))   # lowest sub-box holding X
+        owner += ob * stride_r
+        stride_r *= dims[d]
+        coords[:, d] += off[d]
+    return conn, coords, gid, owner.astype(np.int32)

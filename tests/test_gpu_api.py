@@ -153,3 +153,19 @@ def test_device_resident_path_and_launch_counter(engine_ctx):
     assert engine_ctx.launches > before
     assert rel_frobenius(vals.cpu().numpy(), oracle_csr("linelas", 3, "P2", conn, co, lam=8e6, mu=2e6)[2]) <= TOL
     assert torch.isfinite(vals).all()
+
+
+def test_multi_gpu_exchange_if_available():
+    """Runs tests/dist_gpu_check.py under torchrun when the box has >= 2 GPUs (NCCL ghost-row exchange)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("single-GPU box; the multi-rank logic is covered on CPU by tests/test_dist_cpu.py")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(n, 8)}",
+                          "--master-addr", "127.0.0.1", "--master-port", "29561",
+                          os.path.join(root, "tests", "dist_gpu_check.py")], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
