@@ -5,11 +5,14 @@
  * the reference loop order and floating-point expression order.  Only tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
  *
- * PARITY STATUS: "parity unpinned" by reference golden vectors -- the reference ships no
- * golden matrices, known-answer tests or expected norms for this path.
- * The restatement is pinned instead by (i) the analytic known-answer tests in
- * tests/test_oracle_kat.py and (ii) when oracle/_ref can be built (see oracle/Makefile,
- * target `ref`), by the reference's own FE_def.hpp compiled against mock Trilinos headers.
+ * PARITY STATUS: the reference ships no golden matrices, known-answer tests or expected norms for
+ * this path, so the restatement is pinned by outputs of the reference itself run here:
+ * oracle/_ref (`make -C oracle ref`) compiles FEDDLib's own FE_def.hpp hot-path routines, sliced from
+ * /root/reference at build time, against mock Trilinos containers; tests/test_oracle_vs_ref.py requires
+ * BITWISE equality of every operator, table and quadrature degree between the two.  Analytic
+ * known-answer tests (tests/test_oracle_kat.py) pin both from the other side.
+ * The one thing neither can pin is Tpetra's own insert/fillComplete (Trilinos is absent, version
+ * unpinned by the reference): it is emulated below as append -> stable sort -> sequential sum.
  *
  * Reference lines restated (all under /root/reference/feddlib/core):
  *   FE/FE_def.hpp:83-112     applyBTinv

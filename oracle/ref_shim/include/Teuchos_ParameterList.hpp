@@ -1,0 +1,1 @@
+#include "teuchos_mock.hpp"
