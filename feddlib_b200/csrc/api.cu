@@ -103,34 +103,46 @@ int ensure_gather(feddb200_pat *p)
     const int dim = p->rm->dim, nl = p->rm->nloc;
     FB_LOGIC(p->rm->nloc != p->cm->nloc, "gather path needs a square pattern");
     const int64_t n_rows = p->n_rows;
-    p->posc_stride = nl <= 4 ? 4 : (nl <= 8 ? 8 : 16);
-    FB_LOGIC(p->rm->ne >= (int64_t(1) << 24), "gather path supports up to 2^24 elements per GPU");
-    FB_LOGIC(p->max_len >= 0x8000, "gather path supports node rows of up to 32767 entries");
-    FB_CUDA(cudaMalloc(&p->incp_d, sizeof(uint32_t) * std::max<int64_t>(p->n_inc, 1)));
-    FB_CUDA(cudaMalloc(&p->posc_d, sizeof(uint16_t) * std::max<int64_t>(p->n_inc * p->posc_stride, 1)));
+    p->rec_words = nl <= 6 ? 4 : 8;
+    FB_LOGIC(nl == 6 && p->rm->ne >= (int64_t(1) << 24), "gather path supports up to 2^24 P2 triangles per GPU");
+    FB_LOGIC(p->max_len >= 0xffff, "gather path supports node rows of up to 65534 entries");
+    FB_CUDA(cudaMalloc(&p->rec_d, sizeof(uint32_t) * std::max<int64_t>(p->n_inc * p->rec_words, 1)));
     int8_t *rtype_d = nullptr;
+    uint64_t *sig_d = nullptr;
     FB_CUDA(cudaMalloc(&rtype_d, std::max<int64_t>(n_rows, 1)));
+    FB_CUDA(cudaMalloc(&sig_d, sizeof(uint64_t) * std::max<int64_t>(n_rows, 1)));
     if (n_rows > 0) {
         const int grid = (int)std::min<int64_t>((n_rows + 127) / 128, 148 * 64);
         switch (elem_index(dim, nl)) {
-        case 0: k_canon_pos<2, 3><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->rowptr_d, p->pos_d, p->pos_stride, p->posc_d, p->incp_d, rtype_d); break;
-        case 1: k_canon_pos<2, 6><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->rowptr_d, p->pos_d, p->pos_stride, p->posc_d, p->incp_d, rtype_d); break;
-        case 2: k_canon_pos<3, 4><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->rowptr_d, p->pos_d, p->pos_stride, p->posc_d, p->incp_d, rtype_d); break;
-        case 3: k_canon_pos<3, 10><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->rowptr_d, p->pos_d, p->pos_stride, p->posc_d, p->incp_d, rtype_d); break;
+        case 0: k_make_records<2, 3><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->rowptr_d, p->pos_d, p->pos_stride, p->rec_d, rtype_d, sig_d); break;
+        case 1: k_make_records<2, 6><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->rowptr_d, p->pos_d, p->pos_stride, p->rec_d, rtype_d, sig_d); break;
+        case 2: k_make_records<3, 4><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->rowptr_d, p->pos_d, p->pos_stride, p->rec_d, rtype_d, sig_d); break;
+        case 3: k_make_records<3, 10><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->rowptr_d, p->pos_d, p->pos_stride, p->rec_d, rtype_d, sig_d); break;
         default: set_error("unsupported element"); return FEDDB200_ELOGIC;
         }
         c->launches++;
         FB_CUDA(cudaGetLastError());
     }
     std::vector<int8_t> rtype(n_rows);
+    std::vector<uint64_t> sig(n_rows);
     FB_CUDA(cudaMemcpyAsync(rtype.data(), rtype_d, n_rows, cudaMemcpyDeviceToHost, c->stream));
+    FB_CUDA(cudaMemcpyAsync(sig.data(), sig_d, sizeof(uint64_t) * n_rows, cudaMemcpyDeviceToHost, c->stream));
     FB_CUDA(cudaStreamSynchronize(c->stream));
     cudaFree(rtype_d);
+    cudaFree(sig_d);
+    // launch order: (row type, capacity) buckets; inside a bucket rows of the same stencil class (equal
+    // signature) are adjacent, so the threads of a warp address their accumulator rows identically
     std::vector<int32_t> perm(n_rows);
     for (int64_t r = 0; r < n_rows; r++) perm[r] = (int32_t)r;
     auto cap = [&](int64_t r) { const int l = (int)(p->rowptr_h[r + 1] - p->rowptr_h[r]); return std::max(4, (l + 3) & ~3); };
     auto key = [&](int32_t r) { return (int64_t)(rtype[r] & 1) * 100000 + cap(r); };
-    std::stable_sort(perm.begin(), perm.end(), [&](int32_t a, int32_t b) { return key(a) < key(b); });
+    const bool class_sort = getenv("FEDDB200_NO_CLASS_SORT") == nullptr; // tuning aid
+    std::sort(perm.begin(), perm.end(), [&](int32_t a, int32_t b) {
+        const int64_t ka = key(a), kb = key(b);
+        if (ka != kb) return ka < kb;
+        if (class_sort && sig[a] != sig[b]) return sig[a] < sig[b];
+        return a < b;
+    });
     p->buckets.clear();
     for (int64_t s = 0; s < n_rows;) {
         int64_t e = s;
@@ -193,37 +205,26 @@ void canon_table(const OpTables &t, int dim, int nl, CanonR &R)
 template <int OPG, int DIM, int NL>
 int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
 {
-    constexpr int TPR = OPG == 1 ? DIM : 1;
+    using S = GatherShape<OPG, DIM>;
     const int64_t blocks_geom = (p->rm->ne + 255) / 256;
     if (p->rm->ne > 0) {
         k_geom<DIM, NL><<<(unsigned)blocks_geom, 256, 0, c->stream>>>(p->rm->ne, p->rm->conn_d, p->rm->coords_d, p->geom_d);
         c->launches++;
     }
     for (const Bucket &b : p->buckets) {
-        // accumulators: NB doubles per (thread, column node), interleaved over the block's threads
-        // (lane-private 8-byte banks need a block size that is a multiple of 16).  Prefer >= 2 resident
-        // blocks per SM; shrink the block until the accumulators fit the opt-in shared memory.
-        constexpr int NB = OPG == 1 ? DIM : 1;
+        // accumulators: 32 rows of NBL*L doubles per block, `pitch` doubles apart with pitch == NBL (mod 16), see k_gather
         const size_t budget = c->smem_optin - 1024;
-        const size_t per_thread = (size_t)NB * b.lcap * 8;
-        // block size <= 128 (the kernel is compiled for 3 resident blocks of 128 threads): pick the size that
-        // keeps the most threads resident, preferring more (smaller) blocks so phases of different blocks overlap
-        int nt = 0;
-        size_t best = 0;
-        const char *force_nt = getenv("FEDDB200_GATHER_NT"); // tuning aid
-        for (int cand = 128; cand >= 32; cand -= 32) {
-            if (force_nt && atoi(force_nt) != cand) continue;
-            const size_t fit = budget / (per_thread * cand);
-            const size_t resident = std::min<size_t>(fit, 16) * cand;
-            if (fit >= 1 && (resident > best || (resident == best && fit >= 2))) { best = resident; nt = cand; }
-        }
-        if (nt == 0) {
+        int pitch = S::NBL * b.lcap;
+        while ((pitch & 15) != (S::NBL & 15)) pitch++;
+        const size_t smem = (size_t)pitch * 8 * 32;
+        if (smem > budget) {
             set_error("row too long for the gather path's shared-memory accumulators; use the coloured or atomic mode");
             return FEDDB200_ELOGIC;
         }
-        const size_t smem = per_thread * nt;
-        G.start = b.start; G.count = b.count; G.lcap = b.lcap;
-        const int64_t nthreads = b.count * TPR;
+        const int nt = S::NT;
+        G.pitch = pitch; G.zero = 0;
+        G.start = b.start; G.count = b.count;
+        const int64_t nthreads = b.count * S::CPR;
         const int64_t blocks = (nthreads + nt - 1) / nt;
         auto launch = [&](auto kernel) -> int {
             FB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
@@ -294,8 +295,7 @@ int run_op(feddb200_ctx *c, const feddb200_pat *pc, int op, const double *u_d, d
         rc = ensure_gather(p);
         if (rc != FEDDB200_OK) return rc;
         GatherArgs G;
-        G.rowinfo = (const RowInfo *)p->rowinfo_d; G.incp = p->incp_d;
-        G.posc = p->posc_d; G.geom = p->geom_d;
+        G.rowinfo = (const RowInfo *)p->rowinfo_d; G.rec = p->rec_d; G.geom = p->geom_d;
         G.c0 = c0; G.c1 = c1; G.values = values_d; G.vec_dim = (op == OP_LAP && vec_field) ? dim : 0;
         canon_table(tab_h, dim, nr, G.R);
         return op == OP_LAP ? launch_gather<0>(c, p, G) : launch_gather<1>(c, p, G);

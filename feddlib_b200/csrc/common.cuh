@@ -91,10 +91,9 @@ struct feddb200_pat {
     int64_t *inc_ptr_d = nullptr; // [n_rows+1]
     int32_t *inc_d = nullptr;     // [n_inc]  (e << 4) | i
     int32_t *row_perm_d = nullptr; // rows ordered by bucket (built lazily with the gather maps)
-    uint16_t *posc_d = nullptr;    // [n_inc][posc_stride] canonical position map
+    uint32_t *rec_d = nullptr;     // [n_inc][rec_words] per-incidence gather records (positions | element | permutation)
     void *rowinfo_d = nullptr;     // [n_rows] RowInfo records in bucket order
-    uint32_t *incp_d = nullptr;    // [n_inc] (element << 8) | canonical vertex permutation
-    int posc_stride = 0;
+    int rec_words = 0;
     double *geom_d = nullptr;      // [ne][GS] per-element geometry cache, recomputed by every assembly
     bool gather_ready = false;
     std::vector<fb::Bucket> buckets;

@@ -410,27 +410,60 @@ __host__ __device__ inline int canon_node(const int (&pi)[DIM + 1], int jc)
     else return NVTX + (a == 0 ? (b == 1 ? 0 : (b == 2 ? 2 : 3)) : (a == 1 ? (b == 2 ? 1 : 4) : 5));
 }
 
-// position words per incidence: 16 bit per canonical local node, padded to a 16-byte multiple
-template <int NL> struct PoscStride { static constexpr int value = NL <= 4 ? 4 : (NL <= 8 ? 8 : 16); };
+// -----------------------------------------------------------------------------------------
+// Per-incidence gather records (one-time, pattern build).  One record per (row, incident
+// element): the positions, in the row, of the element's canonical local nodes, the element
+// index and the canonical vertex permutation -- packed so that a thread fetches it with ONE
+// vector load:
+//   NL <= 4 : 16 B = pos[4] u16 | element u32 | perm u32
+//   NL == 6 : 16 B = pos[6] u16 | (element << 8 | perm) u32           (<= 2^24 elements)
+//   NL == 10: 32 B = pos[10] u16 | element u32 | perm u32 | spare u32 | spare u32
+// perm = pi(3)<<6 | pi(2)<<4 | pi(1)<<2 | pi(0)
+// -----------------------------------------------------------------------------------------
+template <int NL> struct RecWords { static constexpr int value = NL <= 6 ? 4 : 8; };
 
-// Per-incidence gather records (one-time, pattern build):
-//   incp[k]  = (element << 8) | (pi(3)<<6 | pi(2)<<4 | pi(1)<<2 | pi(0))   canonical vertex permutation
-//   posc[k][jc] = position, in the row of the incidence's row node, of canonical local node jc
-//   rtype[row]  = 0 vertex node / 1 edge node
-template <int DIM, int NL>
-__global__ void k_canon_pos(int64_t n_rows, const int64_t *__restrict__ inc_ptr, const int32_t *__restrict__ inc,
-                            const int64_t *__restrict__ rowptr, const uint16_t *__restrict__ pos, int pos_stride,
-                            uint16_t *__restrict__ posc, uint32_t *__restrict__ incp, int8_t *__restrict__ rtype)
+template <int NL>
+__host__ __device__ inline void rec_pack_code(uint32_t *w, uint32_t e, uint32_t perm)
 {
-    constexpr int PS = PoscStride<NL>::value;
+    if constexpr (NL <= 4) { w[2] = e; w[3] = perm; }
+    else if constexpr (NL == 6) { w[3] = (e << 8) | perm; }
+    else { w[5] = e; w[6] = perm; w[7] = 0; }
+}
+template <int NL>
+__device__ __forceinline__ uint32_t rec_elem(const uint32_t (&w)[RecWords<NL>::value])
+{
+    if constexpr (NL <= 4) return w[2];
+    else if constexpr (NL == 6) return w[3] >> 8;
+    else return w[5];
+}
+template <int NL>
+__device__ __forceinline__ uint32_t rec_perm(const uint32_t (&w)[RecWords<NL>::value])
+{
+    if constexpr (NL <= 4) return w[3];
+    else if constexpr (NL == 6) return w[3] & 0xffu;
+    else return w[6];
+}
+
+__host__ __device__ inline uint64_t sig_mix(uint64_t h, uint32_t v)
+{
+    h ^= v;
+    h *= 0x100000001b3ull;
+    return h ^ (h >> 29);
+}
+
+// rtype[row] = 0 vertex node / 1 edge node;  sig[row] = hash of the row's stencil shape (row length,
+// permutations and positions of all incidences, NOT the element indices): rows with equal signatures
+// address their accumulators identically and are grouped into the same warps (bank-conflict-free).
+template <int DIM, int NL>
+__global__ void k_make_records(int64_t n_rows, const int64_t *__restrict__ inc_ptr, const int32_t *__restrict__ inc,
+                               const int64_t *__restrict__ rowptr, const uint16_t *__restrict__ pos, int pos_stride,
+                               uint32_t *__restrict__ rec, int8_t *__restrict__ rtype, uint64_t *__restrict__ sig)
+{
+    constexpr int RW = RecWords<NL>::value;
     for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x) {
         int8_t ty = 0;
-        // first-touch bitmap of the row's positions (rows longer than 1024 nodes are zero-initialised instead)
-        uint64_t seen[16];
-        for (int w = 0; w < 16; w++) seen[w] = 0;
-        const int len = (int)(rowptr[r + 1] - rowptr[r]);
-        const bool track = len <= 1024;
-        int ntouched = 0;
+        uint64_t h = 1469598103934665603ull;
+        h = sig_mix(h, (uint32_t)(rowptr[r + 1] - rowptr[r]));
         for (int64_t k = inc_ptr[r]; k < inc_ptr[r + 1]; k++) {
             const int32_t code = inc[k];
             const int64_t e = code >> 4;
@@ -440,22 +473,19 @@ __global__ void k_canon_pos(int64_t n_rows, const int64_t *__restrict__ inc_ptr,
             canon_perm<DIM>(i, pi);
             uint32_t bits = 0;
             for (int v = 0; v <= DIM; v++) bits |= (uint32_t)pi[v] << (2 * v);
-            incp[k] = ((uint32_t)e << 8) | bits;
-            for (int jc = 0; jc < PS; jc++) {
-                uint16_t w = 0;
-                if (jc < NL) {
-                    w = pos[(e * NL + i) * pos_stride + canon_node<DIM>(pi, jc)];
-                    if (track && !((seen[w >> 6] >> (w & 63)) & 1)) {
-                        seen[w >> 6] |= uint64_t(1) << (w & 63);
-                        ntouched++;
-                        w |= 0x8000; // first contribution to this position: store instead of add
-                    }
-                }
-                posc[k * PS + jc] = w;
+            uint32_t w[RW];
+            for (int x = 0; x < RW; x++) w[x] = 0;
+            for (int jc = 0; jc < NL; jc++) {
+                const uint32_t p = pos[(e * NL + i) * pos_stride + canon_node<DIM>(pi, jc)];
+                w[jc >> 1] |= p << (16 * (jc & 1));
             }
+            h = sig_mix(h, bits);
+            for (int x = 0; x < (NL + 1) / 2; x++) h = sig_mix(h, w[x]);
+            rec_pack_code<NL>(w, (uint32_t)e, bits);
+            for (int x = 0; x < RW; x++) rec[k * RW + x] = w[x];
         }
-        // bit 0: row type; bit 1: some position gets no local contribution -> accumulators need zero-init
-        rtype[r] = ty | ((!track || ntouched < len) ? 2 : 0);
+        rtype[r] = ty;
+        sig[r] = h;
     }
 }
 
@@ -478,24 +508,25 @@ struct RowInfo {
 struct GatherArgs {
     const RowInfo *rowinfo;   // rows of this launch: rowinfo[start .. start+count), bucket order
     int64_t start, count;
-    const uint32_t *incp;
-    const uint16_t *posc;
+    const uint32_t *rec;      // incidence records
     const double *geom;
     double c0, c1;            // lambda, mu
     double *values;
-    int lcap;
+    int pitch;                // doubles between consecutive shared-memory accumulator rows (== NBL mod 16)
+    int zero;                 // always 0 (opaque to the compiler; used to order loads after their buffer's last use)
     int vec_dim;              // LAP: 0 scalar, DIM = replicate to the DIM block-diagonal dof rows
     CanonR R;
 };
 
-__device__ __forceinline__ void st_v4(double *p, double a, double b, double c, double d)
-{
-    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
-}
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void ld_v4(const double *p, double (&v)[4])
 {
     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void ld_v8u(const uint32_t *p, uint32_t (&w)[8])
+{
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                 : "l"(p));
 }
 
 // support (canonical vertices) of canonical local node jc
@@ -508,164 +539,97 @@ __device__ __forceinline__ constexpr int canon_sv(int jc, int t)
     else { constexpr int E[6][2] = {{0, 1}, {1, 2}, {0, 2}, {0, 3}, {1, 3}, {2, 3}}; return E[jc - NVTX][t]; }
 }
 
-// one incidence's operands, as loaded from global memory
-template <int DIM, int NL>
-struct IncData {
-    double G[DIM + 1][4];                       // canonical vertex v: (Gx, Gy[, Gz], |det|) -- 2D uses [0],[1] and [3]
-    uint32_t P[PoscStride<NL>::value / 2];      // packed 16-bit positions
+template <int NL>
+struct IncRec {
+    uint32_t w[RecWords<NL>::value];
+};
+template <int DIM>
+struct IncGeo {
+    double G[DIM + 1][4];     // canonical vertex v: (Gx, Gy[, Gz], |det|) -- 2D uses [0],[1] and [3]
 };
 
+template <int NL>
+__device__ __forceinline__ void load_rec(const GatherArgs &A, int64_t k, IncRec<NL> &R)
+{
+    constexpr int RW = RecWords<NL>::value;
+    const uint32_t *p = A.rec + k * RW;
+    if constexpr (RW == 8) ld_v8u(p, R.w);
+    else {
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(p));
+        R.w[0] = a.x; R.w[1] = a.y; R.w[2] = a.z; R.w[3] = a.w;
+    }
+}
+
 template <int DIM, int NL>
-__device__ __forceinline__ void load_inc(const GatherArgs &A, int64_t k, uint32_t code, IncData<DIM, NL> &D)
+__device__ __forceinline__ void load_geo(const GatherArgs &A, const IncRec<NL> &R, IncGeo<DIM> &D)
 {
     constexpr int GS = GeomStride<DIM>::value;
-    constexpr int PW = PoscStride<NL>::value / 2;
-    const double *g = A.geom + (int64_t)(code >> 8) * GS;
+    const uint32_t perm = rec_perm<NL>(R.w);
+    const double *g = A.geom + (int64_t)rec_elem<NL>(R.w) * GS;
     if constexpr (DIM == 3) {
 #pragma unroll
-        for (int v = 0; v < 4; v++) ld_v4(g + 4 * ((code >> (2 * v)) & 3), D.G[v]);
+        for (int v = 0; v < 4; v++) ld_v4(g + 4 * ((perm >> (2 * v)) & 3), D.G[v]);
     } else {
         const double ad = __ldg(g + 6);
 #pragma unroll
         for (int v = 0; v < 3; v++) {
-            const double2 t = __ldg(reinterpret_cast<const double2 *>(g) + ((code >> (2 * v)) & 3));
+            const double2 t = __ldg(reinterpret_cast<const double2 *>(g) + ((perm >> (2 * v)) & 3));
             D.G[v][0] = t.x; D.G[v][1] = t.y; D.G[v][2] = 0.0; D.G[v][3] = ad;
         }
     }
-    const uint32_t *pw = reinterpret_cast<const uint32_t *>(A.posc) + k * PW;
-    if constexpr (PW == 8) {
-        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(pw)), b = __ldg(reinterpret_cast<const uint4 *>(pw) + 1);
-        D.P[0] = a.x; D.P[1] = a.y; D.P[2] = a.z; D.P[3] = a.w; D.P[4] = b.x; D.P[5] = b.y; D.P[6] = b.z; D.P[7] = b.w;
-    } else if constexpr (PW == 4) {
-        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(pw));
-        D.P[0] = a.x; D.P[1] = a.y; D.P[2] = a.z; D.P[3] = a.w;
-    } else {
-        const uint2 a = __ldg(reinterpret_cast<const uint2 *>(pw));
-        D.P[0] = a.x; D.P[1] = a.y;
-    }
 }
 
-__device__ __forceinline__ double sel3(const double (&v)[4], int c) { return c == 0 ? v[0] : (c == 1 ? v[1] : v[2]); }
-
-// One incidence of one thread: evaluate the thread's part of local row i' (canonical) and add it to the
-// lane-private accumulators.  OPG 0: Laplace, 1 value per column node.  OPG 1: elasticity, the thread
-// owns row dof `a` and produces the DIM column dofs b of every column node.
-template <int OPG, int DIM, int NL, int TYPE>
-__device__ __forceinline__ void gather_incidence(const GatherArgs &A, const IncData<DIM, NL> &D, int a, double *my, int NT,
-                                                 double (&dacc)[OPG == 1 ? DIM : 1])
-{
-    constexpr int NVTX = DIM + 1;
-    constexpr int NS = TYPE == 0 ? 1 : 2;   // canonical support size of the row function
-    constexpr int NB = OPG == 1 ? DIM : 1;  // values per column node
-    const double adet = D.G[0][3];
-    // E[s][w][b] for canonical row-support vertex s and canonical vertex w
-    double E[NS][NVTX][NB];
-    if constexpr (OPG == 0) {
-#pragma unroll
-        for (int s = 0; s < NS; s++)
-#pragma unroll
-            for (int w = 0; w < NVTX; w++) {
-                double dot = 0.0;
-#pragma unroll
-                for (int d = 0; d < DIM; d++) dot += D.G[s][d] * D.G[w][d];
-                E[s][w][0] = dot * adet;
-            }
-    } else {
-        const double mu = A.c1 * adet, lam = A.c0 * adet;
-        double Ga[NVTX];
-#pragma unroll
-        for (int w = 0; w < NVTX; w++) Ga[w] = sel3(D.G[w], a);
-#pragma unroll
-        for (int s = 0; s < NS; s++) {
-            const double ls = lam * Ga[s];
-#pragma unroll
-            for (int w = 0; w < NVTX; w++) {
-                double dot = 0.0;
-#pragma unroll
-                for (int d = 0; d < DIM; d++) dot += D.G[s][d] * D.G[w][d];
-                const double mdot = mu * dot, mga = mu * Ga[w];
-                // E^{ab}_{sw} = mu (delta_ab G_s.G_w + G_s[b] G_w[a]) + lambda G_s[a] G_w[b]
-#pragma unroll
-                for (int b = 0; b < DIM; b++) E[s][w][b] = (a == b ? mdot : 0.0) + mga * D.G[s][b] + ls * D.G[w][b];
-            }
-        }
-    }
-    // the row node itself (canonical node 0 of a vertex row, canonical edge (0,1) of an edge row) receives a
-    // contribution from every incidence: it is accumulated in registers
-    constexpr int JD = TYPE == 0 ? 0 : NVTX;
-#pragma unroll
-    for (int b = 0; b < NB; b++) {
-        double v = dacc[b];
-#pragma unroll
-        for (int s = 0; s < NS; s++) {
-            v += A.R.r[TYPE][JD][s][0] * E[s][canon_sv<DIM>(JD, 0)][b];
-            if (JD >= NVTX) v += A.R.r[TYPE][JD][s][1] * E[s][canon_sv<DIM>(JD, 1)][b];
-        }
-        dacc[b] = v;
-    }
-    // distinct canonical nodes hit distinct row positions: per chunk of column nodes load all
-    // accumulators, add, store all (keeps the shared-memory round trips independent).  Bit 15 of a
-    // position word marks the first contribution to that position: it is stored, not added.
-    constexpr int NO = NL - 1;               // off-diagonal column nodes
-    constexpr int JB = NO <= 5 ? NO : (NO == 9 ? 5 : 3);
-#pragma unroll
-    for (int j0 = 0; j0 < NO; j0 += JB) {
-        int idx[JB];
-        double old[JB][NB];
-#pragma unroll
-        for (int jj = 0; jj < JB; jj++) {
-            if (j0 + jj < NO) {
-                const int jc = (j0 + jj) + ((j0 + jj) >= JD ? 1 : 0);
-                const uint32_t w = (D.P[jc >> 1] >> (16 * (jc & 1))) & 0xffffu;
-                idx[jj] = (int)(w & 0x7fffu) * (NB * NT);
-#ifdef FB_FIRST_TOUCH
-                const bool first = (w & 0x8000u) != 0;
-#else
-                const bool first = false;
-#endif
-#pragma unroll
-                for (int b = 0; b < NB; b++) old[jj][b] = first ? 0.0 : my[idx[jj] + b * NT];
-            }
-        }
-#pragma unroll
-        for (int jj = 0; jj < JB; jj++) {
-            if (j0 + jj < NO) {
-                const int jc = (j0 + jj) + ((j0 + jj) >= JD ? 1 : 0);
-#pragma unroll
-                for (int b = 0; b < NB; b++) {
-                    double v = old[jj][b];
-#pragma unroll
-                    for (int s = 0; s < NS; s++) {
-                        v += A.R.r[TYPE][jc][s][0] * E[s][canon_sv<DIM>(jc, 0)][b];
-                        if (jc >= NVTX) v += A.R.r[TYPE][jc][s][1] * E[s][canon_sv<DIM>(jc, 1)][b];
-                    }
-                    my[idx[jj] + b * NT] = v;
-                }
-            }
-        }
-    }
-}
-
-// OPG: 0 Laplace (one thread per row node), 1 elasticity (DIM threads per row node: one per row dof)
-// TYPE: 0 vertex rows, 1 edge rows
+// Row-gather kernel (output-stationary): every CSR value is written exactly once, no atomics, no memset,
+// bitwise reproducible.
+//
+// One thread per scalar COMPONENT row: OPG 0 (Laplace) one thread per row node; OPG 1 (elasticity) DIM*DIM
+// threads per row node, thread (I, a, b) owns the values K^{ab}_{I,J} of every column node J.  The thread
+// walks the elements incident to its row node (records: positions | element | canonical permutation),
+// loads the element's geometry line in canonical vertex order (the row node is canonical vertex 0 or
+// canonical edge (0,1), so the code is fully static), forms
+//     e[s][w] = |det| G_s^T M G_w,   M = mu (delta_ab I + e_b e_a^T) + lambda e_a e_b^T   (Laplace: M = I)
+// for the row support s and the 4 (3) canonical vertices w, and adds  sum_{s,t} R_j^{st} e[s][sv(j,t)]  to
+// its accumulator of column node j (R: the operator's own quadrature applied to the P2 gradient
+// coefficients, see canon_table in api.cu).
+//
+// Accumulators live in shared memory laid out exactly like the CSR rows: one row of NBL*L doubles per dof
+// row (I, a), `pitch` doubles apart, thread (I, a, b) touching entries NBL*p + b.  With pitch == NBL (mod 16)
+// the 16 threads of a half-warp that address the same column position hit 16 distinct 8-byte banks, and a
+// node's own threads never collide, so the data-dependent read-modify-write is (nearly) conflict-free on
+// any mesh.  The write-out is then a plain block-cooperative copy with full-line coalesced stores.
+// Small per-thread state (one accumulator row per DIM threads, ~110 registers) keeps ~16 warps resident
+// per SM, which is what hides the latency of the dependent record -> geometry -> accumulate chain.
 #ifndef FB_GATHER_MINBLOCKS
-#define FB_GATHER_MINBLOCKS 3
+#define FB_GATHER_MINBLOCKS 5
 #endif
+template <int OPG, int DIM> struct GatherShape {
+    static constexpr int NBL = OPG == 1 ? DIM : 1;        // values per column node in a shared-memory row
+    static constexpr int CPR = OPG == 1 ? DIM * DIM : 1;  // threads per row node
+    static constexpr int NT = 32 * NBL;                   // threads per block: 32 accumulator rows
+};
+
 template <int OPG, int DIM, int NL, int TYPE>
-__global__ void __launch_bounds__(128, FB_GATHER_MINBLOCKS) k_gather(const GatherArgs A)
+__global__ void __launch_bounds__(GatherShape<OPG, DIM>::NT, FB_GATHER_MINBLOCKS) k_gather(const GatherArgs A)
 {
-    constexpr int TPR = OPG == 1 ? DIM : 1; // threads per row node
-    constexpr int NB = OPG == 1 ? DIM : 1;  // accumulators per (thread, column node)
-    extern __shared__ double acc[];         // [NB*lcap][blockDim.x], lane-private banks
-    const int NT = blockDim.x;
+    using S = GatherShape<OPG, DIM>;
+    constexpr int NBL = S::NBL, CPR = S::CPR, NT = S::NT;
+    constexpr int NVTX = DIM + 1;
+    constexpr int NS = TYPE == 0 ? 1 : 2;    // canonical support size of the row function
+    constexpr int JD = TYPE == 0 ? 0 : NVTX; // canonical index of the row node itself
+    constexpr int ROWS = 32;                 // accumulator rows per block
+    extern __shared__ double acc[];          // [ROWS][pitch]
+    __shared__ int64_t s_off[ROWS];
+    __shared__ int s_n[ROWS];
     const int tid = threadIdx.x;
+    const int pitch = A.pitch;
     const int64_t t = blockIdx.x * (int64_t)NT + tid;
-    if (t >= A.count * TPR) return;
-    const int64_t rloc = t / TPR;
-    const int a = (int)(t - rloc * TPR);
-    int64_t base, k0;
-    int L, ninc, flags;
-    {
+    const bool live = t < A.count * CPR;
+    const int64_t rloc = live ? t / CPR : 0;
+    const int comp = live ? (int)(t - rloc * CPR) : 0;
+    const int a = comp / NBL, b = comp - a * NBL;
+    int64_t base = 0, k0 = 0;
+    int L = 0, ninc = 0;
+    if (live) {
         double raw[4];
         ld_v4(reinterpret_cast<const double *>(A.rowinfo + A.start + rloc), raw);
         base = __double_as_longlong(raw[0]);
@@ -673,66 +637,129 @@ __global__ void __launch_bounds__(128, FB_GATHER_MINBLOCKS) k_gather(const Gathe
         const int64_t ln = __double_as_longlong(raw[2]);
         L = (int)(ln & 0xffffffff);
         ninc = (int)(ln >> 32);
-        flags = (int)__double_as_longlong(raw[3]);
     }
-    double *my = acc + tid;
-    constexpr int GS = GeomStride<DIM>::value;
-    constexpr int PW = PoscStride<NL>::value / 2;
+    const int64_t k1 = k0 + ninc, kl = k1 - 1;
+    IncRec<NL> rc, rn, r2;
+    IncGeo<DIM> g;
+    if (ninc > 0) {
+        load_rec<NL>(A, k0, rc);
+        load_rec<NL>(A, k0 + 1 < kl ? k0 + 1 : kl, rn);
+        load_rec<NL>(A, k0 + 2 < kl ? k0 + 2 : kl, r2);
+        load_geo<DIM, NL>(A, rc, g);
+    }
+    // zero the block's accumulators while the first loads are in flight; publish the row table
+    for (int x = tid; x < ROWS * pitch; x += NT) acc[x] = 0.0;
+    const int row = tid / NBL;               // accumulator row of this thread inside the block
+    if (b == 0) {
+        s_n[row] = live ? NBL * L : 0;
+        s_off[row] = OPG == 1 ? (int64_t)CPR * base + (int64_t)a * NBL * L : base;
+    }
+    __syncthreads();
+    double *my = acc + (size_t)row * pitch + b;
 
     if (ninc > 0) {
-        // two-deep software pipeline on ping-pong register buffers plus an L2 prefetch three incidences
-        // ahead; prefetch indices are clamped to the row's last incidence so the loads are unconditional
-        IncData<DIM, NL> bufA, bufB;
-        const int64_t k1 = k0 + ninc, kl = k1 - 1;
-        const uint32_t c0 = A.incp[k0];
-        uint32_t code_n = A.incp[k0 + 1 < kl ? k0 + 1 : kl];
-        uint32_t code_f = A.incp[k0 + 3 < kl ? k0 + 3 : kl];
-        load_inc<DIM, NL>(A, k0, c0, bufA);
-#ifdef FB_FIRST_TOUCH
-        if (flags & 2)
-#endif
-            for (int p = 0; p < NB * L; p++) my[p * NT] = 0.0;
-        double dacc[NB];
+        // M^T columns, scaled per incidence by |det|
+        double Mm[DIM][DIM];
+        if constexpr (OPG == 1) {
 #pragma unroll
-        for (int b = 0; b < NB; b++) dacc[b] = 0.0;
-        // position of the row node in its own row (same in every incidence)
-        constexpr int JD = TYPE == 0 ? 0 : DIM + 1;
-        const int pdiag = (int)((bufA.P[JD >> 1] >> (16 * (JD & 1))) & 0x7fffu) * (NB * NT);
-        for (int64_t k = k0; k < k1; k += 2) {
-            const int64_t kb = k + 1 < kl ? k + 1 : kl;
-            load_inc<DIM, NL>(A, kb, code_n, bufB);
-            code_n = A.incp[k + 2 < kl ? k + 2 : kl];
-            prefetch_l2(A.geom + (int64_t)(code_f >> 8) * GS);
-            prefetch_l2(reinterpret_cast<const uint32_t *>(A.posc) + (k + 3 < kl ? k + 3 : kl) * PW);
-            code_f = A.incp[k + 4 < kl ? k + 4 : kl];
-            gather_incidence<OPG, DIM, NL, TYPE>(A, bufA, a, my, NT, dacc);
-            if (k + 1 < k1) {
-                const int64_t ka = k + 2 < kl ? k + 2 : kl;
-                load_inc<DIM, NL>(A, ka, code_n, bufA);
-                code_n = A.incp[k + 3 < kl ? k + 3 : kl];
-                prefetch_l2(A.geom + (int64_t)(code_f >> 8) * GS);
-                prefetch_l2(reinterpret_cast<const uint32_t *>(A.posc) + (k + 4 < kl ? k + 4 : kl) * PW);
-                code_f = A.incp[k + 5 < kl ? k + 5 : kl];
-                gather_incidence<OPG, DIM, NL, TYPE>(A, bufB, a, my, NT, dacc);
-            }
+            for (int c = 0; c < DIM; c++)
+#pragma unroll
+                for (int d = 0; d < DIM; d++)
+                    Mm[c][d] = ((a == b && c == d) ? A.c1 : 0.0) + ((c == b && d == a) ? A.c1 : 0.0) + ((c == a && d == b) ? A.c0 : 0.0);
         }
+        double dacc = 0.0;
+        const int pdiag = (int)((rc.w[JD >> 1] >> (16 * (JD & 1))) & 0xffffu) * NBL;
+        for (int64_t k = k0; k < k1; k++) {
+            // e[s][w] from the current geometry buffer
+            double e[NS][NVTX];
+            const double adet = g.G[0][3];
 #pragma unroll
-        for (int b = 0; b < NB; b++) my[pdiag + b * NT] = dacc[b];
-    } else {
-        for (int p = 0; p < NB * L; p++) my[p * NT] = 0.0;
+            for (int s = 0; s < NS; s++) {
+                double v[DIM];
+#pragma unroll
+                for (int d = 0; d < DIM; d++) {
+                    if constexpr (OPG == 1) {
+                        double x = 0.0;
+#pragma unroll
+                        for (int c = 0; c < DIM; c++) x += g.G[s][c] * Mm[c][d];
+                        v[d] = x * adet;
+                    } else v[d] = g.G[s][d] * adet;
+                }
+#pragma unroll
+                for (int w = 0; w < NVTX; w++) {
+                    double x = 0.0;
+#pragma unroll
+                    for (int d = 0; d < DIM; d++) x += v[d] * g.G[w][d];
+                    e[s][w] = x;
+                }
+            }
+            // the geometry buffer is consumed: refill it for the next incidence (the address is made to depend
+            // on e so the loads cannot be scheduled above the computation that waits for the previous ones),
+            // and fetch the record three incidences ahead.  Indices are clamped to the row's last incidence.
+            IncRec<NL> r3;
+            {
+                const int dep = __double2hiint(e[0][0]) & A.zero;
+                GatherArgs const &AA = A;
+                const uint32_t perm = rec_perm<NL>(rn.w);
+                const double *gp = AA.geom + (int64_t)rec_elem<NL>(rn.w) * GeomStride<DIM>::value + dep;
+                if constexpr (DIM == 3) {
+#pragma unroll
+                    for (int v = 0; v < 4; v++) ld_v4(gp + 4 * ((perm >> (2 * v)) & 3), g.G[v]);
+                } else {
+                    const double ad = __ldg(gp + 6);
+#pragma unroll
+                    for (int v = 0; v < 3; v++) {
+                        const double2 tt = __ldg(reinterpret_cast<const double2 *>(gp) + ((perm >> (2 * v)) & 3));
+                        g.G[v][0] = tt.x; g.G[v][1] = tt.y; g.G[v][2] = 0.0; g.G[v][3] = ad;
+                    }
+                }
+                load_rec<NL>(A, k + 3 < kl ? k + 3 : kl, r3);
+            }
+            // the row node itself receives a contribution from every incidence: accumulated in a register
+#pragma unroll
+            for (int s = 0; s < NS; s++) {
+                dacc += A.R.r[TYPE][JD][s][0] * e[s][canon_sv<DIM>(JD, 0)];
+                if (JD >= NVTX) dacc += A.R.r[TYPE][JD][s][1] * e[s][canon_sv<DIM>(JD, 1)];
+            }
+            // distinct canonical nodes hit distinct row positions: load all accumulators, add, store all
+            constexpr int NO = NL - 1;
+            double *ptr[NO];
+            double old[NO];
+#pragma unroll
+            for (int jj = 0; jj < NO; jj++) {
+                const int jc = jj + (jj >= JD ? 1 : 0);
+                ptr[jj] = my + ((rc.w[jc >> 1] >> (16 * (jc & 1))) & 0xffffu) * NBL;
+                old[jj] = *ptr[jj];
+            }
+#pragma unroll
+            for (int jj = 0; jj < NO; jj++) {
+                const int jc = jj + (jj >= JD ? 1 : 0);
+                double v = old[jj];
+#pragma unroll
+                for (int s = 0; s < NS; s++) {
+                    v += A.R.r[TYPE][jc][s][0] * e[s][canon_sv<DIM>(jc, 0)];
+                    if (jc >= NVTX) v += A.R.r[TYPE][jc][s][1] * e[s][canon_sv<DIM>(jc, 1)];
+                }
+                *ptr[jj] = v;
+            }
+            rc = rn; rn = r2; r2 = r3;
+        }
+        my[pdiag] = dacc;
     }
+    __syncthreads();
 
-    // write-out: the thread's accumulators are exactly one CSR row (scalar / elasticity dof row (I, a)),
-    // contiguous in the values array; the block-diagonal vector Laplacian replicates it DIM times
+    // write-out: every accumulator row is one CSR row (scalar row / elasticity dof row (I, a)); the
+    // block-diagonal vector Laplacian replicates it DIM times.  Warps stride over the block's rows.
     const int nrep = (OPG == 0 && A.vec_dim != 0) ? A.vec_dim : 1;
-    const int n = NB * L;
-    for (int d = 0; d < nrep; d++) {
-        double *out = OPG == 1 ? A.values + (int64_t)DIM * DIM * base + (int64_t)a * n
-                               : A.values + (int64_t)nrep * base + (int64_t)d * L;
-        int p = 0;
-        while (p < n && (reinterpret_cast<uintptr_t>(out + p) & 31)) { out[p] = my[p * NT]; p++; }
-        for (; p + 4 <= n; p += 4) st_v4(out + p, my[p * NT], my[(p + 1) * NT], my[(p + 2) * NT], my[(p + 3) * NT]);
-        for (; p < n; p++) out[p] = my[p * NT];
+    const int lane = tid & 31;
+    for (int r = tid >> 5; r < ROWS; r += NT / 32) {
+        const int nr = s_n[r];
+        const double *src = acc + (size_t)r * pitch;
+        for (int d = 0; d < nrep; d++) {
+            double *out = A.values + (int64_t)nrep * s_off[r] + (int64_t)d * nr;
+#pragma unroll 4
+            for (int x = lane; x < nr; x += 32) out[x] = src[x];
+        }
     }
 }
 
