@@ -111,13 +111,14 @@ int ensure_gather(feddb200_pat *p)
     uint64_t *sig_d = nullptr;
     FB_CUDA(cudaMalloc(&rtype_d, std::max<int64_t>(n_rows, 1)));
     FB_CUDA(cudaMalloc(&sig_d, sizeof(uint64_t) * std::max<int64_t>(n_rows, 1)));
+    const int use_ring = getenv("FEDDB200_NO_RING") == nullptr; // tuning aid: generic kernel for every edge row
     if (n_rows > 0) {
         const int grid = (int)std::min<int64_t>((n_rows + 127) / 128, 148 * 64);
         switch (elem_index(dim, nl)) {
-        case 0: k_make_records<2, 3><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->rowptr_d, p->pos_d, p->pos_stride, p->rec_d, rtype_d, sig_d); break;
-        case 1: k_make_records<2, 6><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->rowptr_d, p->pos_d, p->pos_stride, p->rec_d, rtype_d, sig_d); break;
-        case 2: k_make_records<3, 4><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->rowptr_d, p->pos_d, p->pos_stride, p->rec_d, rtype_d, sig_d); break;
-        case 3: k_make_records<3, 10><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->rowptr_d, p->pos_d, p->pos_stride, p->rec_d, rtype_d, sig_d); break;
+        case 0: k_make_records<2, 3><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->rowptr_d, p->pos_d, p->pos_stride, p->rm->conn_d, use_ring, p->rec_d, rtype_d, sig_d); break;
+        case 1: k_make_records<2, 6><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->rowptr_d, p->pos_d, p->pos_stride, p->rm->conn_d, use_ring, p->rec_d, rtype_d, sig_d); break;
+        case 2: k_make_records<3, 4><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->rowptr_d, p->pos_d, p->pos_stride, p->rm->conn_d, use_ring, p->rec_d, rtype_d, sig_d); break;
+        case 3: k_make_records<3, 10><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->rowptr_d, p->pos_d, p->pos_stride, p->rm->conn_d, use_ring, p->rec_d, rtype_d, sig_d); break;
         default: set_error("unsupported element"); return FEDDB200_ELOGIC;
         }
         c->launches++;
@@ -135,19 +136,26 @@ int ensure_gather(feddb200_pat *p)
     std::vector<int32_t> perm(n_rows);
     for (int64_t r = 0; r < n_rows; r++) perm[r] = (int32_t)r;
     auto cap = [&](int64_t r) { const int l = (int)(p->rowptr_h[r + 1] - p->rowptr_h[r]); return std::max(4, (l + 3) & ~3); };
-    auto key = [&](int32_t r) { return (int64_t)(rtype[r] & 1) * 100000 + cap(r); };
-    const bool class_sort = getenv("FEDDB200_NO_CLASS_SORT") == nullptr; // tuning aid
+    auto key = [&](int32_t r) { return (int64_t)(rtype[r] & 3) * 100000 + cap(r); };
+    // ... but only inside chunks of consecutive rows, so that a launch still sweeps the mesh (and the geometry
+    // lines in L2) once instead of once per stencil class
+    int chunk_shift = 12;
+    if (const char *f = getenv("FEDDB200_CLASS_CHUNK_SHIFT")) chunk_shift = atoi(f); // tuning aid (<0: no class sort)
     std::sort(perm.begin(), perm.end(), [&](int32_t a, int32_t b) {
         const int64_t ka = key(a), kb = key(b);
         if (ka != kb) return ka < kb;
-        if (class_sort && sig[a] != sig[b]) return sig[a] < sig[b];
+        if (chunk_shift >= 0) {
+            const int32_t ca = a >> chunk_shift, cb = b >> chunk_shift;
+            if (ca != cb) return ca < cb;
+            if (sig[a] != sig[b]) return sig[a] < sig[b];
+        }
         return a < b;
     });
     p->buckets.clear();
     for (int64_t s = 0; s < n_rows;) {
         int64_t e = s;
         while (e < n_rows && key(perm[e]) == key(perm[s])) e++;
-        p->buckets.push_back({(int)(rtype[perm[s]] & 1), cap(perm[s]), s, e - s});
+        p->buckets.push_back({(int)(rtype[perm[s]] & 3), cap(perm[s]), s, e - s});
         s = e;
     }
     {
@@ -160,7 +168,7 @@ int ensure_gather(feddb200_pat *p)
             info[q].k0 = inc_ptr[r];
             info[q].len = (int32_t)(p->rowptr_h[r + 1] - p->rowptr_h[r]);
             info[q].ninc = (int32_t)(inc_ptr[r + 1] - inc_ptr[r]);
-            info[q].pad = rtype[r]; // bit 1: accumulators need zero-init
+            info[q].pad = rtype[r]; // bits 0-1 row type, bit 4: the row has positions without a local contribution
         }
         FB_CUDA(cudaMalloc(&p->rowinfo_d, sizeof(RowInfo) * std::max<int64_t>(n_rows, 1)));
         FB_CUDA(cudaMemcpy(p->rowinfo_d, info.data(), sizeof(RowInfo) * n_rows, cudaMemcpyHostToDevice));
@@ -211,33 +219,49 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
         k_geom<DIM, NL><<<(unsigned)blocks_geom, 256, 0, c->stream>>>(p->rm->ne, p->rm->conn_d, p->rm->coords_d, p->geom_d);
         c->launches++;
     }
+    const size_t budget = c->smem_optin - 1024;
     for (const Bucket &b : p->buckets) {
-        // accumulators: 32 rows of NBL*L doubles per block, `pitch` doubles apart with pitch == NBL (mod 16), see k_gather
-        const size_t budget = c->smem_optin - 1024;
-        int pitch = S::NBL * b.lcap;
-        while ((pitch & 15) != (S::NBL & 15)) pitch++;
-        const size_t smem = (size_t)pitch * 8 * 32;
-        if (smem > budget) {
-            set_error("row too long for the gather path's shared-memory accumulators; use the coloured or atomic mode");
-            return FEDDB200_ELOGIC;
-        }
-        const int nt = S::NT;
-        G.pitch = pitch; G.zero = 0;
+        G.zero = 0;
         G.start = b.start; G.count = b.count;
-        const int64_t nthreads = b.count * S::CPR;
-        const int64_t blocks = (nthreads + nt - 1) / nt;
-        auto launch = [&](auto kernel) -> int {
-            FB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
-            kernel<<<(unsigned)blocks, nt, smem, c->stream>>>(G);
-            c->launches++;
-            FB_CUDA(cudaGetLastError());
-            return FEDDB200_OK;
-        };
         int rc;
-        if (b.type == 0) rc = launch(k_gather<OPG, DIM, NL, 0>);
-        else {
-            if constexpr (NL > DIM + 1) rc = launch(k_gather<OPG, DIM, NL, 1>);
-            else { set_error("edge-node row in a P1 pattern"); rc = FEDDB200_ELOGIC; }
+        if (b.type == 1) {
+            // ring-ordered edge rows (3D P2): one thread per CSR row, one shared-memory row per thread (pitch odd)
+            if constexpr (DIM == 3 && NL == 10) {
+                constexpr int TPR = OPG == 1 ? DIM : 1;
+                const int pitch = (TPR * b.lcap + 1) | 1; // one spare double: rows are shifted to the 16-byte phase of their destination
+                int nt = 64;
+                if (const char *f = getenv("FEDDB200_RING_NT")) nt = std::max(32, std::min(64, atoi(f) & ~31)); // tuning aid
+                const size_t smem = (size_t)pitch * 8 * nt;
+                FB_LOGIC(smem > budget, "row too long for the gather path's shared-memory rows; use the coloured or atomic mode");
+                G.pitch = pitch;
+                const int64_t blocks = (b.count * TPR + nt - 1) / nt;
+                FB_CUDA(cudaFuncSetAttribute(k_ring<OPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+                k_ring<OPG><<<(unsigned)blocks, nt, smem, c->stream>>>(G);
+                c->launches++;
+                FB_CUDA(cudaGetLastError());
+                rc = FEDDB200_OK;
+            } else { set_error("ring rows exist for 3D P2 patterns only"); rc = FEDDB200_ELOGIC; }
+        } else {
+            // accumulators: 32 rows of NBL*L doubles per block, `pitch` doubles apart with pitch == NBL (mod 16), see k_gather
+            int pitch = S::NBL * b.lcap;
+            while ((pitch & 15) != (S::NBL & 15)) pitch++;
+            const size_t smem = (size_t)pitch * 8 * 32;
+            FB_LOGIC(smem > budget, "row too long for the gather path's shared-memory accumulators; use the coloured or atomic mode");
+            const int nt = S::NT;
+            G.pitch = pitch;
+            const int64_t blocks = (b.count * S::CPR + nt - 1) / nt;
+            auto launch = [&](auto kernel) -> int {
+                FB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+                kernel<<<(unsigned)blocks, nt, smem, c->stream>>>(G);
+                c->launches++;
+                FB_CUDA(cudaGetLastError());
+                return FEDDB200_OK;
+            };
+            if (b.type == 0) rc = launch(k_gather<OPG, DIM, NL, 0>);
+            else {
+                if constexpr (NL > DIM + 1) rc = launch(k_gather<OPG, DIM, NL, 1>);
+                else { set_error("edge-node row in a P1 pattern"); rc = FEDDB200_ELOGIC; }
+            }
         }
         if (rc != FEDDB200_OK) return rc;
     }

@@ -46,7 +46,7 @@ struct OpTables {
 };
 
 struct Bucket {            // rows of one type with node-row length <= lcap, processed by one gather launch
-    int type;              // 0 vertex-node rows, 1 edge-node rows
+    int type;              // 0 vertex-node rows, 1 ring-ordered edge-node rows (3D P2), 2 edge-node rows (generic)
     int lcap;
     int64_t start, count;  // range in row_perm
 };

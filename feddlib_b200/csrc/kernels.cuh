@@ -451,40 +451,141 @@ __host__ __device__ inline uint64_t sig_mix(uint64_t h, uint32_t v)
     return h ^ (h >> 29);
 }
 
-// rtype[row] = 0 vertex node / 1 edge node;  sig[row] = hash of the row's stencil shape (row length,
-// permutations and positions of all incidences, NOT the element indices): rows with equal signatures
-// address their accumulators identically and are grouped into the same warps (bank-conflict-free).
+// Ring order of the tetrahedra around an edge (3D P2 edge-node rows).  The star of a mesh edge (v0, v1) is a
+// union of fans / closed rings of tetrahedra (v0, v1, w_r, w_{r+1}); consecutive tetrahedra share the face
+// (v0, v1, w_{r+1}).  Ordering the row's incidences along these chains, with the canonical vertex order
+// (v0, v1, w_in, w_out), lets the gather kernel carry the partial sums of the shared face in registers and write
+// every other value exactly once -- no shared-memory read-modify-write (k_ring below).
+//   order[m]  index (into the row's ascending incidence list) of the m-th incidence in chain order
+//   rperm[m]  canonical vertex permutation  l(v0) | l(v1)<<2 | l(w_in)<<4 | l(w_out)<<6
+//   rflag[m]  what happens to the contributions of the out-face (v0, v1, w_out):
+//             0 carried to the next incidence, 1 stored (chain ends on a boundary face), 2 added to the
+//             stored partial of the chain's first in-face (the ring closes)
+// Returns false for stars the scheme does not cover (a face shared by more than two tetrahedra, duplicate or
+// degenerate elements, more than RING_KMAX incidences): such rows use the generic kernel.
+constexpr int RING_KMAX = 32;
+__device__ inline bool ring_order(int ninc, const int32_t *__restrict__ inc_row, const int32_t *__restrict__ conn,
+                                  int *order, uint32_t *rperm, uint32_t *rflag)
+{
+    const int E3[6][2] = {{0, 1}, {1, 2}, {0, 2}, {0, 3}, {1, 3}, {2, 3}};
+    int32_t wa[RING_KMAX], wb[RING_KMAX];
+    int8_t lp[RING_KMAX], lq[RING_KMAX], la[RING_KMAX], lb[RING_KMAX];
+    bool used[RING_KMAX];
+    for (int m = 0; m < ninc; m++) {
+        const int32_t code = inc_row[m];
+        const int64_t e = code >> 4;
+        const int ed = (code & 15) - 4;
+        int p = E3[ed][0], q = E3[ed][1];
+        if (conn[e * 10 + p] > conn[e * 10 + q]) { const int t = p; p = q; q = t; }
+        int o[2], n = 0;
+        for (int v = 0; v < 4; v++)
+            if (v != p && v != q) o[n++] = v;
+        lp[m] = (int8_t)p; lq[m] = (int8_t)q; la[m] = (int8_t)o[0]; lb[m] = (int8_t)o[1];
+        wa[m] = conn[e * 10 + o[0]]; wb[m] = conn[e * 10 + o[1]];
+        used[m] = false;
+        if (wa[m] == wb[m]) return false;
+    }
+    auto count = [&](int32_t w) { int c = 0; for (int m = 0; m < ninc; m++) c += (wa[m] == w) + (wb[m] == w); return c; };
+    for (int m = 0; m < ninc; m++) {
+        if (count(wa[m]) > 2 || count(wb[m]) > 2) return false;
+        for (int m2 = m + 1; m2 < ninc; m2++)
+            if ((wa[m] == wa[m2] && wb[m] == wb[m2]) || (wa[m] == wb[m2] && wb[m] == wa[m2])) return false;
+    }
+    int n_out = 0;
+    while (n_out < ninc) {
+        int start = -1, low = -1;
+        bool in_is_a = true;
+        for (int m = 0; m < ninc && start < 0; m++) {
+            if (used[m]) continue;
+            if (low < 0) low = m;
+            if (count(wa[m]) == 1) { start = m; in_is_a = true; }
+            else if (count(wb[m]) == 1) { start = m; in_is_a = false; }
+        }
+        const bool closed = start < 0;
+        if (closed) { start = low; in_is_a = true; }
+        int cur = start;
+        int32_t w_in = in_is_a ? wa[cur] : wb[cur];
+        const int32_t first_in = w_in;
+        for (;;) {
+            used[cur] = true;
+            const bool cin_a = wa[cur] == w_in;
+            const int l_in = cin_a ? la[cur] : lb[cur], l_out = cin_a ? lb[cur] : la[cur];
+            const int32_t w_out = cin_a ? wb[cur] : wa[cur];
+            int nxt = -1;
+            for (int m = 0; m < ninc && nxt < 0; m++)
+                if (!used[m] && (wa[m] == w_out || wb[m] == w_out)) nxt = m;
+            uint32_t mode;
+            if (nxt >= 0) mode = 0;
+            else if (closed) { if (w_out != first_in || cur == start) return false; mode = 2; }
+            else mode = 1;
+            order[n_out] = cur;
+            rperm[n_out] = (uint32_t)lp[cur] | ((uint32_t)lq[cur] << 2) | ((uint32_t)l_in << 4) | ((uint32_t)l_out << 6);
+            rflag[n_out] = mode;
+            n_out++;
+            if (nxt < 0) break;
+            cur = nxt;
+            w_in = w_out;
+        }
+    }
+    return true;
+}
+
+// rtype[row] = 0 vertex-node row / 1 edge-node row in ring order (3D P2) / 2 edge-node row, generic;
+// sig[row] = hash of the row's stencil shape (row length, permutations, flags and positions of all
+// incidences, NOT the element indices): rows with equal signatures address their accumulators identically
+// and are grouped into the same warps (bank-conflict-free shared-memory accesses).
 template <int DIM, int NL>
 __global__ void k_make_records(int64_t n_rows, const int64_t *__restrict__ inc_ptr, const int32_t *__restrict__ inc,
                                const int64_t *__restrict__ rowptr, const uint16_t *__restrict__ pos, int pos_stride,
+                               const int32_t *__restrict__ conn, int use_ring,
                                uint32_t *__restrict__ rec, int8_t *__restrict__ rtype, uint64_t *__restrict__ sig)
 {
     constexpr int RW = RecWords<NL>::value;
     for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x) {
-        int8_t ty = 0;
+        const int64_t kb = inc_ptr[r];
+        const int ninc = (int)(inc_ptr[r + 1] - kb);
+        const int ty = (ninc > 0 && (inc[kb] & 15) > DIM) ? 1 : 0;
         uint64_t h = 1469598103934665603ull;
         h = sig_mix(h, (uint32_t)(rowptr[r + 1] - rowptr[r]));
-        for (int64_t k = inc_ptr[r]; k < inc_ptr[r + 1]; k++) {
-            const int32_t code = inc[k];
+        bool ring = false;
+        uint64_t seen[4] = {0, 0, 0, 0}; // positions that receive a local contribution (rows of up to 256 nodes)
+        int order[RING_KMAX];
+        uint32_t rperm[RING_KMAX], rflag[RING_KMAX];
+        if constexpr (DIM == 3 && NL == 10) {
+            if (use_ring && ty == 1 && ninc <= RING_KMAX) ring = ring_order(ninc, inc + kb, conn, order, rperm, rflag);
+        }
+        for (int m = 0; m < ninc; m++) {
+            const int32_t code = inc[kb + (ring ? order[m] : m)];
             const int64_t e = code >> 4;
             const int i = code & 15;
-            ty = i > DIM ? 1 : 0;
             int pi[DIM + 1];
-            canon_perm<DIM>(i, pi);
             uint32_t bits = 0;
-            for (int v = 0; v <= DIM; v++) bits |= (uint32_t)pi[v] << (2 * v);
+            if (ring) {
+                bits = rperm[m];
+                for (int v = 0; v <= DIM; v++) pi[v] = (int)((bits >> (2 * v)) & 3);
+                bits |= rflag[m] << 8;
+            } else {
+                canon_perm<DIM>(i, pi);
+                for (int v = 0; v <= DIM; v++) bits |= (uint32_t)pi[v] << (2 * v);
+            }
             uint32_t w[RW];
             for (int x = 0; x < RW; x++) w[x] = 0;
             for (int jc = 0; jc < NL; jc++) {
                 const uint32_t p = pos[(e * NL + i) * pos_stride + canon_node<DIM>(pi, jc)];
                 w[jc >> 1] |= p << (16 * (jc & 1));
+                if (p < 256) seen[p >> 6] |= uint64_t(1) << (p & 63);
             }
             h = sig_mix(h, bits);
             for (int x = 0; x < (NL + 1) / 2; x++) h = sig_mix(h, w[x]);
             rec_pack_code<NL>(w, (uint32_t)e, bits);
-            for (int x = 0; x < RW; x++) rec[k * RW + x] = w[x];
+            for (int x = 0; x < RW; x++) rec[(kb + m) * RW + x] = w[x];
         }
-        rtype[r] = ty;
+        // bit 4: some position of the row gets no local contribution (entries contributed by other ranks only,
+        // or an empty row): the write-once ring kernel must zero its shared-memory row first
+        const int len = (int)(rowptr[r + 1] - rowptr[r]);
+        const int covered = __popcll(seen[0]) + __popcll(seen[1]) + __popcll(seen[2]) + __popcll(seen[3]);
+        const int holes = (len > 256 || covered < len) ? 16 : 0;
+        rtype[r] = (int8_t)((ty == 0 ? 0 : (ring ? 1 : 2)) | holes);
         sig[r] = h;
     }
 }
@@ -518,6 +619,19 @@ struct GatherArgs {
     CanonR R;
 };
 
+// TMA bulk store shared -> global (1-D, no tensor map): both addresses 16-byte aligned, size a multiple of 16
+__device__ __forceinline__ void bulk_store(void *gptr, const void *sptr, int bytes)
+{
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(sptr);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gptr), "r"(s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_commit_wait_read()
+{
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void ld_v4(const double *p, double (&v)[4])
 {
     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
@@ -761,6 +875,222 @@ __global__ void __launch_bounds__(GatherShape<OPG, DIM>::NT, FB_GATHER_MINBLOCKS
             for (int x = lane; x < nr; x += 32) out[x] = src[x];
         }
     }
+}
+
+// Ring kernel: 3D P2 edge-node rows whose incidences are in chain order (ring_order above).  One thread per
+// CSR row: OPG 0 (Laplace) row node, OPG 1 (elasticity) dof row (I, a) with NB = 3 values per column node.
+// With canonical vertices (v0, v1, w_in, w_out) the 10 column nodes of an incidence split into
+//   {0, 1, 4}  v0, v1 and the row node itself: every incidence contributes  -> register accumulators
+//   {2, 6, 5}  nodes of the in-face  (v0, v1, w_in):  carry + contribution is final -> stored once
+//   {3, 7, 8}  nodes of the out-face (v0, v1, w_out): becomes the carry of the next incidence
+//   {9}        node (w_in, w_out), this tetrahedron only -> stored once
+// so apart from the closing face of a ring there is no shared-memory read at all.  The thread's shared-memory
+// row is laid out exactly like its CSR row (`pitch` odd: conflict-free when the threads of a half-warp store
+// to the same position) and is copied out by the warp with full-line coalesced stores.
+#ifndef FB_RING_MINBLOCKS
+#define FB_RING_MINBLOCKS 5
+#endif
+#ifndef FB_RING_UNROLL
+#define FB_RING_UNROLL 1
+#endif
+constexpr int kRingUnroll = FB_RING_UNROLL;
+template <int OPG>
+__global__ void __launch_bounds__(64, FB_RING_MINBLOCKS) k_ring(const GatherArgs A)
+{
+    constexpr int DIM = 3, NL = 10, NVTX = 4;
+    constexpr int TPR = OPG == 1 ? DIM : 1;
+    constexpr int NB = OPG == 1 ? DIM : 1;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ double acc[];          // [blockDim.x][pitch]
+    const int NT = blockDim.x;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int pitch = A.pitch;
+    const int64_t t = blockIdx.x * (int64_t)NT + tid;
+    const bool live = t < A.count * TPR;
+    const int64_t rloc = live ? t / TPR : 0;
+    const int a = live ? (int)(t - rloc * TPR) : 0;
+    int64_t base = 0, k0 = 0;
+    int L = 0, ninc = 0;
+    bool holes = false;
+    if (live) {
+        double raw[4];
+        ld_v4(reinterpret_cast<const double *>(A.rowinfo + A.start + rloc), raw);
+        base = __double_as_longlong(raw[0]);
+        k0 = __double_as_longlong(raw[1]);
+        const int64_t ln = __double_as_longlong(raw[2]);
+        L = (int)(ln & 0xffffffff);
+        ninc = (int)(ln >> 32);
+        holes = (__double_as_longlong(raw[3]) & 16) != 0;
+    }
+    double *wbase = acc + (size_t)(tid - lane) * pitch; // the warp's 32 rows
+    const int nrep = (OPG == 0 && A.vec_dim != 0) ? A.vec_dim : 1;
+    const int n = live ? NB * L : 0;
+    const int64_t off = OPG == 1 ? (int64_t)DIM * DIM * base + (int64_t)a * n : (int64_t)nrep * base;
+#ifndef FB_NO_TMA_STORE
+    // the row is shifted by one double where that gives its shared-memory copy the same 16-byte phase as its
+    // destination in the values array (TMA bulk stores need both sides 16-byte aligned)
+    const int head = (int)(((reinterpret_cast<uintptr_t>(A.values) >> 3) + off) & 1); // 1: destination starts mid-16-bytes
+    double *my = acc + (size_t)tid * pitch + ((tid * pitch + head) & 1);
+#else
+    double *my = acc + (size_t)tid * pitch;
+#endif
+    if (__any_sync(FULL, holes)) { // rare: rows with positions no local element contributes to
+        for (int x = lane; x < 32 * pitch; x += 32) wbase[x] = 0.0;
+        __syncwarp();
+    }
+    auto posof = [&](const IncRec<NL> &r, int jc) { return (int)((r.w[jc >> 1] >> (16 * (jc & 1))) & 0xffffu) * NB; };
+
+    if (ninc > 0) {
+        const int64_t k1 = k0 + ninc, kl = k1 - 1;
+        IncRec<NL> rc, rn, r2;
+        IncGeo<DIM> g;
+        load_rec<NL>(A, k0, rc);
+        load_rec<NL>(A, k0 + 1 < kl ? k0 + 1 : kl, rn);
+        load_rec<NL>(A, k0 + 2 < kl ? k0 + 2 : kl, r2);
+        load_geo<DIM, NL>(A, rc, g);
+        const int p_v0 = posof(rc, 0), p_v1 = posof(rc, 1), p_self = posof(rc, 4);
+        double accE[3][NB], carry[3][NB];
+#pragma unroll
+        for (int x = 0; x < 3; x++)
+#pragma unroll
+            for (int b = 0; b < NB; b++) { accE[x][b] = 0.0; carry[x][b] = 0.0; }
+        const double mu = A.c1, lam = A.c0;
+        constexpr int JE[3] = {0, 1, 4}, JIN[3] = {2, 6, 5}, JOUT[3] = {3, 7, 8};
+#pragma unroll(kRingUnroll)
+        for (int64_t k = k0; k < k1; k++) {
+            // E[s][w][b] for the two row-support vertices s = v0, v1 and the four canonical vertices w
+            double E[2][NVTX][NB];
+            {
+                const double adet = g.G[0][3];
+                if constexpr (OPG == 0) {
+#pragma unroll
+                    for (int s = 0; s < 2; s++)
+#pragma unroll
+                        for (int w = 0; w < NVTX; w++) {
+                            double dot = 0.0;
+#pragma unroll
+                            for (int d = 0; d < DIM; d++) dot += g.G[s][d] * g.G[w][d];
+                            E[s][w][0] = dot * adet;
+                        }
+                } else {
+                    const double mud = mu * adet, lamd = lam * adet;
+                    double Ga[NVTX];
+#pragma unroll
+                    for (int w = 0; w < NVTX; w++) Ga[w] = a == 0 ? g.G[w][0] : (a == 1 ? g.G[w][1] : g.G[w][2]);
+#pragma unroll
+                    for (int s = 0; s < 2; s++) {
+                        const double ls = lamd * Ga[s];
+#pragma unroll
+                        for (int w = 0; w < NVTX; w++) {
+                            double dot = 0.0;
+#pragma unroll
+                            for (int d = 0; d < DIM; d++) dot += g.G[s][d] * g.G[w][d];
+                            const double mdot = mud * dot, mga = mud * Ga[w];
+                            // E^{ab}_{sw} = mu (delta_ab G_s.G_w + G_s[b] G_w[a]) + lambda G_s[a] G_w[b]
+#pragma unroll
+                            for (int b = 0; b < DIM; b++) E[s][w][b] = (a == b ? mdot : 0.0) + mga * g.G[s][b] + ls * g.G[w][b];
+                        }
+                    }
+                }
+            }
+            // refill the geometry buffer for the next incidence (ordered after E by a data dependence so the
+            // loads are not scheduled above the wait for the previous ones); record three incidences ahead
+            IncRec<NL> r3;
+            {
+                const int dep = __double2hiint(E[0][0][0]) & A.zero;
+                const uint32_t perm = rec_perm<NL>(rn.w);
+                const double *gp = A.geom + (int64_t)rec_elem<NL>(rn.w) * GeomStride<DIM>::value + dep;
+#pragma unroll
+                for (int v = 0; v < 4; v++) ld_v4(gp + 4 * ((perm >> (2 * v)) & 3), g.G[v]);
+                load_rec<NL>(A, k + 3 < kl ? k + 3 : kl, r3);
+            }
+            auto contrib = [&](int jc, int b) {
+                double v = 0.0;
+#pragma unroll
+                for (int s = 0; s < 2; s++) {
+                    v += A.R.r[1][jc][s][0] * E[s][canon_sv<DIM>(jc, 0)][b];
+                    if (jc >= NVTX) v += A.R.r[1][jc][s][1] * E[s][canon_sv<DIM>(jc, 1)][b];
+                }
+                return v;
+            };
+            const uint32_t mode = (rec_perm<NL>(rc.w) >> 8) & 3;
+#pragma unroll
+            for (int x = 0; x < 3; x++)
+#pragma unroll
+                for (int b = 0; b < NB; b++) accE[x][b] += contrib(JE[x], b);
+#pragma unroll
+            for (int x = 0; x < 3; x++) {
+                double *p = my + posof(rc, JIN[x]);
+#pragma unroll
+                for (int b = 0; b < NB; b++) p[b] = carry[x][b] + contrib(JIN[x], b);
+            }
+            {
+                double *p = my + posof(rc, 9);
+#pragma unroll
+                for (int b = 0; b < NB; b++) p[b] = contrib(9, b);
+            }
+#pragma unroll
+            for (int x = 0; x < 3; x++)
+#pragma unroll
+                for (int b = 0; b < NB; b++) carry[x][b] = contrib(JOUT[x], b);
+            if (mode != 0) { // the chain ends here: the out-face is final (1) or closes the ring (2)
+#pragma unroll
+                for (int x = 0; x < 3; x++) {
+                    double *p = my + posof(rc, JOUT[x]);
+#pragma unroll
+                    for (int b = 0; b < NB; b++) {
+                        p[b] = carry[x][b] + (mode == 2 ? p[b] : 0.0);
+                        carry[x][b] = 0.0;
+                    }
+                }
+            }
+            rc = rn; rn = r2; r2 = r3;
+        }
+#pragma unroll
+        for (int b = 0; b < NB; b++) { my[p_v0 + b] = accE[0][b]; my[p_v1 + b] = accE[1][b]; my[p_self + b] = accE[2][b]; }
+    }
+
+#ifdef FB_EXP_NOWRITE
+    if (n == 12345) A.values[off] = my[0];
+#elif !defined(FB_NO_TMA_STORE)
+    // write-out: the thread's shared-memory row is its CSR row.  One TMA bulk store per row moves the 16-byte
+    // aligned interior (no LSU instructions, asynchronous); the at most two odd doubles go by plain stores.
+    if (n > 0) {
+        bulk_fence(); // make the generic-proxy shared-memory writes visible to the async proxy
+#pragma unroll 1
+        for (int d = 0; d < nrep; d++) {
+            double *out = A.values + off + (int64_t)d * n;
+            const int h = (int)((reinterpret_cast<uintptr_t>(out) >> 3) & 1);
+            if (OPG == 1 || h == head) {
+                const int body = (n - h) & ~1;
+                if (h) out[0] = my[0];
+                if (body > 0) bulk_store(out + h, my + h, body * 8);
+                if (h + body < n) out[n - 1] = my[n - 1];
+            } else { // replicated scalar row whose copy has the other phase: plain stores
+                for (int x = 0; x < n; x++) out[x] = my[x];
+            }
+        }
+    }
+    bulk_commit_wait_read(); // the bulk stores read this block's shared memory: wait before it is released
+#else
+    __syncwarp();
+    // write-out: thread r's shared-memory row is one CSR row; the warp copies its 32 rows one after the other
+    const double *src = wbase + lane;
+#pragma unroll 1
+    for (int r = 0; r < 32; r++, src += pitch) {
+        const int nr = __shfl_sync(FULL, n, r);
+        const int64_t o = __shfl_sync(FULL, off, r);
+#pragma unroll 1
+        for (int d = 0; d < nrep; d++) {
+            double *out = A.values + o + (int64_t)d * nr + lane;
+            // rows of up to 96 values (3D P2 edge rows: 57 / 81) take the three predicated copies, longer ones loop
+            if (lane < nr) out[0] = src[0];
+            if (lane + 32 < nr) out[32] = src[32];
+            if (lane + 64 < nr) out[64] = src[64];
+            for (int x = lane + 96; x < nr; x += 32) out[x - lane] = src[x - lane];
+        }
+    }
+#endif
 }
 
 } // namespace fb

@@ -3,7 +3,7 @@
 TAG=$1; shift
 CMD="python bench.py --steps 2 --warmup 3 --no-e2e --cpu-M 4 $@"
 $CMD > gpurun_out/plain_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k_gather -s 27 -c 9 -f -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"k_gather|k_ring" -s 27 -c 9 -f -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_$TAG.log 2>&1
 ncu -i gpurun_out/prof_$TAG.ncu-rep --page raw --csv > gpurun_out/raw_$TAG.csv 2>/dev/null
 ncu -i gpurun_out/prof_$TAG.ncu-rep --page source --csv > gpurun_out/src_$TAG.csv 2>/dev/null
 tail -2 gpurun_out/ncu_$TAG.log
