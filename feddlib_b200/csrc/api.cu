@@ -220,7 +220,22 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
         c->launches++;
     }
     const size_t budget = c->smem_optin - 1024;
-    for (const Bucket &b : p->buckets) {
+    // the bucket launches are independent of one another and can be forked over the side streams (measured on
+    // B200: slower than back-to-back launches -- concurrent sweeps of the mesh compete for L2 -- so off by default)
+    int n_side = 0;
+    if (const char *f = getenv("FEDDB200_SIDE_STREAMS")) n_side = std::max(0, std::min(feddb200_ctx::kSide, atoi(f))); // tuning aid
+    if (p->buckets.size() < 2) n_side = 0;
+    if (n_side > 0) {
+        FB_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+        for (int i = 0; i < n_side; i++) FB_CUDA(cudaStreamWaitEvent(c->side[i], c->ev_fork, 0));
+    }
+    std::vector<const Bucket *> order;
+    for (const Bucket &b : p->buckets) order.push_back(&b);
+    std::stable_sort(order.begin(), order.end(), [](const Bucket *x, const Bucket *y) { return x->count * (int64_t)x->lcap > y->count * (int64_t)y->lcap; });
+    int turn = 0;
+    for (const Bucket *bp : order) {
+        const Bucket &b = *bp;
+        cudaStream_t st = n_side > 0 ? c->side[turn++ % n_side] : c->stream;
         G.zero = 0;
         G.start = b.start; G.count = b.count;
         int rc;
@@ -234,9 +249,15 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
                 const size_t smem = (size_t)pitch * 8 * nt;
                 FB_LOGIC(smem > budget, "row too long for the gather path's shared-memory rows; use the coloured or atomic mode");
                 G.pitch = pitch;
-                const int64_t blocks = (b.count * TPR + nt - 1) / nt;
+                const int64_t tiles = (b.count * TPR + nt - 1) / nt;
                 FB_CUDA(cudaFuncSetAttribute(k_ring<OPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
-                k_ring<OPG><<<(unsigned)blocks, nt, smem, c->stream>>>(G);
+                // persistent blocks: as many as are resident at once (times a small factor that evens out the tail)
+                int per_sm = 1;
+                FB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ring<OPG>, nt, smem));
+                int waves = 1;
+                if (const char *f = getenv("FEDDB200_RING_WAVES")) waves = std::max(1, atoi(f)); // tuning aid
+                const int64_t blocks = std::min<int64_t>(tiles, (int64_t)std::max(per_sm, 1) * c->sm_count * waves);
+                k_ring<OPG><<<(unsigned)blocks, nt, smem, st>>>(G);
                 c->launches++;
                 FB_CUDA(cudaGetLastError());
                 rc = FEDDB200_OK;
@@ -252,7 +273,7 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
             const int64_t blocks = (b.count * S::CPR + nt - 1) / nt;
             auto launch = [&](auto kernel) -> int {
                 FB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
-                kernel<<<(unsigned)blocks, nt, smem, c->stream>>>(G);
+                kernel<<<(unsigned)blocks, nt, smem, st>>>(G);
                 c->launches++;
                 FB_CUDA(cudaGetLastError());
                 return FEDDB200_OK;
@@ -264,6 +285,10 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
             }
         }
         if (rc != FEDDB200_OK) return rc;
+    }
+    for (int i = 0; i < n_side; i++) {
+        FB_CUDA(cudaEventRecord(c->ev_join[i], c->side[i]));
+        FB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join[i], 0));
     }
     return FEDDB200_OK;
 }

@@ -57,6 +57,11 @@ struct feddb200_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
+    // side streams + events: independent bucket launches of one assembly run concurrently (fork after the
+    // geometry pre-pass, join before the call returns to the caller's stream)
+    static constexpr int kSide = 3;
+    cudaStream_t side[kSide] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[kSide] = {nullptr, nullptr, nullptr};
     int mode = FEDDB200_SCATTER_GATHER;
     int64_t launches = 0;
     int sm_count = 148;

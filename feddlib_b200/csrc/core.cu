@@ -55,6 +55,11 @@ extern "C" int feddb200_create(feddb200_ctx **out, int device)
     c->smem_optin = prop.sharedMemPerBlockOptin;
     FB_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
+    for (int i = 0; i < feddb200_ctx::kSide; i++) {
+        FB_CUDA(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
+        FB_CUDA(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+    }
+    FB_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     FB_CUDA(cudaMalloc(&c->tab_d, 8 * sizeof(OpTables)));
     *out = c;
     return FEDDB200_OK;
@@ -68,6 +73,11 @@ extern "C" void feddb200_destroy(feddb200_ctx *c)
     cudaFree(c->tab_d);
     cudaFree(c->scratch_d[0]);
     cudaFree(c->scratch_d[1]);
+    for (int i = 0; i < feddb200_ctx::kSide; i++) {
+        if (c->side[i]) cudaStreamDestroy(c->side[i]);
+        if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+    }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }

@@ -905,192 +905,240 @@ __global__ void __launch_bounds__(64, FB_RING_MINBLOCKS) k_ring(const GatherArgs
     const int NT = blockDim.x;
     const int tid = threadIdx.x, lane = tid & 31;
     const int pitch = A.pitch;
-    const int64_t t = blockIdx.x * (int64_t)NT + tid;
-    const bool live = t < A.count * TPR;
-    const int64_t rloc = live ? t / TPR : 0;
-    const int a = live ? (int)(t - rloc * TPR) : 0;
-    int64_t base = 0, k0 = 0;
-    int L = 0, ninc = 0;
-    bool holes = false;
-    if (live) {
-        double raw[4];
-        ld_v4(reinterpret_cast<const double *>(A.rowinfo + A.start + rloc), raw);
-        base = __double_as_longlong(raw[0]);
-        k0 = __double_as_longlong(raw[1]);
-        const int64_t ln = __double_as_longlong(raw[2]);
-        L = (int)(ln & 0xffffffff);
-        ninc = (int)(ln >> 32);
-        holes = (__double_as_longlong(raw[3]) & 16) != 0;
-    }
-    double *wbase = acc + (size_t)(tid - lane) * pitch; // the warp's 32 rows
+    const int64_t nthreads = A.count * TPR;
+    const int64_t ntiles = (nthreads + NT - 1) / NT;
     const int nrep = (OPG == 0 && A.vec_dim != 0) ? A.vec_dim : 1;
-    const int n = live ? NB * L : 0;
-    const int64_t off = OPG == 1 ? (int64_t)DIM * DIM * base + (int64_t)a * n : (int64_t)nrep * base;
-#ifndef FB_NO_TMA_STORE
-    // the row is shifted by one double where that gives its shared-memory copy the same 16-byte phase as its
-    // destination in the values array (TMA bulk stores need both sides 16-byte aligned)
-    const int head = (int)(((reinterpret_cast<uintptr_t>(A.values) >> 3) + off) & 1); // 1: destination starts mid-16-bytes
-    double *my = acc + (size_t)tid * pitch + ((tid * pitch + head) & 1);
-#else
-    double *my = acc + (size_t)tid * pitch;
-#endif
-    if (__any_sync(FULL, holes)) { // rare: rows with positions no local element contributes to
-        for (int x = lane; x < 32 * pitch; x += 32) wbase[x] = 0.0;
-        __syncwarp();
-    }
+    const double mu = A.c1, lam = A.c0;
+    double *wbase = acc + (size_t)(tid - lane) * pitch; // the warp's 32 rows
     auto posof = [&](const IncRec<NL> &r, int jc) { return (int)((r.w[jc >> 1] >> (16 * (jc & 1))) & 0xffffu) * NB; };
 
-    if (ninc > 0) {
-        const int64_t k1 = k0 + ninc, kl = k1 - 1;
-        IncRec<NL> rc, rn, r2;
-        IncGeo<DIM> g;
-        load_rec<NL>(A, k0, rc);
-        load_rec<NL>(A, k0 + 1 < kl ? k0 + 1 : kl, rn);
-        load_rec<NL>(A, k0 + 2 < kl ? k0 + 2 : kl, r2);
-        load_geo<DIM, NL>(A, rc, g);
-        const int p_v0 = posof(rc, 0), p_v1 = posof(rc, 1), p_self = posof(rc, 4);
-        double accE[3][NB], carry[3][NB];
+    // Persistent blocks: a block walks tiles of blockDim.x rows.  The row record of the NEXT tile is fetched at
+    // the start of the current one, its first incidence records after the current main loop and its first
+    // geometry line while the bulk stores of the current tile drain, so the dependent chain
+    // row record -> incidence record -> geometry is off the critical path for all but a block's first tile.
+    int64_t tile = blockIdx.x;
+    if (tile >= ntiles) return;
+    double raw[4] = {0.0, 0.0, 0.0, 0.0};
+    IncRec<NL> rc, rn, r2;
+    IncGeo<DIM> g;
+    {
+        const int64_t t = tile * NT + tid;
+        if (t < nthreads) {
+            ld_v4(reinterpret_cast<const double *>(A.rowinfo + A.start + t / TPR), raw);
+            const int64_t k0 = __double_as_longlong(raw[1]);
+            const int ninc = (int)(__double_as_longlong(raw[2]) >> 32);
+            if (ninc > 0) {
+                const int64_t kl = k0 + ninc - 1;
+                load_rec<NL>(A, k0, rc);
+                load_rec<NL>(A, k0 + 1 < kl ? k0 + 1 : kl, rn);
+                load_rec<NL>(A, k0 + 2 < kl ? k0 + 2 : kl, r2);
+                load_geo<DIM, NL>(A, rc, g);
+            }
+        }
+    }
+    for (;;) {
+        const int64_t t = tile * NT + tid;
+        const bool live = t < nthreads;
+        const int a = live ? (int)(t % TPR) : 0;
+        const int64_t base = __double_as_longlong(raw[0]);
+        const int64_t k0 = __double_as_longlong(raw[1]);
+        const int L = live ? (int)(__double_as_longlong(raw[2]) & 0xffffffff) : 0;
+        const int ninc = live ? (int)(__double_as_longlong(raw[2]) >> 32) : 0;
+        const bool holes = live && (__double_as_longlong(raw[3]) & 16) != 0;
+        // row record of the next tile
+        const int64_t tile_n = tile + gridDim.x;
+        const int64_t tn = tile_n * NT + tid;
+        const bool live_n = tile_n < ntiles && tn < nthreads;
+        double rawn[4] = {0.0, 0.0, 0.0, 0.0};
+        if (live_n) ld_v4(reinterpret_cast<const double *>(A.rowinfo + A.start + tn / TPR), rawn);
+
+        const int n = NB * L;
+        const int64_t off = OPG == 1 ? (int64_t)DIM * DIM * base + (int64_t)a * n : (int64_t)nrep * base;
+#ifndef FB_NO_TMA_STORE
+        // the row is shifted by one double where that gives its shared-memory copy the same 16-byte phase as its
+        // destination in the values array (TMA bulk stores need both sides 16-byte aligned)
+        const int head = (int)(((reinterpret_cast<uintptr_t>(A.values) >> 3) + off) & 1);
+        double *my = acc + (size_t)tid * pitch + ((tid * pitch + head) & 1);
+#else
+        double *my = acc + (size_t)tid * pitch;
+#endif
+        if (__any_sync(FULL, holes)) { // rare: rows with positions no local element contributes to
+            for (int x = lane; x < 32 * pitch; x += 32) wbase[x] = 0.0;
+            __syncwarp();
+        }
+
+        if (ninc > 0) {
+            const int64_t k1 = k0 + ninc, kl = k1 - 1;
+            const int p_v0 = posof(rc, 0), p_v1 = posof(rc, 1), p_self = posof(rc, 4);
+            double accE[3][NB], carry[3][NB];
 #pragma unroll
-        for (int x = 0; x < 3; x++)
+            for (int x = 0; x < 3; x++)
 #pragma unroll
-            for (int b = 0; b < NB; b++) { accE[x][b] = 0.0; carry[x][b] = 0.0; }
-        const double mu = A.c1, lam = A.c0;
-        constexpr int JE[3] = {0, 1, 4}, JIN[3] = {2, 6, 5}, JOUT[3] = {3, 7, 8};
+                for (int b = 0; b < NB; b++) { accE[x][b] = 0.0; carry[x][b] = 0.0; }
+            constexpr int JE[3] = {0, 1, 4}, JIN[3] = {2, 6, 5}, JOUT[3] = {3, 7, 8};
 #pragma unroll(kRingUnroll)
-        for (int64_t k = k0; k < k1; k++) {
-            // E[s][w][b] for the two row-support vertices s = v0, v1 and the four canonical vertices w
-            double E[2][NVTX][NB];
-            {
-                const double adet = g.G[0][3];
-                if constexpr (OPG == 0) {
+            for (int64_t k = k0; k < k1; k++) {
+                // E[s][w][b] for the two row-support vertices s = v0, v1 and the four canonical vertices w
+                double E[2][NVTX][NB];
+                {
+                    const double adet = g.G[0][3];
+                    if constexpr (OPG == 0) {
 #pragma unroll
-                    for (int s = 0; s < 2; s++)
+                        for (int s = 0; s < 2; s++)
 #pragma unroll
-                        for (int w = 0; w < NVTX; w++) {
-                            double dot = 0.0;
+                            for (int w = 0; w < NVTX; w++) {
+                                double dot = 0.0;
 #pragma unroll
-                            for (int d = 0; d < DIM; d++) dot += g.G[s][d] * g.G[w][d];
-                            E[s][w][0] = dot * adet;
+                                for (int d = 0; d < DIM; d++) dot += g.G[s][d] * g.G[w][d];
+                                E[s][w][0] = dot * adet;
+                            }
+                    } else {
+                        const double mud = mu * adet, lamd = lam * adet;
+                        double Ga[NVTX];
+#pragma unroll
+                        for (int w = 0; w < NVTX; w++) Ga[w] = a == 0 ? g.G[w][0] : (a == 1 ? g.G[w][1] : g.G[w][2]);
+#pragma unroll
+                        for (int s = 0; s < 2; s++) {
+                            const double ls = lamd * Ga[s];
+#pragma unroll
+                            for (int w = 0; w < NVTX; w++) {
+                                double dot = 0.0;
+#pragma unroll
+                                for (int d = 0; d < DIM; d++) dot += g.G[s][d] * g.G[w][d];
+                                const double mdot = mud * dot, mga = mud * Ga[w];
+                                // E^{ab}_{sw} = mu (delta_ab G_s.G_w + G_s[b] G_w[a]) + lambda G_s[a] G_w[b]
+#pragma unroll
+                                for (int b = 0; b < DIM; b++) E[s][w][b] = (a == b ? mdot : 0.0) + mga * g.G[s][b] + ls * g.G[w][b];
+                            }
                         }
-                } else {
-                    const double mud = mu * adet, lamd = lam * adet;
-                    double Ga[NVTX];
+                    }
+                }
+                // refill the geometry buffer for the next incidence (ordered after E by a data dependence so the
+                // loads are not scheduled above the wait for the previous ones); record three incidences ahead
+                IncRec<NL> r3;
+                {
+                    const int dep = __double2hiint(E[0][0][0]) & A.zero;
+                    const uint32_t perm = rec_perm<NL>(rn.w);
+                    const double *gp = A.geom + (int64_t)rec_elem<NL>(rn.w) * GeomStride<DIM>::value + dep;
 #pragma unroll
-                    for (int w = 0; w < NVTX; w++) Ga[w] = a == 0 ? g.G[w][0] : (a == 1 ? g.G[w][1] : g.G[w][2]);
+                    for (int v = 0; v < 4; v++) ld_v4(gp + 4 * ((perm >> (2 * v)) & 3), g.G[v]);
+                    load_rec<NL>(A, k + 3 < kl ? k + 3 : kl, r3);
+#ifndef FB_NO_L2_PREFETCH
+                    prefetch_l2(A.geom + (int64_t)rec_elem<NL>(r2.w) * GeomStride<DIM>::value);
+#endif
+                }
+                auto contrib = [&](int jc, int b) {
+                    double v = 0.0;
 #pragma unroll
                     for (int s = 0; s < 2; s++) {
-                        const double ls = lamd * Ga[s];
+                        v += A.R.r[1][jc][s][0] * E[s][canon_sv<DIM>(jc, 0)][b];
+                        if (jc >= NVTX) v += A.R.r[1][jc][s][1] * E[s][canon_sv<DIM>(jc, 1)][b];
+                    }
+                    return v;
+                };
+                const uint32_t mode = (rec_perm<NL>(rc.w) >> 8) & 3;
 #pragma unroll
-                        for (int w = 0; w < NVTX; w++) {
-                            double dot = 0.0;
+                for (int x = 0; x < 3; x++)
 #pragma unroll
-                            for (int d = 0; d < DIM; d++) dot += g.G[s][d] * g.G[w][d];
-                            const double mdot = mud * dot, mga = mud * Ga[w];
-                            // E^{ab}_{sw} = mu (delta_ab G_s.G_w + G_s[b] G_w[a]) + lambda G_s[a] G_w[b]
+                    for (int b = 0; b < NB; b++) accE[x][b] += contrib(JE[x], b);
 #pragma unroll
-                            for (int b = 0; b < DIM; b++) E[s][w][b] = (a == b ? mdot : 0.0) + mga * g.G[s][b] + ls * g.G[w][b];
+                for (int x = 0; x < 3; x++) {
+                    double *p = my + posof(rc, JIN[x]);
+#pragma unroll
+                    for (int b = 0; b < NB; b++) p[b] = carry[x][b] + contrib(JIN[x], b);
+                }
+                {
+                    double *p = my + posof(rc, 9);
+#pragma unroll
+                    for (int b = 0; b < NB; b++) p[b] = contrib(9, b);
+                }
+#pragma unroll
+                for (int x = 0; x < 3; x++)
+#pragma unroll
+                    for (int b = 0; b < NB; b++) carry[x][b] = contrib(JOUT[x], b);
+                if (mode != 0) { // the chain ends here: the out-face is final (1) or closes the ring (2)
+#pragma unroll
+                    for (int x = 0; x < 3; x++) {
+                        double *p = my + posof(rc, JOUT[x]);
+#pragma unroll
+                        for (int b = 0; b < NB; b++) {
+                            p[b] = carry[x][b] + (mode == 2 ? p[b] : 0.0);
+                            carry[x][b] = 0.0;
                         }
                     }
                 }
-            }
-            // refill the geometry buffer for the next incidence (ordered after E by a data dependence so the
-            // loads are not scheduled above the wait for the previous ones); record three incidences ahead
-            IncRec<NL> r3;
-            {
-                const int dep = __double2hiint(E[0][0][0]) & A.zero;
-                const uint32_t perm = rec_perm<NL>(rn.w);
-                const double *gp = A.geom + (int64_t)rec_elem<NL>(rn.w) * GeomStride<DIM>::value + dep;
-#pragma unroll
-                for (int v = 0; v < 4; v++) ld_v4(gp + 4 * ((perm >> (2 * v)) & 3), g.G[v]);
-                load_rec<NL>(A, k + 3 < kl ? k + 3 : kl, r3);
-            }
-            auto contrib = [&](int jc, int b) {
-                double v = 0.0;
-#pragma unroll
-                for (int s = 0; s < 2; s++) {
-                    v += A.R.r[1][jc][s][0] * E[s][canon_sv<DIM>(jc, 0)][b];
-                    if (jc >= NVTX) v += A.R.r[1][jc][s][1] * E[s][canon_sv<DIM>(jc, 1)][b];
-                }
-                return v;
-            };
-            const uint32_t mode = (rec_perm<NL>(rc.w) >> 8) & 3;
-#pragma unroll
-            for (int x = 0; x < 3; x++)
-#pragma unroll
-                for (int b = 0; b < NB; b++) accE[x][b] += contrib(JE[x], b);
-#pragma unroll
-            for (int x = 0; x < 3; x++) {
-                double *p = my + posof(rc, JIN[x]);
-#pragma unroll
-                for (int b = 0; b < NB; b++) p[b] = carry[x][b] + contrib(JIN[x], b);
-            }
-            {
-                double *p = my + posof(rc, 9);
-#pragma unroll
-                for (int b = 0; b < NB; b++) p[b] = contrib(9, b);
+                rc = rn; rn = r2; r2 = r3;
             }
 #pragma unroll
-            for (int x = 0; x < 3; x++)
-#pragma unroll
-                for (int b = 0; b < NB; b++) carry[x][b] = contrib(JOUT[x], b);
-            if (mode != 0) { // the chain ends here: the out-face is final (1) or closes the ring (2)
-#pragma unroll
-                for (int x = 0; x < 3; x++) {
-                    double *p = my + posof(rc, JOUT[x]);
-#pragma unroll
-                    for (int b = 0; b < NB; b++) {
-                        p[b] = carry[x][b] + (mode == 2 ? p[b] : 0.0);
-                        carry[x][b] = 0.0;
-                    }
-                }
-            }
-            rc = rn; rn = r2; r2 = r3;
+            for (int b = 0; b < NB; b++) { my[p_v0 + b] = accE[0][b]; my[p_v1 + b] = accE[1][b]; my[p_self + b] = accE[2][b]; }
         }
-#pragma unroll
-        for (int b = 0; b < NB; b++) { my[p_v0 + b] = accE[0][b]; my[p_v1 + b] = accE[1][b]; my[p_self + b] = accE[2][b]; }
-    }
+
+        // first incidence records of the next tile (their addresses come from the row record fetched above)
+        const int64_t k0n = __double_as_longlong(rawn[1]);
+        const int nincn = live_n ? (int)(__double_as_longlong(rawn[2]) >> 32) : 0;
+        if (nincn > 0) {
+            const int64_t kln = k0n + nincn - 1;
+            load_rec<NL>(A, k0n, rc);
+            load_rec<NL>(A, k0n + 1 < kln ? k0n + 1 : kln, rn);
+            load_rec<NL>(A, k0n + 2 < kln ? k0n + 2 : kln, r2);
+        }
 
 #ifdef FB_EXP_NOWRITE
-    if (n == 12345) A.values[off] = my[0];
+        if (n == 12345) A.values[off] = my[0];
+        if (nincn > 0) load_geo<DIM, NL>(A, rc, g);
 #elif !defined(FB_NO_TMA_STORE)
-    // write-out: the thread's shared-memory row is its CSR row.  One TMA bulk store per row moves the 16-byte
-    // aligned interior (no LSU instructions, asynchronous); the at most two odd doubles go by plain stores.
-    if (n > 0) {
-        bulk_fence(); // make the generic-proxy shared-memory writes visible to the async proxy
+        // write-out: the thread's shared-memory row is its CSR row.  One TMA bulk store per row moves the 16-byte
+        // aligned interior (no LSU instructions, asynchronous); the at most two odd doubles go by plain stores.
+        if (n > 0) {
+            bulk_fence(); // make the generic-proxy shared-memory writes visible to the async proxy
 #pragma unroll 1
-        for (int d = 0; d < nrep; d++) {
-            double *out = A.values + off + (int64_t)d * n;
-            const int h = (int)((reinterpret_cast<uintptr_t>(out) >> 3) & 1);
-            if (OPG == 1 || h == head) {
-                const int body = (n - h) & ~1;
-                if (h) out[0] = my[0];
-                if (body > 0) bulk_store(out + h, my + h, body * 8);
-                if (h + body < n) out[n - 1] = my[n - 1];
-            } else { // replicated scalar row whose copy has the other phase: plain stores
-                for (int x = 0; x < n; x++) out[x] = my[x];
+            for (int d = 0; d < nrep; d++) {
+                double *out = A.values + off + (int64_t)d * n;
+                const int h = (int)((reinterpret_cast<uintptr_t>(out) >> 3) & 1);
+                if (OPG == 1 || h == head) {
+                    const int body = (n - h) & ~1;
+                    if (h) out[0] = my[0];
+                    if (body > 0) bulk_store(out + h, my + h, body * 8);
+                    if (h + body < n) out[n - 1] = my[n - 1];
+                } else { // replicated scalar row whose copy has the other phase: plain stores
+                    for (int x = 0; x < n; x++) out[x] = my[x];
+                }
             }
         }
-    }
-    bulk_commit_wait_read(); // the bulk stores read this block's shared memory: wait before it is released
+        if (nincn > 0) load_geo<DIM, NL>(A, rc, g); // next tile's first geometry line lands while the stores drain
+        bulk_commit_wait_read(); // the bulk stores read this block's shared memory: wait before it is reused
 #else
-    __syncwarp();
-    // write-out: thread r's shared-memory row is one CSR row; the warp copies its 32 rows one after the other
-    const double *src = wbase + lane;
+        __syncwarp();
+        // write-out: thread r's shared-memory row is one CSR row; the warp copies its 32 rows one after the other
+        {
+            const double *src = wbase + lane;
 #pragma unroll 1
-    for (int r = 0; r < 32; r++, src += pitch) {
-        const int nr = __shfl_sync(FULL, n, r);
-        const int64_t o = __shfl_sync(FULL, off, r);
-#pragma unroll 1
-        for (int d = 0; d < nrep; d++) {
-            double *out = A.values + o + (int64_t)d * nr + lane;
-            // rows of up to 96 values (3D P2 edge rows: 57 / 81) take the three predicated copies, longer ones loop
-            if (lane < nr) out[0] = src[0];
-            if (lane + 32 < nr) out[32] = src[32];
-            if (lane + 64 < nr) out[64] = src[64];
-            for (int x = lane + 96; x < nr; x += 32) out[x - lane] = src[x - lane];
-        }
-    }
+            for (int r = 0; r < 32; r++, src += pitch) {
+                const int nr = __shfl_sync(FULL, n, r);
+#ifdef FB_EXP_STREAMWRITE
+                const int64_t o = (tile * NT + (tid - lane) + r) * (int64_t)nr; (void)off; // timing experiment: dense, in launch order
+#else
+                const int64_t o = __shfl_sync(FULL, off, r);
 #endif
+#pragma unroll 1
+                for (int d = 0; d < nrep; d++) {
+                    double *out = A.values + o + (int64_t)d * nr + lane;
+                    // rows of up to 96 values (3D P2 edge rows: 57 / 81) take the three predicated copies, longer ones loop
+                    if (lane < nr) out[0] = src[0];
+                    if (lane + 32 < nr) out[32] = src[32];
+                    if (lane + 64 < nr) out[64] = src[64];
+                    for (int x = lane + 96; x < nr; x += 32) out[x - lane] = src[x - lane];
+                }
+            }
+        }
+        if (nincn > 0) load_geo<DIM, NL>(A, rc, g);
+        __syncwarp();
+#endif
+        if (tile_n >= ntiles) break;
+        tile = tile_n;
+#pragma unroll
+        for (int x = 0; x < 4; x++) raw[x] = rawn[x];
+    }
 }
 
 } // namespace fb
