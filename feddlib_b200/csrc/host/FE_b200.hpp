@@ -1,0 +1,302 @@
+// FE_b200.hpp -- C++ host side of the drop-in: FEDD::FE_b200<SC,LO,GO,NO> keeps the member signatures of
+// FEDD::FE<SC,LO,GO,NO> for the element-wise matrix assembly hot path (feddlib/core/FE/FE_decl.hpp:116,
+// 130-135, 153-157, 194-224, 252-257) and forwards the work to libfeddb200.so through the C ABI of
+// include/feddb200.h.  What it reads of the FEDDLib containers is exactly what the reference routines read
+// (Domain::getDimension/getFEType/getElementsC/getPointsRepeated/getMapRepeated, Elements::numberElements/
+// getElement, FiniteElement::getVectorNodeList, Map::getNodeNumElements/getGlobalElement,
+// MultiVector::getData), so it compiles unchanged against
+//   * FEDDLib + Trilinos (define FEDD_B200_TRILINOS) -- the returned matrix is a
+//     fill-complete Tpetra::CrsMatrix on the caller's row map, built from the engine's CSR arrays, and
+//   * the mock containers of oracle/ref_shim (tests/cpp/fe_b200_driver.cpp), where the reference's own
+//     FE_def.hpp routines run side by side on the same Domain objects.
+// Include the FEDDLib headers (or the mocks) BEFORE this header; it includes nothing of FEDDLib itself.
+//
+// Error behaviour mirrors the reference: std::logic_error for unsupported FE types / missing addFE
+// (FE_def.hpp:610, 676, 2746, 6950), std::runtime_error for engine failures.  There is no CPU fallback.
+#pragma once
+
+#include <cstdint>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "feddb200.h"
+
+namespace FEDD {
+namespace b200 {
+
+inline void check(int rc)
+{
+    if (rc == FEDDB200_OK) return;
+    const std::string msg = feddb200_last_error();
+    if (rc == FEDDB200_ELOGIC) throw std::logic_error(msg);
+    throw std::runtime_error(msg);
+}
+
+// CSR of one assembled matrix, as handed to the seat step: local rows in row-map order, local column
+// indices into `colmap` (global dof ids of the column map, owned first), values on the host.
+template <class SC, class LO, class GO>
+struct LocalCsr {
+    std::vector<std::int64_t> rowptr;
+    std::vector<std::int32_t> colind;
+    std::vector<GO> colmap;
+    std::vector<SC> values;
+};
+
+#ifdef FEDD_B200_TRILINOS
+// Seat step for the real containers: wrap the CSR in a Tpetra::CrsMatrix on the caller's row map and re-seat
+// `A` (passed as MatrixPtr_Type&, as in the reference).  domain/range default to the row map, like
+// Matrix::fillComplete() (Matrix_def.hpp:192-194); B / B^T pass (map1,map2) / (map2,map1) (FE_def.hpp:2052-2055).
+template <class SC, class LO, class GO, class NO>
+void seat_csr(Teuchos::RCP<Matrix<SC, LO, GO, NO> > &A, LocalCsr<SC, LO, GO> &csr,
+              Teuchos::RCP<const Map<LO, GO, NO> > domainMap, Teuchos::RCP<const Map<LO, GO, NO> > rangeMap,
+              bool callFillComplete)
+{
+    typedef Tpetra::Map<LO, GO, NO> TMap;
+    typedef Tpetra::CrsMatrix<SC, LO, GO, NO> TCrs;
+    Teuchos::RCP<const Map<LO, GO, NO> > rowMapF = A->getMap();
+    Teuchos::RCP<const TMap> rowMap = Xpetra::toTpetra(rowMapF->getXpetraMap());
+    Teuchos::RCP<const TMap> colMap = Teuchos::rcp(new TMap(Teuchos::OrdinalTraits<Tpetra::global_size_t>::invalid(),
+                                                              Teuchos::ArrayView<const GO>(csr.colmap.data(), csr.colmap.size()),
+                                                              rowMap->getIndexBase(), rowMap->getComm()));
+    Teuchos::ArrayRCP<std::size_t> rp(csr.rowptr.size());
+    for (std::size_t k = 0; k < csr.rowptr.size(); k++) rp[k] = (std::size_t)csr.rowptr[k];
+    Teuchos::ArrayRCP<LO> ci(csr.colind.size());
+    for (std::size_t k = 0; k < csr.colind.size(); k++) ci[k] = (LO)csr.colind[k];
+    Teuchos::ArrayRCP<SC> va(csr.values.size());
+    for (std::size_t k = 0; k < csr.values.size(); k++) va[k] = csr.values[k];
+    Teuchos::RCP<TCrs> T = Teuchos::rcp(new TCrs(rowMap, colMap, rp, ci, va));
+    if (callFillComplete) {
+        Teuchos::RCP<const TMap> dom = domainMap.is_null() ? rowMap : Xpetra::toTpetra(domainMap->getXpetraMap());
+        Teuchos::RCP<const TMap> ran = rangeMap.is_null() ? rowMap : Xpetra::toTpetra(rangeMap->getXpetraMap());
+        T->expertStaticFillComplete(dom, ran);
+    }
+    Teuchos::RCP<Xpetra::CrsMatrix<SC, LO, GO, NO> > xCrs = Teuchos::rcp(new Xpetra::TpetraCrsMatrix<SC, LO, GO, NO>(T));
+    Teuchos::RCP<Xpetra::Matrix<SC, LO, GO, NO> > xMat = Teuchos::rcp(new Xpetra::CrsMatrixWrap<SC, LO, GO, NO>(xCrs));
+    A = Teuchos::rcp(new Matrix<SC, LO, GO, NO>(xMat));
+}
+#endif
+
+} // namespace b200
+
+template <class SC = double, class LO = int, class GO = long long, class NO = int>
+class FE_b200 {
+  public:
+    typedef Domain<SC, LO, GO, NO> Domain_Type;
+    typedef Teuchos::RCP<const Domain_Type> DomainConstPtr_Type;
+    typedef Matrix<SC, LO, GO, NO> Matrix_Type;
+    typedef Teuchos::RCP<Matrix_Type> MatrixPtr_Type;
+    typedef Map<LO, GO, NO> Map_Type;
+    typedef Teuchos::RCP<const Map_Type> MapConstPtr_Type;
+    typedef MultiVector<SC, LO, GO, NO> MultiVector_Type;
+    typedef Teuchos::RCP<MultiVector_Type> MultiVectorPtr_Type;
+
+    explicit FE_b200(bool /*saveAssembly*/ = false, int device = 0) : ctx_(nullptr)
+    {
+        b200::check(feddb200_create(&ctx_, device));
+    }
+    ~FE_b200()
+    {
+        for (auto &kv : pats_) feddb200_pat_free(kv.second);
+        for (auto &s : slots_) feddb200_mesh_free(s.mesh);
+        feddb200_destroy(ctx_);
+    }
+    FE_b200(const FE_b200 &) = delete;
+    FE_b200 &operator=(const FE_b200 &) = delete;
+
+    // FE::addFE (FE_def.hpp:64-72): registers the domain; here also the one-time mesh upload
+    void addFE(DomainConstPtr_Type domain)
+    {
+        Slot s;
+        s.domain = domain;
+        s.dim = domain->getDimension();
+        s.FEType = domain->getFEType();
+        auto elements = domain->getElementsC();
+        auto points = domain->getPointsRepeated();
+        s.ne = elements->numberElements();
+        s.nloc = s.ne > 0 ? (int)elements->getElement(0).getVectorNodeList().size() : nloc_of(s.dim, s.FEType);
+        s.nn = (std::int64_t)points->size();
+        std::vector<std::int32_t> conn((std::size_t)s.ne * s.nloc);
+        for (std::int64_t T = 0; T < s.ne; T++) {
+            const std::vector<int> &nodes = elements->getElement((int)T).getVectorNodeList();
+            for (int i = 0; i < s.nloc; i++) conn[(std::size_t)T * s.nloc + i] = nodes[i];
+        }
+        std::vector<double> xyz((std::size_t)s.nn * s.dim);
+        for (std::int64_t k = 0; k < s.nn; k++)
+            for (int c = 0; c < s.dim; c++) xyz[(std::size_t)k * s.dim + c] = (*points)[k][c];
+        b200::check(feddb200_mesh_upload(ctx_, &s.mesh, s.dim, s.nloc, s.ne, conn.data(), s.nn, xyz.data()));
+        slots_.push_back(s);
+    }
+
+    void setScatterMode(int mode) { b200::check(feddb200_set_scatter_mode(ctx_, mode)); }
+
+    // FE::assemblyLaplace (FE_def.hpp:604-667); `degree` is ignored exactly as in the reference (:626)
+    void assemblyLaplace(int dim, std::string FEType, int /*degree*/, MatrixPtr_Type &A, bool callFillComplete = true,
+                         int FELocExternal = -1)
+    {
+        if (FEType == "P0") throw std::logic_error("Not implemented for P0");
+        const int loc = FELocExternal < 0 ? checkFE(dim, FEType) : FELocExternal;
+        feddb200_pat *p = pattern(loc, loc);
+        b200::LocalCsr<SC, LO, GO> csr;
+        expand(p, loc, 1, 1, FEDDB200_BLOCK_SCALAR, csr);
+        b200::check(feddb200_assemble_laplace(ctx_, p, 0, csr.values.data()));
+        seat_csr(A, csr, MapConstPtr_Type(), MapConstPtr_Type(), callFillComplete);
+    }
+
+    // FE::assemblyLaplaceVecField (FE_def.hpp:670-734)
+    void assemblyLaplaceVecField(int dim, std::string FEType, int /*degree*/, MatrixPtr_Type &A, bool callFillComplete = true)
+    {
+        if (FEType == "P0") throw std::logic_error("Not implemented for P0");
+        const int loc = checkFE(dim, FEType);
+        feddb200_pat *p = pattern(loc, loc);
+        b200::LocalCsr<SC, LO, GO> csr;
+        expand(p, loc, dim, dim, FEDDB200_BLOCK_DIAG, csr);
+        b200::check(feddb200_assemble_laplace(ctx_, p, 1, csr.values.data()));
+        seat_csr(A, csr, MapConstPtr_Type(), MapConstPtr_Type(), callFillComplete);
+    }
+
+    // FE::assemblyLinElasXDim (FE_def.hpp:2739-3040)
+    void assemblyLinElasXDim(int dim, std::string FEType, MatrixPtr_Type &A, double lambda, double mu, bool callFillComplete = true)
+    {
+        if (FEType == "P0") throw std::logic_error("Not implemented for P0");
+        const int loc = checkFE(dim, FEType);
+        feddb200_pat *p = pattern(loc, loc);
+        b200::LocalCsr<SC, LO, GO> csr;
+        expand(p, loc, dim, dim, FEDDB200_BLOCK_FULL, csr);
+        b200::check(feddb200_assemble_linelas(ctx_, p, lambda, mu, csr.values.data()));
+        seat_csr(A, csr, MapConstPtr_Type(), MapConstPtr_Type(), callFillComplete);
+    }
+
+    // FE::assemblyAdvectionVecField (FE_def.hpp:1685-1836); u is the repeated, node-wise interleaved velocity
+    void assemblyAdvectionVecField(int dim, std::string FEType, MatrixPtr_Type &A, MultiVectorPtr_Type u, bool callFillComplete)
+    {
+        if (FEType == "P0") throw std::logic_error("Not implemented for P0");
+        if (u->getNumVectors() > 1) throw std::logic_error("Implement for numberMV > 1 .");
+        const int loc = checkFE(dim, FEType);
+        feddb200_pat *p = pattern(loc, loc);
+        b200::LocalCsr<SC, LO, GO> csr;
+        expand(p, loc, dim, dim, FEDDB200_BLOCK_DIAG, csr);
+        Teuchos::ArrayRCP<const SC> uArray = u->getData(0);
+        b200::check(feddb200_assemble_advection(ctx_, p, (uArray.size() ? &uArray[0] : nullptr), csr.values.data()));
+        seat_csr(A, csr, MapConstPtr_Type(), MapConstPtr_Type(), callFillComplete);
+    }
+
+    // FE::assemblyAdvectionInUVecField (FE_def.hpp:1839-1929)
+    void assemblyAdvectionInUVecField(int dim, std::string FEType, MatrixPtr_Type &A, MultiVectorPtr_Type u, bool callFillComplete)
+    {
+        if (FEType == "P0") throw std::logic_error("Not implemented for P0");
+        const int loc = checkFE(dim, FEType);
+        feddb200_pat *p = pattern(loc, loc);
+        b200::LocalCsr<SC, LO, GO> csr;
+        expand(p, loc, dim, dim, FEDDB200_BLOCK_FULL, csr);
+        Teuchos::ArrayRCP<const SC> uArray = u->getData(0);
+        b200::check(feddb200_assemble_advection_in_u(ctx_, p, (uArray.size() ? &uArray[0] : nullptr), csr.values.data()));
+        seat_csr(A, csr, MapConstPtr_Type(), MapConstPtr_Type(), callFillComplete);
+    }
+
+    // FE::assemblyDivAndDivT (FE_def.hpp:1932-2057): FEType1 = velocity space, FEType2 = pressure space; rows of
+    // Bmat are pressure dofs, fillComplete(map1, map2) / (map2, map1) (:2052-2055)
+    void assemblyDivAndDivT(int dim, std::string FEType1, std::string FEType2, int /*degree*/, MatrixPtr_Type &Bmat,
+                            MatrixPtr_Type &BTmat, MapConstPtr_Type map1, MapConstPtr_Type map2, bool callFillComplete = true)
+    {
+        if (FEType2 == "P0" || FEType2 == "P1-disc" || FEType2 == "P1-disc-global")
+            throw std::logic_error("assemblyDivAndDivT: discontinuous pressure spaces are not implemented in the B200 engine");
+        const int loc1 = checkFE(dim, FEType1), loc2 = checkFE(dim, FEType2);
+        feddb200_pat *pB = pattern(loc2, loc1), *pBT = pattern(loc1, loc2);
+        b200::LocalCsr<SC, LO, GO> cB, cBT;
+        expand(pB, loc1, 1, dim, FEDDB200_BLOCK_FULL, cB);
+        expand(pBT, loc2, dim, 1, FEDDB200_BLOCK_FULL, cBT);
+        b200::check(feddb200_assemble_div_divT(ctx_, pB, pBT, cB.values.data(), cBT.values.data()));
+        seat_csr(Bmat, cB, map1, map2, callFillComplete);
+        seat_csr(BTmat, cBT, map2, map1, callFillComplete);
+    }
+    // FE::assemblyDivAndDivTFast (FE_def.hpp:2061-2148): same matrices, single-entry inserts in the reference
+    void assemblyDivAndDivTFast(int dim, std::string FEType1, std::string FEType2, int degree, MatrixPtr_Type &Bmat,
+                                MatrixPtr_Type &BTmat, MapConstPtr_Type map1, MapConstPtr_Type map2, bool callFillComplete = true)
+    {
+        assemblyDivAndDivT(dim, FEType1, FEType2, degree, Bmat, BTmat, map1, map2, callFillComplete);
+    }
+
+    // Fused (0,0) block of the Navier-Stokes system: rho*nu*LaplaceVecField + rho*N(u) [+ rho*W(u)], the three
+    // assemblies and two TwoMatrixAdd of NavierStokes::reAssemble (problems/specific/NavierStokes_def.hpp:140-152,
+    // 297-313) in one pass on the union pattern.  Not a member of the reference's FE; optional fast path.
+    void assemblyNavierStokesJacobian(int dim, std::string FEType, MatrixPtr_Type &A, MultiVectorPtr_Type u, double rho,
+                                      double nu, bool newton, bool callFillComplete = true)
+    {
+        const int loc = checkFE(dim, FEType);
+        feddb200_pat *p = pattern(loc, loc);
+        b200::LocalCsr<SC, LO, GO> csr;
+        expand(p, loc, dim, dim, FEDDB200_BLOCK_FULL, csr);
+        Teuchos::ArrayRCP<const SC> uArray = u->getData(0);
+        b200::check(feddb200_assemble_ns_jacobian(ctx_, p, rho, nu, (uArray.size() ? &uArray[0] : nullptr), newton ? 1 : 0, csr.values.data()));
+        seat_csr(A, csr, MapConstPtr_Type(), MapConstPtr_Type(), callFillComplete);
+    }
+
+    // FE::checkFE (FE_def.hpp:6932-6953): last registered domain with this dimension and FE type
+    int checkFE(int dim, std::string FEType)
+    {
+        int loc = -1;
+        for (std::size_t i = 0; i < slots_.size(); i++)
+            if (slots_[i].dim == dim && slots_[i].FEType == FEType) loc = (int)i;
+        if (loc < 0)
+            throw std::logic_error("Combination of dimenson(2/3) and FE Type(P1/P2) not defined yet. Use addFE(domain)");
+        return loc;
+    }
+
+    std::int64_t launchCount() const { return feddb200_launch_count(ctx_); }
+
+  private:
+    struct Slot {
+        DomainConstPtr_Type domain;
+        feddb200_mesh *mesh = nullptr;
+        int dim = 0, nloc = 0;
+        std::int64_t ne = 0, nn = 0;
+        std::string FEType;
+    };
+
+    static int nloc_of(int dim, const std::string &fe)
+    {
+        if (fe == "P1") return dim + 1;
+        if (fe == "P2") return dim == 2 ? 6 : 10;
+        throw std::logic_error("FE_b200: only P1/P2 triangles and tetrahedra are implemented");
+    }
+
+    // one pattern per (row space, column space), built on first use (single rank: the unique map lists the
+    // repeated nodes in order, Map_def.hpp:201-206; the multi-rank row/column maps are described in INTEGRATION.md)
+    feddb200_pat *pattern(int rowLoc, int colLoc)
+    {
+        const std::pair<int, int> key(rowLoc, colLoc);
+        auto it = pats_.find(key);
+        if (it != pats_.end()) return it->second;
+        feddb200_pat *p = nullptr;
+        b200::check(feddb200_pattern_build(ctx_, &p, slots_[rowLoc].mesh, slots_[colLoc].mesh, 0, 0, nullptr, 0, nullptr, 0,
+                                           nullptr, nullptr));
+        pats_[key] = p;
+        return p;
+    }
+
+    // dof-level CSR + column map of global dof ids (node-wise numbering dofs*g + d, Map_def.hpp:95-108)
+    void expand(feddb200_pat *p, int colLoc, int rowDofs, int colDofs, int mode, b200::LocalCsr<SC, LO, GO> &csr)
+    {
+        std::int64_t nRows = 0, nCols = 0;
+        b200::check(feddb200_pattern_info(p, &nRows, nullptr, &nCols, nullptr, nullptr, nullptr, nullptr));
+        const std::int64_t nnz = feddb200_pattern_nnz(p, rowDofs, colDofs, mode);
+        csr.rowptr.resize((std::size_t)nRows * rowDofs + 1);
+        csr.colind.resize((std::size_t)nnz);
+        csr.values.resize((std::size_t)nnz);
+        b200::check(feddb200_pattern_expand(ctx_, p, rowDofs, colDofs, mode, csr.rowptr.data(), csr.colind.data()));
+        MapConstPtr_Type mapRep = slots_[colLoc].domain->getMapRepeated();
+        csr.colmap.resize((std::size_t)nCols * colDofs);
+        for (std::int64_t j = 0; j < nCols; j++)
+            for (int d = 0; d < colDofs; d++)
+                csr.colmap[(std::size_t)j * colDofs + d] = (GO)colDofs * mapRep->getGlobalElement((LO)j) + d;
+    }
+
+    feddb200_ctx *ctx_;
+    std::vector<Slot> slots_;
+    std::map<std::pair<int, int>, feddb200_pat *> pats_;
+};
+
+} // namespace FEDD
