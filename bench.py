@@ -42,6 +42,17 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(M):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one assembly pass (all its launches) from the committed
+    `ncu --set full` capture of this command (profiles/r01_step_traffic.json); None for other sizes."""
+    p = os.path.join(ROOT, "profiles", "r01_step_traffic.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        if int(d.get("M", -1)) == int(M):
+            return d["dram_bytes_per_step"]
+    return None
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
 
@@ -160,6 +171,7 @@ def main():
     ap.add_argument("--cpu-M", dest="cpu_M", type=int, default=16)
     ap.add_argument("--e2e-steps", dest="e2e_steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: exchange after the whole assembly")
     ap.add_argument("--all-modes", action="store_true", help="also time the other scatter modes (extra keys)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -200,10 +212,15 @@ def main():
     nnz = pat.nnz(dim, dim, BLOCK_FULL)
     values = ctx.empty_values(nnz)
 
+    overlap = runner is not None and args.mode == "gather" and not args.no_overlap
+
     def step():
-        pat.assemble_linelas_d(values, LAM, MU)
-        if runner is not None:
-            runner.exchange(values)
+        if overlap:      # ghost rows first, NCCL exchange on a side stream while the owned rows are assembled
+            runner.assemble_linelas_overlapped(values, LAM, MU)
+        else:
+            pat.assemble_linelas_d(values, LAM, MU)
+            if runner is not None:
+                runner.exchange(values)
 
     def barrier():
         if world > 1:
@@ -241,8 +258,10 @@ def main():
     peak, peak_src = peaks()
     achieved = alg_bytes / (ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_step": alg_bytes,
-                "kernel": f"assembly pass = k_geom + k_gather bucket launches ({launches} launches/step)"
+                "traffic": ncu_traffic(M) if args.mode == "gather" and world == 1 else None,
+                "peak_source": peak_src, "algorithmic_bytes_per_step": alg_bytes,
+                "kernel": f"assembly pass = k_geom + k_ring (edge-node rows, ring order, TMA bulk stores) + k_gather "
+                          f"(vertex-node rows) bucket launches ({launches} launches/step); time = whole pass, CUDA events"
                 if args.mode == "gather" else f"{args.mode} scatter pass ({launches} launches/step)"}
 
     extra = {}
@@ -302,7 +321,9 @@ def main():
                                        f"{nnz} CSR values/GPU (30x30 local blocks)",
                            "lambda": LAM, "mu": MU, "scatter_mode": args.mode,
                            "l2_policy": "outputs (5.7 GB at M=70) exceed the 126 MB L2; no flush needed",
-                           "parallelism": f"element partition over {world} GPU(s)",
+                           "parallelism": f"element partition over {world} GPU(s)" + (
+                               "; ghost rows assembled first, NCCL ghost-row exchange overlapped with the owned rows"
+                               if overlap else ("; NCCL ghost-row exchange after the assembly" if world > 1 else "")),
                            "pattern_build_s": t_pattern},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
                 "clocks": clocks, "checksum_first_1Mi_values": checksum}

@@ -42,6 +42,7 @@ SIGNATURES = {
     "feddb200_use_own_stream": (C.c_int, [_vp]),
     "feddb200_set_scatter_mode": (C.c_int, [_vp, C.c_int]),
     "feddb200_get_scatter_mode": (C.c_int, [_vp]),
+    "feddb200_set_row_phase": (C.c_int, [_vp, C.c_int]),
     "feddb200_synchronize": (C.c_int, [_vp]),
     "feddb200_launch_count": (_i64, [_vp]),
     "feddb200_dev_alloc": (C.c_int, [_vp, C.POINTER(_vp), _i64]),

@@ -136,7 +136,7 @@ int ensure_gather(feddb200_pat *p)
     std::vector<int32_t> perm(n_rows);
     for (int64_t r = 0; r < n_rows; r++) perm[r] = (int32_t)r;
     auto cap = [&](int64_t r) { const int l = (int)(p->rowptr_h[r + 1] - p->rowptr_h[r]); return std::max(4, (l + 3) & ~3); };
-    auto key = [&](int32_t r) { return (int64_t)(rtype[r] & 3) * 100000 + cap(r); };
+    auto key = [&](int32_t r) { return (int64_t)(r >= p->n_owned ? 0 : 1) * 1000000 + (int64_t)(rtype[r] & 3) * 100000 + cap(r); };
     // ... but only inside chunks of consecutive rows, so that a launch still sweeps the mesh (and the geometry
     // lines in L2) once instead of once per stencil class
     int chunk_shift = 12;
@@ -155,7 +155,7 @@ int ensure_gather(feddb200_pat *p)
     for (int64_t s = 0; s < n_rows;) {
         int64_t e = s;
         while (e < n_rows && key(perm[e]) == key(perm[s])) e++;
-        p->buckets.push_back({(int)(rtype[perm[s]] & 3), cap(perm[s]), s, e - s});
+        p->buckets.push_back({(int)(rtype[perm[s]] & 3), perm[s] >= p->n_owned ? 1 : 0, cap(perm[s]), s, e - s});
         s = e;
     }
     {
@@ -215,7 +215,8 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
 {
     using S = GatherShape<OPG, DIM>;
     const int64_t blocks_geom = (p->rm->ne + 255) / 256;
-    if (p->rm->ne > 0) {
+    const int phase = c->row_phase;
+    if (p->rm->ne > 0 && phase != FEDDB200_ROWS_OWNED) {
         k_geom<DIM, NL><<<(unsigned)blocks_geom, 256, 0, c->stream>>>(p->rm->ne, p->rm->conn_d, p->rm->coords_d, p->geom_d);
         c->launches++;
     }
@@ -235,6 +236,7 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
     int turn = 0;
     for (const Bucket *bp : order) {
         const Bucket &b = *bp;
+        if ((phase == FEDDB200_ROWS_GHOST && !b.ghost) || (phase == FEDDB200_ROWS_OWNED && b.ghost)) continue;
         cudaStream_t st = n_side > 0 ? c->side[turn++ % n_side] : c->stream;
         G.zero = 0;
         G.start = b.start; G.count = b.count;
@@ -350,6 +352,7 @@ int run_op(feddb200_ctx *c, const feddb200_pat *pc, int op, const double *u_d, d
         return op == OP_LAP ? launch_gather<0>(c, p, G) : launch_gather<1>(c, p, G);
     }
 
+    if (c->row_phase == FEDDB200_ROWS_OWNED) return FEDDB200_OK; // element-wise modes did everything in the ROWS_GHOST call
     ElemArgs A;
     A.conn_r = rm->conn_d; A.conn_c = cm->conn_d; A.conn_v = vm->conn_d; A.coords = vm->coords_d;
     A.row_lid = p->row_lid_d; A.rowptr = p->rowptr_d; A.pos = p->pos_d; A.pos_stride = p->pos_stride;

@@ -47,6 +47,7 @@ struct OpTables {
 
 struct Bucket {            // rows of one type with node-row length <= lcap, processed by one gather launch
     int type;              // 0 vertex-node rows, 1 ring-ordered edge-node rows (3D P2), 2 edge-node rows (generic)
+    int ghost;             // 1: rows owned by another rank (index >= n_owned); their values are shipped after the assembly
     int lcap;
     int64_t start, count;  // range in row_perm
 };
@@ -63,6 +64,7 @@ struct feddb200_ctx {
     cudaStream_t side[kSide] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[kSide] = {nullptr, nullptr, nullptr};
     int mode = FEDDB200_SCATTER_GATHER;
+    int row_phase = FEDDB200_ROWS_ALL;
     int64_t launches = 0;
     int sm_count = 148;
     size_t smem_optin = 0;

@@ -104,6 +104,13 @@ extern "C" int feddb200_set_scatter_mode(feddb200_ctx *c, int mode)
     return FEDDB200_OK;
 }
 extern "C" int feddb200_get_scatter_mode(const feddb200_ctx *c) { return c ? c->mode : -1; }
+extern "C" int feddb200_set_row_phase(feddb200_ctx *c, int phase)
+{
+    FB_LOGIC(!c, "null context");
+    FB_LOGIC(phase < 0 || phase > 2, "feddb200_set_row_phase: phase must be 0 (all), 1 (ghost rows) or 2 (owned rows)");
+    c->row_phase = phase;
+    return FEDDB200_OK;
+}
 
 extern "C" int feddb200_synchronize(feddb200_ctx *c)
 {

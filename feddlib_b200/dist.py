@@ -283,16 +283,56 @@ class DistributedMatrixAssembler:
         self._slot_t = {}
         self._recv_buf = {}
 
+    def _exchange_buffers(self, rd, cd, mode):
+        import torch
+        key = (rd, cd, mode)
+        if key not in self._slot_t:
+            self._slot_t[key] = torch.from_numpy(self.plan.recv_slots(rd, cd, mode)).to(self._dev)
+            self._recv_buf[key] = torch.empty(self._slot_t[key].numel(), dtype=torch.float64, device=self._dev)
+        return key
+
+    def assemble_overlapped(self, values, rd, cd, mode, assemble):
+        """`assemble()` launches one assembly of this pattern into `values`.  Ghost rows are assembled first and
+        shipped (NCCL, side stream) while the owned rows are assembled; the received values are added last."""
+        import torch
+        import torch.distributed as dist
+        if self.size == 1:
+            assemble()
+            return
+        key = self._exchange_buffers(rd, cd, mode)
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self._dev)
+        ssz, rsz = self.plan.split_sizes(rd, cd, mode)
+        send, recv = values[self.pat.nnz_owned(rd, cd, mode):], self._recv_buf[key]
+        main = torch.cuda.current_stream(self._dev)
+        self.ctx.set_row_phase(1)
+        try:
+            assemble()                      # geometry pre-pass + ghost rows
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                dist.all_to_all_single(recv, send, rsz, ssz)
+            self.ctx.set_row_phase(2)
+            assemble()                      # owned rows, concurrent with the exchange
+        finally:
+            self.ctx.set_row_phase(0)
+        main.wait_stream(self._side)
+        self._unpack(values, key, rsz)
+
+    def _unpack(self, values, key, rsz):
+        recv, slots = self._recv_buf[key], self._slot_t[key]
+        off = 0
+        for n in rsz:
+            if n:
+                self.ctx.unpack_add_d(values, recv[off:off + n], slots[off:off + n])
+            off += n
+
     def exchange(self, values, rd, cd, mode):
         """Ship ghost-row values to their owners (NCCL all-to-all-v) and add them into the owned CSR."""
         import torch
         import torch.distributed as dist
         if self.size == 1:
             return
-        key = (rd, cd, mode)
-        if key not in self._slot_t:
-            self._slot_t[key] = torch.from_numpy(self.plan.recv_slots(rd, cd, mode)).to(self._dev)
-            self._recv_buf[key] = torch.empty(self._slot_t[key].numel(), dtype=torch.float64, device=self._dev)
+        key = self._exchange_buffers(rd, cd, mode)
         ssz, rsz = self.plan.split_sizes(rd, cd, mode)
         n_owned_vals = self.pat.nnz_owned(rd, cd, mode)
         send = values[n_owned_vals:]
@@ -333,3 +373,6 @@ class DistributedElasticity(DistributedMatrixAssembler):
 
     def exchange(self, values):
         super().exchange(values, self.dim, self.dim, BLOCK_FULL)
+
+    def assemble_linelas_overlapped(self, values, lam, mu):
+        self.assemble_overlapped(values, self.dim, self.dim, BLOCK_FULL, lambda: self.pat.assemble_linelas_d(values, lam, mu))

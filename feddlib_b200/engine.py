@@ -53,6 +53,10 @@ class Context:
     def scatter_mode(self) -> int:
         return self._L.feddb200_get_scatter_mode(self._h)
 
+    def set_row_phase(self, phase: int):
+        """0 all rows, 1 geometry + ghost rows, 2 owned rows (feddb200_set_row_phase)."""
+        check(self._L.feddb200_set_row_phase(self._h, int(phase)))
+
     def synchronize(self):
         check(self._L.feddb200_synchronize(self._h))
 

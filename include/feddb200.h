@@ -61,6 +61,15 @@ int  feddb200_set_stream(feddb200_ctx *ctx, void *cuda_stream);
 int  feddb200_use_own_stream(feddb200_ctx *ctx);
 int  feddb200_set_scatter_mode(feddb200_ctx *ctx, int mode);
 int  feddb200_get_scatter_mode(const feddb200_ctx *ctx);
+/* Row phases of the gather mode, for overlapping the ghost-row exchange with the assembly of the owned rows:
+ * ROWS_GHOST = geometry pre-pass + the rows owned by other ranks (their values, contiguous behind the owned
+ * ones, can be shipped as soon as this call's work is done); ROWS_OWNED = the owned rows, using the geometry
+ * of the preceding ROWS_GHOST call on the same pattern; ROWS_ALL (default) = both.  The atomic and coloured
+ * modes do everything in the ROWS_GHOST call. */
+#define FEDDB200_ROWS_ALL   0
+#define FEDDB200_ROWS_GHOST 1
+#define FEDDB200_ROWS_OWNED 2
+int  feddb200_set_row_phase(feddb200_ctx *ctx, int phase);
 int  feddb200_synchronize(feddb200_ctx *ctx);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 int64_t feddb200_launch_count(const feddb200_ctx *ctx);

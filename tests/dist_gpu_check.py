@@ -64,8 +64,18 @@ def main():
         assert rel <= 1e-12, f"rank {rank} mode {mode}: relative Frobenius error {rel:.3e}"
         tot = torch.tensor([checked], device="cuda"); dist.all_reduce(tot)
         assert int(tot) == Gs.nnz
+        # overlapped variant (ghost rows first, exchange concurrent with the owned rows): same owned values, bitwise
+        values2 = ctx.empty_values(pat.nnz(dim, dim, BLOCK_FULL))
+        values2.fill_(float("nan"))
+        run.assemble_linelas_overlapped(values2, lam, mu)
+        ctx.synchronize()
+        n_owned_vals = pat.nnz_owned(dim, dim, BLOCK_FULL)
+        if mode == "atomic":   # atomics: summation order not fixed
+            assert torch.allclose(values2[:n_owned_vals], values[:n_owned_vals], rtol=1e-12, atol=1e-6), f"rank {rank} mode {mode}: overlapped exchange differs"
+        else:
+            assert torch.equal(values2[:n_owned_vals], values[:n_owned_vals]), f"rank {rank} mode {mode}: overlapped exchange differs"
         print(f"[dist_gpu_check] rank {rank}/{world} mode {mode}: owned rows {plan.n_owned}, ghost rows {plan.n_ghost}, "
-              f"rel. error {rel:.2e} OK", flush=True)
+              f"rel. error {rel:.2e} OK (overlapped exchange equal)", flush=True)
     dist.destroy_process_group()
 
 
