@@ -101,10 +101,9 @@ int ensure_gather(feddb200_pat *p)
     if (p->gather_ready) return FEDDB200_OK;
     feddb200_ctx *c = p->ctx;
     const int dim = p->rm->dim, nl = p->rm->nloc;
-    FB_LOGIC(p->rm->nloc != p->cm->nloc, "gather path needs a square pattern");
     const int64_t n_rows = p->n_rows;
-    p->rec_words = nl <= 6 ? 4 : 8;
-    FB_LOGIC(nl == 6 && p->rm->ne >= (int64_t(1) << 24), "gather path supports up to 2^24 P2 triangles per GPU");
+    const int nlc = p->cm->nloc;
+    p->rec_words = nlc <= 4 ? 4 : 8;
     FB_LOGIC(p->max_len >= 0xffff, "gather path supports node rows of up to 65534 entries");
     FB_CUDA(cudaMalloc(&p->rec_d, sizeof(uint32_t) * std::max<int64_t>(p->n_inc * p->rec_words, 1)));
     int8_t *rtype_d = nullptr;
@@ -114,13 +113,20 @@ int ensure_gather(feddb200_pat *p)
     const int use_ring = getenv("FEDDB200_NO_RING") == nullptr; // tuning aid: generic kernel for every edge row
     if (n_rows > 0) {
         const int grid = (int)std::min<int64_t>((n_rows + 127) / 128, 148 * 64);
-        switch (elem_index(dim, nl)) {
-        case 0: k_make_records<2, 3><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->rowptr_d, p->pos_d, p->pos_stride, p->rm->conn_d, use_ring, p->rec_d, rtype_d, sig_d); break;
-        case 1: k_make_records<2, 6><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->rowptr_d, p->pos_d, p->pos_stride, p->rm->conn_d, use_ring, p->rec_d, rtype_d, sig_d); break;
-        case 2: k_make_records<3, 4><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->rowptr_d, p->pos_d, p->pos_stride, p->rm->conn_d, use_ring, p->rec_d, rtype_d, sig_d); break;
-        case 3: k_make_records<3, 10><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->rowptr_d, p->pos_d, p->pos_stride, p->rm->conn_d, use_ring, p->rec_d, rtype_d, sig_d); break;
-        default: set_error("unsupported element"); return FEDDB200_ELOGIC;
+#define FB_MKREC(D, NR, NC) k_make_records<D, NR, NC><<<grid, 128, 0, c->stream>>>(n_rows, p->inc_ptr_d, p->inc_d, p->rowptr_d, p->pos_d, p->pos_stride, p->rm->conn_d, use_ring, p->rec_d, rtype_d, sig_d)
+        const int combo = dim * 10000 + nl * 100 + nlc;
+        switch (combo) {
+        case 20303: FB_MKREC(2, 3, 3); break;
+        case 20606: FB_MKREC(2, 6, 6); break;
+        case 30404: FB_MKREC(3, 4, 4); break;
+        case 31010: FB_MKREC(3, 10, 10); break;
+        case 20306: FB_MKREC(2, 3, 6); break;   // B:   P1 pressure rows x P2 velocity columns
+        case 20603: FB_MKREC(2, 6, 3); break;   // B^T
+        case 30410: FB_MKREC(3, 4, 10); break;
+        case 31004: FB_MKREC(3, 10, 4); break;
+        default: set_error("gather path: unsupported combination of row and column elements"); return FEDDB200_ELOGIC;
         }
+#undef FB_MKREC
         c->launches++;
         FB_CUDA(cudaGetLastError());
     }
@@ -308,6 +314,157 @@ int launch_gather(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
     return FEDDB200_ELOGIC;
 }
 
+// coefficient tensors of the operator gather kernels (kernels.cuh: OpCoef), from the operators' own quadrature
+// tables: c_{jt} = coefficient of G_t in grad phi_j (P2 vertex v: 4 lambda_v - 1 on v; edge (p,q): 4 lambda_q on p,
+// 4 lambda_p on q; P1: 1); canonical row node i' = vertex 0 (type 0) or edge (0,1) (type 1).
+void op_coefficients(const OpTables &t, int dim, int nl_vel, OpCoef &C, int what /*0 N+W, 1 B, 2 BT*/)
+{
+    const int nv = dim + 1;
+    const bool p2 = nl_vel > nv;
+    static const int E2[3][2] = {{0, 1}, {1, 2}, {0, 2}};
+    static const int E3[6][2] = {{0, 1}, {1, 2}, {0, 2}, {0, 3}, {1, 3}, {2, 3}};
+    auto sv = [&](int j, int k) { return j < nv ? j : (dim == 2 ? E2[j - nv][k] : E3[j - nv][k]); };
+    auto cgrad = [&](const double *lam, int j, int tt) { // coefficient of G_{sv(j,tt)} in grad phi_j
+        if (!p2) return 1.0;
+        return j < nv ? 4.0 * lam[j] - 1.0 : 4.0 * lam[sv(j, 1 - tt)];
+    };
+    const int ntypes = p2 ? 2 : 1;
+    for (int q = 0; q < t.nq; q++) {
+        const double *lam = &t.lam[q * 4];
+        const double w = t.w[q];
+        if (what == 0) {
+            const double *phi = &t.phi[q * t.np];
+            for (int type = 0; type < ntypes; type++) {
+                const int ir = type == 0 ? 0 : nv;
+                for (int j = 0; j < nl_vel; j++) {
+                    for (int m = 0; m < nl_vel; m++)
+                        for (int tt = 0; tt < (j < nv ? 1 : 2); tt++) C.TN[type][m][j][tt] += w * phi[ir] * phi[m] * cgrad(lam, j, tt);
+                    for (int v = 0; v < nv; v++) C.MW[type][j][v] += w * lam[v] * phi[ir] * phi[j];
+                }
+            }
+        } else if (what == 1) {
+            const double psi0 = t.phi[q * t.np + 0];
+            for (int j = 0; j < nl_vel; j++)
+                for (int tt = 0; tt < (j < nv ? 1 : 2); tt++) C.BC[j][tt] += w * psi0 * cgrad(lam, j, tt);
+        } else {
+            for (int type = 0; type < ntypes; type++) {
+                const int ir = type == 0 ? 0 : nv;
+                for (int j = 0; j < t.np && j < 4; j++)
+                    for (int s2 = 0; s2 < (type == 0 ? 1 : 2); s2++) C.BTC[type][j][s2] += w * t.phi[q * t.np + j] * cgrad(lam, ir, s2);
+            }
+        }
+    }
+}
+
+template <int OPX, int DIM, int NLR, int NL>
+int launch_gatherx_t(feddb200_ctx *c, feddb200_pat *p, const feddb200_mesh *vm, const double *u_d, double *values_d)
+{
+    using S = OpXShape<OPX, DIM>;
+    constexpr int NLV = OPX == X_BT ? NLR : NL; // nodes of the velocity space
+    const int64_t ne = p->rm->ne;
+    if (ne > 0) {
+        k_geom<DIM, NLV><<<(unsigned)((ne + 255) / 256), 256, 0, c->stream>>>(ne, vm->conn_d, vm->coords_d, p->geom_d);
+        c->launches++;
+        if constexpr (S::SQUARE) {
+            if (!p->uel_d) {
+                FB_CUDA(cudaMalloc(&p->uel_d, sizeof(double) * 4 * NLV * ne));
+                FB_CUDA(cudaMalloc(&p->dt_d, sizeof(double) * 4 * DIM * DIM * ne));
+            }
+            k_udata<DIM, NLV><<<(unsigned)((ne + 255) / 256), 256, 0, c->stream>>>(ne, vm->conn_d, p->geom_d, u_d, p->uel_d, p->dt_d,
+                                                                                   OPX != X_ADV);
+            c->launches++;
+        }
+    }
+    GatherXArgs G;
+    G.rowinfo = (const RowInfo *)p->rowinfo_d; G.rec = p->rec_d; G.geom = p->geom_d; G.uel = p->uel_d; G.dt = p->dt_d;
+    G.values = values_d;
+    const size_t budget = c->smem_optin - 1024;
+    for (const Bucket &b : p->buckets) {
+        if ((c->row_phase == FEDDB200_ROWS_GHOST && !b.ghost) || (c->row_phase == FEDDB200_ROWS_OWNED && b.ghost)) continue;
+        G.start = b.start; G.count = b.count;
+        G.pitch = (S::NB * b.lcap) | 1;
+        int nt = 64;
+        while (nt > 32 && (size_t)G.pitch * 8 * nt > budget) nt -= 32;
+        const size_t smem = (size_t)G.pitch * 8 * nt;
+        FB_LOGIC(smem > budget, "row too long for the gather path's shared-memory accumulators; use the coloured or atomic mode");
+        const int64_t blocks = (b.count * S::RD + nt - 1) / nt;
+        auto launch = [&](auto kernel) -> int {
+            FB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+            kernel<<<(unsigned)blocks, nt, smem, c->stream>>>(G);
+            c->launches++;
+            FB_CUDA(cudaGetLastError());
+            return FEDDB200_OK;
+        };
+        int rc;
+        if (b.type == 0) rc = launch(k_gatherx<OPX, DIM, NLR, NL, 0>);
+        else {
+            if constexpr (NLR > DIM + 1) rc = launch(k_gatherx<OPX, DIM, NLR, NL, 1>);
+            else { set_error("edge-node row in a P1 row space"); rc = FEDDB200_ELOGIC; }
+        }
+        if (rc != FEDDB200_OK) return rc;
+    }
+    return FEDDB200_OK;
+}
+
+// returns 1 if this (operator, element) combination has no gather kernel (the caller falls back to the coloured mode)
+int launch_gatherx(feddb200_ctx *c, feddb200_pat *p, int op, const feddb200_mesh *vm, const double *u_d, double c0, double c1,
+                   double c2, double *values_d, int *handled)
+{
+    const int dim = p->rm->dim, nr = p->rm->nloc, nc = p->cm->nloc;
+    const int combo = dim * 10000 + nr * 100 + nc;
+    *handled = 0;
+    const bool square = (op == OP_ADV || op == OP_ADVU || op == OP_NSJ);
+    if (square && !(combo == 20303 || combo == 20606 || combo == 30404 || combo == 31010)) return FEDDB200_OK;
+    if (op == OP_B && !(combo == 20306 || combo == 30410 || combo == 20303 || combo == 30404)) return FEDDB200_OK;
+    if (op == OP_BT && !(combo == 20603 || combo == 31004 || combo == 20303 || combo == 30404)) return FEDDB200_OK;
+    int rc = ensure_gather(p);
+    if (rc != FEDDB200_OK) return rc;
+    // coefficient tensors -> constant memory (stream ordered)
+    OpCoef C;
+    std::memset(&C, 0, sizeof(C));
+    OpTables t;
+    if (square) {
+        if (build_tables(t, OP_ADV, dim, nr, nr) != 0) { set_error("no tables"); return FEDDB200_ELOGIC; }
+        op_coefficients(t, dim, nr, C, 0);
+        if (op == OP_NSJ) {
+            OpTables tl;
+            if (build_tables(tl, OP_LAP, dim, nr, nr) != 0) { set_error("no tables"); return FEDDB200_ELOGIC; }
+            CanonR R;
+            canon_table(tl, dim, nr, R);
+            std::memcpy(C.RL, R.r, sizeof(C.RL));
+        }
+    } else {
+        const int nvel = op == OP_B ? nc : nr, npre = op == OP_B ? nr : nc;
+        if (build_tables(t, op, dim, nvel, npre) != 0) { set_error("no tables"); return FEDDB200_ELOGIC; }
+        op_coefficients(t, dim, nvel, C, op == OP_B ? 1 : 2);
+    }
+    C.c0 = c0; C.c1 = c1; C.c2 = c2;
+    FB_CUDA(cudaMemcpyToSymbolAsync(g_coef, &C, sizeof(OpCoef), 0, cudaMemcpyHostToDevice, c->stream));
+    FB_CUDA(cudaStreamSynchronize(c->stream)); // C is a stack object
+    *handled = 1;
+#define FB_GX(OPX, D, NR, NC) return launch_gatherx_t<OPX, D, NR, NC>(c, p, vm, u_d, values_d)
+    switch (op) {
+    case OP_ADV:
+        switch (combo) { case 20303: FB_GX(X_ADV, 2, 3, 3); case 20606: FB_GX(X_ADV, 2, 6, 6); case 30404: FB_GX(X_ADV, 3, 4, 4); case 31010: FB_GX(X_ADV, 3, 10, 10); }
+        break;
+    case OP_ADVU:
+        switch (combo) { case 20303: FB_GX(X_ADVU, 2, 3, 3); case 20606: FB_GX(X_ADVU, 2, 6, 6); case 30404: FB_GX(X_ADVU, 3, 4, 4); case 31010: FB_GX(X_ADVU, 3, 10, 10); }
+        break;
+    case OP_NSJ:
+        switch (combo) { case 20303: FB_GX(X_NSJ, 2, 3, 3); case 20606: FB_GX(X_NSJ, 2, 6, 6); case 30404: FB_GX(X_NSJ, 3, 4, 4); case 31010: FB_GX(X_NSJ, 3, 10, 10); }
+        break;
+    case OP_B:
+        switch (combo) { case 20306: FB_GX(X_B, 2, 3, 6); case 30410: FB_GX(X_B, 3, 4, 10); case 20303: FB_GX(X_B, 2, 3, 3); case 30404: FB_GX(X_B, 3, 4, 4); }
+        break;
+    case OP_BT:
+        switch (combo) { case 20603: FB_GX(X_BT, 2, 6, 3); case 31004: FB_GX(X_BT, 3, 10, 4); case 20303: FB_GX(X_BT, 2, 3, 3); case 30404: FB_GX(X_BT, 3, 4, 4); }
+        break;
+    }
+#undef FB_GX
+    set_error("gather path: internal dispatch error");
+    return FEDDB200_ELOGIC;
+}
+
 // common driver of every assembly call
 int run_op(feddb200_ctx *c, const feddb200_pat *pc, int op, const double *u_d, double c0, double c1, double c2,
            int vec_field, double *values_d)
@@ -340,7 +497,15 @@ int run_op(feddb200_ctx *c, const feddb200_pat *pc, int op, const double *u_d, d
     if (nnz == 0) return FEDDB200_OK;
 
     int mode = c->mode;
-    if (mode == FEDDB200_SCATTER_GATHER && !(op == OP_LAP || op == OP_ELAS)) mode = FEDDB200_SCATTER_COLOURED;
+    if (mode == FEDDB200_SCATTER_GATHER && !(op == OP_LAP || op == OP_ELAS)) {
+        int handled = 0;
+        if (getenv("FEDDB200_NO_GATHERX") == nullptr) { // tuning aid
+            rc = launch_gatherx(c, p, op, vm, u_d, c0, c1, c2, values_d, &handled);
+            if (rc != FEDDB200_OK || handled) return rc;
+        }
+        mode = FEDDB200_SCATTER_COLOURED; // no gather kernel for this combination of elements
+    }
+    if (mode == FEDDB200_SCATTER_GATHER && rm->nloc != cm->nloc) mode = FEDDB200_SCATTER_COLOURED;
 
     if (mode == FEDDB200_SCATTER_GATHER) {
         rc = ensure_gather(p);

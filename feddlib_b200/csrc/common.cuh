@@ -102,6 +102,8 @@ struct feddb200_pat {
     void *rowinfo_d = nullptr;     // [n_rows] RowInfo records in bucket order
     int rec_words = 0;
     double *geom_d = nullptr;      // [ne][GS] per-element geometry cache, recomputed by every assembly
+    double *uel_d = nullptr;       // [ne][nloc][4] nodal velocities of each element (operators with a velocity argument)
+    double *dt_d = nullptr;        // [ne][dim][dim][4] |det| * grad u at the element's vertices
     bool gather_ready = false;
     std::vector<fb::Bucket> buckets;
     // element colouring (lazy)

@@ -416,32 +416,38 @@ __host__ __device__ inline int canon_node(const int (&pi)[DIM + 1], int jc)
 // index and the canonical vertex permutation -- packed so that a thread fetches it with ONE
 // vector load:
 //   NL <= 4 : 16 B = pos[4] u16 | element u32 | perm u32
-//   NL == 6 : 16 B = pos[6] u16 | (element << 8 | perm) u32           (<= 2^24 elements)
-//   NL == 10: 32 B = pos[10] u16 | element u32 | perm u32 | spare u32 | spare u32
-// perm = pi(3)<<6 | pi(2)<<4 | pi(1)<<2 | pi(0)
+//   NL 6, 10: 32 B = pos[NL] u16 (words 0-4) | element u32 | perm u32 | natural-index word
+// (NL = nodes of the COLUMN space).  perm word: bits 0-7 pi(3)<<6 | pi(2)<<4 | pi(1)<<2 | pi(0), bits 8-9 ring
+// flags (k_ring), bits 16-23 natural local index of canonical nodes 8, 9; the last word holds the natural local
+// index (4 bits each) of canonical nodes 0..7 -- the operators with a velocity argument use it to fetch the
+// element's nodal values in canonical order.
 // -----------------------------------------------------------------------------------------
-template <int NL> struct RecWords { static constexpr int value = NL <= 6 ? 4 : 8; };
+template <int NL> struct RecWords { static constexpr int value = NL <= 4 ? 4 : 8; };
 
 template <int NL>
-__host__ __device__ inline void rec_pack_code(uint32_t *w, uint32_t e, uint32_t perm)
+__host__ __device__ inline void rec_pack_code(uint32_t *w, uint32_t e, uint32_t perm, uint64_t natidx = 0)
 {
     if constexpr (NL <= 4) { w[2] = e; w[3] = perm; }
-    else if constexpr (NL == 6) { w[3] = (e << 8) | perm; }
-    else { w[5] = e; w[6] = perm; w[7] = 0; }
+    else { w[5] = e; w[6] = perm | ((uint32_t)(natidx >> 32) & 0xffu) << 16; w[7] = (uint32_t)natidx; }
 }
 template <int NL>
 __device__ __forceinline__ uint32_t rec_elem(const uint32_t (&w)[RecWords<NL>::value])
 {
     if constexpr (NL <= 4) return w[2];
-    else if constexpr (NL == 6) return w[3] >> 8;
     else return w[5];
 }
 template <int NL>
 __device__ __forceinline__ uint32_t rec_perm(const uint32_t (&w)[RecWords<NL>::value])
 {
     if constexpr (NL <= 4) return w[3];
-    else if constexpr (NL == 6) return w[3] & 0xffu;
     else return w[6];
+}
+// natural local index of canonical node jc (P1: the permutation itself)
+template <int NL>
+__device__ __forceinline__ int rec_natidx(const uint32_t (&w)[RecWords<NL>::value], int jc)
+{
+    if constexpr (NL <= 4) return (int)((w[3] >> (2 * jc)) & 3);
+    else return jc < 8 ? (int)((w[7] >> (4 * jc)) & 15) : (int)((w[6] >> (16 + 4 * (jc - 8))) & 15);
 }
 
 __host__ __device__ inline uint64_t sig_mix(uint64_t h, uint32_t v)
@@ -534,12 +540,13 @@ __device__ inline bool ring_order(int ninc, const int32_t *__restrict__ inc_row,
 // sig[row] = hash of the row's stencil shape (row length, permutations, flags and positions of all
 // incidences, NOT the element indices): rows with equal signatures address their accumulators identically
 // and are grouped into the same warps (bank-conflict-free shared-memory accesses).
-template <int DIM, int NL>
+template <int DIM, int NLR, int NL>
 __global__ void k_make_records(int64_t n_rows, const int64_t *__restrict__ inc_ptr, const int32_t *__restrict__ inc,
                                const int64_t *__restrict__ rowptr, const uint16_t *__restrict__ pos, int pos_stride,
                                const int32_t *__restrict__ conn, int use_ring,
                                uint32_t *__restrict__ rec, int8_t *__restrict__ rtype, uint64_t *__restrict__ sig)
 {
+    // NLR / NL: local nodes of the row / column space (equal for the square operators)
     constexpr int RW = RecWords<NL>::value;
     for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x) {
         const int64_t kb = inc_ptr[r];
@@ -551,7 +558,7 @@ __global__ void k_make_records(int64_t n_rows, const int64_t *__restrict__ inc_p
         uint64_t seen[4] = {0, 0, 0, 0}; // positions that receive a local contribution (rows of up to 256 nodes)
         int order[RING_KMAX];
         uint32_t rperm[RING_KMAX], rflag[RING_KMAX];
-        if constexpr (DIM == 3 && NL == 10) {
+        if constexpr (DIM == 3 && NL == 10 && NLR == 10) {
             if (use_ring && ty == 1 && ninc <= RING_KMAX) ring = ring_order(ninc, inc + kb, conn, order, rperm, rflag);
         }
         for (int m = 0; m < ninc; m++) {
@@ -570,14 +577,17 @@ __global__ void k_make_records(int64_t n_rows, const int64_t *__restrict__ inc_p
             }
             uint32_t w[RW];
             for (int x = 0; x < RW; x++) w[x] = 0;
+            uint64_t natidx = 0;
             for (int jc = 0; jc < NL; jc++) {
-                const uint32_t p = pos[(e * NL + i) * pos_stride + canon_node<DIM>(pi, jc)];
+                const int jn = canon_node<DIM>(pi, jc);
+                natidx |= (uint64_t)jn << (4 * jc);
+                const uint32_t p = pos[(e * NLR + i) * pos_stride + jn];
                 w[jc >> 1] |= p << (16 * (jc & 1));
                 if (p < 256) seen[p >> 6] |= uint64_t(1) << (p & 63);
             }
             h = sig_mix(h, bits);
             for (int x = 0; x < (NL + 1) / 2; x++) h = sig_mix(h, w[x]);
-            rec_pack_code<NL>(w, (uint32_t)e, bits);
+            rec_pack_code<NL>(w, (uint32_t)e, bits, natidx);
             for (int x = 0; x < RW; x++) rec[(kb + m) * RW + x] = w[x];
         }
         // bit 4: some position of the row gets no local contribution (entries contributed by other ranks only,
@@ -1139,6 +1149,304 @@ __global__ void __launch_bounds__(64, FB_RING_MINBLOCKS) k_ring(const GatherArgs
 #pragma unroll
         for (int x = 0; x < 4; x++) raw[x] = rawn[x];
     }
+}
+
+// =========================================================================================
+// Row-gather kernels of the operators with their own coefficient tensors: advection N(u)
+// (FE_def.hpp:1685-1836), advection-in-u W(u) (:1839-1929), the fused Navier-Stokes (0,0) block, and the
+// divergence pair B / B^T (:1932-2148).  In barycentric form (grad phi_j = sum_t c_jt(lambda) G_t, P2 values
+// quadratic in lambda) every local entry is a contraction of per-element data with a CONSTANT tensor that the
+// host forms once from the operator's own quadrature rule (api.cu: op_coefficients), e.g.
+//   N_ij     = |det| sum_{m,t} TN[i][m][j][t] (u_m . G_t)           160 FMA per local row instead of 15 points
+//   W_ij^ab  = |det| sum_v     MW[i][j][v] D^(v)[b][a]              (D = sum_m u_m (x) grad phi_m is affine)
+//   B_i,(j,d)= |det| sum_t     BC[j][t] G_t[d]
+// One thread per CSR dof row (I, a); accumulators in a shared-memory row laid out like the CSR row.
+// =========================================================================================
+struct OpCoef {
+    double TN[2][MAXN][MAXN][2];  // [row type][m'][j'][t']   sum_q w phi_i' phi_m' c_{j' t'}
+    double MW[2][MAXN][4];        // [row type][j'][v']       sum_q w lambda_v' phi_i' phi_j'
+    double RL[2][MAXN][2][2];     // Laplace part of the fused block, as CanonR
+    double BC[MAXN][2];           // B:   [j'][t']            sum_q w psi_0 c_{j' t'}
+    double BTC[2][4][2];          // B^T: [row type][j'][s']  sum_q w psi_j' c_{i' s'}
+    double c0, c1, c2;            // rho*nu, rho, rho (Newton) of the fused block
+};
+__constant__ OpCoef g_coef;
+
+// per-element velocity data (natural local order), written by k_udata after k_geom:
+//   uel[e][m]    = (u_m.x, u_m.y, u_m.z, 0)
+//   dt[e][a][b]  = |det| * (D^(v)[d2 = b][d1 = a] for the element's vertices v = 0..3)
+template <int DIM, int NL>
+__global__ void __launch_bounds__(256) k_udata(int64_t ne, const int32_t *__restrict__ conn, const double *__restrict__ geom,
+                                               const double *__restrict__ u, double *__restrict__ uel, double *__restrict__ dt,
+                                               int want_dt)
+{
+    constexpr int NVTX = DIM + 1, GS = GeomStride<DIM>::value;
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    double U[NL][DIM], G[NVTX][DIM];
+#pragma unroll
+    for (int m = 0; m < NL; m++) {
+        const int64_t n = conn[e * NL + m];
+        double *o = uel + (e * NL + m) * 4;
+#pragma unroll
+        for (int d = 0; d < DIM; d++) { U[m][d] = u[n * DIM + d]; o[d] = U[m][d]; }
+#pragma unroll
+        for (int d = DIM; d < 4; d++) o[d] = 0.0;
+    }
+    if (!want_dt) return;
+    const double *g = geom + e * GS;
+    double adet;
+    if constexpr (DIM == 3) {
+#pragma unroll
+        for (int v = 0; v < 4; v++)
+#pragma unroll
+            for (int d = 0; d < 3; d++) G[v][d] = g[4 * v + d];
+        adet = g[3];
+    } else {
+#pragma unroll
+        for (int v = 0; v < 3; v++) { G[v][0] = g[2 * v]; G[v][1] = g[2 * v + 1]; }
+        adet = g[6];
+    }
+#pragma unroll
+    for (int a = 0; a < DIM; a++)
+#pragma unroll
+        for (int b = 0; b < DIM; b++) {
+            double *o = dt + ((e * DIM + a) * DIM + b) * 4;
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                double s = 0.0;
+                if (v < NVTX) {
+                    if constexpr (NL == NVTX) { // P1: the gradient of u is constant
+#pragma unroll
+                        for (int w = 0; w < NVTX; w++) s += U[w][a] * G[w][b];
+                    } else {
+                        // grad phi_w(e_v) = (4 delta_wv - 1) G_w;  edge (p,q) containing v: 4 G_{other end}
+#pragma unroll
+                        for (int w = 0; w < NVTX; w++) s += (w == v ? 3.0 : -1.0) * U[w][a] * G[w][b];
+#pragma unroll
+                        for (int ed = 0; ed < NL - NVTX; ed++) {
+                            const int p = canon_sv<DIM>(NVTX + ed, 0), q = canon_sv<DIM>(NVTX + ed, 1);
+                            if (p == v) s += 4.0 * U[NVTX + ed][a] * G[q][b];
+                            if (q == v) s += 4.0 * U[NVTX + ed][a] * G[p][b];
+                        }
+                    }
+                }
+                o[v] = s * adet;
+            }
+        }
+}
+
+enum OpX { X_ADV = 0, X_ADVU = 1, X_NSJ = 2, X_B = 3, X_BT = 4 };
+template <int OPX, int DIM> struct OpXShape {
+    static constexpr int RD = (OPX == X_ADV || OPX == X_B) ? 1 : DIM;     // threads (row dofs) per row node
+    static constexpr int NB = (OPX == X_ADV || OPX == X_BT) ? 1 : DIM;    // values per column node in a thread's row
+    static constexpr bool SQUARE = OPX == X_ADV || OPX == X_ADVU || OPX == X_NSJ;
+};
+
+struct GatherXArgs {
+    const RowInfo *rowinfo;
+    int64_t start, count;
+    const uint32_t *rec;
+    const double *geom, *uel, *dt;
+    double *values;
+    int pitch;                // doubles per thread in shared memory (odd)
+};
+
+// the warp copies the 32 shared-memory rows of its threads to their CSR rows with coalesced stores
+__device__ __forceinline__ void warp_write_rows(const double *wbase, int pitch, int lane, int n, int64_t off, int nrep, double *values)
+{
+    const double *src = wbase + lane;
+#pragma unroll 1
+    for (int r = 0; r < 32; r++, src += pitch) {
+        const int nr = __shfl_sync(0xffffffffu, n, r);
+        const int64_t o = __shfl_sync(0xffffffffu, off, r);
+#pragma unroll 1
+        for (int d = 0; d < nrep; d++) {
+            double *out = values + o + (int64_t)d * nr + lane;
+            if (lane < nr) out[0] = src[0];
+            if (lane + 32 < nr) out[32] = src[32];
+            if (lane + 64 < nr) out[64] = src[64];
+            for (int x = lane + 96; x < nr; x += 32) out[x - lane] = src[x - lane];
+        }
+    }
+}
+
+// NLR / NL: local nodes of the row / column space;  TYPE: 0 vertex-node rows, 1 edge-node rows (of the row space)
+template <int OPX, int DIM, int NLR, int NL, int TYPE>
+__global__ void __launch_bounds__(64, 4) k_gatherx(const GatherXArgs A)
+{
+    using S = OpXShape<OPX, DIM>;
+    constexpr int RD = S::RD, NB = S::NB, NVTX = DIM + 1;
+    constexpr int NS = TYPE == 0 ? 1 : 2;
+    constexpr int JD = !S::SQUARE ? -1 : (TYPE == 0 ? 0 : NVTX); // column that is the row node itself
+    constexpr int GS = GeomStride<DIM>::value;
+    constexpr bool P2C = NL > NVTX;                                // P2 column space
+    extern __shared__ double acc[];                                // [blockDim.x][pitch]
+    const int NT = blockDim.x, tid = threadIdx.x, lane = tid & 31, pitch = A.pitch;
+    const int64_t t = blockIdx.x * (int64_t)NT + tid;
+    const bool live = t < A.count * RD;
+    const int64_t rloc = live ? t / RD : 0;
+    const int a = live ? (int)(t - rloc * RD) : 0;
+    int64_t base = 0, k0 = 0;
+    int L = 0, ninc = 0;
+    if (live) {
+        double raw[4];
+        ld_v4(reinterpret_cast<const double *>(A.rowinfo + A.start + rloc), raw);
+        base = __double_as_longlong(raw[0]);
+        k0 = __double_as_longlong(raw[1]);
+        const int64_t ln = __double_as_longlong(raw[2]);
+        L = (int)(ln & 0xffffffff);
+        ninc = (int)(ln >> 32);
+    }
+    double *wbase = acc + (size_t)(tid - lane) * pitch;
+    double *my = acc + (size_t)tid * pitch;
+    for (int x = lane; x < 32 * pitch; x += 32) wbase[x] = 0.0;
+    __syncwarp();
+
+    GatherArgs RA; // only .rec / .geom are used by the shared load helpers
+    RA.rec = A.rec; RA.geom = A.geom;
+    double dacc[NB];
+#pragma unroll
+    for (int b = 0; b < NB; b++) dacc[b] = 0.0;
+    int pdiag = 0;
+    IncRec<NL> rc, rn;
+    if (ninc > 0) load_rec<NL>(RA, k0, rc);
+    for (int k = 0; k < ninc; k++) {
+        if (k + 1 < ninc) load_rec<NL>(RA, k0 + k + 1, rn);
+        const uint32_t perm = rec_perm<NL>(rc.w);
+        const int64_t e = rec_elem<NL>(rc.w);
+        IncGeo<DIM> g;
+        if constexpr (OPX != X_ADVU) load_geo<DIM, NL>(RA, rc, g);
+        double val[NL][NB];
+#pragma unroll
+        for (int j = 0; j < NL; j++)
+#pragma unroll
+            for (int b = 0; b < NB; b++) val[j][b] = 0.0;
+
+        if constexpr (OPX == X_ADV || OPX == X_NSJ) {
+            // N_{i'j'} = sum_{m',t'} TN[m'][j'][t'] s[m'][t'],  s = |det| u_{m'} . G_{t'}   (added to column dof b = a only)
+            const double adet = g.G[0][3];
+            double vn[NL];
+#pragma unroll
+            for (int j = 0; j < NL; j++) vn[j] = 0.0;
+#pragma unroll
+            for (int m = 0; m < NL; m++) {
+                double um[4];
+                ld_v4(A.uel + (e * NL + rec_natidx<NL>(rc.w, m)) * 4, um);
+                double s[NVTX];
+#pragma unroll
+                for (int w = 0; w < NVTX; w++) {
+                    double x = 0.0;
+#pragma unroll
+                    for (int d = 0; d < DIM; d++) x += um[d] * g.G[w][d];
+                    s[w] = x * adet;
+                }
+#pragma unroll
+                for (int j = 0; j < NL; j++) {
+                    vn[j] += g_coef.TN[TYPE][m][j][0] * s[canon_sv<DIM>(j, 0)];
+                    if (P2C && j >= NVTX) vn[j] += g_coef.TN[TYPE][m][j][1] * s[canon_sv<DIM>(j, 1)];
+                }
+            }
+            if constexpr (OPX == X_ADV) {
+#pragma unroll
+                for (int j = 0; j < NL; j++) val[j][0] = vn[j];
+            } else {
+                // Laplace part: e[s][w] = |det| G_s . G_w
+                double el[NS][NVTX];
+#pragma unroll
+                for (int s2 = 0; s2 < NS; s2++)
+#pragma unroll
+                    for (int w = 0; w < NVTX; w++) {
+                        double x = 0.0;
+#pragma unroll
+                        for (int d = 0; d < DIM; d++) x += g.G[s2][d] * g.G[w][d];
+                        el[s2][w] = x * adet;
+                    }
+#pragma unroll
+                for (int j = 0; j < NL; j++) {
+                    double lap = 0.0;
+#pragma unroll
+                    for (int s2 = 0; s2 < NS; s2++) {
+                        lap += g_coef.RL[TYPE][j][s2][0] * el[s2][canon_sv<DIM>(j, 0)];
+                        if (P2C && j >= NVTX) lap += g_coef.RL[TYPE][j][s2][1] * el[s2][canon_sv<DIM>(j, 1)];
+                    }
+                    const double dg = g_coef.c0 * lap + g_coef.c1 * vn[j];
+#pragma unroll
+                    for (int b = 0; b < NB; b++) val[j][b] = (b == a) ? dg : 0.0;
+                }
+            }
+        }
+        if constexpr (OPX == X_ADVU || OPX == X_NSJ) {
+            // W^{ab}_{i'j'} = sum_{v'} MW[j'][v'] dt[a][b][pi(v')]
+            const double cw = OPX == X_NSJ ? g_coef.c2 : 1.0;
+#pragma unroll
+            for (int b = 0; b < DIM; b++) {
+                double dn[4], dv[NVTX];
+                ld_v4(A.dt + ((e * DIM + a) * DIM + b) * 4, dn);
+#pragma unroll
+                for (int v = 0; v < NVTX; v++) {
+                    const int pv = (perm >> (2 * v)) & 3;
+                    dv[v] = pv == 0 ? dn[0] : (pv == 1 ? dn[1] : (pv == 2 ? dn[2] : dn[3]));
+                }
+#pragma unroll
+                for (int j = 0; j < NL; j++) {
+                    double x = 0.0;
+#pragma unroll
+                    for (int v = 0; v < NVTX; v++) x += g_coef.MW[TYPE][j][v] * dv[v];
+                    val[j][b] += cw * x;
+                }
+            }
+        }
+        if constexpr (OPX == X_B) {
+            // row = pressure vertex (canonical vertex 0); B_{i',(j',d)} = |det| sum_t' BC[j'][t'] G_{t'}[d]
+            const double adet = g.G[0][3];
+#pragma unroll
+            for (int j = 0; j < NL; j++)
+#pragma unroll
+                for (int d = 0; d < DIM; d++) {
+                    double x = g_coef.BC[j][0] * g.G[canon_sv<DIM>(j, 0)][d];
+                    if (P2C && j >= NVTX) x += g_coef.BC[j][1] * g.G[canon_sv<DIM>(j, 1)][d];
+                    val[j][d] = x * adet;
+                }
+        }
+        if constexpr (OPX == X_BT) {
+            // row = velocity node i' dof a, columns = the element's pressure vertices (canonical order)
+            const double adet = g.G[0][3];
+#pragma unroll
+            for (int j = 0; j < NL; j++) {
+                double x = 0.0;
+#pragma unroll
+                for (int s2 = 0; s2 < NS; s2++) {
+                    const double ga = a == 0 ? g.G[s2][0] : (a == 1 ? g.G[s2][1] : g.G[s2][2]);
+                    x += g_coef.BTC[TYPE][j][s2] * ga;
+                }
+                val[j][0] = x * adet;
+            }
+        }
+        // accumulate: the row node's own column in registers, the others in the thread's shared-memory row
+#pragma unroll
+        for (int j = 0; j < NL; j++) {
+            if (j == JD) {
+                if (k == 0) pdiag = (int)((rc.w[j >> 1] >> (16 * (j & 1))) & 0xffffu) * NB;
+#pragma unroll
+                for (int b = 0; b < NB; b++) dacc[b] += val[j][b];
+            } else {
+                double *p = my + ((rc.w[j >> 1] >> (16 * (j & 1))) & 0xffffu) * NB;
+#pragma unroll
+                for (int b = 0; b < NB; b++) p[b] += val[j][b];
+            }
+        }
+        rc = rn;
+    }
+    if (JD >= 0 && ninc > 0) {
+#pragma unroll
+        for (int b = 0; b < NB; b++) my[pdiag + b] = dacc[b];
+    }
+    __syncwarp();
+    const int n = live ? NB * L : 0;
+    const int nrep = OPX == X_ADV ? DIM : 1;
+    const int64_t off = OPX == X_ADV ? (int64_t)DIM * base : (int64_t)RD * NB * base + (int64_t)a * n;
+    warp_write_rows(wbase, pitch, lane, n, off, nrep, A.values);
 }
 
 } // namespace fb
