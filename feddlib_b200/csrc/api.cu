@@ -254,10 +254,10 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
                 const int pitch = (TPR * b.lcap + 1) | 1; // one spare double: rows are shifted to the 16-byte phase of their destination
                 int nt = 64;
                 if (const char *f = getenv("FEDDB200_RING_NT")) nt = std::max(32, std::min(64, atoi(f) & ~31)); // tuning aid
+                const int64_t tiles = (b.count * TPR + nt - 1) / nt;
                 const size_t smem = (size_t)pitch * 8 * nt;
                 FB_LOGIC(smem > budget, "row too long for the gather path's shared-memory rows; use the coloured or atomic mode");
                 G.pitch = pitch;
-                const int64_t tiles = (b.count * TPR + nt - 1) / nt;
                 FB_CUDA(cudaFuncSetAttribute(k_ring<OPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
                 // persistent blocks: as many as are resident at once (times a small factor that evens out the tail)
                 int per_sm = 1;
