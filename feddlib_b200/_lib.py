@@ -60,6 +60,8 @@ SIGNATURES = {
     "feddb200_pattern_nnz_owned": (_i64, [_vp, C.c_int, C.c_int, C.c_int]),
     "feddb200_pattern_expand": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "feddb200_assemble_laplace_d": (C.c_int, [_vp, _vp, C.c_int, _vp]),
+    "feddb200_assemble_mass_d": (C.c_int, [_vp, _vp, C.c_int, _vp]),
+    "feddb200_assemble_mass": (C.c_int, [_vp, _vp, C.c_int, _vp]),
     "feddb200_assemble_linelas_d": (C.c_int, [_vp, _vp, C.c_double, C.c_double, _vp]),
     "feddb200_assemble_advection_d": (C.c_int, [_vp, _vp, _vp, _vp]),
     "feddb200_assemble_advection_in_u_d": (C.c_int, [_vp, _vp, _vp, _vp]),

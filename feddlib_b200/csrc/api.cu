@@ -83,6 +83,7 @@ int launch_elem_op(feddb200_ctx *c, int op, int dim, int nr, int nc, ElemArgs &A
     case OP_LAP:  return launch_elem<OP_LAP>(c, dim, nr, nc, A, atomic);
     case OP_ELAS: return launch_elem<OP_ELAS>(c, dim, nr, nc, A, atomic);
     case OP_ADV:  return launch_elem<OP_ADV>(c, dim, nr, nc, A, atomic);
+    case OP_MASS: return launch_elem<OP_MASS>(c, dim, nr, nc, A, atomic);
     case OP_ADVU: return launch_elem<OP_ADVU>(c, dim, nr, nc, A, atomic);
     case OP_NSJ:  return launch_elem<OP_NSJ>(c, dim, nr, nc, A, atomic);
     case OP_B:    return launch_elem<OP_B>(c, dim, nr, nc, A, atomic);
@@ -317,7 +318,7 @@ int launch_gather(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
 // coefficient tensors of the operator gather kernels (kernels.cuh: OpCoef), from the operators' own quadrature
 // tables: c_{jt} = coefficient of G_t in grad phi_j (P2 vertex v: 4 lambda_v - 1 on v; edge (p,q): 4 lambda_q on p,
 // 4 lambda_p on q; P1: 1); canonical row node i' = vertex 0 (type 0) or edge (0,1) (type 1).
-void op_coefficients(const OpTables &t, int dim, int nl_vel, OpCoef &C, int what /*0 N+W, 1 B, 2 BT*/)
+void op_coefficients(const OpTables &t, int dim, int nl_vel, OpCoef &C, int what /*0 N+W, 1 B, 2 BT, 3 mass*/)
 {
     const int nv = dim + 1;
     const bool p2 = nl_vel > nv;
@@ -342,6 +343,10 @@ void op_coefficients(const OpTables &t, int dim, int nl_vel, OpCoef &C, int what
                     for (int v = 0; v < nv; v++) C.MW[type][j][v] += w * lam[v] * phi[ir] * phi[j];
                 }
             }
+        } else if (what == 3) {
+            const double *phi = &t.phi[q * t.np];
+            for (int type = 0; type < ntypes; type++)
+                for (int j = 0; j < nl_vel; j++) C.MM[type][j] += w * phi[type == 0 ? 0 : nv] * phi[j];
         } else if (what == 1) {
             const double psi0 = t.phi[q * t.np + 0];
             for (int j = 0; j < nl_vel; j++)
@@ -357,7 +362,7 @@ void op_coefficients(const OpTables &t, int dim, int nl_vel, OpCoef &C, int what
 }
 
 template <int OPX, int DIM, int NLR, int NL>
-int launch_gatherx_t(feddb200_ctx *c, feddb200_pat *p, const feddb200_mesh *vm, const double *u_d, double *values_d)
+int launch_gatherx_t(feddb200_ctx *c, feddb200_pat *p, const feddb200_mesh *vm, const double *u_d, double *values_d, int vec_dim)
 {
     using S = OpXShape<OPX, DIM>;
     constexpr int NLV = OPX == X_BT ? NLR : NL; // nodes of the velocity space
@@ -365,7 +370,7 @@ int launch_gatherx_t(feddb200_ctx *c, feddb200_pat *p, const feddb200_mesh *vm, 
     if (ne > 0) {
         k_geom<DIM, NLV><<<(unsigned)((ne + 255) / 256), 256, 0, c->stream>>>(ne, vm->conn_d, vm->coords_d, p->geom_d);
         c->launches++;
-        if constexpr (S::SQUARE) {
+        if constexpr (S::NEEDS_U) {
             if (!p->uel_d) {
                 FB_CUDA(cudaMalloc(&p->uel_d, sizeof(double) * 4 * NLV * ne));
                 FB_CUDA(cudaMalloc(&p->dt_d, sizeof(double) * 4 * DIM * DIM * ne));
@@ -377,7 +382,7 @@ int launch_gatherx_t(feddb200_ctx *c, feddb200_pat *p, const feddb200_mesh *vm, 
     }
     GatherXArgs G;
     G.rowinfo = (const RowInfo *)p->rowinfo_d; G.rec = p->rec_d; G.geom = p->geom_d; G.uel = p->uel_d; G.dt = p->dt_d;
-    G.values = values_d;
+    G.values = values_d; G.vec_dim = vec_dim;
     const size_t budget = c->smem_optin - 1024;
     for (const Bucket &b : p->buckets) {
         if ((c->row_phase == FEDDB200_ROWS_GHOST && !b.ghost) || (c->row_phase == FEDDB200_ROWS_OWNED && b.ghost)) continue;
@@ -408,12 +413,12 @@ int launch_gatherx_t(feddb200_ctx *c, feddb200_pat *p, const feddb200_mesh *vm, 
 
 // returns 1 if this (operator, element) combination has no gather kernel (the caller falls back to the coloured mode)
 int launch_gatherx(feddb200_ctx *c, feddb200_pat *p, int op, const feddb200_mesh *vm, const double *u_d, double c0, double c1,
-                   double c2, double *values_d, int *handled)
+                   double c2, double *values_d, int vec_dim, int *handled)
 {
     const int dim = p->rm->dim, nr = p->rm->nloc, nc = p->cm->nloc;
     const int combo = dim * 10000 + nr * 100 + nc;
     *handled = 0;
-    const bool square = (op == OP_ADV || op == OP_ADVU || op == OP_NSJ);
+    const bool square = (op == OP_ADV || op == OP_ADVU || op == OP_NSJ || op == OP_MASS);
     if (square && !(combo == 20303 || combo == 20606 || combo == 30404 || combo == 31010)) return FEDDB200_OK;
     if (op == OP_B && !(combo == 20306 || combo == 30410 || combo == 20303 || combo == 30404)) return FEDDB200_OK;
     if (op == OP_BT && !(combo == 20603 || combo == 31004 || combo == 20303 || combo == 30404)) return FEDDB200_OK;
@@ -423,7 +428,10 @@ int launch_gatherx(feddb200_ctx *c, feddb200_pat *p, int op, const feddb200_mesh
     OpCoef C;
     std::memset(&C, 0, sizeof(C));
     OpTables t;
-    if (square) {
+    if (op == OP_MASS) {
+        if (build_tables(t, OP_MASS, dim, nr, nr) != 0) { set_error("no tables"); return FEDDB200_ELOGIC; }
+        op_coefficients(t, dim, nr, C, 3);
+    } else if (square) {
         if (build_tables(t, OP_ADV, dim, nr, nr) != 0) { set_error("no tables"); return FEDDB200_ELOGIC; }
         op_coefficients(t, dim, nr, C, 0);
         if (op == OP_NSJ) {
@@ -442,10 +450,13 @@ int launch_gatherx(feddb200_ctx *c, feddb200_pat *p, int op, const feddb200_mesh
     FB_CUDA(cudaMemcpyToSymbolAsync(g_coef, &C, sizeof(OpCoef), 0, cudaMemcpyHostToDevice, c->stream));
     FB_CUDA(cudaStreamSynchronize(c->stream)); // C is a stack object
     *handled = 1;
-#define FB_GX(OPX, D, NR, NC) return launch_gatherx_t<OPX, D, NR, NC>(c, p, vm, u_d, values_d)
+#define FB_GX(OPX, D, NR, NC) return launch_gatherx_t<OPX, D, NR, NC>(c, p, vm, u_d, values_d, vec_dim)
     switch (op) {
     case OP_ADV:
         switch (combo) { case 20303: FB_GX(X_ADV, 2, 3, 3); case 20606: FB_GX(X_ADV, 2, 6, 6); case 30404: FB_GX(X_ADV, 3, 4, 4); case 31010: FB_GX(X_ADV, 3, 10, 10); }
+        break;
+    case OP_MASS:
+        switch (combo) { case 20303: FB_GX(X_MASS, 2, 3, 3); case 20606: FB_GX(X_MASS, 2, 6, 6); case 30404: FB_GX(X_MASS, 3, 4, 4); case 31010: FB_GX(X_MASS, 3, 10, 10); }
         break;
     case OP_ADVU:
         switch (combo) { case 20303: FB_GX(X_ADVU, 2, 3, 3); case 20606: FB_GX(X_ADVU, 2, 6, 6); case 30404: FB_GX(X_ADVU, 3, 4, 4); case 31010: FB_GX(X_ADVU, 3, 10, 10); }
@@ -488,6 +499,7 @@ int run_op(feddb200_ctx *c, const feddb200_pat *pc, int op, const double *u_d, d
     int64_t factor;
     switch (op) {
     case OP_LAP:  factor = vec_field ? dim : 1; break;
+    case OP_MASS: factor = vec_field ? dim : 1; break;
     case OP_ADV:  factor = dim; break;
     case OP_B: case OP_BT: factor = dim; break;
     default:      factor = (int64_t)dim * dim; break;
@@ -500,7 +512,7 @@ int run_op(feddb200_ctx *c, const feddb200_pat *pc, int op, const double *u_d, d
     if (mode == FEDDB200_SCATTER_GATHER && !(op == OP_LAP || op == OP_ELAS)) {
         int handled = 0;
         if (getenv("FEDDB200_NO_GATHERX") == nullptr) { // tuning aid
-            rc = launch_gatherx(c, p, op, vm, u_d, c0, c1, c2, values_d, &handled);
+            rc = launch_gatherx(c, p, op, vm, u_d, c0, c1, c2, values_d, (op == OP_MASS && vec_field) ? dim : 0, &handled);
             if (rc != FEDDB200_OK || handled) return rc;
         }
         mode = FEDDB200_SCATTER_COLOURED; // no gather kernel for this combination of elements
@@ -522,7 +534,7 @@ int run_op(feddb200_ctx *c, const feddb200_pat *pc, int op, const double *u_d, d
     A.conn_r = rm->conn_d; A.conn_c = cm->conn_d; A.conn_v = vm->conn_d; A.coords = vm->coords_d;
     A.row_lid = p->row_lid_d; A.rowptr = p->rowptr_d; A.pos = p->pos_d; A.pos_stride = p->pos_stride;
     A.elems = nullptr; A.n_items = rm->ne; A.u = u_d; A.c0 = c0; A.c1 = c1; A.c2 = c2; A.tab = tab_d;
-    A.values = values_d; A.vec_dim = (op == OP_LAP && vec_field) ? dim : 0;
+    A.values = values_d; A.vec_dim = ((op == OP_LAP || op == OP_MASS) && vec_field) ? dim : 0;
     if (nnz > 0) FB_CUDA(cudaMemsetAsync(values_d, 0, sizeof(double) * nnz, c->stream));
     if (mode == FEDDB200_SCATTER_ATOMIC) return launch_elem_op(c, op, dim, nr, nc, A, true);
     rc = ensure_colouring(p);
@@ -589,6 +601,10 @@ extern "C" int feddb200_assemble_laplace_d(feddb200_ctx *c, const feddb200_pat *
 {
     return run_op(c, p, OP_LAP, nullptr, 0, 0, 0, vec_field, v);
 }
+extern "C" int feddb200_assemble_mass_d(feddb200_ctx *c, const feddb200_pat *p, int vec_field, double *v)
+{
+    return run_op(c, p, OP_MASS, nullptr, 0, 0, 0, vec_field, v);
+}
 extern "C" int feddb200_assemble_linelas_d(feddb200_ctx *c, const feddb200_pat *p, double lambda, double mu, double *v)
 {
     return run_op(c, p, OP_ELAS, nullptr, lambda, mu, 0, 0, v);
@@ -620,6 +636,13 @@ extern "C" int feddb200_assemble_laplace(feddb200_ctx *c, const feddb200_pat *p,
     const int64_t nnz = (vec_field ? p->rm->dim : 1) * p->nnz;
     return with_host_buffers(c, p, nnz, nullptr, 0, values,
                              [&](double *, double *v_d) { return feddb200_assemble_laplace_d(c, p, vec_field, v_d); });
+}
+extern "C" int feddb200_assemble_mass(feddb200_ctx *c, const feddb200_pat *p, int vec_field, double *values)
+{
+    FB_LOGIC(!p, "null pattern");
+    const int64_t nnz = (vec_field ? p->rm->dim : 1) * p->nnz;
+    return with_host_buffers(c, p, nnz, nullptr, 0, values,
+                             [&](double *, double *v_d) { return feddb200_assemble_mass_d(c, p, vec_field, v_d); });
 }
 extern "C" int feddb200_assemble_linelas(feddb200_ctx *c, const feddb200_pat *p, double lambda, double mu, double *values)
 {

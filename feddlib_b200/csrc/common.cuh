@@ -31,7 +31,7 @@ void set_error(const std::string &msg);
     } while (0)
 
 // operators of the hot path
-enum Op { OP_LAP = 0, OP_ELAS = 1, OP_ADV = 2, OP_ADVU = 3, OP_B = 4, OP_BT = 5, OP_NSJ = 6 };
+enum Op { OP_LAP = 0, OP_ELAS = 1, OP_ADV = 2, OP_ADVU = 3, OP_B = 4, OP_BT = 5, OP_NSJ = 6, OP_MASS = 7, OP_COUNT = 8 };
 
 // Reference-element tables of one operator (restated from the FE type and quadrature degree,
 // see tables.cu): weights, gradients of the "velocity" space, values of the "value" space.
@@ -69,7 +69,7 @@ struct feddb200_ctx {
     int sm_count = 148;
     size_t smem_optin = 0;
     fb::OpTables *tab_d = nullptr; // device copies of the operator tables, one slot per operator
-    int tab_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int tab_key[fb::OP_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
     void *scratch_d[2] = {nullptr, nullptr}; // grow-only device scratch of the host-pointer entry points
     size_t scratch_bytes[2] = {0, 0};
 };

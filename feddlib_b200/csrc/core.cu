@@ -60,7 +60,7 @@ extern "C" int feddb200_create(feddb200_ctx **out, int device)
         FB_CUDA(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
     }
     FB_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-    FB_CUDA(cudaMalloc(&c->tab_d, 8 * sizeof(OpTables)));
+    FB_CUDA(cudaMalloc(&c->tab_d, OP_COUNT * sizeof(OpTables)));
     *out = c;
     return FEDDB200_OK;
 }

@@ -132,6 +132,21 @@ class FE_b200 {
 
     void setScatterMode(int mode) { b200::check(feddb200_set_scatter_mode(ctx_, mode)); }
 
+    // FE::assemblyMass (FE_def.hpp:454-521): fieldType "Scalar" or "Vector" (same value on the dim diagonal blocks)
+    void assemblyMass(int dim, std::string FEType, std::string fieldType, MatrixPtr_Type &A, bool callFillComplete = true)
+    {
+        if (FEType == "P0") throw std::logic_error("Not implemented for P0");
+        const int loc = checkFE(dim, FEType);
+        const bool vec = fieldType == "Vector";
+        if (!vec && fieldType != "Scalar") throw std::logic_error("Specify valid vieldType for assembly of mass matrix.");
+        feddb200_pat *p = pattern(loc, loc);
+        b200::LocalCsr<SC, LO, GO> csr;
+        if (vec) expand(p, loc, dim, dim, FEDDB200_BLOCK_DIAG, csr);
+        else expand(p, loc, 1, 1, FEDDB200_BLOCK_SCALAR, csr);
+        b200::check(feddb200_assemble_mass(ctx_, p, vec ? 1 : 0, csr.values.data()));
+        seat_csr(A, csr, MapConstPtr_Type(), MapConstPtr_Type(), callFillComplete);
+    }
+
     // FE::assemblyLaplace (FE_def.hpp:604-667); `degree` is ignored exactly as in the reference (:626)
     void assemblyLaplace(int dim, std::string FEType, int /*degree*/, MatrixPtr_Type &A, bool callFillComplete = true,
                          int FELocExternal = -1)

@@ -156,6 +156,17 @@ __global__ void __launch_bounds__(128) k_elem(const ElemArgs A)
             if (A.vec_dim == 0) add_to<ATOMIC>(A.values + base + p, v);
             else for (int d = 0; d < DIM; d++) add_to<ATOMIC>(A.values + DIM * base + d * L + p, v);
         }
+    } else if constexpr (OP == OP_MASS) {
+        // M_ij = |det| sum_q w_q phi_i phi_j  (FE_def.hpp:493-500); "Vector": the same value on the DIM diagonal blocks
+#pragma unroll
+        for (int j = 0; j < NC; j++) {
+            double v = 0.0;
+            for (int q = 0; q < nq; q++) v += T.w[q] * T.phi[q * NP + i] * T.phi[q * NP + j];
+            v *= adet;
+            const int64_t p = pos[j];
+            if (A.vec_dim == 0) add_to<ATOMIC>(A.values + base + p, v);
+            else for (int d = 0; d < DIM; d++) add_to<ATOMIC>(A.values + DIM * base + d * L + p, v);
+        }
     } else if constexpr (OP == OP_ELAS) {
         const double lambda = A.c0, mu = A.c1;
         double acc[NC][DIM];
@@ -1178,6 +1189,7 @@ struct OpCoef {
     double RL[2][MAXN][2][2];     // Laplace part of the fused block, as CanonR
     double BC[MAXN][2];           // B:   [j'][t']            sum_q w psi_0 c_{j' t'}
     double BTC[2][4][2];          // B^T: [row type][j'][s']  sum_q w psi_j' c_{i' s'}
+    double MM[2][MAXN];           // mass: [row type][j']     sum_q w phi_i' phi_j'
     double c0, c1, c2;            // rho*nu, rho, rho (Newton) of the fused block
 };
 __constant__ OpCoef g_coef;
@@ -1246,11 +1258,12 @@ __global__ void __launch_bounds__(256) k_udata(int64_t ne, const int32_t *__rest
         }
 }
 
-enum OpX { X_ADV = 0, X_ADVU = 1, X_NSJ = 2, X_B = 3, X_BT = 4 };
+enum OpX { X_ADV = 0, X_ADVU = 1, X_NSJ = 2, X_B = 3, X_BT = 4, X_MASS = 5 };
 template <int OPX, int DIM> struct OpXShape {
-    static constexpr int RD = (OPX == X_ADV || OPX == X_B) ? 1 : DIM;     // threads (row dofs) per row node
-    static constexpr int NB = (OPX == X_ADV || OPX == X_BT) ? 1 : DIM;    // values per column node in a thread's row
-    static constexpr bool SQUARE = OPX == X_ADV || OPX == X_ADVU || OPX == X_NSJ;
+    static constexpr int RD = (OPX == X_ADV || OPX == X_B || OPX == X_MASS) ? 1 : DIM;   // threads (row dofs) per row node
+    static constexpr int NB = (OPX == X_ADV || OPX == X_BT || OPX == X_MASS) ? 1 : DIM;  // values per column node in a thread's row
+    static constexpr bool SQUARE = OPX == X_ADV || OPX == X_ADVU || OPX == X_NSJ || OPX == X_MASS;
+    static constexpr bool NEEDS_U = OPX == X_ADV || OPX == X_ADVU || OPX == X_NSJ;
 };
 
 struct GatherXArgs {
@@ -1260,6 +1273,7 @@ struct GatherXArgs {
     const double *geom, *uel, *dt;
     double *values;
     int pitch;                // doubles per thread in shared memory (odd)
+    int vec_dim;              // mass: 0 scalar, DIM = replicate to the DIM block-diagonal dof rows
 };
 
 // the warp copies the 32 shared-memory rows of its threads to their CSR rows with coalesced stores
@@ -1326,7 +1340,8 @@ __global__ void __launch_bounds__(64, 4) k_gatherx(const GatherXArgs A)
         const uint32_t perm = rec_perm<NL>(rc.w);
         const int64_t e = rec_elem<NL>(rc.w);
         IncGeo<DIM> g;
-        if constexpr (OPX != X_ADVU) load_geo<DIM, NL>(RA, rc, g);
+        if constexpr (OPX == X_MASS) g.G[0][3] = __ldg(RA.geom + e * GS + (DIM == 3 ? 3 : 6)); // only |det| is needed
+        else if constexpr (OPX != X_ADVU) load_geo<DIM, NL>(RA, rc, g);
         double val[NL][NB];
 #pragma unroll
         for (int j = 0; j < NL; j++)
@@ -1407,6 +1422,11 @@ __global__ void __launch_bounds__(64, 4) k_gatherx(const GatherXArgs A)
                 }
             }
         }
+        if constexpr (OPX == X_MASS) {
+            const double adet = g.G[0][3];
+#pragma unroll
+            for (int j = 0; j < NL; j++) val[j][0] = g_coef.MM[TYPE][j] * adet;
+        }
         if constexpr (OPX == X_B) {
             // row = pressure vertex (canonical vertex 0); B_{i',(j',d)} = |det| sum_t' BC[j'][t'] G_{t'}[d]
             const double adet = g.G[0][3];
@@ -1454,8 +1474,8 @@ __global__ void __launch_bounds__(64, 4) k_gatherx(const GatherXArgs A)
     }
     __syncwarp();
     const int n = live ? NB * L : 0;
-    const int nrep = OPX == X_ADV ? DIM : 1;
-    const int64_t off = OPX == X_ADV ? (int64_t)DIM * base : (int64_t)RD * NB * base + (int64_t)a * n;
+    const int nrep = OPX == X_ADV ? DIM : ((OPX == X_MASS && A.vec_dim != 0) ? A.vec_dim : 1);
+    const int64_t off = (OPX == X_ADV || OPX == X_MASS) ? (int64_t)nrep * base : (int64_t)RD * NB * base + (int64_t)a * n;
     warp_write_rows(wbase, pitch, lane, n, off, nrep, A.values);
 }
 

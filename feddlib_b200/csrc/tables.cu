@@ -115,7 +115,7 @@ static void basis_grad(int dim, int order, int i, const double *x, double *g)
     }
 }
 
-// quadrature degree each operator asks for (FE_def.hpp:626, 1770-1772, 1859-1861, 1963, 2758)
+// quadrature degree each operator asks for (FE_def.hpp:474, 626, 1770-1772, 1859-1861, 1963, 2758)
 static int op_degree(int op, int ov, int op_)
 {
     const int gradv = ov - 1, stdv = ov, stdp = op_;
@@ -128,6 +128,7 @@ static int op_degree(int op, int ov, int op_)
     case OP_NSJ:  deg = stdv + stdv + (gradv == 0 ? 1 : gradv); break;     // extra = degree of grad u_h (0 -> 1)
     case OP_B:
     case OP_BT:   deg = gradv + stdp; break;
+    case OP_MASS: deg = stdv + stdv; break;                                 // FE_def.hpp:474
     default: return -1;
     }
     return deg == 0 ? 1 : deg;

@@ -176,6 +176,9 @@ class Pattern:
     def assemble_laplace_d(self, values, vec_field=False):
         check(self.ctx._L.feddb200_assemble_laplace_d(self.ctx._h, self._h, int(bool(vec_field)), ptr(values)))
 
+    def assemble_mass_d(self, values, vec_field=False):
+        check(self.ctx._L.feddb200_assemble_mass_d(self.ctx._h, self._h, int(bool(vec_field)), ptr(values)))
+
     def assemble_linelas_d(self, values, lam, mu):
         check(self.ctx._L.feddb200_assemble_linelas_d(self.ctx._h, self._h, float(lam), float(mu), ptr(values)))
 
@@ -193,6 +196,11 @@ class Pattern:
     def assemble_laplace(self, vec_field=False):
         out = np.empty(self.nnz(self.dim, self.dim, BLOCK_DIAG) if vec_field else self.nnz(), dtype=np.float64)
         check(self.ctx._L.feddb200_assemble_laplace(self.ctx._h, self._h, int(bool(vec_field)), ptr(out)))
+        return out
+
+    def assemble_mass(self, vec_field=False):
+        out = np.empty(self.nnz(self.dim, self.dim, BLOCK_DIAG) if vec_field else self.nnz(), dtype=np.float64)
+        check(self.ctx._L.feddb200_assemble_mass(self.ctx._h, self._h, int(bool(vec_field)), ptr(out)))
         return out
 
     def assemble_linelas(self, lam, mu, out=None):

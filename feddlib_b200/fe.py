@@ -201,6 +201,22 @@ class FE:
         rowptr, colind = self._csr(pat, (id(drow), id(dcol)), rd, cd, mode)
         A._seat(self.ctx, rowptr, colind, values, colmap, domainMap or colmap, rangeMap or rowmap, callFillComplete)
 
+    # ---- FE_def.hpp:454-521 ----
+    def assemblyMass(self, dim, FEType, fieldType, A: Matrix, callFillComplete=True):
+        if FEType == "P0":
+            raise LogicError("Not implemented for P0")
+        d = self.domainVec_[self.checkFE(dim, FEType)]
+        if fieldType not in ("Scalar", "Vector"):
+            raise LogicError("Specify valid vieldType for assembly of mass matrix.")
+        vec = fieldType == "Vector"
+        pat = self._pattern(d, d)
+        values = self.ctx.empty_values(pat.nnz(dim, dim, BLOCK_DIAG) if vec else pat.nnz())
+        pat.assemble_mass_d(values, vec_field=vec)
+        if vec:
+            self._finish(A, d, d, pat, values, dim, dim, BLOCK_DIAG, callFillComplete)
+        else:
+            self._finish(A, d, d, pat, values, 1, 1, BLOCK_SCALAR, callFillComplete)
+
     # ---- FE_def.hpp:604-667 ----
     def assemblyLaplace(self, dim, FEType, degree, A: Matrix, callFillComplete=True, FELocExternal=-1):
         if FEType == "P0":

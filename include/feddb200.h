@@ -136,6 +136,9 @@ int  feddb200_pattern_expand(feddb200_ctx *ctx, const feddb200_pat *pat, int row
 /* FE::assemblyLaplace (core/FE/FE_def.hpp:604-667) [vec_field=0, BLOCK_SCALAR] and
  * FE::assemblyLaplaceVecField (:670-734) [vec_field=1, BLOCK_DIAG with dim dofs] */
 int  feddb200_assemble_laplace_d(feddb200_ctx *ctx, const feddb200_pat *pat, int vec_field, double *values_d);
+/* FE::assemblyMass (core/FE/FE_def.hpp:454-521): fieldType "Scalar" [vec_field=0, BLOCK_SCALAR] / "Vector"
+ * [vec_field=1, BLOCK_DIAG with dim dofs] -- SURVEY.md 8(f) rank 2 */
+int  feddb200_assemble_mass_d(feddb200_ctx *ctx, const feddb200_pat *pat, int vec_field, double *values_d);
 /* FE::assemblyLinElasXDim (core/FE/FE_def.hpp:2739-3040) [BLOCK_FULL, dim x dim] */
 int  feddb200_assemble_linelas_d(feddb200_ctx *ctx, const feddb200_pat *pat, double lambda, double mu, double *values_d);
 /* FE::assemblyAdvectionVecField (core/FE/FE_def.hpp:1685-1836) [BLOCK_DIAG]; u_rep_d is the
@@ -159,6 +162,7 @@ int  feddb200_assemble_ns_jacobian_d(feddb200_ctx *ctx, const feddb200_pat *pat,
 /* host-pointer forms of the same calls (what the glue uses when the matrix lives on the
  * host): H2D of u, D2H of the values inside the call */
 int  feddb200_assemble_laplace(feddb200_ctx *ctx, const feddb200_pat *pat, int vec_field, double *values);
+int  feddb200_assemble_mass(feddb200_ctx *ctx, const feddb200_pat *pat, int vec_field, double *values);
 int  feddb200_assemble_linelas(feddb200_ctx *ctx, const feddb200_pat *pat, double lambda, double mu, double *values);
 int  feddb200_assemble_advection(feddb200_ctx *ctx, const feddb200_pat *pat, const double *u_rep, double *values);
 int  feddb200_assemble_advection_in_u(feddb200_ctx *ctx, const feddb200_pat *pat, const double *u_rep, double *values);

@@ -544,6 +544,42 @@ int fo_assembly_laplace_vecfield(int dim, const char *fe, int64_t ne, const int3
     return 0;
 }
 
+/* FE_def.hpp:454-521 assemblyMass (fieldType "Scalar": vec_field = 0, "Vector": vec_field = 1).
+ * deg = determineDegree(Std, Std) (:474); only |det B| of the affine map is used (:489-491). */
+int fo_assembly_mass(int dim, const char *fe, int64_t ne, const int32_t *conn, const double *coords,
+                     const int64_t *gid, int vec_field, fo_matrix *A)
+{
+    int nloc = fo_nloc(dim, fe);
+    if (nloc < 0) return -1;
+    double phi[FO_MAXQ * FO_MAXN], w[FO_MAXQ];
+    int deg = fo_determine_degree2(dim, fe, fe, FO_STD, FO_STD, 0);
+    int nq = fo_get_phi(dim, fe, deg, phi, w);
+    if (nq < 0) return -1;
+    double value[FO_MAXN];
+    int64_t indices[FO_MAXN];
+    for (int64_t T = 0; T < ne; T++) {
+        const int32_t *el = conn + T * nloc;
+        double B[3][3];
+        fo_build_transformation(dim, el, coords, B);
+        double absDetB = fabs(fo_det(dim, B));
+        for (int i = 0; i < nloc; i++) {
+            for (int j = 0; j < nloc; j++) {
+                value[j] = 0.;
+                for (int q = 0; q < nq; q++) value[j] += w[q] * phi[q * nloc + i] * phi[q * nloc + j];
+                value[j] *= absDetB;
+                if (!vec_field) indices[j] = gid[el[j]];
+            }
+            if (!vec_field) fo_insert(A, gid[el[i]], nloc, indices, value);
+            else
+                for (int d = 0; d < dim; d++) {
+                    for (int j = 0; j < nloc; j++) indices[j] = dim * gid[el[j]] + d;
+                    fo_insert(A, dim * gid[el[i]] + d, nloc, indices, value);
+                }
+        }
+    }
+    return 0;
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* FE_def.hpp:2739-3040 assemblyLinElasXDim                                               */
 /* ------------------------------------------------------------------------------------ */

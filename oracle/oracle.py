@@ -44,6 +44,7 @@ def lib():
         common = [C.c_int, C.c_char_p, C.c_int64, _I32P, _F64P, _I64P]
         L.fo_assembly_laplace.argtypes = common + [C.c_void_p]
         L.fo_assembly_laplace_vecfield.argtypes = common + [C.c_void_p]
+        L.fo_assembly_mass.argtypes = common + [C.c_int, C.c_void_p]
         L.fo_assembly_linelas.argtypes = common + [C.c_double, C.c_double, C.c_void_p]
         L.fo_assembly_advection.argtypes = common + [_F64P, C.c_void_p]
         L.fo_assembly_advection_in_u.argtypes = common + [_F64P, C.c_void_p]
@@ -120,6 +121,12 @@ def _prep(conn, coords, gid):
 def assembly_laplace(dim, fe, conn, coords, gid, A: Matrix):
     conn, coords, gid = _prep(conn, coords, gid)
     _chk(lib().fo_assembly_laplace(dim, fe.encode(), conn.shape[0], conn, coords, gid, A._h), "assemblyLaplace")
+
+
+def assembly_mass(dim, fe, conn, coords, gid, A: Matrix, vec_field=False):
+    """FE::assemblyMass, fieldType "Scalar" / "Vector" (FE_def.hpp:454-521)."""
+    conn, coords, gid = _prep(conn, coords, gid)
+    _chk(lib().fo_assembly_mass(dim, fe.encode(), conn.shape[0], conn, coords, gid, int(bool(vec_field)), A._h), "assemblyMass")
 
 
 def assembly_laplace_vecfield(dim, fe, conn, coords, gid, A: Matrix):

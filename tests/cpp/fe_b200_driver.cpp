@@ -134,7 +134,8 @@ int main(int argc, char **argv)
 
         struct Case { const char *name; int op; int rowDofs; };
         const Case cases[] = {{"assemblyLaplace", 0, 1}, {"assemblyLaplaceVecField", 1, dim}, {"assemblyLinElasXDim", 2, dim},
-                              {"assemblyAdvectionVecField", 3, dim}, {"assemblyAdvectionInUVecField", 4, dim}};
+                              {"assemblyAdvectionVecField", 3, dim}, {"assemblyAdvectionInUVecField", 4, dim},
+                              {"assemblyMass Scalar", 7, 1}, {"assemblyMass Vector", 8, dim}};
         for (const Case &c : cases) {
             // reference
             fo_matrix *rA = fo_matrix_new(c.rowDofs * nglob1, 64), *rB = fo_matrix_new(1, 8);
@@ -150,6 +151,8 @@ int main(int argc, char **argv)
             case 2: fe.assemblyLinElasXDim(dim, fe1, A, lambda, mu); break;
             case 3: fe.assemblyAdvectionVecField(dim, fe1, A, uMV, true); break;
             case 4: fe.assemblyAdvectionInUVecField(dim, fe1, A, uMV, true); break;
+            case 7: fe.assemblyMass(dim, fe1, "Scalar", A); break;
+            case 8: fe.assemblyMass(dim, fe1, "Vector", A); break;
             }
             all = compare(c.name, g_seated[A.get()], ref, gid1, c.rowDofs) && all;
             all = (A->fillCompleteCalls_ == 1) && all;

@@ -66,6 +66,16 @@ def test_laplace(case, mode):
 
 
 @pytest.mark.parametrize("mode", MODES)
+def test_mass(case, mode):
+    """FE::assemblyMass, fieldType "Scalar" and "Vector" (FE_def.hpp:454-521; SURVEY.md 8(f) rank 2)."""
+    from feddlib_b200 import BLOCK_DIAG, BLOCK_SCALAR
+    case["ctx"].set_scatter_mode(mode)
+    check(case, "mass", case["pat"].assemble_mass(False), 1, 1, BLOCK_SCALAR)
+    d = case["dim"]
+    check(case, "mass_vec", case["pat"].assemble_mass(True), d, d, BLOCK_DIAG)
+
+
+@pytest.mark.parametrize("mode", MODES)
 def test_linear_elasticity(case, mode):
     from feddlib_b200 import BLOCK_FULL
     case["ctx"].set_scatter_mode(mode)

@@ -209,3 +209,29 @@ def test_unsupported_fe_type_is_an_error():
     conn, co, gid = OM.structured(3, "P1", 1, 1)
     with pytest.raises(ValueError):
         O.assembly_laplace(3, "P0", conn, co, gid, O.Matrix(co.shape[0]))
+
+
+@pytest.mark.parametrize("dim,fe,M", [(2, "P1", 5), (2, "P2", 4), (3, "P1", 3), (3, "P2", 2)])
+def test_mass_matrix_known_answers(dim, fe, M):
+    """assemblyMass: 1^T M 1 = |Omega| (partition of unity), M symmetric, and x^T M x = int x_0^2 = 1/3 exactly for the
+    coordinate function (P2 and P1 rules are exact for it only with P2; P1 checks the volume and symmetry)."""
+    from oracle import mesh as OM
+    conn, coords, gid = OM.structured(dim, fe, 1, M)
+    n = coords.shape[0]
+    A = O.Matrix(n, 64)
+    O.assembly_mass(dim, fe, conn, coords, gid, A, False)
+    S = A.scipy().tocsr()
+    one = np.ones(n)
+    assert abs(one @ (S @ one) - 1.0) < 1e-13
+    assert abs(S - S.T).max() < 1e-15
+    assert S.diagonal().min() > 0
+    if fe == "P2":
+        x = coords[:, 0]
+        assert abs(x @ (S @ x) - 1.0 / 3.0) < 1e-13
+    V = O.Matrix(dim * n, 64)
+    O.assembly_mass(dim, fe, conn, coords, gid, V, True)
+    Sv = V.scipy().tocsr()
+    for d in range(dim):   # "Vector": the scalar matrix on every diagonal block, nothing off the diagonal blocks
+        blk = Sv[d::dim, :][:, d::dim]
+        assert abs(blk - S).max() == 0.0
+    assert Sv.nnz == dim * S.nnz

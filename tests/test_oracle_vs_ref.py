@@ -23,7 +23,7 @@ CASES = [(2, "P1", lambda: mesh_structured(2, "P1", 5)), (2, "P2", lambda: mesh_
 def test_restatement_is_bitwise_equal_to_reference_code(dim, fe, make):
     conn, coords = make()
     u = random_u(dim, coords.shape[0])
-    for op, kw in (("laplace", {}), ("laplace_vec", {}), ("linelas", dict(lam=8e6, mu=2e6)),
+    for op, kw in (("mass", {}), ("mass_vec", {}), ("laplace", {}), ("laplace_vec", {}), ("linelas", dict(lam=8e6, mu=2e6)),
                    ("advection", dict(u=u)), ("advection_in_u", dict(u=u))):
         a = oracle_csr(op, dim, fe, conn, coords, **kw)
         b = R.assemble(op, dim, fe, conn, coords, **kw)

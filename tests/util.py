@@ -44,6 +44,10 @@ def oracle_csr(op, dim, fe, conn, coords, u=None, lam=None, mu=None, fe2=None, c
     gid = np.arange(nn, dtype=np.int64)
     if op == "laplace":
         A = O.Matrix(nn); O.assembly_laplace(dim, fe, conn, coords, gid, A)
+    elif op == "mass":
+        A = O.Matrix(nn); O.assembly_mass(dim, fe, conn, coords, gid, A, False)
+    elif op == "mass_vec":
+        A = O.Matrix(dim * nn); O.assembly_mass(dim, fe, conn, coords, gid, A, True)
     elif op == "laplace_vec":
         A = O.Matrix(dim * nn); O.assembly_laplace_vecfield(dim, fe, conn, coords, gid, A)
     elif op == "linelas":
