@@ -555,6 +555,37 @@ __global__ void k_unpack_add(double *__restrict__ values, const double *__restri
         atomicAdd(values + slot[t], recv[t]);
 }
 
+// BCBuilder::setLocalRowOne / setLocalRowZero (core/General/BCBuilder_def.hpp:653-709) on the resident CSR values:
+// one warp per owned row node; for every dof a selected by the node's mask the dof row is zeroed and, on a diagonal
+// block, its diagonal entry set to one.
+__global__ void k_dirichlet_rows(int64_t n_owned, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
+                                 const uint8_t *__restrict__ mask, int rd, int cd, int diag_layout, int diagonal_block,
+                                 double *__restrict__ values)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t I = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (I >= n_owned) return;
+    const unsigned m = mask[I];
+    if (m == 0) return;
+    const int64_t b0 = rowptr[I];
+    const int L = (int)(rowptr[I + 1] - b0);
+    const int per = diag_layout ? 1 : cd;          // values per column node in a dof row
+    int pd = -1;                                   // position of the row node's own column (owned node I <-> column I)
+    if (diagonal_block) {
+        int lo = 0, hi = L;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (colind[b0 + mid] < (int32_t)I) lo = mid + 1; else hi = mid; }
+        if (lo < L && colind[b0 + lo] == (int32_t)I) pd = lo;
+    }
+    for (int a = 0; a < rd; a++) {
+        if (!((m >> a) & 1u)) continue;
+        double *row = values + (int64_t)rd * per * b0 + (int64_t)a * per * L;
+        for (int x = lane; x < per * L; x += 32) row[x] = 0.0;
+        __syncwarp();
+        if (lane == 0 && pd >= 0) row[diag_layout ? pd : pd * cd + a] = 1.0;
+        __syncwarp();
+    }
+}
+
 __global__ void k_scale(double *__restrict__ v, int64_t n, double a)
 {
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) v[t] *= a;
@@ -695,6 +726,24 @@ extern "C" int feddb200_unpack_add_d(feddb200_ctx *c, double *values_d, const do
     if (n == 0) return FEDDB200_OK;
     FB_CUDA(cudaSetDevice(c->device));
     k_unpack_add<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16), 256, 0, c->stream>>>(values_d, recv_d, slot_d, n);
+    c->launches++;
+    FB_CUDA(cudaGetLastError());
+    return FEDDB200_OK;
+}
+
+extern "C" int feddb200_set_dirichlet_rows_d(feddb200_ctx *c, const feddb200_pat *p, int rd, int cd, int mode,
+                                             const uint8_t *node_mask_d, int diagonal_block, double *values_d)
+{
+    FB_LOGIC(!c || !p || !node_mask_d || !values_d, "set_dirichlet_rows: null argument");
+    FB_LOGIC(!((mode == FEDDB200_BLOCK_SCALAR && rd == 1 && cd == 1) || (mode == FEDDB200_BLOCK_DIAG && rd == cd && rd >= 1 && rd <= 3) ||
+               (mode == FEDDB200_BLOCK_FULL && rd >= 1 && rd <= 3 && cd >= 1 && cd <= 3)),
+             "set_dirichlet_rows: unsupported dof layout");
+    FB_LOGIC(diagonal_block && rd != cd, "set_dirichlet_rows: a diagonal block has as many row as column dofs");
+    if (p->n_owned == 0) return FEDDB200_OK;
+    FB_CUDA(cudaSetDevice(c->device));
+    const int64_t threads = p->n_owned * 32;
+    k_dirichlet_rows<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(p->n_owned, p->rowptr_d, p->colind_d, node_mask_d, rd, cd,
+                                                                             mode != FEDDB200_BLOCK_FULL, diagonal_block, values_d);
     c->launches++;
     FB_CUDA(cudaGetLastError());
     return FEDDB200_OK;

@@ -192,6 +192,12 @@ class Pattern:
         check(self.ctx._L.feddb200_assemble_ns_jacobian_d(self.ctx._h, self._h, float(rho), float(nu), ptr(u),
                                                           int(bool(newton)), ptr(values)))
 
+    def set_dirichlet_rows_d(self, values, node_mask, row_dofs=1, col_dofs=1, mode=BLOCK_SCALAR, diagonal_block=True):
+        """BCBuilder::setDirichletBC on resident values (BCBuilder_def.hpp:618-709): node_mask = uint8 CUDA tensor, one
+        byte per owned row node, bit a set when dof a is a Dirichlet dof."""
+        check(self.ctx._L.feddb200_set_dirichlet_rows_d(self.ctx._h, self._h, int(row_dofs), int(col_dofs), int(mode),
+                                                       ptr(node_mask), int(bool(diagonal_block)), ptr(values)))
+
     # ---- host-buffer forms (H2D / D2H inside the call) ----
     def assemble_laplace(self, vec_field=False):
         out = np.empty(self.nnz(self.dim, self.dim, BLOCK_DIAG) if vec_field else self.nnz(), dtype=np.float64)

@@ -177,6 +177,12 @@ int  feddb200_assemble_ns_jacobian(feddb200_ctx *ctx, const feddb200_pat *pat, d
  * (NCCL) and calls unpack_add on the receiving side:  values_d[slot[k]] += recv_d[k]. */
 int64_t feddb200_pattern_nnz_owned(const feddb200_pat *pat, int row_dofs, int col_dofs, int block_mode);
 int  feddb200_unpack_add_d(feddb200_ctx *ctx, double *values_d, const double *recv_d, const int64_t *slot_d, int64_t n);
+/* BCBuilder::setDirichletBC -> setLocalRowOne / setLocalRowZero (core/General/BCBuilder_def.hpp:618-709; SURVEY.md
+ * 8(f) rank 1) on resident values: node_mask_d[I] (one byte per OWNED row node, device) has bit a set when dof a of
+ * node I carries a Dirichlet condition ("Dirichlet" = all dofs, "Dirichlet_X" = bit 0, "Dirichlet_X_Z" = bits 0|2, ...).
+ * Every selected dof row is zeroed; on a diagonal block (diagonal_block != 0) its diagonal entry becomes 1. */
+int  feddb200_set_dirichlet_rows_d(feddb200_ctx *ctx, const feddb200_pat *pat, int row_dofs, int col_dofs, int block_mode,
+                                   const uint8_t *node_mask_d, int diagonal_block, double *values_d);
 /* Matrix::scale (core/LinearAlgebra/Matrix_def.hpp:257) on resident values */
 int  feddb200_scale_d(feddb200_ctx *ctx, double *values_d, int64_t n, double alpha);
 

@@ -197,3 +197,19 @@ def determine_degree(dim, fe1, fe2, t1, t2, extra=0):
 
 def determine_degree1(dim, fe, t):
     return lib().fo_determine_degree1(dim, fe.encode(), t)
+
+
+def set_dirichlet_rows(rowptr, colgid, values, row_gid_of_dof, dof_is_dirichlet, diagonal_block=True):
+    """BCBuilder::setLocalRowOne / setLocalRowZero (core/General/BCBuilder_def.hpp:653-709) on a dof-level CSR:
+    every Dirichlet dof row is replaced by zeros (:672, :704) and, on a diagonal block, the entry whose column gid
+    equals the row gid by one (:674-679).  Parity unpinned: BCBuilder needs the full Trilinos stack, so this
+    restatement is checked by review only.  Returns a new values array."""
+    out = np.array(values, dtype=np.float64, copy=True)
+    for r in np.nonzero(dof_is_dirichlet)[0]:
+        a, b = rowptr[r], rowptr[r + 1]
+        out[a:b] = 0.0
+        if diagonal_block:
+            hit = np.nonzero(colgid[a:b] == row_gid_of_dof[r])[0]
+            if hit.size:
+                out[a + hit[0]] = 1.0
+    return out
