@@ -317,7 +317,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"config 3: linear elasticity P2 3D cube H/h={M} per GPU, {ne} tets/GPU, "
+                "config": {"workload": f"config {3 if M == 70 else (5 if M == 101 else '3-like')}: linear elasticity P2 3D cube H/h={M} per GPU, {ne} tets/GPU, "
                                        f"{nnz} CSR values/GPU (30x30 local blocks)",
                            "lambda": LAM, "mu": MU, "scatter_mode": args.mode,
                            "l2_policy": "outputs (5.7 GB at M=70) exceed the 126 MB L2; no flush needed",

@@ -74,6 +74,8 @@ SIGNATURES = {
     "feddb200_assemble_div_divT": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "feddb200_assemble_ns_jacobian": (C.c_int, [_vp, _vp, C.c_double, C.c_double, _vp, C.c_int, _vp]),
     "feddb200_unpack_add_d": (C.c_int, [_vp, _vp, _vp, _vp, _i64]),
+    "feddb200_assemble_rhs_d": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp]),
+    "feddb200_assemble_rhs": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp]),
     "feddb200_set_dirichlet_rows_d": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp]),
     "feddb200_scale_d": (C.c_int, [_vp, _vp, _i64, C.c_double]),
 }

@@ -586,6 +586,35 @@ __global__ void k_dirichlet_rows(int64_t n_owned, const int64_t *__restrict__ ro
     }
 }
 
+// FE::assemblyRHS (FE_def.hpp:4694-4766), constant source: one thread per pattern row (node); the row's incidences
+// are walked in ascending element order -- the order in which the reference's element loop adds into valuesRhs[row].
+struct RhsArgs {
+    int64_t n_rows;
+    const int64_t *inc_ptr;
+    const int32_t *inc;
+    const double *geom;
+    int det_off, gs, dofs, vec_field;
+    double c[MAXN], f[3];
+    double *rhs;
+};
+__global__ void k_rhs(const RhsArgs A)
+{
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= A.n_rows) return;
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int64_t k = A.inc_ptr[r]; k < A.inc_ptr[r + 1]; k++) {
+        const int32_t code = A.inc[k];
+        const double adet = A.geom[(int64_t)(code >> 4) * A.gs + A.det_off];
+        double value = A.c[code & 15];
+        if (!A.vec_field) acc[0] += value * (adet * A.f[0]);          // value *= absDetB * valueFunc[0]   (:4750)
+        else {
+            value *= adet;                                            // value *= absDetB                  (:4755)
+            for (int d = 0; d < A.dofs; d++) acc[d] += value * A.f[d];
+        }
+    }
+    for (int d = 0; d < A.dofs; d++) A.rhs[r * A.dofs + d] = acc[d];
+}
+
 __global__ void k_scale(double *__restrict__ v, int64_t n, double a)
 {
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) v[t] *= a;
@@ -729,6 +758,57 @@ extern "C" int feddb200_unpack_add_d(feddb200_ctx *c, double *values_d, const do
     c->launches++;
     FB_CUDA(cudaGetLastError());
     return FEDDB200_OK;
+}
+
+extern "C" int feddb200_assemble_rhs_d(feddb200_ctx *c, const feddb200_pat *pc, int vec_field, int deg_func,
+                                       const double *value_func, double *rhs_d)
+{
+    FB_LOGIC(!c || !pc || !value_func || !rhs_d, "assemble_rhs: null argument");
+    feddb200_pat *p = const_cast<feddb200_pat *>(pc);
+    const feddb200_mesh *m = p->rm;
+    FB_CUDA(cudaSetDevice(c->device));
+    RhsArgs A;
+    std::memset(&A, 0, sizeof(A));
+    FB_LOGIC(rhs_coefficients(m->dim, m->nloc, deg_func, A.c) != 0, "assemble_rhs: no quadrature rule for this FE type and function degree");
+    if (p->n_rows == 0) return FEDDB200_OK;
+    const int gs = m->dim == 3 ? 16 : 8;
+    if (!p->geom_d) FB_CUDA(cudaMalloc(&p->geom_d, sizeof(double) * std::max<int64_t>(m->ne * gs, 1)));
+    if (m->ne > 0) {
+        const unsigned blocks = (unsigned)((m->ne + 255) / 256);
+        switch (elem_index(m->dim, m->nloc)) {
+        case 0: k_geom<2, 3><<<blocks, 256, 0, c->stream>>>(m->ne, m->conn_d, m->coords_d, p->geom_d); break;
+        case 1: k_geom<2, 6><<<blocks, 256, 0, c->stream>>>(m->ne, m->conn_d, m->coords_d, p->geom_d); break;
+        case 2: k_geom<3, 4><<<blocks, 256, 0, c->stream>>>(m->ne, m->conn_d, m->coords_d, p->geom_d); break;
+        case 3: k_geom<3, 10><<<blocks, 256, 0, c->stream>>>(m->ne, m->conn_d, m->coords_d, p->geom_d); break;
+        default: set_error("unsupported element"); return FEDDB200_ELOGIC;
+        }
+        c->launches++;
+    }
+    A.n_rows = p->n_rows; A.inc_ptr = p->inc_ptr_d; A.inc = p->inc_d; A.geom = p->geom_d;
+    A.gs = gs; A.det_off = m->dim == 3 ? 3 : 6;
+    A.vec_field = vec_field ? 1 : 0; A.dofs = vec_field ? m->dim : 1;
+    for (int d = 0; d < A.dofs; d++) A.f[d] = value_func[d];
+    A.rhs = rhs_d;
+    k_rhs<<<(unsigned)((p->n_rows + 255) / 256), 256, 0, c->stream>>>(A);
+    c->launches++;
+    FB_CUDA(cudaGetLastError());
+    return FEDDB200_OK;
+}
+
+extern "C" int feddb200_assemble_rhs(feddb200_ctx *c, const feddb200_pat *p, int vec_field, int deg_func, const double *value_func,
+                                     double *rhs)
+{
+    FB_LOGIC(!c || !p || !rhs, "assemble_rhs: null argument");
+    const int64_t n = p->n_rows * (vec_field ? p->rm->dim : 1);
+    double *r_d = nullptr;
+    int rc = scratch(c, 0, sizeof(double) * n, &r_d);
+    if (rc != FEDDB200_OK) return rc;
+    rc = feddb200_assemble_rhs_d(c, p, vec_field, deg_func, value_func, r_d);
+    if (rc == FEDDB200_OK && n > 0) {
+        FB_CUDA(cudaMemcpyAsync(rhs, r_d, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+        FB_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return rc;
 }
 
 extern "C" int feddb200_set_dirichlet_rows_d(feddb200_ctx *c, const feddb200_pat *p, int rd, int cd, int mode,

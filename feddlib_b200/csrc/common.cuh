@@ -115,5 +115,6 @@ struct feddb200_pat {
 
 namespace fb {
 int build_tables(OpTables &t, int op, int dim, int nloc_v, int nloc_p);
+int rhs_coefficients(int dim, int nloc, int deg_func, double *c);
 int ensure_colouring(feddb200_pat *pat);
 } // namespace fb

@@ -132,6 +132,29 @@ class FE_b200 {
 
     void setScatterMode(int mode) { b200::check(feddb200_set_scatter_mode(ctx_, mode)); }
 
+    // FE::assemblyRHS (FE_def.hpp:4694-4766): constant source; func is evaluated once on the host (:4735), the last
+    // entry of funcParameter is the degree of the function (:4716); the result is ADDED to the repeated vector `a`
+    template <class RhsFunc>
+    void assemblyRHS(int dim, std::string FEType, MultiVectorPtr_Type a, std::string fieldType, RhsFunc func,
+                     std::vector<SC> &funcParameter)
+    {
+        if (FEType == "P0") throw std::logic_error("Not implemented for P0");
+        if (a.is_null()) throw std::runtime_error("MultiVector in assemblyConstRHS is null.");
+        if (a->getNumVectors() > 1) throw std::logic_error("Implement for numberMV > 1 .");
+        const bool vec = fieldType == "Vector";
+        if (!vec && fieldType != "Scalar") throw std::logic_error("Invalid field type.");
+        const int loc = checkFE(dim, FEType);
+        const int degFunc = (int)(funcParameter[funcParameter.size() - 1] + 1.e-14);
+        double x = 0.0;
+        std::vector<double> valueFunc(3, 0.0);
+        func(&x, &valueFunc[0], &funcParameter[0]);
+        feddb200_pat *p = pattern(loc, loc);
+        std::vector<double> rhs((std::size_t)slots_[loc].nn * (vec ? dim : 1));
+        b200::check(feddb200_assemble_rhs(ctx_, p, vec ? 1 : 0, degFunc, valueFunc.data(), rhs.data()));
+        Teuchos::ArrayRCP<SC> valuesRhs = a->getDataNonConst(0);
+        for (std::size_t k = 0; k < rhs.size(); k++) valuesRhs[k] += rhs[k];
+    }
+
     // FE::assemblyMass (FE_def.hpp:454-521): fieldType "Scalar" or "Vector" (same value on the dim diagonal blocks)
     void assemblyMass(int dim, std::string FEType, std::string fieldType, MatrixPtr_Type &A, bool callFillComplete = true)
     {

@@ -134,6 +134,24 @@ static int op_degree(int op, int ov, int op_)
     return deg == 0 ? 1 : deg;
 }
 
+// c[i] = sum_q w_q phi_i(q) for the rule of degree determineDegree(FEType, Std) + deg_func (FE_def.hpp:4716-4717, 4746-4747)
+int rhs_coefficients(int dim, int nloc, int deg_func, double *c)
+{
+    const int order = fe_order(dim, nloc);
+    if (order < 0 || deg_func < 0) return -1;
+    int deg = order + deg_func;
+    if (deg == 0) deg = 1;
+    double pts[MAXQ][3], w[MAXQ];
+    const int nq = quad_rule(dim, deg, pts, w);
+    if (nq < 0) return -1;
+    for (int i = 0; i < nloc; i++) {
+        double v = 0.0;
+        for (int q = 0; q < nq; q++) v += w[q] * basis(dim, order, i, pts[q]);
+        c[i] = v;
+    }
+    return 0;
+}
+
 int build_tables(OpTables &t, int op, int dim, int nloc_v, int nloc_p)
 {
     std::memset(&t, 0, sizeof(t));

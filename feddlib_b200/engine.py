@@ -192,6 +192,15 @@ class Pattern:
         check(self.ctx._L.feddb200_assemble_ns_jacobian_d(self.ctx._h, self._h, float(rho), float(nu), ptr(u),
                                                           int(bool(newton)), ptr(values)))
 
+    def assemble_rhs(self, value_func, deg_func=0, vec_field=False):
+        """FE::assemblyRHS with a constant source (FE_def.hpp:4694-4766): load vector in pattern-row order (host array)."""
+        f = np.zeros(3)
+        vf = np.atleast_1d(np.asarray(value_func, dtype=np.float64))
+        f[:vf.size] = vf
+        out = np.empty(self.n_rows * (self.dim if vec_field else 1), dtype=np.float64)
+        check(self.ctx._L.feddb200_assemble_rhs(self.ctx._h, self._h, int(bool(vec_field)), int(deg_func), ptr(f), ptr(out)))
+        return out
+
     def set_dirichlet_rows_d(self, values, node_mask, row_dofs=1, col_dofs=1, mode=BLOCK_SCALAR, diagonal_block=True):
         """BCBuilder::setDirichletBC on resident values (BCBuilder_def.hpp:618-709): node_mask = uint8 CUDA tensor, one
         byte per owned row node, bit a set when dof a is a Dirichlet dof."""

@@ -201,6 +201,23 @@ class FE:
         rowptr, colind = self._csr(pat, (id(drow), id(dcol)), rd, cd, mode)
         A._seat(self.ctx, rowptr, colind, values, colmap, domainMap or colmap, rangeMap or rowmap, callFillComplete)
 
+    # ---- FE_def.hpp:4694-4766 ----
+    def assemblyRHS(self, dim, FEType, a, fieldType, func, funcParameter):
+        """`a`: repeated (vector-field) array, added to in place; `func(x, res, parameters)` fills res[0:dim] and is
+        evaluated once, as in the reference (:4735); funcParameter[-1] is the degree of the function (:4716)."""
+        if FEType == "P0":
+            raise LogicError("Not implemented for P0")
+        if a is None:
+            raise RuntimeError("MultiVector in assemblyConstRHS is null.")
+        if fieldType not in ("Scalar", "Vector"):
+            raise LogicError("Invalid field type.")
+        d = self.domainVec_[self.checkFE(dim, FEType)]
+        res = np.zeros(dim)
+        func(np.zeros(dim), res, np.asarray(funcParameter, dtype=np.float64))
+        degFunc = int(funcParameter[-1] + 1.e-14)
+        pat = self._pattern(d, d)
+        a += pat.assemble_rhs(res, degFunc, fieldType == "Vector")
+
     # ---- FE_def.hpp:454-521 ----
     def assemblyMass(self, dim, FEType, fieldType, A: Matrix, callFillComplete=True):
         if FEType == "P0":

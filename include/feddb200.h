@@ -177,6 +177,17 @@ int  feddb200_assemble_ns_jacobian(feddb200_ctx *ctx, const feddb200_pat *pat, d
  * (NCCL) and calls unpack_add on the receiving side:  values_d[slot[k]] += recv_d[k]. */
 int64_t feddb200_pattern_nnz_owned(const feddb200_pat *pat, int row_dofs, int col_dofs, int block_mode);
 int  feddb200_unpack_add_d(feddb200_ctx *ctx, double *values_d, const double *recv_d, const int64_t *slot_d, int64_t n);
+/* FE::assemblyRHS (core/FE/FE_def.hpp:4694-4766) for the constant source the reference
+ * supports ("for now just const", :4730): value_func[dim] = the host callback's result (evaluated once by the
+ * caller, as :4735 does), deg_func = its declared polynomial degree (last entry of funcParameter, :4716).  Output: the
+ * load vector in pattern-row order (one rank: repeated-node order; owned rows first, ghost rows behind, to be shipped
+ * like ghost matrix rows = the reference's exportFromVector(..., "Add"), Problem_def.hpp:213), dofs = 1 ("Scalar",
+ * vec_field = 0) or dim ("Vector"), node-wise interleaved.  The vector is overwritten. */
+int  feddb200_assemble_rhs_d(feddb200_ctx *ctx, const feddb200_pat *pat, int vec_field, int deg_func,
+                             const double *value_func, double *rhs_d);
+int  feddb200_assemble_rhs(feddb200_ctx *ctx, const feddb200_pat *pat, int vec_field, int deg_func,
+                           const double *value_func, double *rhs);
+
 /* BCBuilder::setDirichletBC -> setLocalRowOne / setLocalRowZero (core/General/BCBuilder_def.hpp:618-709; SURVEY.md
  * 8(f) rank 1) on resident values: node_mask_d[I] (one byte per OWNED row node, device) has bit a set when dof a of
  * node I carries a Dirichlet condition ("Dirichlet" = all dofs, "Dirichlet_X" = bit 0, "Dirichlet_X_Z" = bits 0|2, ...).

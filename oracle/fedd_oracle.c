@@ -544,6 +544,37 @@ int fo_assembly_laplace_vecfield(int dim, const char *fe, int64_t ne, const int3
     return 0;
 }
 
+/* FE_def.hpp:4694-4766 assemblyRHS: constant source term f (the reference evaluates func once, :4735), added into the
+ * repeated vector with LOCAL node ids (:4751, :4758).  deg = determineDegree(FEType, Std) + degFunc (:4716-4717). */
+int fo_assembly_rhs(int dim, const char *fe, int64_t ne, const int32_t *conn, const double *coords,
+                    int vec_field, int deg_func, const double *value_func, double *rhs)
+{
+    int nloc = fo_nloc(dim, fe);
+    if (nloc < 0) return -1;
+    double phi[FO_MAXQ * FO_MAXN], w[FO_MAXQ];
+    int deg = fo_determine_degree1(dim, fe, FO_STD) + deg_func;
+    int nq = fo_get_phi(dim, fe, deg, phi, w);
+    if (nq < 0) return -1;
+    for (int64_t T = 0; T < ne; T++) {
+        const int32_t *el = conn + T * nloc;
+        double B[3][3];
+        fo_build_transformation(dim, el, coords, B);
+        double absDetB = fabs(fo_det(dim, B));
+        for (int i = 0; i < nloc; i++) {
+            double value = 0.;
+            for (int q = 0; q < nq; q++) value += w[q] * phi[q * nloc + i];
+            if (!vec_field) {
+                value *= absDetB * value_func[0];
+                rhs[el[i]] += value;
+            } else {
+                value *= absDetB;
+                for (int d = 0; d < dim; d++) rhs[(int64_t)dim * el[i] + d] += value * value_func[d];
+            }
+        }
+    }
+    return 0;
+}
+
 /* FE_def.hpp:454-521 assemblyMass (fieldType "Scalar": vec_field = 0, "Vector": vec_field = 1).
  * deg = determineDegree(Std, Std) (:474); only |det B| of the affine map is used (:489-491). */
 int fo_assembly_mass(int dim, const char *fe, int64_t ne, const int32_t *conn, const double *coords,

@@ -86,6 +86,21 @@ def assemble(op, dim, fe, conn, coords, gid=None, u=None, lam=0.0, mu=0.0, fe2=N
         L.fo_matrix_free(hA); L.fo_matrix_free(hB)
 
 
+def assemble_rhs(dim, fe, conn, coords, value_func, deg_func=0, vec_field=False):
+    """Reference FE::assemblyRHS (constant source) -> repeated vector."""
+    L = lib()
+    L.ref_assemble_rhs.argtypes = [C.c_int, C.c_char_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                   C.c_void_p, C.c_void_p]
+    conn = np.ascontiguousarray(conn, dtype=np.int32); coords = np.ascontiguousarray(coords, dtype=np.float64)
+    f = np.ascontiguousarray(value_func, dtype=np.float64)
+    out = np.zeros(coords.shape[0] * (dim if vec_field else 1))
+    rc = L.ref_assemble_rhs(dim, fe.encode(), conn.shape[0], _p(conn), conn.shape[1], _p(coords), coords.shape[0],
+                            int(bool(vec_field)), int(deg_func), _p(f), _p(out))
+    if rc != 0:
+        raise ValueError("reference: " + L.ref_last_error().decode())
+    return out
+
+
 def get_dphi(dim, fe, deg):
     n = O.lib().fo_nloc(dim, fe.encode())
     d = np.zeros(30 * 10 * 3); w = np.zeros(30)

@@ -73,6 +73,7 @@ class MultiVector {
     MultiVector(const SC *data, std::size_t n) : data_(data, data + n) {}
     int getNumVectors() const { return 1; }
     Teuchos::ArrayRCP<const SC> getData(int) const { return Teuchos::ArrayRCP<const SC>(data_.data(), data_.size()); }
+    Teuchos::ArrayRCP<SC> getDataNonConst(int) { return Teuchos::ArrayRCP<SC>(data_.data(), data_.size()); }
   private:
     std::vector<SC> data_;
 };

@@ -87,7 +87,7 @@ class ArrayRCP {
     std::size_t n_;
 };
 
-template <class T> struct ScalarTraits { static T eps() { return std::numeric_limits<T>::epsilon(); } };
+template <class T> struct ScalarTraits { static T eps() { return std::numeric_limits<T>::epsilon(); } static T zero() { return T(0); } static T one() { return T(1); } };
 template <class T> struct OrdinalTraits { static T invalid() { return T(-1); } };
 
 class ParameterList { };

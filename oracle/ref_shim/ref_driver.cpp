@@ -82,6 +82,33 @@ extern "C" int ref_assemble(int op, int dim, const char *fe1, const char *fe2, i
     }
 }
 
+// FE::assemblyRHS with a constant source: rhs[nn * dofs] (repeated vector, zero on entry)
+extern "C" int ref_assemble_rhs(int dim, const char *fe1, int64_t ne, const int32_t *conn1, int nloc1, const double *coords1,
+                                int64_t nn1, int vec_field, int deg_func, const double *value_func, double *rhs)
+{
+    try {
+        FE_t fe;
+        std::vector<int64_t> gid(nn1);
+        for (int64_t k = 0; k < nn1; k++) gid[k] = k;
+        Teuchos::RCP<Domain_t> d1 = make_domain(dim, fe1, ne, conn1, nloc1, coords1, nn1, gid.data());
+        fe.addFE(d1);
+        const std::size_t n = (std::size_t)nn1 * (vec_field ? dim : 1);
+        std::vector<double> zero(n, 0.0);
+        Teuchos::RCP<MV_t> mv(new MV_t(zero.data(), n));
+        std::vector<double> f(value_func, value_func + dim);
+        RhsFunc_Type func = [f, dim](double *, double *res, double *) { for (int d = 0; d < dim; d++) res[d] = f[d]; };
+        std::vector<double> para(2, 0.0);
+        para[1] = (double)deg_func; // "last parameter should always be the degree" (FE_def.hpp:4715)
+        fe.assemblyRHS(dim, std::string(fe1), mv, std::string(vec_field ? "Vector" : "Scalar"), func, para);
+        Teuchos::ArrayRCP<const double> out = mv->getData(0);
+        for (std::size_t k = 0; k < n; k++) rhs[k] = out[k];
+        return 0;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -2;
+    }
+}
+
 // reference tables, for direct comparison with the restatement
 extern "C" int ref_get_dphi(int dim, const char *fe, int deg, double *dphi, double *w)
 {

@@ -29,6 +29,8 @@ void fo_get_csr(const fo_matrix *A, int64_t *rowptr, int64_t *colgid, double *va
 int ref_assemble(int op, int dim, const char *fe1, const char *fe2, int64_t ne, const int32_t *conn1, int nloc1,
                  const double *coords1, int64_t nn1, const int64_t *gid1, const int32_t *conn2, int nloc2, int64_t nn2,
                  const int64_t *gid2, const double *u, double lambda, double mu, fo_matrix *A, fo_matrix *B);
+int ref_assemble_rhs(int dim, const char *fe1, int64_t ne, const int32_t *conn1, int nloc1, const double *coords1, int64_t nn1,
+                     int vec_field, int deg_func, const double *value_func, double *rhs);
 const char *ref_last_error(void);
 }
 
@@ -167,6 +169,23 @@ int main(int argc, char **argv)
             fe.assemblyDivAndDivT(dim, fe1, fe2, 2, B, BT, Teuchos::RCP<const Map_t>(), Teuchos::RCP<const Map_t>(), true);
             all = compare("assemblyDivAndDivT: B", g_seated[B.get()], refB, gid2, 1) && all;
             all = compare("assemblyDivAndDivT: BT", g_seated[BT.get()], refBT, gid1, dim) && all;
+        }
+        // assemblyRHS (constant source), "Scalar" and "Vector"
+        for (int vec = 0; vec < 2; vec++) {
+            const double f[3] = {1.5, -2.0, 0.25};
+            const std::size_t n = (std::size_t)nn1 * (vec ? dim : 1);
+            std::vector<double> want(n, 0.0), zero(n, 0.0);
+            if (ref_assemble_rhs(dim, fe1, ne, conn1.data(), nloc1, xyz.data(), nn1, vec, 1, f, want.data()) != 0) { std::printf("reference failed: %s\n", ref_last_error()); return 1; }
+            Teuchos::RCP<MV_t> a(new MV_t(zero.data(), n));
+            std::vector<double> para(2, 0.0); para[1] = 1.0;
+            auto func = [&](double *, double *res, double *) { for (int d = 0; d < dim; d++) res[d] = f[d]; };
+            fe.assemblyRHS(dim, fe1, a, vec ? "Vector" : "Scalar", func, para);
+            Teuchos::ArrayRCP<const double> got = a->getData(0);
+            double num = 0.0, den = 0.0;
+            for (std::size_t k = 0; k < n; k++) { num += (got[k] - want[k]) * (got[k] - want[k]); den += want[k] * want[k]; }
+            const double err = std::sqrt(num / den);
+            std::printf("%-28s n   %10lld                 rel. 2-norm   %.3e  %s\n", vec ? "assemblyRHS Vector" : "assemblyRHS Scalar", (long long)n, err, err <= 1e-12 ? "PASS" : "FAIL");
+            all = (err <= 1e-12) && all;
         }
         // error behaviour of the boundary (FE_def.hpp:610, 6950)
         bool threw = false;

@@ -65,6 +65,20 @@ def test_laplace(case, mode):
     check(case, "laplace_vec", case["pat"].assemble_laplace(True), d, d, BLOCK_DIAG)
 
 
+def test_rhs(case):
+    """FE::assemblyRHS, constant source (FE_def.hpp:4694-4766; SURVEY.md 8(f) rank 2): the load vector on the repeated
+    map equals the oracle's; rows are added in the reference's element order, so the tolerance is that of the tables."""
+    from oracle import oracle as O
+    d = case["dim"]
+    f = np.array([1.5, -2.0, 0.25])[:d]
+    for vec in (False, True):
+        for deg_func in (0, 1):
+            want = O.assembly_rhs(d, case["fe"], case["conn"], case["coords"], f, deg_func, vec)
+            got = case["pat"].assemble_rhs(f, deg_func, vec)
+            assert got.shape == want.shape
+            assert np.linalg.norm(got - want) <= TOL * np.linalg.norm(want)
+
+
 @pytest.mark.parametrize("mode", MODES)
 def test_mass(case, mode):
     """FE::assemblyMass, fieldType "Scalar" and "Vector" (FE_def.hpp:454-521; SURVEY.md 8(f) rank 2)."""

@@ -82,3 +82,21 @@ def test_reference_error_behaviour():
     conn, coords = mesh_structured(2, "P1", 2)
     with pytest.raises(ValueError, match="Not implemented for P0"):
         R.assemble("laplace", 2, "P0", conn, coords)
+
+
+@pytest.mark.parametrize("dim,fe,make", CASES, ids=[f"{c[0]}d-{c[1]}-{i}" for i, c in enumerate(CASES)])
+def test_rhs_restatement_is_bitwise_equal_to_reference_code(dim, fe, make):
+    """FE::assemblyRHS (constant source, FE_def.hpp:4694-4766), "Scalar" and "Vector", function degrees 0..2."""
+    conn, coords = make()
+    f = np.array([1.5, -2.0, 0.25])[:dim]
+    for vec in (False, True):
+        for deg_func in (0, 1, 2):
+            a = O.assembly_rhs(dim, fe, conn, coords, f, deg_func, vec)
+            b = R.assemble_rhs(dim, fe, conn, coords, f, deg_func, vec)
+            assert np.array_equal(a, b), (vec, deg_func)
+            assert abs(a.reshape(-1, dim if vec else 1).sum(axis=0) - f[: dim if vec else 1] * _volume(dim, conn, coords)).max() < 1e-12
+
+
+def _volume(dim, conn, coords):
+    v = coords[conn[:, 1:dim + 1]] - coords[conn[:, :1]]
+    return float(np.abs(np.linalg.det(v)).sum() / (2 if dim == 2 else 6))
