@@ -120,6 +120,44 @@ def oracle_elasticity_time(M, repeat=1):
     return best, conn.shape[0]
 
 
+def ns_jacobian_numbers(ctx, M, peak):
+    """Times the (0,0) block (rho*nu*A + rho*N(u) + rho*W(u), fused), N, W and B/B^T on a structured P2-P1 cube."""
+    import torch
+    from feddlib_b200 import BLOCK_DIAG, BLOCK_FULL, Mesh, Pattern
+    from feddlib_b200 import mesh as PM
+    from feddlib_b200.engine import assemble_div_divT_d
+    dim = 3
+    conn, coords, _ = PM.build_structured(dim, "P2", 1, M)
+    verts = np.unique(conn[:, :4])
+    lid = -np.ones(coords.shape[0], dtype=np.int64)
+    lid[verts] = np.arange(verts.size)
+    mv, mp = Mesh(ctx, dim, conn, coords), Mesh(ctx, dim, lid[conn[:, :4]].astype(np.int32), coords[verts])
+    pat, patB, patBT = Pattern(ctx, mv), Pattern(ctx, mp, mv), Pattern(ctx, mv, mp)
+    u = torch.from_numpy(np.random.default_rng(1234).uniform(-1, 1, dim * coords.shape[0])).cuda()
+    vd, vf = ctx.empty_values(pat.nnz(dim, dim, BLOCK_DIAG)), ctx.empty_values(pat.nnz(dim, dim, BLOCK_FULL))
+    vB, vBT = ctx.empty_values(patB.nnz(1, dim, BLOCK_FULL)), ctx.empty_values(patBT.nnz(dim, 1, BLOCK_FULL))
+    ne = conn.shape[0]
+    ops = {"ns_jacobian_00_block": (lambda: pat.assemble_ns_jacobian_d(vf, u, 1.0, 1e-3, True), vf.numel()),
+           "advection_N": (lambda: pat.assemble_advection_d(vd, u), vd.numel()),
+           "advection_in_u_W": (lambda: pat.assemble_advection_in_u_d(vf, u), vf.numel()),
+           "div_B_and_BT": (lambda: assemble_div_divT_d(ctx, patB, patBT, vB, vBT), vB.numel() + vBT.numel())}
+    out = {"workload": f"structured P2-P1 cube H/h={M}, {ne} tets, u ~ U(-1,1) seed 1234, rho=1, nu=1e-3, scatter mode gather"}
+    for name, (fn, nnz) in ops.items():
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        alg = ne * 10 * 4 + (M + 1) ** 3 * dim * 8 + nnz * 8 + (0 if name.startswith("div") else dim * coords.shape[0] * 8)
+        out[name] = {"ms": ms, "elements_per_s": ne / (ms * 1e-3), "hbm_frac": alg / (ms * 1e-3) / 1e9 / peak}
+    return out
+
+
 def _worker(M):
     return oracle_elasticity_time(M)
 
@@ -172,6 +210,8 @@ def main():
     ap.add_argument("--e2e-steps", dest="e2e_steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: exchange after the whole assembly")
+    ap.add_argument("--no-ns", action="store_true", help="skip the secondary Navier-Stokes block timings")
+    ap.add_argument("--ns-M", dest="ns_M", type=int, default=50, help="H/h of the P2-P1 cube of the secondary timings")
     ap.add_argument("--all-modes", action="store_true", help="also time the other scatter modes (extra keys)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -304,6 +344,11 @@ def main():
     else:
         checksum = float(values[: min(nnz, 1 << 20)].sum().item())
 
+    # secondary numbers (not the headline): the Navier-Stokes blocks of config 4 on a structured P2-P1 cube, same engine
+    ns_extra = None
+    if world == 1 and not args.no_ns:
+        ns_extra = ns_jacobian_numbers(ctx, args.ns_M, peak)
+
     cpu_baseline = None
     if rank == 0:
         t_cpu, ne_cpu = oracle_elasticity_time(args.cpu_M)
@@ -329,6 +374,8 @@ def main():
                 "clocks": clocks, "checksum_first_1Mi_values": checksum}
         if extra:
             line["other_scatter_modes"] = extra
+        if ns_extra:
+            line["navier_stokes_blocks"] = ns_extra
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -4,7 +4,7 @@ TAG=$1; shift
 i=0
 for cfg in "$@"; do
   i=$((i+1))
-  env $cfg python bench.py --steps 10 --warmup 3 --no-e2e --cpu-M 4 > gpurun_out/${TAG}_$i.json 2> gpurun_out/${TAG}_$i.err
+  env $cfg python bench.py --steps 10 --warmup 3 --no-e2e --no-ns --cpu-M 4 > gpurun_out/${TAG}_$i.json 2> gpurun_out/${TAG}_$i.err
   python - "$cfg" gpurun_out/${TAG}_$i.json <<'PY'
 import json,sys
 try:
