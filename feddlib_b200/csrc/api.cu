@@ -252,13 +252,24 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
             // ring-ordered edge rows (3D P2): one thread per CSR row, one shared-memory row per thread (pitch odd)
             if constexpr (DIM == 3 && NL == 10) {
                 constexpr int TPR = OPG == 1 ? DIM : 1;
-                const int pitch = (TPR * b.lcap + 1) | 1; // one spare double: rows are shifted to the 16-byte phase of their destination
+                constexpr int NBr = OPG == 1 ? DIM : 1;
                 int nt = 64;
                 if (const char *f = getenv("FEDDB200_RING_NT")) nt = std::max(32, std::min(64, atoi(f) & ~31)); // tuning aid
-                const int64_t tiles = (b.count * TPR + nt - 1) / nt;
-                const size_t smem = (size_t)pitch * 8 * nt;
+                const int npt = nt / TPR;                       // row nodes per tile
+                // node pitch: room for the TPR dof rows + the phase shift; among the next candidates the one with the fewest
+                // bank conflicts when the threads of a half-warp store to the same position of their rows
+                const int n_row = NBr * std::max(1, b.lcap - 1), need = TPR * NBr * b.lcap + 1; // typical row: lcap rounds L up to a multiple of 4
+                int pitch = need, best_conf = 1 << 30;
+                for (int cand = need; cand < need + 16; cand++) {
+                    int hist[16] = {0}, conf = 0;
+                    for (int t = 0; t < 16; t++) hist[((t / TPR) * cand + (t % TPR) * n_row) & 15]++;
+                    for (int k = 0; k < 16; k++) conf += hist[k] > 1 ? hist[k] - 1 : 0;
+                    if (conf < best_conf) { best_conf = conf; pitch = cand; }
+                }
+                const size_t smem = (size_t)pitch * 8 * npt;
                 FB_LOGIC(smem > budget, "row too long for the gather path's shared-memory rows; use the coloured or atomic mode");
                 G.pitch = pitch;
+                const int64_t tiles = (b.count + npt - 1) / npt;
                 FB_CUDA(cudaFuncSetAttribute(k_ring<OPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
                 // persistent blocks: as many as are resident at once (times a small factor that evens out the tail)
                 int per_sm = 1;

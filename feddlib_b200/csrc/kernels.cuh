@@ -926,8 +926,12 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
     const int NT = blockDim.x;
     const int tid = threadIdx.x, lane = tid & 31;
     const int pitch = A.pitch;
-    const int64_t nthreads = A.count * TPR;           // thread t owns dof a = t % TPR of row t / TPR
-    const int64_t ntiles = (nthreads + NT - 1) / NT;
+    // a tile = NPT row nodes; thread tid < NPT * TPR owns dof a = tid % TPR of the tile's node tid / TPR, so the TPR dof
+    // rows of a node are always in the same block (they are contiguous in the values array and leave in ONE bulk store)
+    const int NPT = NT / TPR;
+    const int slot = tid / TPR;
+    const bool lane_used = tid < NPT * TPR;
+    const int64_t ntiles = (A.count + NPT - 1) / NPT;
     const int nrep = (OPG == 0 && A.vec_dim != 0) ? A.vec_dim : 1;
     const double mu = A.c1, lam = A.c0;
     double *wbase = acc + (size_t)(tid - lane) * pitch; // the warp's 32 rows
@@ -943,9 +947,9 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
     IncRec<NL> rc, rn, r2;
     IncGeo<DIM> g;
     {
-        const int64_t t = tile * NT + tid;
-        if (t < nthreads) {
-            ld_v4(reinterpret_cast<const double *>(A.rowinfo + A.start + t / TPR), raw);
+        const int64_t node = tile * NPT + slot;
+        if (lane_used && node < A.count) {
+            ld_v4(reinterpret_cast<const double *>(A.rowinfo + A.start + node), raw);
             const int64_t k0 = __double_as_longlong(raw[1]);
             const int ninc = (int)(__double_as_longlong(raw[2]) >> 32);
             if (ninc > 0) {
@@ -958,9 +962,8 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
         }
     }
     for (;;) {
-        const int64_t t = tile * NT + tid;
-        const bool live = t < nthreads;
-        const int a = live ? (int)(t % TPR) : 0;
+        const bool live = lane_used && tile * NPT + slot < A.count;
+        const int a = tid - slot * TPR;
         const int64_t base = __double_as_longlong(raw[0]);
         const int64_t k0 = __double_as_longlong(raw[1]);
         const int L = live ? (int)(__double_as_longlong(raw[2]) & 0xffffffff) : 0;
@@ -968,24 +971,21 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
         const bool holes = live && (__double_as_longlong(raw[3]) & 16) != 0;
         // row record of the next tile
         const int64_t tile_n = tile + gridDim.x;
-        const int64_t tn = tile_n * NT + tid;
-        const bool live_n = tile_n < ntiles && tn < nthreads;
+        const int64_t node_n = tile_n * NPT + slot;
+        const bool live_n = lane_used && tile_n < ntiles && node_n < A.count;
         double rawn[4] = {0.0, 0.0, 0.0, 0.0};
-        if (live_n) ld_v4(reinterpret_cast<const double *>(A.rowinfo + A.start + tn / TPR), rawn);
+        if (live_n) ld_v4(reinterpret_cast<const double *>(A.rowinfo + A.start + node_n), rawn);
 
-        const int n = NB * L;
-        const int64_t off = OPG == 1 ? (int64_t)DIM * DIM * base + (int64_t)a * n : (int64_t)nrep * base;
-#ifndef FB_NO_TMA_STORE
-        // the row is shifted by one double where that gives its shared-memory copy the same 16-byte phase as its
-        // destination in the values array (TMA bulk stores need both sides 16-byte aligned)
-        const int head = (int)(((reinterpret_cast<uintptr_t>(A.values) >> 3) + off) & 1);
-        double *my = acc + (size_t)tid * pitch + ((tid * pitch + head) & 1);
-#else
-        double *my = acc + (size_t)tid * pitch;
-#endif
-        if (__any_sync(FULL, holes)) { // rare: rows with positions no local element contributes to
-            for (int x = lane; x < 32 * pitch; x += 32) wbase[x] = 0.0;
-            __syncwarp();
+        const int n = NB * L;                         // values of this thread's dof row
+        const int64_t off_node = (int64_t)TPR * NB * nrep * base; // first value of the node's TPR dof rows (contiguous)
+        // the node's rows are stored back to back in shared memory (node pitch A.pitch), shifted by one double where
+        // that gives them the 16-byte phase of their destination (TMA bulk stores need both sides 16-byte aligned)
+        const int head = (int)(((reinterpret_cast<uintptr_t>(A.values) >> 3) + off_node) & 1);
+        double *nodep = acc + (size_t)slot * pitch + ((slot * pitch + head) & 1);
+        double *my = nodep + a * n;
+        if (__syncthreads_or(holes)) { // rare: rows with positions no local element contributes to
+            for (int x = tid; x < NPT * pitch; x += NT) acc[x] = 0.0;
+            __syncthreads();
         }
 
         if (ninc > 0) {
@@ -1104,57 +1104,30 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
             load_rec<NL>(A, k0n + 2 < kln ? k0n + 2 : kln, r2);
         }
 
-#ifdef FB_EXP_NOWRITE
-        if (n == 12345) A.values[off] = my[0];
-        if (nincn > 0) load_geo<DIM, NL>(A, rc, g);
-#elif !defined(FB_NO_TMA_STORE)
-        // write-out: the thread's shared-memory row is its CSR row.  One TMA bulk store per row moves the 16-byte
-        // aligned interior (no LSU instructions, asynchronous); the at most two odd doubles go by plain stores.
-        if (n > 0) {
+        // write-out: the node's TPR dof rows are one contiguous run of the values array and of shared memory: ONE TMA
+        // bulk store per node (SASS UBLKCP) moves the 16-byte aligned interior; the at most two odd doubles go by plain
+        // stores.  (One store per dof row is limited by the rate of bulk operations: 45 cycles per SM each.)
+        __syncthreads();
+        if (a == 0 && n > 0) {
             bulk_fence(); // make the generic-proxy shared-memory writes visible to the async proxy
+            const int total = TPR * n;
 #pragma unroll 1
             for (int d = 0; d < nrep; d++) {
-                double *out = A.values + off + (int64_t)d * n;
+                double *out = A.values + off_node + (int64_t)d * total;
                 const int h = (int)((reinterpret_cast<uintptr_t>(out) >> 3) & 1);
                 if (OPG == 1 || h == head) {
-                    const int body = (n - h) & ~1;
-                    if (h) out[0] = my[0];
-                    if (body > 0) bulk_store(out + h, my + h, body * 8);
-                    if (h + body < n) out[n - 1] = my[n - 1];
+                    const int body_n = (total - h) & ~1;
+                    if (h) out[0] = nodep[0];
+                    if (body_n > 0) bulk_store(out + h, nodep + h, body_n * 8);
+                    if (h + body_n < total) out[total - 1] = nodep[total - 1];
                 } else { // replicated scalar row whose copy has the other phase: plain stores
-                    for (int x = 0; x < n; x++) out[x] = my[x];
+                    for (int x = 0; x < total; x++) out[x] = nodep[x];
                 }
             }
         }
         if (nincn > 0) load_geo<DIM, NL>(A, rc, g); // next tile's first geometry line lands while the stores drain
         bulk_commit_wait_read(); // the bulk stores read this block's shared memory: wait before it is reused
-#else
-        __syncwarp();
-        // write-out: thread r's shared-memory row is one CSR row; the warp copies its 32 rows one after the other
-        {
-            const double *src = wbase + lane;
-#pragma unroll 1
-            for (int r = 0; r < 32; r++, src += pitch) {
-                const int nr = __shfl_sync(FULL, n, r);
-#ifdef FB_EXP_STREAMWRITE
-                const int64_t o = (tile * NT + (tid - lane) + r) * (int64_t)nr; (void)off; // timing experiment: dense, in launch order
-#else
-                const int64_t o = __shfl_sync(FULL, off, r);
-#endif
-#pragma unroll 1
-                for (int d = 0; d < nrep; d++) {
-                    double *out = A.values + o + (int64_t)d * nr + lane;
-                    // rows of up to 96 values (3D P2 edge rows: 57 / 81) take the three predicated copies, longer ones loop
-                    if (lane < nr) out[0] = src[0];
-                    if (lane + 32 < nr) out[32] = src[32];
-                    if (lane + 64 < nr) out[64] = src[64];
-                    for (int x = lane + 96; x < nr; x += 32) out[x - lane] = src[x - lane];
-                }
-            }
-        }
-        if (nincn > 0) load_geo<DIM, NL>(A, rc, g);
-        __syncwarp();
-#endif
+        __syncthreads();
         if (tile_n >= ntiles) break;
         tile = tile_n;
 #pragma unroll
