@@ -255,7 +255,7 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
                 constexpr int NBr = OPG == 1 ? DIM : 1;
                 int nt = 64;
                 if (const char *f = getenv("FEDDB200_RING_NT")) nt = std::max(32, std::min(64, atoi(f) & ~31)); // tuning aid
-                const int npt = nt / TPR;                       // row nodes per tile
+                const int npt = 32 / TPR;                       // row nodes per warp tile
                 // node pitch: room for the TPR dof rows + the phase shift; among the next candidates the one with the fewest
                 // bank conflicts when the threads of a half-warp store to the same position of their rows
                 const int n_row = NBr * std::max(1, b.lcap - 1), need = TPR * NBr * b.lcap + 1; // typical row: lcap rounds L up to a multiple of 4
@@ -266,10 +266,10 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
                     for (int k = 0; k < 16; k++) conf += hist[k] > 1 ? hist[k] - 1 : 0;
                     if (conf < best_conf) { best_conf = conf; pitch = cand; }
                 }
-                const size_t smem = (size_t)pitch * 8 * npt;
+                const size_t smem = (size_t)pitch * 8 * npt * (nt / 32);
                 FB_LOGIC(smem > budget, "row too long for the gather path's shared-memory rows; use the coloured or atomic mode");
                 G.pitch = pitch;
-                const int64_t tiles = (b.count + npt - 1) / npt;
+                const int64_t tiles = ((b.count + npt - 1) / npt + nt / 32 - 1) / (nt / 32); // in blocks
                 FB_CUDA(cudaFuncSetAttribute(k_ring<OPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
                 // persistent blocks: as many as are resident at once (times a small factor that evens out the tail)
                 int per_sm = 1;

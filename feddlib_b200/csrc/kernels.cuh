@@ -926,12 +926,15 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
     const int NT = blockDim.x;
     const int tid = threadIdx.x, lane = tid & 31;
     const int pitch = A.pitch;
-    // a tile = NPT row nodes; thread tid < NPT * TPR owns dof a = tid % TPR of the tile's node tid / TPR, so the TPR dof
-    // rows of a node are always in the same block (they are contiguous in the values array and leave in ONE bulk store)
-    const int NPT = NT / TPR;
-    const int slot = tid / TPR;
-    const bool lane_used = tid < NPT * TPR;
+    // a tile = the NPT row nodes of ONE WARP; lane < NPT * TPR owns dof a = lane % TPR of the tile's node lane / TPR, so
+    // the TPR dof rows of a node are always in the same warp (they are contiguous in the values array and leave in ONE
+    // bulk store) and warps never wait for one another
+    constexpr int NPT = 32 / TPR;
+    const int slot = lane / TPR;
+    const bool lane_used = lane < NPT * TPR;
     const int64_t ntiles = (A.count + NPT - 1) / NPT;
+    acc += (size_t)(tid >> 5) * NPT * A.pitch;        // this warp's shared-memory rows
+    const int64_t tile_step = (int64_t)gridDim.x * (NT >> 5);
     const int nrep = (OPG == 0 && A.vec_dim != 0) ? A.vec_dim : 1;
     const double mu = A.c1, lam = A.c0;
     double *wbase = acc + (size_t)(tid - lane) * pitch; // the warp's 32 rows
@@ -941,7 +944,7 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
     // the start of the current one, its first incidence records after the current main loop and its first
     // geometry line while the bulk stores of the current tile drain, so the dependent chain
     // row record -> incidence record -> geometry is off the critical path for all but a block's first tile.
-    int64_t tile = blockIdx.x;
+    int64_t tile = (int64_t)blockIdx.x * (NT >> 5) + (tid >> 5);
     if (tile >= ntiles) return;
     double raw[4] = {0.0, 0.0, 0.0, 0.0};
     IncRec<NL> rc, rn, r2;
@@ -963,14 +966,14 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
     }
     for (;;) {
         const bool live = lane_used && tile * NPT + slot < A.count;
-        const int a = tid - slot * TPR;
+        const int a = lane - slot * TPR;
         const int64_t base = __double_as_longlong(raw[0]);
         const int64_t k0 = __double_as_longlong(raw[1]);
         const int L = live ? (int)(__double_as_longlong(raw[2]) & 0xffffffff) : 0;
         const int ninc = live ? (int)(__double_as_longlong(raw[2]) >> 32) : 0;
         const bool holes = live && (__double_as_longlong(raw[3]) & 16) != 0;
         // row record of the next tile
-        const int64_t tile_n = tile + gridDim.x;
+        const int64_t tile_n = tile + tile_step;
         const int64_t node_n = tile_n * NPT + slot;
         const bool live_n = lane_used && tile_n < ntiles && node_n < A.count;
         double rawn[4] = {0.0, 0.0, 0.0, 0.0};
@@ -983,9 +986,9 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
         const int head = (int)(((reinterpret_cast<uintptr_t>(A.values) >> 3) + off_node) & 1);
         double *nodep = acc + (size_t)slot * pitch + ((slot * pitch + head) & 1);
         double *my = nodep + a * n;
-        if (__syncthreads_or(holes)) { // rare: rows with positions no local element contributes to
-            for (int x = tid; x < NPT * pitch; x += NT) acc[x] = 0.0;
-            __syncthreads();
+        if (__any_sync(FULL, holes)) { // rare: rows with positions no local element contributes to
+            for (int x = lane; x < NPT * pitch; x += 32) acc[x] = 0.0;
+            __syncwarp();
         }
 
         if (ninc > 0) {
@@ -1107,7 +1110,7 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
         // write-out: the node's TPR dof rows are one contiguous run of the values array and of shared memory: ONE TMA
         // bulk store per node (SASS UBLKCP) moves the 16-byte aligned interior; the at most two odd doubles go by plain
         // stores.  (One store per dof row is limited by the rate of bulk operations: 45 cycles per SM each.)
-        __syncthreads();
+        __syncwarp();
         if (a == 0 && n > 0) {
             bulk_fence(); // make the generic-proxy shared-memory writes visible to the async proxy
             const int total = TPR * n;
@@ -1126,8 +1129,8 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
             }
         }
         if (nincn > 0) load_geo<DIM, NL>(A, rc, g); // next tile's first geometry line lands while the stores drain
-        bulk_commit_wait_read(); // the bulk stores read this block's shared memory: wait before it is reused
-        __syncthreads();
+        bulk_commit_wait_read(); // the bulk stores read this warp's shared memory: wait before it is reused
+        __syncwarp();
         if (tile_n >= ntiles) break;
         tile = tile_n;
 #pragma unroll
