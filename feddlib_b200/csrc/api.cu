@@ -284,7 +284,7 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
             } else { set_error("ring rows exist for 3D P2 patterns only"); rc = FEDDB200_ELOGIC; }
         } else {
             // accumulators: 32 rows of NBL*L doubles per block, `pitch` doubles apart with pitch == NBL (mod 16), see k_gather
-            int pitch = S::NBL * b.lcap + 1;                 // + 1: room for the 16-byte phase shift of the bulk store
+            int pitch = S::NBL * b.lcap;
             while ((pitch & 15) != (S::NBL & 15)) pitch++;
             const size_t smem = (size_t)pitch * 8 * 32;
             FB_LOGIC(smem > budget, "row too long for the gather path's shared-memory accumulators; use the coloured or atomic mode");

@@ -753,6 +753,8 @@ __global__ void __launch_bounds__(GatherShape<OPG, DIM>::NT, FB_GATHER_MINBLOCKS
     constexpr int JD = TYPE == 0 ? 0 : NVTX; // canonical index of the row node itself
     constexpr int ROWS = 32;                 // accumulator rows per block
     extern __shared__ double acc[];          // [ROWS][pitch]
+    __shared__ int64_t s_off[ROWS];
+    __shared__ int s_n[ROWS];
     const int tid = threadIdx.x;
     const int pitch = A.pitch;
     const int64_t t = blockIdx.x * (int64_t)NT + tid;
@@ -783,14 +785,12 @@ __global__ void __launch_bounds__(GatherShape<OPG, DIM>::NT, FB_GATHER_MINBLOCKS
     // zero the block's accumulators while the first loads are in flight; publish the row table
     for (int x = tid; x < ROWS * pitch; x += NT) acc[x] = 0.0;
     const int row = tid / NBL;               // accumulator row of this thread inside the block
-    const int nrep = (OPG == 0 && A.vec_dim != 0) ? A.vec_dim : 1;
-    const int n = live ? NBL * L : 0;
-    const int64_t off = OPG == 1 ? (int64_t)CPR * base + (int64_t)a * NBL * L : (int64_t)nrep * base;
-    // the row is shifted by one double where that gives it the 16-byte phase of its destination (TMA bulk store)
-    const int head = (int)(((reinterpret_cast<uintptr_t>(A.values) >> 3) + off) & 1);
-    double *rowp = acc + (size_t)row * pitch + ((row * pitch + head) & 1);
+    if (b == 0) {
+        s_n[row] = live ? NBL * L : 0;
+        s_off[row] = OPG == 1 ? (int64_t)CPR * base + (int64_t)a * NBL * L : base;
+    }
     __syncthreads();
-    double *my = rowp + b;
+    double *my = acc + (size_t)row * pitch + b;
 
     if (ninc > 0) {
         // M^T columns, scaled per incidence by |det|
@@ -883,26 +883,19 @@ __global__ void __launch_bounds__(GatherShape<OPG, DIM>::NT, FB_GATHER_MINBLOCKS
     }
     __syncthreads();
 
-    // write-out: every accumulator row is one CSR row (scalar row / elasticity dof row (I, a)); the thread with b == 0
-    // sends it with one TMA bulk store (16-byte aligned interior; the at most two odd doubles by plain stores).  The
-    // block-diagonal vector Laplacian replicates the row DIM times.
-    if (b == 0 && n > 0) {
-        bulk_fence();
-#pragma unroll 1
+    // write-out: every accumulator row is one CSR row (scalar row / elasticity dof row (I, a)); the
+    // block-diagonal vector Laplacian replicates it DIM times.  Warps stride over the block's rows.
+    const int nrep = (OPG == 0 && A.vec_dim != 0) ? A.vec_dim : 1;
+    const int lane = tid & 31;
+    for (int r = tid >> 5; r < ROWS; r += NT / 32) {
+        const int nr = s_n[r];
+        const double *src = acc + (size_t)r * pitch;
         for (int d = 0; d < nrep; d++) {
-            double *out = A.values + off + (int64_t)d * n;
-            const int h = (int)((reinterpret_cast<uintptr_t>(out) >> 3) & 1);
-            if (OPG == 1 || h == head) {
-                const int body_n = (n - h) & ~1;
-                if (h) out[0] = rowp[0];
-                if (body_n > 0) bulk_store(out + h, rowp + h, body_n * 8);
-                if (h + body_n < n) out[n - 1] = rowp[n - 1];
-            } else {
-                for (int x = 0; x < n; x++) out[x] = rowp[x];
-            }
+            double *out = A.values + (int64_t)nrep * s_off[r] + (int64_t)d * nr;
+#pragma unroll 4
+            for (int x = lane; x < nr; x += 32) out[x] = src[x];
         }
     }
-    bulk_commit_wait_read(); // the stores read this block's shared memory: wait before the block retires
 }
 
 // Ring kernel: 3D P2 edge-node rows whose incidences are in chain order (ring_order above).  One thread per
