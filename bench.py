@@ -210,6 +210,9 @@ def main():
     ap.add_argument("--e2e-steps", dest="e2e_steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: exchange after the whole assembly")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="multi-GPU ghost rows: 'fused' = stored straight into the owners' buffers over NVLink peer memory by the "
+                         "ghost-row kernels; 'nccl' = all-to-all-v of the ghost values on a side stream")
     ap.add_argument("--no-ns", action="store_true", help="skip the secondary Navier-Stokes block timings")
     ap.add_argument("--ns-M", dest="ns_M", type=int, default=50, help="H/h of the P2-P1 cube of the secondary timings")
     ap.add_argument("--all-modes", action="store_true", help="also time the other scatter modes (extra keys)")
@@ -254,8 +257,12 @@ def main():
 
     overlap = runner is not None and args.mode == "gather" and not args.no_overlap
 
+    fused = overlap and args.exchange == "fused" and world <= 8
+
     def step():
-        if overlap:      # ghost rows first, NCCL exchange on a side stream while the owned rows are assembled
+        if fused:        # ghost rows first, stored by their kernels into the owners' receive buffers (peer memory)
+            runner.assemble_linelas_fused(values, LAM, MU)
+        elif overlap:    # ghost rows first, NCCL exchange on a side stream while the owned rows are assembled
             runner.assemble_linelas_overlapped(values, LAM, MU)
         else:
             pat.assemble_linelas_d(values, LAM, MU)
@@ -367,7 +374,9 @@ def main():
                            "lambda": LAM, "mu": MU, "scatter_mode": args.mode,
                            "l2_policy": "outputs (5.7 GB at M=70) exceed the 126 MB L2; no flush needed",
                            "parallelism": f"element partition over {world} GPU(s)" + (
-                               "; ghost rows assembled first, NCCL ghost-row exchange overlapped with the owned rows"
+                               "; ghost rows assembled first and stored by their kernels into the owners' receive buffers over NVLink "
+                               "peer memory (CUDA IPC), one-element all-reduce as barrier under the owned rows, unpack-add"
+                               if fused else "; ghost rows assembled first, NCCL ghost-row exchange overlapped with the owned rows"
                                if overlap else ("; NCCL ghost-row exchange after the assembly" if world > 1 else "")),
                            "pattern_build_s": t_pattern},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,

@@ -74,6 +74,10 @@ SIGNATURES = {
     "feddb200_assemble_div_divT": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "feddb200_assemble_ns_jacobian": (C.c_int, [_vp, _vp, C.c_double, C.c_double, _vp, C.c_int, _vp]),
     "feddb200_unpack_add_d": (C.c_int, [_vp, _vp, _vp, _vp, _i64]),
+    "feddb200_ipc_alloc": (C.c_int, [_vp, _i64, C.POINTER(C.c_void_p), _vp]),
+    "feddb200_ipc_open": (C.c_int, [_vp, _vp, C.POINTER(C.c_void_p)]),
+    "feddb200_ipc_close": (C.c_int, [_vp, _vp]),
+    "feddb200_set_ghost_targets": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "feddb200_assemble_rhs_d": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp]),
     "feddb200_assemble_rhs": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp]),
     "feddb200_set_dirichlet_rows_d": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp]),

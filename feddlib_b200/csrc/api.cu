@@ -247,6 +247,10 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
         cudaStream_t st = n_side > 0 ? c->side[turn++ % n_side] : c->stream;
         G.zero = 0;
         G.start = b.start; G.count = b.count;
+        // ghost rows go straight into their owners' receive buffers (peer memory) when targets are set
+        G.nseg = b.ghost ? c->n_ghost_seg : 0;
+        for (int i = 0; i < kMaxGhostSeg; i++) { G.seg_begin[i] = c->ghost_seg_begin[i]; G.seg_ptr[i] = c->ghost_seg_ptr[i]; }
+        G.seg_begin[kMaxGhostSeg] = c->ghost_seg_begin[kMaxGhostSeg];
         int rc;
         if (b.type == 1) {
             // ring-ordered edge rows (3D P2): one thread per CSR row, one shared-memory row per thread (pitch odd)
@@ -758,6 +762,55 @@ extern "C" int feddb200_assemble_ns_jacobian(feddb200_ctx *c, const feddb200_pat
     FB_LOGIC(!p || !u, "null argument");
     return with_host_buffers(c, p, (int64_t)p->rm->dim * p->rm->dim * p->nnz, u, (int64_t)p->rm->dim * p->rm->nn, values,
                              [&](double *u_d, double *v_d) { return feddb200_assemble_ns_jacobian_d(c, p, rho, nu, u_d, newton, v_d); });
+}
+
+// ---- peer memory (one process per GPU, CUDA IPC) and ghost-row targets -----------------------------------
+extern "C" int feddb200_ipc_alloc(feddb200_ctx *c, int64_t bytes, void **ptr_d, unsigned char *handle64)
+{
+    FB_LOGIC(!c || !ptr_d || !handle64 || bytes < 0, "ipc_alloc: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    FB_CUDA(cudaSetDevice(c->device));
+    FB_CUDA(cudaMalloc(ptr_d, (size_t)std::max<int64_t>(bytes, 256)));
+    cudaIpcMemHandle_t h;
+    FB_CUDA(cudaIpcGetMemHandle(&h, *ptr_d));
+    std::memcpy(handle64, &h, 64);
+    return FEDDB200_OK;
+}
+
+extern "C" int feddb200_ipc_open(feddb200_ctx *c, const unsigned char *handle64, void **ptr_d)
+{
+    FB_LOGIC(!c || !ptr_d || !handle64, "ipc_open: bad arguments");
+    FB_CUDA(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, 64);
+    FB_CUDA(cudaIpcOpenMemHandle(ptr_d, h, cudaIpcMemLazyEnablePeerAccess));
+    return FEDDB200_OK;
+}
+
+extern "C" int feddb200_ipc_close(feddb200_ctx *c, void *ptr_d)
+{
+    FB_LOGIC(!c, "ipc_close: bad arguments");
+    if (!ptr_d) return FEDDB200_OK;
+    FB_CUDA(cudaSetDevice(c->device));
+    FB_CUDA(cudaIpcCloseMemHandle(ptr_d));
+    return FEDDB200_OK;
+}
+
+extern "C" int feddb200_set_ghost_targets(feddb200_ctx *c, int nseg, const int64_t *seg_begin, void *const *seg_ptr_d)
+{
+    FB_LOGIC(!c || nseg < 0 || nseg > kMaxGhostSeg || (nseg > 0 && (!seg_begin || !seg_ptr_d)), "set_ghost_targets: bad arguments");
+    for (int i = 0; i < nseg; i++) {
+        FB_LOGIC(seg_begin[i + 1] < seg_begin[i], "set_ghost_targets: segment offsets must ascend");
+        FB_LOGIC(seg_begin[i + 1] > seg_begin[i] && !seg_ptr_d[i], "set_ghost_targets: non-empty segment without a target");
+    }
+    c->n_ghost_seg = nseg;
+    for (int i = 0; i < kMaxGhostSeg; i++) {
+        c->ghost_seg_begin[i] = i <= nseg && nseg > 0 ? seg_begin[std::min(i, nseg)] : 0;
+        c->ghost_seg_ptr[i] = i < nseg ? static_cast<double *>(seg_ptr_d[i]) : nullptr;
+    }
+    c->ghost_seg_begin[kMaxGhostSeg] = nseg > 0 ? seg_begin[nseg] : 0;
+    for (int i = nseg + 1; i <= kMaxGhostSeg && nseg > 0; i++) c->ghost_seg_begin[i] = seg_begin[nseg];
+    return FEDDB200_OK;
 }
 
 extern "C" int feddb200_unpack_add_d(feddb200_ctx *c, double *values_d, const double *recv_d, const int64_t *slot_d, int64_t n)

@@ -71,6 +71,10 @@ struct feddb200_ctx {
     fb::OpTables *tab_d = nullptr; // device copies of the operator tables, one slot per operator
     int tab_key[fb::OP_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
     void *scratch_d[2] = {nullptr, nullptr}; // grow-only device scratch of the host-pointer entry points
+    // ghost-row targets of the next gather assemblies (feddb200_set_ghost_targets); n_ghost_seg == 0: none
+    int n_ghost_seg = 0;
+    int64_t ghost_seg_begin[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    double *ghost_seg_ptr[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t scratch_bytes[2] = {0, 0};
 };
 

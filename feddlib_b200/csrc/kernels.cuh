@@ -627,6 +627,8 @@ struct RowInfo {
     int64_t pad;
 };
 
+constexpr int kMaxGhostSeg = 8;   // ranks of one box
+
 struct GatherArgs {
     const RowInfo *rowinfo;   // rows of this launch: rowinfo[start .. start+count), bucket order
     int64_t start, count;
@@ -637,8 +639,24 @@ struct GatherArgs {
     int pitch;                // doubles between consecutive shared-memory accumulator rows (== NBL mod 16)
     int zero;                 // always 0 (opaque to the compiler; used to order loads after their buffer's last use)
     int vec_dim;              // LAP: 0 scalar, DIM = replicate to the DIM block-diagonal dof rows
+    // ghost-row launches of a multi-GPU assembly (feddb200_set_ghost_targets): values at offsets
+    // [seg_begin[o], seg_begin[o+1]) are written to seg_ptr[o] + (offset - seg_begin[o]) -- the receive buffer of the
+    // row's owner, mapped over NVLink -- instead of values + offset.  nseg == 0: everything goes to `values`.
+    int nseg;
+    int64_t seg_begin[kMaxGhostSeg + 1];
+    double *seg_ptr[kMaxGhostSeg];
     CanonR R;
 };
+
+// destination of the values at offset `off` of the values array (see GatherArgs::nseg)
+__device__ __forceinline__ double *out_ptr(const GatherArgs &A, int64_t off)
+{
+    if (A.nseg == 0) return A.values + off;
+    int o = 0;
+#pragma unroll 1
+    while (o + 1 < A.nseg && off >= A.seg_begin[o + 1]) o++;
+    return A.seg_ptr[o] + (off - A.seg_begin[o]);
+}
 
 // TMA bulk store shared -> global (1-D, no tensor map): both addresses 16-byte aligned, size a multiple of 16
 __device__ __forceinline__ void bulk_store(void *gptr, const void *sptr, int bytes)
@@ -891,7 +909,7 @@ __global__ void __launch_bounds__(GatherShape<OPG, DIM>::NT, FB_GATHER_MINBLOCKS
         const int nr = s_n[r];
         const double *src = acc + (size_t)r * pitch;
         for (int d = 0; d < nrep; d++) {
-            double *out = A.values + (int64_t)nrep * s_off[r] + (int64_t)d * nr;
+            double *out = out_ptr(A, (int64_t)nrep * s_off[r]) + (int64_t)d * nr;
 #pragma unroll 4
             for (int x = lane; x < nr; x += 32) out[x] = src[x];
         }
@@ -983,7 +1001,8 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
         const int64_t off_node = (int64_t)TPR * NB * nrep * base; // first value of the node's TPR dof rows (contiguous)
         // the node's rows are stored back to back in shared memory (node pitch A.pitch), shifted by one double where
         // that gives them the 16-byte phase of their destination (TMA bulk stores need both sides 16-byte aligned)
-        const int head = (int)(((reinterpret_cast<uintptr_t>(A.values) >> 3) + off_node) & 1);
+        double *const outp = out_ptr(A, off_node);
+        const int head = (int)((reinterpret_cast<uintptr_t>(outp) >> 3) & 1);
         double *nodep = acc + (size_t)slot * pitch + ((slot * pitch + head) & 1);
         double *my = nodep + a * n;
         if (__any_sync(FULL, holes)) { // rare: rows with positions no local element contributes to
@@ -1116,7 +1135,7 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
             const int total = TPR * n;
 #pragma unroll 1
             for (int d = 0; d < nrep; d++) {
-                double *out = A.values + off_node + (int64_t)d * total;
+                double *out = outp + (int64_t)d * total;
                 const int h = (int)((reinterpret_cast<uintptr_t>(out) >> 3) & 1);
                 if (OPG == 1 || h == head) {
                     const int body_n = (total - h) & ~1;

@@ -318,6 +318,84 @@ class DistributedMatrixAssembler:
         main.wait_stream(self._side)
         self._unpack(values, key, rsz)
 
+    # ---- fused exchange over NVLink peer memory ------------------------------------------------------------
+    def _peer_setup(self, key, rd, cd, mode):
+        """Two receive buffers per rank (step parity), mapped into every sender (CUDA IPC).  A sender's segment of the
+        receiver's buffer starts at the receiver's own arrival offset of that sender, so unpack_add is unchanged."""
+        import torch.distributed as dist
+        ssz, rsz = self.plan.split_sizes(rd, cd, mode)
+        mine = [self.ctx.ipc_alloc(8 * max(1, sum(rsz))) for _ in range(2)]
+        info = [None] * self.size
+        dist.all_gather_object(info, ([h for _, h in mine], rsz))
+        seg_ptr = [[0] * self.size for _ in range(2)]
+        opened = []
+        for o in range(self.size):
+            if o == self.rank or ssz[o] == 0:
+                continue
+            handles, rsz_o = info[o]
+            off = 8 * int(sum(rsz_o[:self.rank]))
+            assert rsz_o[self.rank] == ssz[o]
+            for par in range(2):
+                base = self.ctx.ipc_open(handles[par])
+                opened.append(base)
+                seg_ptr[par][o] = base + off
+        n_owned_vals = self.pat.nnz_owned(rd, cd, mode)
+        seg_begin = [n_owned_vals + int(sum(ssz[:o])) for o in range(self.size + 1)]
+        return {"recv": [p for p, _ in mine], "seg_ptr": seg_ptr, "seg_begin": seg_begin, "opened": opened, "step": 0}
+
+    def assemble_fused(self, values, rd, cd, mode, assemble):
+        """Like assemble_overlapped, but no collective moves data: the ghost-row kernels store their rows straight into
+        the owners' receive buffers over NVLink (feddb200_set_ghost_targets) as they are computed.  A one-element
+        all-reduce on the side stream is the cross-rank barrier between those stores and the owners' unpack_add; it
+        runs under the assembly of the owned rows.  Receive buffers alternate with the step parity, so one barrier
+        per assembly orders everything.  Gather mode, Laplace / elasticity operators, at most 8 ranks."""
+        import torch
+        import torch.distributed as dist
+        if self.size == 1:
+            assemble()
+            return
+        key = self._exchange_buffers(rd, cd, mode)
+        if not hasattr(self, "_peer"):
+            self._peer = {}
+        if key not in self._peer:
+            self._peer[key] = self._peer_setup(key, rd, cd, mode)
+            self._flag = torch.zeros(1, dtype=torch.int32, device=self._dev)
+        P = self._peer[key]
+        par = P["step"] & 1
+        P["step"] += 1
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self._dev)
+        _, rsz = self.plan.split_sizes(rd, cd, mode)
+        main = torch.cuda.current_stream(self._dev)
+        self.ctx.set_ghost_targets(P["seg_begin"], P["seg_ptr"][par])
+        self.ctx.set_row_phase(1)
+        try:
+            assemble()                      # geometry pre-pass + ghost rows -> peer memory
+            self.ctx.set_ghost_targets()
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                dist.all_reduce(self._flag)  # barrier: every rank's ghost rows have been stored
+            self.ctx.set_row_phase(2)
+            assemble()                      # owned rows
+        finally:
+            self.ctx.set_ghost_targets()
+            self.ctx.set_row_phase(0)
+        main.wait_stream(self._side)
+        slots = self._slot_t[key]
+        off = 0
+        for n in rsz:                       # one launch per sender, fixed order: deterministic sums
+            if n:
+                self.ctx.unpack_add_d(values, P["recv"][par] + 8 * off, slots[off:off + n], n)
+            off += n
+
+    def close_peer(self):
+        for P in getattr(self, "_peer", {}).values():
+            for b in P["opened"]:
+                self.ctx.ipc_close(b)
+            for b in P["recv"]:
+                self.ctx.free_d(b)
+        self._peer = {}
+
     def _unpack(self, values, key, rsz):
         recv, slots = self._recv_buf[key], self._slot_t[key]
         off = 0
@@ -373,6 +451,9 @@ class DistributedElasticity(DistributedMatrixAssembler):
 
     def exchange(self, values):
         super().exchange(values, self.dim, self.dim, BLOCK_FULL)
+
+    def assemble_linelas_fused(self, values, lam, mu):
+        self.assemble_fused(values, self.dim, self.dim, BLOCK_FULL, lambda: self.pat.assemble_linelas_d(values, lam, mu))
 
     def assemble_linelas_overlapped(self, values, lam, mu):
         self.assemble_overlapped(values, self.dim, self.dim, BLOCK_FULL, lambda: self.pat.assemble_linelas_d(values, lam, mu))

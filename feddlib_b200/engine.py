@@ -71,8 +71,40 @@ class Context:
     def scale_d(self, values, alpha: float):
         check(self._L.feddb200_scale_d(self._h, ptr(values), values.numel(), float(alpha)))
 
-    def unpack_add_d(self, values, recv, slots):
-        check(self._L.feddb200_unpack_add_d(self._h, ptr(values), ptr(recv), ptr(slots), recv.numel()))
+    def unpack_add_d(self, values, recv, slots, n=None):
+        """values[slots[k]] += recv[k]; `recv` is a tensor or a raw device pointer (then `n` values)."""
+        check(self._L.feddb200_unpack_add_d(self._h, ptr(values), ptr(recv), ptr(slots), recv.numel() if n is None else int(n)))
+
+    # ---- peer memory (CUDA IPC) and ghost-row targets: the fused ghost-row exchange --------------------
+    def ipc_alloc(self, nbytes: int):
+        """Device buffer that other processes can map: returns (device pointer, 64-byte handle)."""
+        p = C.c_void_p()
+        h = (C.c_ubyte * 64)()
+        check(self._L.feddb200_ipc_alloc(self._h, int(nbytes), C.byref(p), C.cast(h, C.c_void_p)))
+        return int(p.value), bytes(h)
+
+    def ipc_open(self, handle: bytes) -> int:
+        p = C.c_void_p()
+        h = (C.c_ubyte * 64).from_buffer_copy(handle)
+        check(self._L.feddb200_ipc_open(self._h, C.cast(h, C.c_void_p), C.byref(p)))
+        return int(p.value)
+
+    def ipc_close(self, p: int):
+        check(self._L.feddb200_ipc_close(self._h, C.c_void_p(p)))
+
+    def free_d(self, p: int):
+        check(self._L.feddb200_dev_free(self._h, C.c_void_p(p)))
+
+    def set_ghost_targets(self, seg_begin=None, seg_ptr=None):
+        """Ghost rows of the next gather assemblies go to seg_ptr[o] + (offset - seg_begin[o]) (feddb200_set_ghost_targets);
+        no arguments: back to the values array."""
+        if seg_begin is None:
+            check(self._L.feddb200_set_ghost_targets(self._h, 0, None, None))
+            return
+        n = len(seg_ptr)
+        b = (C.c_int64 * (n + 1))(*[int(x) for x in seg_begin])
+        q = (C.c_void_p * n)(*[C.c_void_p(int(x)) if x else C.c_void_p(None) for x in seg_ptr])
+        check(self._L.feddb200_set_ghost_targets(self._h, n, C.cast(b, C.c_void_p), C.cast(q, C.c_void_p)))
 
 
 class Mesh:

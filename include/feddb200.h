@@ -177,6 +177,18 @@ int  feddb200_assemble_ns_jacobian(feddb200_ctx *ctx, const feddb200_pat *pat, d
  * (NCCL) and calls unpack_add on the receiving side:  values_d[slot[k]] += recv_d[k]. */
 int64_t feddb200_pattern_nnz_owned(const feddb200_pat *pat, int row_dofs, int col_dofs, int block_mode);
 int  feddb200_unpack_add_d(feddb200_ctx *ctx, double *values_d, const double *recv_d, const int64_t *slot_d, int64_t n);
+/* Fused variant of the same step over NVLink peer memory (one process per GPU, CUDA IPC): every rank allocates its
+ * receive buffer with ipc_alloc, publishes the 64-byte handle, and opens the buffers of its peers.  With ghost targets
+ * set, the row-gather kernels of the Laplace / elasticity operators write the ghost rows -- the values at offsets
+ * [seg_begin[o], seg_begin[o+1]) of the values array, o = 0..nseg-1 (destination ranks in rank order, nseg <= 8) --
+ * directly to seg_ptr_d[o] + (offset - seg_begin[o]) as they are computed (TMA bulk stores / coalesced stores to the
+ * peer mapping) instead of behind the owned rows; no send buffer, no collective moves data.  The owner adds the
+ * received values with unpack_add after a cross-rank barrier.  nseg = 0 switches the targets off.  The other
+ * operators and the atomic / coloured modes keep the NCCL path (they ignore the targets and write behind the owned rows). */
+int  feddb200_ipc_alloc(feddb200_ctx *ctx, int64_t bytes, void **ptr_d, unsigned char *handle64);
+int  feddb200_ipc_open(feddb200_ctx *ctx, const unsigned char *handle64, void **ptr_d);
+int  feddb200_ipc_close(feddb200_ctx *ctx, void *ptr_d);
+int  feddb200_set_ghost_targets(feddb200_ctx *ctx, int nseg, const int64_t *seg_begin, void *const *seg_ptr_d);
 /* FE::assemblyRHS (core/FE/FE_def.hpp:4694-4766) for the constant source the reference
  * supports ("for now just const", :4730): value_func[dim] = the host callback's result (evaluated once by the
  * caller, as :4735 does), deg_func = its declared polynomial degree (last entry of funcParameter, :4716).  Output: the

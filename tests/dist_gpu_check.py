@@ -74,6 +74,17 @@ def main():
             assert torch.allclose(values2[:n_owned_vals], values[:n_owned_vals], rtol=1e-12, atol=1e-6), f"rank {rank} mode {mode}: overlapped exchange differs"
         else:
             assert torch.equal(values2[:n_owned_vals], values[:n_owned_vals]), f"rank {rank} mode {mode}: overlapped exchange differs"
+        if mode == "gather":
+            # fused variant: ghost rows stored straight into the owners' receive buffers over NVLink peer memory; run it
+            # several times (the receive buffers alternate) -- every result must equal the NCCL exchange bitwise
+            for it in range(4):
+                values3 = ctx.empty_values(pat.nnz(dim, dim, BLOCK_FULL))
+                values3.fill_(float("nan"))
+                run.assemble_linelas_fused(values3, lam, mu)
+                ctx.synchronize()
+                assert torch.equal(values3[:n_owned_vals], values[:n_owned_vals]), f"rank {rank}: fused peer-memory exchange differs (pass {it})"
+            dist.barrier()
+            run.close_peer()
         print(f"[dist_gpu_check] rank {rank}/{world} mode {mode}: owned rows {plan.n_owned}, ghost rows {plan.n_ghost}, "
               f"rel. error {rel:.2e} OK (overlapped exchange equal)", flush=True)
     dist.destroy_process_group()
