@@ -356,6 +356,11 @@ __global__ void __launch_bounds__(128) k_elem(const ElemArgs A)
 // with G_v = grad lambda_v, the gradients of the barycentric coordinates.
 template <int DIM> struct GeomStride { static constexpr int value = DIM == 3 ? 16 : 8; };
 
+__device__ __forceinline__ void st_v4(double *p, double a, double b, double c, double d)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
 template <int DIM, int NL>
 __global__ void __launch_bounds__(256) k_geom(int64_t ne, const int32_t *__restrict__ conn,
                                               const double *__restrict__ coords, double *__restrict__ geom)
@@ -375,15 +380,13 @@ __global__ void __launch_bounds__(256) k_geom(int64_t ne, const int32_t *__restr
         for (int k = 0; k < DIM; k++) { G[k + 1][d] = Binv[k][d]; s -= Binv[k][d]; }
         G[0][d] = s;
     }
+    // whole 32-byte sectors per store instruction (st.global.v4.f64): 4 (2) stores per element instead of 16 (8)
     if constexpr (DIM == 3) {
 #pragma unroll
-        for (int v = 0; v < 4; v++) {
-            g[4 * v + 0] = G[v][0]; g[4 * v + 1] = G[v][1]; g[4 * v + 2] = G[v][2]; g[4 * v + 3] = adet;
-        }
+        for (int v = 0; v < 4; v++) st_v4(g + 4 * v, G[v][0], G[v][1], G[v][2], adet);
     } else {
-#pragma unroll
-        for (int v = 0; v < 3; v++) { g[2 * v] = G[v][0]; g[2 * v + 1] = G[v][1]; }
-        g[6] = adet; g[7] = adet;
+        st_v4(g, G[0][0], G[0][1], G[1][0], G[1][1]);
+        st_v4(g + 4, G[2][0], G[2][1], adet, adet);
     }
 }
 
@@ -1206,9 +1209,8 @@ __global__ void __launch_bounds__(256) k_udata(int64_t ne, const int32_t *__rest
         const int64_t n = conn[e * NL + m];
         double *o = uel + (e * NL + m) * 4;
 #pragma unroll
-        for (int d = 0; d < DIM; d++) { U[m][d] = u[n * DIM + d]; o[d] = U[m][d]; }
-#pragma unroll
-        for (int d = DIM; d < 4; d++) o[d] = 0.0;
+        for (int d = 0; d < DIM; d++) U[m][d] = u[n * DIM + d];
+        st_v4(o, U[m][0], U[m][1], DIM == 3 ? U[m][DIM - 1] : 0.0, 0.0);
     }
     if (!want_dt) return;
     const double *g = geom + e * GS;
@@ -1229,6 +1231,7 @@ __global__ void __launch_bounds__(256) k_udata(int64_t ne, const int32_t *__rest
 #pragma unroll
         for (int b = 0; b < DIM; b++) {
             double *o = dt + ((e * DIM + a) * DIM + b) * 4;
+            double ov[4];
 #pragma unroll
             for (int v = 0; v < 4; v++) {
                 double s = 0.0;
@@ -1248,8 +1251,9 @@ __global__ void __launch_bounds__(256) k_udata(int64_t ne, const int32_t *__rest
                         }
                     }
                 }
-                o[v] = s * adet;
+                ov[v] = s * adet;
             }
+            st_v4(o, ov[0], ov[1], ov[2], ov[3]);
         }
 }
 
