@@ -62,6 +62,8 @@ SIGNATURES = {
     "feddb200_assemble_laplace_d": (C.c_int, [_vp, _vp, C.c_int, _vp]),
     "feddb200_assemble_mass_d": (C.c_int, [_vp, _vp, C.c_int, _vp]),
     "feddb200_assemble_mass": (C.c_int, [_vp, _vp, C.c_int, _vp]),
+    "feddb200_assemble_bdstab_d": (C.c_int, [_vp, _vp, _vp]),
+    "feddb200_assemble_bdstab": (C.c_int, [_vp, _vp, _vp]),
     "feddb200_assemble_linelas_d": (C.c_int, [_vp, _vp, C.c_double, C.c_double, _vp]),
     "feddb200_assemble_advection_d": (C.c_int, [_vp, _vp, _vp, _vp]),
     "feddb200_assemble_advection_in_u_d": (C.c_int, [_vp, _vp, _vp, _vp]),
@@ -82,6 +84,10 @@ SIGNATURES = {
     "feddb200_assemble_rhs": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp]),
     "feddb200_set_dirichlet_rows_d": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp]),
     "feddb200_scale_d": (C.c_int, [_vp, _vp, _i64, C.c_double]),
+    "feddb200_csr_add_symbolic_d": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_int64)]),
+    "feddb200_csr_add_numeric_d": (C.c_int, [_vp, _i64, C.c_double, _vp, _vp, _vp, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "feddb200_block_merge_symbolic_d": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.POINTER(C.c_int64)]),
+    "feddb200_block_merge_numeric_d": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -680,6 +680,14 @@ extern "C" int feddb200_assemble_mass_d(feddb200_ctx *c, const feddb200_pat *p, 
 {
     return run_op(c, p, OP_MASS, nullptr, 0, 0, 0, vec_field, v);
 }
+extern "C" int feddb200_assemble_bdstab_d(feddb200_ctx *c, const feddb200_pat *p, double *v)
+{
+    FB_LOGIC(!p, "null pattern");
+    const int dim = p->rm->dim;
+    FB_LOGIC(p->rm->nloc != dim + 1 || p->cm->nloc != dim + 1, "Only implemented for P1. Q1 is equivalent but we need to adjust scaling for the reference element.");
+    // refElementSize, refElementScale (FE_def.hpp:2183-2190)
+    return run_op(c, p, OP_MASS, nullptr, dim == 2 ? 0.5 : 1. / 6., dim == 2 ? 1. / 9. : 1. / 16., 0, 0, v);
+}
 extern "C" int feddb200_assemble_linelas_d(feddb200_ctx *c, const feddb200_pat *p, double lambda, double mu, double *v)
 {
     return run_op(c, p, OP_ELAS, nullptr, lambda, mu, 0, 0, v);
@@ -718,6 +726,11 @@ extern "C" int feddb200_assemble_mass(feddb200_ctx *c, const feddb200_pat *p, in
     const int64_t nnz = (vec_field ? p->rm->dim : 1) * p->nnz;
     return with_host_buffers(c, p, nnz, nullptr, 0, values,
                              [&](double *, double *v_d) { return feddb200_assemble_mass_d(c, p, vec_field, v_d); });
+}
+extern "C" int feddb200_assemble_bdstab(feddb200_ctx *c, const feddb200_pat *p, double *values)
+{
+    FB_LOGIC(!p, "null pattern");
+    return with_host_buffers(c, p, p->nnz, nullptr, 0, values, [&](double *, double *v_d) { return feddb200_assemble_bdstab_d(c, p, v_d); });
 }
 extern "C" int feddb200_assemble_linelas(feddb200_ctx *c, const feddb200_pat *p, double lambda, double mu, double *values)
 {

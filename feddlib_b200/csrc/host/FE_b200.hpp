@@ -155,6 +155,19 @@ class FE_b200 {
         for (std::size_t k = 0; k < rhs.size(); k++) valuesRhs[k] += rhs[k];
     }
 
+    // FE::assemblyBDStabilization (FE_def.hpp:2151-2220): P1 only, like the reference (:2156)
+    void assemblyBDStabilization(int dim, std::string FEType, MatrixPtr_Type &A, bool callFillComplete = true)
+    {
+        if (FEType != "P1")
+            throw std::logic_error("Only implemented for P1. Q1 is equivalent but we need to adjust scaling for the reference element.");
+        const int loc = checkFE(dim, FEType);
+        feddb200_pat *p = pattern(loc, loc);
+        b200::LocalCsr<SC, LO, GO> csr;
+        expand(p, loc, 1, 1, FEDDB200_BLOCK_SCALAR, csr);
+        b200::check(feddb200_assemble_bdstab(ctx_, p, csr.values.data()));
+        seat_csr(A, csr, MapConstPtr_Type(), MapConstPtr_Type(), callFillComplete);
+    }
+
     // FE::assemblyMass (FE_def.hpp:454-521): fieldType "Scalar" or "Vector" (same value on the dim diagonal blocks)
     void assemblyMass(int dim, std::string FEType, std::string fieldType, MatrixPtr_Type &A, bool callFillComplete = true)
     {

@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(128) k_elem(const ElemArgs A)
             double v = 0.0;
             for (int q = 0; q < nq; q++) v += T.w[q] * T.phi[q * NP + i] * T.phi[q * NP + j];
             v *= adet;
+            v -= A.c0 * adet * A.c1;   // assemblyBDStabilization (FE_def.hpp:2207): refElementSize * absDetB * refElementScale; mass: c0 = 0
             const int64_t p = pos[j];
             if (A.vec_dim == 0) add_to<ATOMIC>(A.values + base + p, v);
             else for (int d = 0; d < DIM; d++) add_to<ATOMIC>(A.values + DIM * base + d * L + p, v);
@@ -1424,7 +1425,7 @@ __global__ void __launch_bounds__(64, 4) k_gatherx(const GatherXArgs A)
         if constexpr (OPX == X_MASS) {
             const double adet = g.G[0][3];
 #pragma unroll
-            for (int j = 0; j < NL; j++) val[j][0] = g_coef.MM[TYPE][j] * adet;
+            for (int j = 0; j < NL; j++) val[j][0] = g_coef.MM[TYPE][j] * adet - g_coef.c0 * adet * g_coef.c1; // c0 = 0: mass; else BD stabilisation
         }
         if constexpr (OPX == X_B) {
             // row = pressure vertex (canonical vertex 0); B_{i',(j',d)} = |det| sum_t' BC[j'][t'] G_{t'}[d]

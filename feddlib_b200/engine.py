@@ -10,7 +10,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import (BLOCK_DIAG, BLOCK_FULL, BLOCK_SCALAR, SCATTER_ATOMIC, SCATTER_COLOURED, SCATTER_GATHER, check,
+from ._lib import (BLOCK_DIAG, BLOCK_FULL, BLOCK_SCALAR, SCATTER_ATOMIC, SCATTER_COLOURED, SCATTER_GATHER, LogicError, check,
                    ptr)
 
 _MODES = {"atomic": SCATTER_ATOMIC, "coloured": SCATTER_COLOURED, "colored": SCATTER_COLOURED,
@@ -105,6 +105,84 @@ class Context:
         b = (C.c_int64 * (n + 1))(*[int(x) for x in seg_begin])
         q = (C.c_void_p * n)(*[C.c_void_p(int(x)) if x else C.c_void_p(None) for x in seg_ptr])
         check(self._L.feddb200_set_ghost_targets(self._h, n, C.cast(b, C.c_void_p), C.cast(q, C.c_void_p)))
+
+
+class DeviceCsr:
+    """A dof-level CSR matrix resident on the GPU: int64 rowptr, int32 colind (ascending per row), f64 values (torch tensors)."""
+
+    def __init__(self, rowptr, colind, values, n_cols):
+        self.rowptr, self.colind, self.values, self.n_cols = rowptr, colind, values, int(n_cols)
+
+    @property
+    def n_rows(self):
+        return self.rowptr.numel() - 1
+
+    @classmethod
+    def from_host(cls, ctx, rowptr, colind, values, n_cols):
+        import torch
+        dev = f"cuda:{ctx.device}"
+        return cls(torch.from_numpy(np.ascontiguousarray(rowptr, dtype=np.int64)).to(dev),
+                   torch.from_numpy(np.ascontiguousarray(colind, dtype=np.int32)).to(dev),
+                   values if hasattr(values, "data_ptr") else torch.from_numpy(np.ascontiguousarray(values, dtype=np.float64)).to(dev),
+                   n_cols)
+
+    def to_host(self):
+        return self.rowptr.cpu().numpy(), self.colind.cpu().numpy(), self.values.cpu().numpy()
+
+
+def csr_add(ctx: "Context", alpha: float, A: DeviceCsr, beta: float, B: DeviceCsr) -> DeviceCsr:
+    """Matrix::addMatrix / TwoMatrixAdd (Matrix_def.hpp:281-287): alpha*A + beta*B on the union pattern, on the device."""
+    import torch
+    if A.n_rows != B.n_rows or A.n_cols != B.n_cols:
+        raise LogicError("addMatrix: the matrices live on different maps")
+    dev = A.rowptr.device
+    rpC = torch.empty(A.n_rows + 1, dtype=torch.int64, device=dev)
+    nnz = C.c_int64(0)
+    check(ctx._L.feddb200_csr_add_symbolic_d(ctx._h, A.n_rows, ptr(A.rowptr), ptr(A.colind), ptr(B.rowptr), ptr(B.colind),
+                                             ptr(rpC), C.byref(nnz)))
+    ciC = torch.empty(nnz.value, dtype=torch.int32, device=dev)
+    vC = torch.empty(nnz.value, dtype=torch.float64, device=dev)
+    check(ctx._L.feddb200_csr_add_numeric_d(ctx._h, A.n_rows, float(alpha), ptr(A.rowptr), ptr(A.colind), ptr(A.values), float(beta),
+                                            ptr(B.rowptr), ptr(B.colind), ptr(B.values), ptr(rpC), ptr(ciC), ptr(vC)))
+    return DeviceCsr(rpC, ciC, vC, A.n_cols)
+
+
+def block_merge(ctx: "Context", blocks) -> DeviceCsr:
+    """BlockMatrix::merge (BlockMatrix_def.hpp:119-289): blocks[i][j] is a DeviceCsr or None; returns the monolithic matrix."""
+    import torch
+    nb = len(blocks)
+    if any(len(row) != nb for row in blocks):
+        raise LogicError("merge: the block matrix must be square")
+    n_rows, n_cols = [None] * nb, [None] * nb
+    for i in range(nb):
+        for j in range(nb):
+            b = blocks[i][j]
+            if b is None:
+                continue
+            if n_rows[i] not in (None, b.n_rows) or n_cols[j] not in (None, b.n_cols):
+                raise LogicError("merge: blocks of one block row / column have different sizes")
+            n_rows[i], n_cols[j] = b.n_rows, b.n_cols
+    if any(x is None for x in n_rows) or any(x is None for x in n_cols):
+        raise LogicError("merge: a block row or column has no block")
+    some = next(b for row in blocks for b in row if b is not None)
+    dev = some.rowptr.device
+    nr = (C.c_int64 * nb)(*n_rows)
+    ncl = (C.c_int32 * nb)(*n_cols)
+
+    def parr(attr):
+        return (C.c_void_p * (nb * nb))(*[C.c_void_p(getattr(blocks[i][j], attr).data_ptr()) if blocks[i][j] is not None else C.c_void_p(None)
+                                          for i in range(nb) for j in range(nb)])
+
+    rp, ci, v = parr("rowptr"), parr("colind"), parr("values")
+    total = int(sum(n_rows))
+    rpM = torch.empty(total + 1, dtype=torch.int64, device=dev)
+    nnz = C.c_int64(0)
+    vp = lambda a: C.cast(a, C.c_void_p)
+    check(ctx._L.feddb200_block_merge_symbolic_d(ctx._h, nb, vp(nr), vp(ncl), vp(rp), ptr(rpM), C.byref(nnz)))
+    ciM = torch.empty(nnz.value, dtype=torch.int32, device=dev)
+    vM = torch.empty(nnz.value, dtype=torch.float64, device=dev)
+    check(ctx._L.feddb200_block_merge_numeric_d(ctx._h, nb, vp(nr), vp(ncl), vp(rp), vp(ci), vp(v), ptr(rpM), ptr(ciM), ptr(vM)))
+    return DeviceCsr(rpM, ciM, vM, int(sum(n_cols)))
 
 
 class Mesh:
@@ -210,6 +288,14 @@ class Pattern:
 
     def assemble_mass_d(self, values, vec_field=False):
         check(self.ctx._L.feddb200_assemble_mass_d(self.ctx._h, self._h, int(bool(vec_field)), ptr(values)))
+
+    def assemble_bdstab_d(self, values):
+        check(self.ctx._L.feddb200_assemble_bdstab_d(self.ctx._h, self._h, ptr(values)))
+
+    def assemble_bdstab(self):
+        out = np.empty(self.nnz(), dtype=np.float64)
+        check(self.ctx._L.feddb200_assemble_bdstab(self.ctx._h, self._h, ptr(out)))
+        return out
 
     def assemble_linelas_d(self, values, lam, mu):
         check(self.ctx._L.feddb200_assemble_linelas_d(self.ctx._h, self._h, float(lam), float(mu), ptr(values)))

@@ -218,6 +218,16 @@ class FE:
         pat = self._pattern(d, d)
         a += pat.assemble_rhs(res, degFunc, fieldType == "Vector")
 
+    # ---- FE_def.hpp:2151-2220 ----
+    def assemblyBDStabilization(self, dim, FEType, A: Matrix, callFillComplete=True):
+        if FEType != "P1":
+            raise LogicError("Only implemented for P1. Q1 is equivalent but we need to adjust scaling for the reference element.")
+        d = self.domainVec_[self.checkFE(dim, FEType)]
+        pat = self._pattern(d, d)
+        values = self.ctx.empty_values(pat.nnz())
+        pat.assemble_bdstab_d(values)
+        self._finish(A, d, d, pat, values, 1, 1, BLOCK_SCALAR, callFillComplete)
+
     # ---- FE_def.hpp:454-521 ----
     def assemblyMass(self, dim, FEType, fieldType, A: Matrix, callFillComplete=True):
         if FEType == "P0":

@@ -139,6 +139,10 @@ int  feddb200_assemble_laplace_d(feddb200_ctx *ctx, const feddb200_pat *pat, int
 /* FE::assemblyMass (core/FE/FE_def.hpp:454-521): fieldType "Scalar" [vec_field=0, BLOCK_SCALAR] / "Vector"
  * [vec_field=1, BLOCK_DIAG with dim dofs] -- SURVEY.md 8(f) rank 2 */
 int  feddb200_assemble_mass_d(feddb200_ctx *ctx, const feddb200_pat *pat, int vec_field, double *values_d);
+/* FE::assemblyBDStabilization (core/FE/FE_def.hpp:2151-2220): the pressure stabilisation of the
+ * P1-P1 Stokes / Navier-Stokes drivers (Stokes_def.hpp:97-104), C_ij = |det B| (sum_q w phi_i phi_j - size * scale) on a
+ * P1 x P1 BLOCK_SCALAR pattern; any other FE type is the reference's logic_error "Only implemented for P1". */
+int  feddb200_assemble_bdstab_d(feddb200_ctx *ctx, const feddb200_pat *pat, double *values_d);
 /* FE::assemblyLinElasXDim (core/FE/FE_def.hpp:2739-3040) [BLOCK_FULL, dim x dim] */
 int  feddb200_assemble_linelas_d(feddb200_ctx *ctx, const feddb200_pat *pat, double lambda, double mu, double *values_d);
 /* FE::assemblyAdvectionVecField (core/FE/FE_def.hpp:1685-1836) [BLOCK_DIAG]; u_rep_d is the
@@ -163,6 +167,7 @@ int  feddb200_assemble_ns_jacobian_d(feddb200_ctx *ctx, const feddb200_pat *pat,
  * host): H2D of u, D2H of the values inside the call */
 int  feddb200_assemble_laplace(feddb200_ctx *ctx, const feddb200_pat *pat, int vec_field, double *values);
 int  feddb200_assemble_mass(feddb200_ctx *ctx, const feddb200_pat *pat, int vec_field, double *values);
+int  feddb200_assemble_bdstab(feddb200_ctx *ctx, const feddb200_pat *pat, double *values);
 int  feddb200_assemble_linelas(feddb200_ctx *ctx, const feddb200_pat *pat, double lambda, double mu, double *values);
 int  feddb200_assemble_advection(feddb200_ctx *ctx, const feddb200_pat *pat, const double *u_rep, double *values);
 int  feddb200_assemble_advection_in_u(feddb200_ctx *ctx, const feddb200_pat *pat, const double *u_rep, double *values);
@@ -208,6 +213,30 @@ int  feddb200_set_dirichlet_rows_d(feddb200_ctx *ctx, const feddb200_pat *pat, i
                                    const uint8_t *node_mask_d, int diagonal_block, double *values_d);
 /* Matrix::scale (core/LinearAlgebra/Matrix_def.hpp:257) on resident values */
 int  feddb200_scale_d(feddb200_ctx *ctx, double *values_d, int64_t n, double alpha);
+
+/* ---- CSR algebra on resident matrices ---------------------------------------------------------
+ * Device CSR arrays (int64 rowptr, int32 column indices ascending per row, f64 values), e.g. from pattern_expand +
+ * assemble_*_d.  Two phases each: symbolic fills rowptr of the result and returns its nnz, the caller allocates, numeric
+ * fills column indices and values.  Explicit zeros are kept.
+ *
+ * Matrix::addMatrix (core/LinearAlgebra/Matrix_def.hpp:281-287 -> Xpetra TwoMatrixAdd; callers NavierStokes_def.hpp:303-304,
+ * 312-313):  C = alpha*A + beta*B on the union of the two patterns (same row and column index spaces). */
+int  feddb200_csr_add_symbolic_d(feddb200_ctx *ctx, int64_t n_rows, const int64_t *rowptrA_d, const int32_t *colindA_d,
+                                 const int64_t *rowptrB_d, const int32_t *colindB_d, int64_t *rowptrC_d, int64_t *nnzC);
+int  feddb200_csr_add_numeric_d(feddb200_ctx *ctx, int64_t n_rows, double alpha, const int64_t *rowptrA_d,
+                                const int32_t *colindA_d, const double *valuesA_d, double beta, const int64_t *rowptrB_d,
+                                const int32_t *colindB_d, const double *valuesB_d, const int64_t *rowptrC_d,
+                                int32_t *colindC_d, double *valuesC_d);
+/* BlockMatrix::merge / mergeBlockNew (core/LinearAlgebra/BlockMatrix_def.hpp:119-289): the monolithic matrix of an
+ * nb x nb block system (nb <= 4).  Block (i, j) = rowptr_d[i*nb + j] (NULL: absent block), its rows offset by the row
+ * counts of the block rows above, its column indices by the column counts n_cols[0..j-1] of the block columns to its
+ * left (determineLocalOffsets, :170-209); the pointer arrays are HOST arrays of device pointers. */
+int  feddb200_block_merge_symbolic_d(feddb200_ctx *ctx, int nb, const int64_t *n_rows, const int32_t *n_cols,
+                                     const int64_t *const *rowptr_d, int64_t *rowptrM_d, int64_t *nnzM);
+int  feddb200_block_merge_numeric_d(feddb200_ctx *ctx, int nb, const int64_t *n_rows, const int32_t *n_cols,
+                                    const int64_t *const *rowptr_d, const int32_t *const *colind_d,
+                                    const double *const *values_d, const int64_t *rowptrM_d, int32_t *colindM_d,
+                                    double *valuesM_d);
 
 #ifdef __cplusplus
 }

@@ -611,6 +611,44 @@ int fo_assembly_mass(int dim, const char *fe, int64_t ne, const int32_t *conn, c
     return 0;
 }
 
+/* FE_def.hpp:2151-2220 assemblyBDStabilization (P1 only, :2156): the P1 mass entry minus the mean-value term,
+ *   value[j] = (sum_w weights[w] phi[w][i] phi[w][j]) * absDetB - refElementSize * absDetB * refElementScale   (:2203-2207)
+ * with refElementSize / refElementScale = 1/2, 1/9 (2D) and 1/6, 1/16 (3D) (:2183-2190); deg = determineDegree(Std, Std). */
+int fo_assembly_bdstab(int dim, const char *fe, int64_t ne, const int32_t *conn, const double *coords,
+                       const int64_t *gid, fo_matrix *A)
+{
+    if (strcmp(fe, "P1") != 0) return -1; /* "Only implemented for P1." */
+    int nloc = fo_nloc(dim, fe);
+    if (nloc < 0) return -1;
+    double phi[FO_MAXQ * FO_MAXN], w[FO_MAXQ];
+    int deg = fo_determine_degree2(dim, fe, fe, FO_STD, FO_STD, 0);
+    int nq = fo_get_phi(dim, fe, deg, phi, w);
+    if (nq < 0) return -1;
+    double refElementSize, refElementScale;
+    if (dim == 2) { refElementSize = 0.5; refElementScale = 1. / 9.; }
+    else if (dim == 3) { refElementSize = 1. / 6.; refElementScale = 1. / 16.; }
+    else return -1;
+    double value[FO_MAXN];
+    int64_t indices[FO_MAXN];
+    for (int64_t T = 0; T < ne; T++) {
+        const int32_t *el = conn + T * nloc;
+        double B[3][3];
+        fo_build_transformation(dim, el, coords, B);
+        double absDetB = fabs(fo_det(dim, B));
+        for (int i = 0; i < nloc; i++) {
+            for (int j = 0; j < nloc; j++) {
+                value[j] = 0.;
+                for (int q = 0; q < nq; q++) value[j] += w[q] * phi[q * nloc + i] * phi[q * nloc + j];
+                value[j] *= absDetB;
+                value[j] -= refElementSize * absDetB * refElementScale;
+                indices[j] = gid[el[j]];
+            }
+            fo_insert(A, gid[el[i]], nloc, indices, value);
+        }
+    }
+    return 0;
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* FE_def.hpp:2739-3040 assemblyLinElasXDim                                               */
 /* ------------------------------------------------------------------------------------ */

@@ -45,6 +45,7 @@ def lib():
         L.fo_assembly_laplace.argtypes = common + [C.c_void_p]
         L.fo_assembly_laplace_vecfield.argtypes = common + [C.c_void_p]
         L.fo_assembly_mass.argtypes = common + [C.c_int, C.c_void_p]
+        L.fo_assembly_bdstab.argtypes = common + [C.c_void_p]
         L.fo_assembly_rhs.argtypes = [C.c_int, C.c_char_p, C.c_int64, _I32P, _F64P, C.c_int, C.c_int, _F64P, _F64P]
         L.fo_assembly_linelas.argtypes = common + [C.c_double, C.c_double, C.c_void_p]
         L.fo_assembly_advection.argtypes = common + [_F64P, C.c_void_p]
@@ -132,6 +133,12 @@ def assembly_rhs(dim, fe, conn, coords, value_func, deg_func=0, vec_field=False,
     rhs = np.zeros(n) if rhs is None else rhs
     _chk(lib().fo_assembly_rhs(dim, fe.encode(), conn.shape[0], conn, coords, int(bool(vec_field)), int(deg_func), f, rhs), "assemblyRHS")
     return rhs
+
+
+def assembly_bdstab(dim, fe, conn, coords, gid, A: Matrix):
+    """FE::assemblyBDStabilization (FE_def.hpp:2151-2220), P1 only."""
+    conn, coords, gid = _prep(conn, coords, gid)
+    _chk(lib().fo_assembly_bdstab(dim, fe.encode(), conn.shape[0], conn, coords, gid, A._h), "assemblyBDStabilization")
 
 
 def assembly_mass(dim, fe, conn, coords, gid, A: Matrix, vec_field=False):

@@ -15,7 +15,7 @@ from . import oracle as O
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(_HERE, "_ref", "libfedd_ref.so")
 _lib = None
-OPS = {"laplace": 0, "laplace_vec": 1, "linelas": 2, "advection": 3, "advection_in_u": 4, "div": 5, "div_fast": 6, "mass": 7, "mass_vec": 8}
+OPS = {"laplace": 0, "laplace_vec": 1, "linelas": 2, "advection": 3, "advection_in_u": 4, "div": 5, "div_fast": 6, "mass": 7, "mass_vec": 8, "bdstab": 9}
 
 
 def available() -> bool:
@@ -63,7 +63,7 @@ def assemble(op, dim, fe, conn, coords, gid=None, u=None, lam=0.0, mu=0.0, fe2=N
     nn = coords.shape[0]
     gid = np.arange(nn, dtype=np.int64) if gid is None else np.ascontiguousarray(gid, dtype=np.int64)
     nglob = int(nrows_global if nrows_global is not None else gid.max() + 1)
-    dofs = 1 if op in ("laplace", "mass") else dim
+    dofs = 1 if op in ("laplace", "mass", "bdstab") else dim
     is_div = op in ("div", "div_fast")
     if is_div:
         conn2 = np.ascontiguousarray(conn2, dtype=np.int32)

@@ -37,7 +37,7 @@ extern "C" const char *ref_last_error(void) { return g_err.c_str(); }
 
 // op: 0 assemblyLaplace, 1 assemblyLaplaceVecField, 2 assemblyLinElasXDim, 3 assemblyAdvectionVecField,
 //     4 assemblyAdvectionInUVecField, 5 assemblyDivAndDivT, 6 assemblyDivAndDivTFast,
-//     7 assemblyMass "Scalar", 8 assemblyMass "Vector"
+//     7 assemblyMass "Scalar", 8 assemblyMass "Vector", 9 assemblyBDStabilization
 extern "C" int ref_assemble(int op, int dim, const char *fe1, const char *fe2, int64_t ne,
                             const int32_t *conn1, int nloc1, const double *coords1, int64_t nn1, const int64_t *gid1,
                             const int32_t *conn2, int nloc2, int64_t nn2, const int64_t *gid2,
@@ -55,6 +55,7 @@ extern "C" int ref_assemble(int op, int dim, const char *fe1, const char *fe2, i
         case 2: fe.assemblyLinElasXDim(dim, t1, mA, lambda, mu, true); break;
         case 7: fe.assemblyMass(dim, t1, std::string("Scalar"), mA, true); break;
         case 8: fe.assemblyMass(dim, t1, std::string("Vector"), mA, true); break;
+        case 9: fe.assemblyBDStabilization(dim, t1, mA, true); break;
         case 3:
         case 4: {
             Teuchos::RCP<MV_t> mv(new MV_t(u, (std::size_t)dim * nn1));

@@ -138,7 +138,9 @@ int main(int argc, char **argv)
         const Case cases[] = {{"assemblyLaplace", 0, 1}, {"assemblyLaplaceVecField", 1, dim}, {"assemblyLinElasXDim", 2, dim},
                               {"assemblyAdvectionVecField", 3, dim}, {"assemblyAdvectionInUVecField", 4, dim},
                               {"assemblyMass Scalar", 7, 1}, {"assemblyMass Vector", 8, dim}};
-        for (const Case &c : cases) {
+        std::vector<Case> todo(std::begin(cases), std::end(cases));
+        if (std::string(fe1) == "P1") todo.push_back({"assemblyBDStabilization", 9, 1});
+        for (const Case &c : todo) {
             // reference
             fo_matrix *rA = fo_matrix_new(c.rowDofs * nglob1, 64), *rB = fo_matrix_new(1, 8);
             if (ref_assemble(c.op, dim, fe1, fe1, ne, conn1.data(), nloc1, xyz.data(), nn1, gid1.data(), nullptr, 0, 0, nullptr, u.data(),
@@ -155,6 +157,7 @@ int main(int argc, char **argv)
             case 4: fe.assemblyAdvectionInUVecField(dim, fe1, A, uMV, true); break;
             case 7: fe.assemblyMass(dim, fe1, "Scalar", A); break;
             case 8: fe.assemblyMass(dim, fe1, "Vector", A); break;
+            case 9: fe.assemblyBDStabilization(dim, fe1, A); break;
             }
             all = compare(c.name, g_seated[A.get()], ref, gid1, c.rowDofs) && all;
             all = (A->fillCompleteCalls_ == 1) && all;

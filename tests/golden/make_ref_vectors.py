@@ -34,6 +34,9 @@ if __name__ == "__main__":
                        ("advection", dict(u=u)), ("advection_in_u", dict(u=u))):
             rp, ci, v = R.assemble(op, dim, fe, conn, coords, **kw)
             out[f"{name}/{op}/rowptr"], out[f"{name}/{op}/col"], out[f"{name}/{op}/val"] = rp, ci, v
+        if fe == "P1":  # assemblyBDStabilization is P1 only (FE_def.hpp:2156)
+            rp, ci, v = R.assemble("bdstab", dim, fe, conn, coords)
+            out[f"{name}/bdstab/rowptr"], out[f"{name}/bdstab/col"], out[f"{name}/bdstab/val"] = rp, ci, v
         (B, BT) = R.assemble("div", dim, fe, conn, coords, fe2="P1", conn2=conn_p)
         for tag, (rp, ci, v) in (("B", B), ("BT", BT)):
             out[f"{name}/div{tag}/rowptr"], out[f"{name}/div{tag}/col"], out[f"{name}/div{tag}/val"] = rp, ci, v

@@ -90,6 +90,18 @@ def test_mass(case, mode):
 
 
 @pytest.mark.parametrize("mode", MODES)
+def test_bd_stabilization(case, mode):
+    """FE::assemblyBDStabilization (FE_def.hpp:2151-2220; SURVEY.md 8(f) rank 4): P1 only, logic_error otherwise."""
+    from feddlib_b200 import BLOCK_SCALAR, LogicError
+    case["ctx"].set_scatter_mode(mode)
+    if case["fe"] == "P1":
+        check(case, "bdstab", case["pat"].assemble_bdstab(), 1, 1, BLOCK_SCALAR)
+    else:
+        with pytest.raises(LogicError):
+            case["pat"].assemble_bdstab()
+
+
+@pytest.mark.parametrize("mode", MODES)
 def test_linear_elasticity(case, mode):
     from feddlib_b200 import BLOCK_FULL
     case["ctx"].set_scatter_mode(mode)

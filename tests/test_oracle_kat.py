@@ -235,3 +235,27 @@ def test_mass_matrix_known_answers(dim, fe, M):
         blk = Sv[d::dim, :][:, d::dim]
         assert abs(blk - S).max() == 0.0
     assert Sv.nnz == dim * S.nnz
+
+
+@pytest.mark.parametrize("dim,M", [(2, 5), (3, 3)])
+def test_bd_stabilization_known_answers(dim, M):
+    """assemblyBDStabilization (FE_def.hpp:2151-2220): C = M_P1 - |T| * scale * 1 1^T per element.  With scale = 1/9
+    (2D: 3 nodes) and 1/16 (3D: 4 nodes) the element row sums of the mean-value term equal those of the mass matrix, so
+    C 1 = 0; C is symmetric and C = M - (rank-one element terms) is positive semi-definite on mean-free vectors."""
+    from oracle import mesh as OM
+    conn, coords, gid = OM.structured(dim, "P1", 1, M)
+    n = coords.shape[0]
+    A = O.Matrix(n, 64)
+    O.assembly_bdstab(dim, "P1", conn, coords, gid, A)
+    S = A.scipy().tocsr()
+    if dim == 2:   # 3 * (1/2 * 1/9) = 1/6 = row sum of the reference P1 mass matrix
+        assert abs(S @ np.ones(n)).max() < 1e-15
+    else:          # 3D: 4 * (1/6 * 1/16) = 1/24 = row sum of the reference P1 mass matrix
+        assert abs(S @ np.ones(n)).max() < 1e-15
+    assert abs(S - S.T).max() < 1e-16
+    Mm = O.Matrix(n, 64)
+    O.assembly_mass(dim, "P1", conn, coords, gid, Mm, False)
+    D = (Mm.scipy().tocsr() - S).toarray()
+    assert D.min() >= 0 and D.max() > 0 and np.linalg.matrix_rank(D) <= conn.shape[0]
+    with pytest.raises(ValueError):
+        O.assembly_bdstab(dim, "P2", conn, coords, gid, O.Matrix(n, 64))

@@ -29,6 +29,10 @@ def test_restatement_is_bitwise_equal_to_reference_code(dim, fe, make):
         b = R.assemble(op, dim, fe, conn, coords, **kw)
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), op
         assert np.array_equal(a[2], b[2]), f"{op}: max abs diff {np.abs(a[2] - b[2]).max():.3e}"
+    if fe == "P1":  # assemblyBDStabilization (FE_def.hpp:2151-2220) is P1 only
+        a = oracle_csr("bdstab", dim, fe, conn, coords)
+        b = R.assemble("bdstab", dim, fe, conn, coords)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b)), "bdstab"
 
 
 @pytest.mark.parametrize("dim,fe1", [(2, "P2"), (3, "P2"), (3, "P1"), (2, "P1")])

@@ -46,6 +46,8 @@ def oracle_csr(op, dim, fe, conn, coords, u=None, lam=None, mu=None, fe2=None, c
         A = O.Matrix(nn); O.assembly_laplace(dim, fe, conn, coords, gid, A)
     elif op == "mass":
         A = O.Matrix(nn); O.assembly_mass(dim, fe, conn, coords, gid, A, False)
+    elif op == "bdstab":
+        A = O.Matrix(nn); O.assembly_bdstab(dim, fe, conn, coords, gid, A)
     elif op == "mass_vec":
         A = O.Matrix(dim * nn); O.assembly_mass(dim, fe, conn, coords, gid, A, True)
     elif op == "laplace_vec":
