@@ -258,6 +258,23 @@ class HaloPlan:
         return out
 
 
+    # -- vectors on the pattern rows (FE::assemblyRHS + exportFromVector(..., "Add"), Problem_def.hpp:184-216) -------
+    def vec_split_sizes(self, dofs):
+        """(send, recv) counts per rank of the ghost part of a row vector with `dofs` entries per node."""
+        send = np.array([(self.ghost_row_owner == d).sum() for d in range(self.comm.size)], dtype=np.int64) * dofs
+        first = self.recv_q == 0
+        off = np.concatenate([[0], np.cumsum(self.recv_counts_nodes)])
+        recv = np.array([first[off[s]:off[s + 1]].sum() for s in range(self.comm.size)], dtype=np.int64) * dofs
+        return send.tolist(), recv.tolist()
+
+    def vec_recv_slots(self, dofs):
+        """Entry (into this rank's row vector, owned part) of every received vector value, in arrival order: a sender
+        ships its ghost rows in order, node-wise interleaved dofs; the first pattern entry of each received ghost row
+        names the owner's row."""
+        I = self.recv_row[self.recv_q == 0]
+        return (dofs * I[:, None] + np.arange(dofs)[None, :]).ravel().astype(np.int64)
+
+
 class DistributedMatrixAssembler:
     """Device-side driver: per-rank mesh + pattern from a HaloPlan, assembly + ghost exchange."""
 
@@ -395,6 +412,36 @@ class DistributedMatrixAssembler:
             for b in P["recv"]:
                 self.ctx.free_d(b)
         self._peer = {}
+
+    def export_add_vector(self, vec, dofs):
+        """Reference: MultiVector::exportFromVector(repeated, ..., "Add") after FE::assemblyRHS (Problem_def.hpp:213):
+        the entries of rows owned elsewhere (behind the owned ones in pattern-row order) are shipped to the owners and
+        added; afterwards vec[: dofs * n_owned] is the vector on the unique map."""
+        import torch
+        import torch.distributed as dist
+        if self.size == 1:
+            return vec
+        key = ("vec", dofs)
+        if key not in self._slot_t:
+            self._slot_t[key] = torch.from_numpy(self.plan.vec_recv_slots(dofs)).to(self._dev)
+            self._recv_buf[key] = torch.empty(self._slot_t[key].numel(), dtype=torch.float64, device=self._dev)
+        ssz, rsz = self.plan.vec_split_sizes(dofs)
+        send, recv = vec[dofs * self.plan.n_owned:], self._recv_buf[key]
+        dist.all_to_all_single(recv, send, rsz, ssz)
+        off = 0
+        for n in rsz:                       # one launch per sender: deterministic sums
+            if n:
+                self.ctx.unpack_add_d(vec, recv[off:off + n], self._slot_t[key][off:off + n])
+            off += n
+        return vec
+
+    def assemble_rhs(self, value_func, deg_func=0, vec_field=False):
+        """FE::assemblyRHS on this rank's elements + the export/ADD to the owners; returns the device vector in
+        pattern-row order (owned rows first = the unique-map vector)."""
+        import torch
+        dofs = self.dim if vec_field else 1
+        vec = torch.from_numpy(self.pat.assemble_rhs(value_func, deg_func, vec_field)).to(self._dev)
+        return self.export_add_vector(vec, dofs)
 
     def _unpack(self, values, key, rsz):
         recv, slots = self._recv_buf[key], self._slot_t[key]

@@ -85,6 +85,18 @@ def main():
                 assert torch.equal(values3[:n_owned_vals], values[:n_owned_vals]), f"rank {rank}: fused peer-memory exchange differs (pass {it})"
             dist.barrier()
             run.close_peer()
+        if mode == "gather":
+            # load vector: FE::assemblyRHS on the device + export/ADD of the ghost rows (NCCL) = global oracle vector
+            f = np.array([1.5, -2.0, 0.25])
+            for vec_field in (False, True):
+                dofs = dim if vec_field else 1
+                got = run.assemble_rhs(f, 1, vec_field)[: dofs * plan.n_owned].cpu().numpy()
+                glob = np.zeros(dofs * nglob)
+                for r in range(world):
+                    c2, x2, g2, _ = PM.build_structured_box(dim, fe, dims, M, r)
+                    np.add.at(glob, (dofs * g2[:, None] + np.arange(dofs)[None, :]).ravel(), O.assembly_rhs(dim, fe, c2, x2, f, 1, vec_field))
+                want = glob[(dofs * plan.unique_gids[:, None] + np.arange(dofs)[None, :]).ravel()]
+                assert np.abs(got - want).max() <= 1e-13 * np.abs(want).max(), f"rank {rank}: load vector export/ADD"
         print(f"[dist_gpu_check] rank {rank}/{world} mode {mode}: owned rows {plan.n_owned}, ghost rows {plan.n_ghost}, "
               f"rel. error {rel:.2e} OK (overlapped exchange equal)", flush=True)
     dist.destroy_process_group()

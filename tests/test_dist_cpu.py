@@ -102,6 +102,28 @@ dist.all_reduce(cnt)
 assert int(cnt.min()) == 1 and int(cnt.max()) == 1
 tot = torch.tensor([nnz_checked]); dist.all_reduce(tot)
 assert int(tot) == Gs.nnz
+# --- load vector: FE::assemblyRHS on the repeated map + exportFromVector(..., "Add") (Problem_def.hpp:184-216) ---
+for vec_field in (False, True):
+    dofs = dim if vec_field else 1
+    f = np.array([1.5, -2.0, 0.25])[:dim]
+    loc = O.assembly_rhs(dim, fe, conn, coords, f, 1, vec_field)                 # repeated-node order
+    vec = np.zeros(dofs * plan.n_rows)
+    rows = plan.row_lid.astype(np.int64)
+    vec[(dofs * rows[:, None] + np.arange(dofs)[None, :]).ravel()] = loc
+    ssz, rsz = plan.vec_split_sizes(dofs)
+    send = torch.from_numpy(vec[dofs * plan.n_owned:].copy())
+    recv = torch.empty(int(sum(rsz)), dtype=torch.float64)
+    dist.all_to_all_single(recv, send, rsz, ssz)
+    vs = plan.vec_recv_slots(dofs)
+    assert vs.size == recv.numel() and (vs < dofs * plan.n_owned).all()
+    np.add.at(vec, vs, recv.numpy())
+    glob = np.zeros(dofs * nglob)
+    for r in range(world):
+        c2, x2, g2, _ = PM.build_structured_box(dim, fe, dims, M, r)
+        part = O.assembly_rhs(dim, fe, c2, x2, f, 1, vec_field)
+        np.add.at(glob, (dofs * g2[:, None] + np.arange(dofs)[None, :]).ravel(), part)
+    want = glob[(dofs * plan.unique_gids[:, None] + np.arange(dofs)[None, :]).ravel()]
+    assert np.abs(vec[: dofs * plan.n_owned] - want).max() <= 1e-13 * np.abs(want).max(), "load vector export/ADD"
 print(f"rank {rank}/{world} OK: owned {plan.n_owned} ghost {plan.n_ghost} extra {plan.extra_row.size} recv {slots.size}")
 dist.destroy_process_group()
 '''
