@@ -176,9 +176,18 @@ int ensure_gather(feddb200_pat *p)
             info[q].len = (int32_t)(p->rowptr_h[r + 1] - p->rowptr_h[r]);
             info[q].ninc = (int32_t)(inc_ptr[r + 1] - inc_ptr[r]);
             info[q].pad = rtype[r]; // bits 0-1 row type, bit 4: the row has positions without a local contribution
+            for (int j = 0; j < 8; j++) info[q].e[j] = 0;
         }
         FB_CUDA(cudaMalloc(&p->rowinfo_d, sizeof(RowInfo) * std::max<int64_t>(n_rows, 1)));
         FB_CUDA(cudaMemcpy(p->rowinfo_d, info.data(), sizeof(RowInfo) * n_rows, cudaMemcpyHostToDevice));
+        if (dim == 3 && nl == 10 && nlc == 10 && n_rows > 0) { // 3D P2: look-ahead elements of k_gather_s
+            FB_CUDA(cudaMalloc(&p->ahead_d, sizeof(uint32_t) * std::max<int64_t>(p->n_inc, 1)));
+            FB_CUDA(cudaMemsetAsync(p->ahead_d, 0, sizeof(uint32_t) * std::max<int64_t>(p->n_inc, 1), c->stream));
+            k_ring_ahead<<<(unsigned)std::min<int64_t>((n_rows + 127) / 128, 148 * 64), 128, 0, c->stream>>>(n_rows, (RowInfo *)p->rowinfo_d, p->rec_d, p->ahead_d);
+            c->launches++;
+            FB_CUDA(cudaGetLastError());
+            FB_CUDA(cudaStreamSynchronize(c->stream));
+        }
     }
     const int gs = dim == 3 ? 16 : 8;
     FB_CUDA(cudaMalloc(&p->geom_d, sizeof(double) * std::max<int64_t>(p->rm->ne * gs, 1)));
@@ -271,9 +280,9 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
                     if (conf < best_conf) { best_conf = conf; pitch = cand; }
                 }
                 const size_t smem = (size_t)pitch * 8 * npt * (nt / 32);
-                FB_LOGIC(smem > budget, "row too long for the gather path's shared-memory rows; use the coloured or atomic mode");
                 G.pitch = pitch;
                 const int64_t tiles = ((b.count + npt - 1) / npt + nt / 32 - 1) / (nt / 32); // in blocks
+                FB_LOGIC(smem > budget, "row too long for the gather path's shared-memory rows; use the coloured or atomic mode");
                 FB_CUDA(cudaFuncSetAttribute(k_ring<OPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
                 // persistent blocks: as many as are resident at once (times a small factor that evens out the tail)
                 int per_sm = 1;
@@ -294,6 +303,24 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
             FB_LOGIC(smem > budget, "row too long for the gather path's shared-memory accumulators; use the coloured or atomic mode");
             const int nt = S::NT;
             G.pitch = pitch;
+            if constexpr (OPG == 1 && DIM == 3 && NL == 10) {
+                // vertex-node rows of 3D P2 elasticity: streamed inputs (k_gather_s), 3 row nodes per warp
+                static const bool stream_ok = [] { const char *f = getenv("FEDDB200_GATHER_STREAM"); return !f || atoi(f) != 0; }(); // tuning aid
+                int nts = 64;
+                if (const char *f = getenv("FEDDB200_GATHER_NT")) nts = std::max(32, std::min(128, atoi(f) & ~31)); // tuning aid
+                const size_t smem_s = ((((size_t)pitch * 8 * 9 + 15) & ~(size_t)15) + 3 * kRsNodeB) * (nts / 32);
+                if (stream_ok && b.type == 0 && p->ahead_d && smem_s <= budget) {
+                    FB_CUDA(cudaFuncSetAttribute(k_gather_s, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+                    int per_sm = 1;
+                    FB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gather_s, nts, smem_s));
+                    const int64_t tiles = ((b.count + 2) / 3 + nts / 32 - 1) / (nts / 32); // in blocks
+                    const int64_t blocks_s = std::min<int64_t>(tiles, (int64_t)std::max(per_sm, 1) * c->sm_count);
+                    k_gather_s<<<(unsigned)blocks_s, nts, smem_s, st>>>(G);
+                    c->launches++;
+                    FB_CUDA(cudaGetLastError());
+                    continue;
+                }
+            }
             const int64_t blocks = (b.count * S::CPR + nt - 1) / nt;
             auto launch = [&](auto kernel) -> int {
                 FB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
@@ -538,7 +565,7 @@ int run_op(feddb200_ctx *c, const feddb200_pat *pc, int op, const double *u_d, d
         rc = ensure_gather(p);
         if (rc != FEDDB200_OK) return rc;
         GatherArgs G;
-        G.rowinfo = (const RowInfo *)p->rowinfo_d; G.rec = p->rec_d; G.geom = p->geom_d;
+        G.rowinfo = (const RowInfo *)p->rowinfo_d; G.rec = p->rec_d; G.geom = p->geom_d; G.ahead = p->ahead_d;
         G.c0 = c0; G.c1 = c1; G.values = values_d; G.vec_dim = (op == OP_LAP && vec_field) ? dim : 0;
         canon_table(tab_h, dim, nr, G.R);
         return op == OP_LAP ? launch_gather<0>(c, p, G) : launch_gather<1>(c, p, G);

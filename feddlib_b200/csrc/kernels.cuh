@@ -629,6 +629,8 @@ struct RowInfo {
     int32_t len;    // node-row length
     int32_t ninc;   // number of incidences
     int64_t pad;
+    uint32_t e[8];  // elements of the row's first incidences -- lets k_gather_s request the geometry lines of a
+                    // row's first incidences from the row record alone (second 32-byte half)
 };
 
 constexpr int kMaxGhostSeg = 8;   // ranks of one box
@@ -649,6 +651,7 @@ struct GatherArgs {
     int nseg;
     int64_t seg_begin[kMaxGhostSeg + 1];
     double *seg_ptr[kMaxGhostSeg];
+    const uint32_t *ahead;    // k_gather_s: element of the incidence kRsAhead places further along the same row
     CanonR R;
 };
 
@@ -1169,6 +1172,280 @@ __global__ void __launch_bounds__(64, FB_RING_MINBLOCKS) k_ring(const GatherArgs
     // (a warp-uniform, compile-time row dof -- 32 row nodes per 96-thread block -- removes the
     // delta_ab selects but makes every geometry load touch 32 lines instead of 11: measured 3.49 ms vs 3.08 ms)
     ring_tiles<OPG>(A, acc);
+}
+
+// -----------------------------------------------------------------------------------------
+// Streamed inputs (k_gather_s below).  Every row node owns a small ring of kRsD slots in shared memory; a slot holds
+// everything one incidence needs
+//     [ record 32 B | geometry line 128 B | element of the incidence kRsAhead places further on, 4 B ]
+// and is filled by asynchronous copies (cp.async, SASS LDGSTS) issued kRsAhead = kRsD - 1 incidences before it is
+// consumed; the lanes of a node share the 11 chunks.  No register is held across the latency, the main loop contains
+// no global load, and the request stream of a row continues into the row the lane processes next (its first elements
+// come with the row record, RowInfo::e), so a warp only waits for memory on its very first tile.  The element
+// look-ahead word removes the record -> geometry dependence: the address of a geometry line is known kRsAhead
+// incidences early without a second level of prefetching.
+//
+// Bookkeeping per lane (identical in the lanes of a node): `gcount` cp.async groups committed so far and, per ring
+// slot, the group that filled it; before a slot is consumed the lane waits until at most (gcount - 1 - group) newer
+// groups are pending, which is kRsAhead - 1 in steady state and 0 right after a catch-up (first tile, rows with fewer
+// than kRsAhead incidences).
+// -----------------------------------------------------------------------------------------
+#ifndef FB_RS_D
+#define FB_RS_D 3
+#endif
+constexpr int kRsD = FB_RS_D;                 // ring slots per row node
+constexpr int kRsAhead = kRsD - 1;            // incidences between request and use
+constexpr int kRsSlotB = 176;                 // bytes per slot: 32 + 128 + 4, rounded up to 16
+// bytes per node ring, padded to 16 * (8 k + 1): with nine lanes per node the 16-byte chunk that lane l copies then
+// falls into bank group l mod 8, so the eight lanes of a quarter-warp never collide while the nodes use the same slot
+constexpr int kRsNodeB = 16 * (((kRsD * kRsSlotB / 16 + 6) / 8) * 8 + 1);
+static_assert(kRsNodeB >= kRsD * kRsSlotB && (kRsNodeB / 16) % 8 == 1, "ring stride");
+static_assert(kRsD >= 2 && kRsD <= 8, "ring depth");
+
+__device__ __forceinline__ void cp_async16(void *sdst, const void *gsrc)
+{
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(sdst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *sdst, const void *gsrc)
+{
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(sdst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// wait until at most min(allowed, kRsAhead - 1) of this thread's newest groups are pending
+__device__ __forceinline__ void cp_async_wait_upto(int allowed)
+{
+    if constexpr (kRsAhead >= 4) { if (allowed >= 3) { cp_async_wait<3>(); return; } }
+    if constexpr (kRsAhead >= 3) { if (allowed >= 2) { cp_async_wait<2>(); return; } }
+    if constexpr (kRsAhead >= 2) { if (allowed >= 1) { cp_async_wait<1>(); return; } }
+    cp_async_wait<0>();
+}
+
+// one-time (pattern build): look-ahead elements of every row -- RowInfo::e (first incidences) and ahead[k]
+__global__ void k_ring_ahead(int64_t n_rows, RowInfo *__restrict__ info, const uint32_t *__restrict__ rec, uint32_t *__restrict__ ahead)
+{
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n_rows; q += (int64_t)gridDim.x * blockDim.x) {
+        RowInfo &R = info[q];
+        for (int j = 0; j < 8; j++) R.e[j] = j < R.ninc ? rec[(R.k0 + j) * 8 + 5] : 0u;
+        for (int m = 0; m < R.ninc; m++) ahead[R.k0 + m] = m + kRsAhead < R.ninc ? rec[(R.k0 + m + kRsAhead) * 8 + 5] : 0u;
+    }
+}
+
+// -----------------------------------------------------------------------------------------
+// Vertex-node rows of 3D P2 elasticity with streamed inputs: the arithmetic of k_gather<1,3,10,0> (one thread per
+// component row (I, a, b), read-modify-write accumulators laid out like the CSR rows, pitch == 3 (mod 16): conflict
+// free) behind the input rings above.  k_gather is limited by the L1 data pipe, and 2/3 of its load is the global-load
+// return path: each of the nine threads of a node pulls the same 160 bytes per incidence into its registers
+// (LDG.256 x 5 = 40 wavefront-equivalents per warp and incidence).  Here the record and the geometry line enter shared
+// memory ONCE per node and incidence and are read back with shared-memory loads whose lanes share addresses
+// (LDS.128 x 10 = 20 wavefronts: ncu counts two per instruction for three distinct addresses).
+// A warp owns NPT = 3 row nodes (27 lanes); warps are persistent and never wait for one another.
+// -----------------------------------------------------------------------------------------
+#ifndef FB_GS_MINBLOCKS
+#define FB_GS_MINBLOCKS 6
+#endif
+__global__ void __launch_bounds__(64, FB_GS_MINBLOCKS) k_gather_s(const GatherArgs A)
+{
+    constexpr int DIM = 3, NVTX = 4, NL = 10, NB = 3, CPR = 9, NPT = 3, ROWS = NPT * DIM;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ double acc[];          // per warp: ROWS accumulator rows of `pitch` doubles, then NPT rings
+    const int tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
+    const int pitch = A.pitch;
+    const int slot = lane / CPR;             // node of this lane inside the warp's tile (3 = the five spare lanes)
+    const bool lane_used = lane < NPT * CPR;
+    const int comp = lane - slot * CPR;
+    const int a = comp / NB, b = comp - a * NB;
+    const unsigned nmask = lane_used ? (0x1ffu << (CPR * slot)) : (0x1fu << 27);
+    const int64_t ntiles = (A.count + NPT - 1) / NPT;
+    const size_t rows_bytes = ((size_t)ROWS * pitch * 8 + 15) & ~(size_t)15;   // the rings are 16-byte aligned
+    const size_t warp_bytes = rows_bytes + (size_t)NPT * kRsNodeB;
+    char *const wbase = reinterpret_cast<char *>(acc) + (size_t)(tid >> 5) * warp_bytes;
+    double *const rows = reinterpret_cast<double *>(wbase);
+    char *const ring = wbase + rows_bytes + (size_t)(lane_used ? slot : 0) * kRsNodeB;
+    const int64_t tile_step = (int64_t)gridDim.x * (NT >> 5);
+
+    // this lane's share of the 11 chunks of a slot: chunk `comp` (record: 0, 1; geometry: 2..8), lane 0 also the
+    // last geometry chunk, lane 1 the look-ahead word
+    auto request = [&](int rs, int64_t k, uint32_t e) {
+        char *dst = ring + rs * kRsSlotB;
+        const char *rsrc = reinterpret_cast<const char *>(A.rec + k * 8);
+        const char *gsrc = reinterpret_cast<const char *>(A.geom + (int64_t)e * 16);
+        cp_async16(dst + 16 * comp, comp < 2 ? rsrc + 16 * comp : gsrc + 16 * (comp - 2));
+        if (comp == 0) cp_async16(dst + 144, gsrc + 112);
+        if (comp == 1) cp_async4(dst + 160, A.ahead + k);
+    };
+    auto wrap = [](int x) { return x >= kRsD ? x - kRsD : x; };
+
+    // M^T of this component: e = |det| G_s^T M G_w,  M = mu (delta_ab I + e_b e_a^T) + lambda e_a e_b^T
+    double Mm[DIM][DIM];
+#pragma unroll
+    for (int c = 0; c < DIM; c++)
+#pragma unroll
+        for (int d = 0; d < DIM; d++)
+            Mm[c][d] = ((a == b && c == d) ? A.c1 : 0.0) + ((c == b && d == a) ? A.c1 : 0.0) + ((c == a && d == b) ? A.c0 : 0.0);
+
+    int64_t tile = (int64_t)blockIdx.x * (NT >> 5) + (tid >> 5);
+    if (tile >= ntiles) return;
+    double raw[4] = {0.0, 0.0, 0.0, 0.0};
+    {
+        const int64_t node = tile * NPT + slot;
+        if (lane_used && node < A.count) ld_v4(reinterpret_cast<const double *>(A.rowinfo + A.start + node), raw);
+    }
+    uint32_t gcount = 0, gis = 0;            // committed groups; the group that filled each slot (see above)
+    int s0 = 0, nis = 0;
+    auto note = [&](int rs) { gis = (gis & ~(0xffu << (8 * rs))) | ((gcount & 0xffu) << (8 * rs)); };
+
+    for (;;) {
+        const bool live = lane_used && tile * NPT + slot < A.count;
+        const int64_t base = __double_as_longlong(raw[0]);
+        const int64_t k0 = __double_as_longlong(raw[1]);
+        const int L = live ? (int)(__double_as_longlong(raw[2]) & 0xffffffff) : 0;
+        const int ninc = live ? (int)(__double_as_longlong(raw[2]) >> 32) : 0;
+        const int64_t tile_n = tile + tile_step;
+        const int64_t node_n = tile_n * NPT + slot;
+        const bool live_n = lane_used && tile_n < ntiles && node_n < A.count;
+        double rawn[4] = {0.0, 0.0, 0.0, 0.0};
+        uint4 en = make_uint4(0u, 0u, 0u, 0u);
+        if (live_n) {
+            ld_v4(reinterpret_cast<const double *>(A.rowinfo + A.start + node_n), rawn);
+            en = __ldg(reinterpret_cast<const uint4 *>(A.rowinfo[A.start + node_n].e));
+        }
+        int nisn = 0;
+        const int sn0 = (s0 + ninc) % kRsD;
+
+        const int row = (lane_used ? slot : 0) * DIM + a;
+        double *my = rows + (size_t)row * pitch + b;
+        // the warp's rows were copied out by the warp itself (below): zero them for this tile
+        for (int x = lane; x < ROWS * pitch; x += 32) rows[x] = 0.0;
+        __syncwarp();
+        const int nmax = __reduce_max_sync(FULL, ninc);
+
+        if (ninc > 0 && nis < ninc && nis < kRsAhead) { // catch-up (first tile, short rows)
+#pragma unroll
+            for (int j = 0; j < kRsAhead; j++)
+                if (j >= nis && j < ninc) {
+                    const int rs = wrap(s0 + j);
+                    request(rs, k0 + j, __ldg(A.rowinfo[A.start + tile * NPT + slot].e + j));
+                    note(rs);
+                }
+            nis = ninc < kRsAhead ? ninc : kRsAhead;
+            cp_async_commit();
+            gcount++;
+        }
+        double dacc = 0.0;
+        int pdiag = 0;
+        int cs = s0;
+#pragma unroll 1
+        for (int m = 0; m < nmax; m++) {
+            if (m >= ninc) continue;
+            cp_async_wait_upto((int)((gcount - 1u - (gis >> (8 * cs))) & 0xffu));
+            __syncwarp(nmask);
+            const char *sl = ring + cs * kRsSlotB;
+            {
+                const int j = m + kRsAhead;
+                if (j < ninc) {
+                    const int rs = wrap(cs + kRsAhead);
+                    request(rs, k0 + j, *reinterpret_cast<const uint32_t *>(sl + 160));
+                    note(rs);
+                    nis = j + 1;
+                } else if (live_n) {
+                    const int jn = j - ninc;
+                    const int nincn = (int)(__double_as_longlong(rawn[2]) >> 32);
+                    const int64_t k0n = __double_as_longlong(rawn[1]);
+                    const int lim = nincn < kRsAhead ? nincn : kRsAhead;
+#pragma unroll
+                    for (int q = 0; q < kRsAhead; q++)
+                        if (q >= nisn && q <= jn && q < lim) {
+                            const int rs = wrap(sn0 + q);
+                            request(rs, k0n + q, q == 0 ? en.x : (q == 1 ? en.y : (q == 2 ? en.z : en.w)));
+                            note(rs);
+                        }
+                    if (jn + 1 > nisn) nisn = jn + 1 < lim ? jn + 1 : lim;
+                }
+                cp_async_commit();
+                gcount++;
+            }
+            const uint4 w0 = *reinterpret_cast<const uint4 *>(sl);
+            const uint4 w1 = *reinterpret_cast<const uint4 *>(sl + 16);
+            const uint32_t pw[5] = {w0.x, w0.y, w0.z, w0.w, w1.x};
+            const uint32_t perm = w1.z;
+            auto posof = [&](int jc) { return (int)((pw[jc >> 1] >> (16 * (jc & 1))) & 0xffffu) * NB; };
+            if (m == 0) pdiag = posof(0);
+            double G[NVTX][DIM], adet;
+#pragma unroll
+            for (int v = 0; v < NVTX; v++) {
+                const char *gp = sl + 32 + 32 * ((perm >> (2 * v)) & 3);
+                const double2 x = *reinterpret_cast<const double2 *>(gp);
+                const double2 y = *reinterpret_cast<const double2 *>(gp + 16);
+                G[v][0] = x.x; G[v][1] = x.y; G[v][2] = y.x;
+                if (v == 0) adet = y.y;
+            }
+            // e[w] = |det| G_0^T M G_w (the row function is canonical vertex 0)
+            double e[NVTX];
+            {
+                double v[DIM];
+#pragma unroll
+                for (int d = 0; d < DIM; d++) {
+                    double x = 0.0;
+#pragma unroll
+                    for (int c = 0; c < DIM; c++) x += G[0][c] * Mm[c][d];
+                    v[d] = x * adet;
+                }
+#pragma unroll
+                for (int w = 0; w < NVTX; w++) {
+                    double x = 0.0;
+#pragma unroll
+                    for (int d = 0; d < DIM; d++) x += v[d] * G[w][d];
+                    e[w] = x;
+                }
+            }
+            dacc += A.R.r[0][0][0][0] * e[0];
+            // distinct canonical nodes hit distinct row positions: load all accumulators, add, store all
+            double *ptr[NL - 1];
+            double old[NL - 1];
+#pragma unroll
+            for (int jj = 0; jj < NL - 1; jj++) {
+                ptr[jj] = my + posof(jj + 1);
+                old[jj] = *ptr[jj];
+            }
+#pragma unroll
+            for (int jj = 0; jj < NL - 1; jj++) {
+                const int jc = jj + 1;
+                double v = old[jj] + A.R.r[0][jc][0][0] * e[canon_sv<DIM>(jc, 0)];
+                if (jc >= NVTX) v += A.R.r[0][jc][0][1] * e[canon_sv<DIM>(jc, 1)];
+                *ptr[jj] = v;
+            }
+            cs = wrap(cs + 1);
+        }
+        if (ninc > 0) my[pdiag] = dacc;
+
+        // write-out: the three dof rows of a node are one contiguous run of 9 L values in the values array (ghost rows:
+        // in the owner's receive buffer); the warp copies them with full-line coalesced stores
+        __syncwarp();
+#pragma unroll 1
+        for (int sl = 0; sl < NPT; sl++) {
+            const int64_t base_s = __shfl_sync(FULL, base, sl * CPR);
+            const int L_s = __shfl_sync(FULL, L, sl * CPR);
+            if (L_s == 0) continue;
+            const int n_s = NB * L_s;
+            double *out = out_ptr(A, (int64_t)CPR * base_s);
+#pragma unroll
+            for (int aa = 0; aa < DIM; aa++) {
+                const double *src = rows + (size_t)(sl * DIM + aa) * pitch;
+                for (int x = lane; x < n_s; x += 32) out[aa * n_s + x] = src[x];
+            }
+        }
+        __syncwarp();
+        if (tile_n >= ntiles) break;
+        tile = tile_n;
+        s0 = cs;
+        nis = nisn;
+#pragma unroll
+        for (int x = 0; x < 4; x++) raw[x] = rawn[x];
+    }
+    cp_async_wait<0>();
 }
 
 // =========================================================================================
