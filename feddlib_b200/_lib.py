@@ -63,6 +63,9 @@ SIGNATURES = {
     "feddb200_assemble_mass_d": (C.c_int, [_vp, _vp, C.c_int, _vp]),
     "feddb200_assemble_mass": (C.c_int, [_vp, _vp, C.c_int, _vp]),
     "feddb200_assemble_bdstab_d": (C.c_int, [_vp, _vp, _vp]),
+    "feddb200_stress_quadrature": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), _vp, _vp]),
+    "feddb200_assemble_stress_d": (C.c_int, [_vp, _vp, C.c_double, _vp, _vp]),
+    "feddb200_assemble_stress": (C.c_int, [_vp, _vp, C.c_double, _vp, _i64, _vp]),
     "feddb200_assemble_bdstab": (C.c_int, [_vp, _vp, _vp]),
     "feddb200_assemble_linelas_d": (C.c_int, [_vp, _vp, C.c_double, C.c_double, _vp]),
     "feddb200_assemble_advection_d": (C.c_int, [_vp, _vp, _vp, _vp]),

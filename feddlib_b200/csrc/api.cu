@@ -520,7 +520,7 @@ int launch_gatherx(feddb200_ctx *c, feddb200_pat *p, int op, const feddb200_mesh
 
 // common driver of every assembly call
 int run_op(feddb200_ctx *c, const feddb200_pat *pc, int op, const double *u_d, double c0, double c1, double c2,
-           int vec_field, double *values_d)
+           int vec_field, double *values_d, const double *coef_d = nullptr)
 {
     FB_LOGIC(!c || !pc, "assembly: null argument");
     FB_LOGIC(pc->ctx != c, "assembly: pattern belongs to another context");
@@ -551,6 +551,8 @@ int run_op(feddb200_ctx *c, const feddb200_pat *pc, int op, const double *u_d, d
     if (nnz == 0) return FEDDB200_OK;
 
     int mode = c->mode;
+    // a coefficient that varies inside the elements needs the quadrature loop of the element-row kernels
+    if (coef_d && mode == FEDDB200_SCATTER_GATHER) mode = FEDDB200_SCATTER_COLOURED;
     if (mode == FEDDB200_SCATTER_GATHER && !(op == OP_LAP || op == OP_ELAS)) {
         int handled = 0;
         if (getenv("FEDDB200_NO_GATHERX") == nullptr) { // tuning aid
@@ -575,7 +577,7 @@ int run_op(feddb200_ctx *c, const feddb200_pat *pc, int op, const double *u_d, d
     ElemArgs A;
     A.conn_r = rm->conn_d; A.conn_c = cm->conn_d; A.conn_v = vm->conn_d; A.coords = vm->coords_d;
     A.row_lid = p->row_lid_d; A.rowptr = p->rowptr_d; A.pos = p->pos_d; A.pos_stride = p->pos_stride;
-    A.elems = nullptr; A.n_items = rm->ne; A.u = u_d; A.c0 = c0; A.c1 = c1; A.c2 = c2; A.tab = tab_d;
+    A.elems = nullptr; A.n_items = rm->ne; A.u = u_d; A.coef = coef_d; A.c0 = c0; A.c1 = c1; A.c2 = c2; A.tab = tab_d;
     A.values = values_d; A.vec_dim = ((op == OP_LAP || op == OP_MASS) && vec_field) ? dim : 0;
     if (nnz > 0) FB_CUDA(cudaMemsetAsync(values_d, 0, sizeof(double) * nnz, c->stream));
     if (mode == FEDDB200_SCATTER_ATOMIC) return launch_elem_op(c, op, dim, nr, nc, A, true);
@@ -707,6 +709,24 @@ extern "C" int feddb200_assemble_mass_d(feddb200_ctx *c, const feddb200_pat *p, 
 {
     return run_op(c, p, OP_MASS, nullptr, 0, 0, 0, vec_field, v);
 }
+extern "C" int feddb200_stress_quadrature(int dim, int nloc, int *nq, double *ref_points, double *weights)
+{
+    FB_LOGIC(!nq, "stress_quadrature: null argument");
+    OpTables t;
+    FB_LOGIC(build_tables(t, OP_ELAS, dim, nloc, nloc) != 0, "stress_quadrature: no quadrature rule for this element");
+    *nq = t.nq;
+    for (int q = 0; q < t.nq; q++) {
+        if (ref_points)
+            for (int d = 0; d < dim; d++) ref_points[q * dim + d] = t.lam[q * 4 + 1 + d]; // reference point = (lambda_1, .., lambda_dim)
+        if (weights) weights[q] = t.w[q];
+    }
+    return FEDDB200_OK;
+}
+extern "C" int feddb200_assemble_stress_d(feddb200_ctx *c, const feddb200_pat *p, double coef_const, const double *coef_d, double *v)
+{
+    // the symmetric-gradient block is the mu-part of the elasticity operator: lambda = 0, mu = the coefficient
+    return run_op(c, p, OP_ELAS, nullptr, 0.0, coef_d ? 1.0 : coef_const, 0, 0, v, coef_d);
+}
 extern "C" int feddb200_assemble_bdstab_d(feddb200_ctx *c, const feddb200_pat *p, double *v)
 {
     FB_LOGIC(!p, "null pattern");
@@ -753,6 +773,20 @@ extern "C" int feddb200_assemble_mass(feddb200_ctx *c, const feddb200_pat *p, in
     const int64_t nnz = (vec_field ? p->rm->dim : 1) * p->nnz;
     return with_host_buffers(c, p, nnz, nullptr, 0, values,
                              [&](double *, double *v_d) { return feddb200_assemble_mass_d(c, p, vec_field, v_d); });
+}
+extern "C" int feddb200_assemble_stress(feddb200_ctx *c, const feddb200_pat *p, double coef_const, const double *coef, int64_t n_coef,
+                                        double *values)
+{
+    FB_LOGIC(!p, "null pattern");
+    if (coef) {
+        int nq = 0;
+        int rc = feddb200_stress_quadrature(p->rm->dim, p->rm->nloc, &nq, nullptr, nullptr);
+        if (rc != FEDDB200_OK) return rc;
+        FB_LOGIC(n_coef != p->rm->ne * nq, "assemble_stress: the coefficient array must hold one value per element and quadrature point");
+    }
+    const int64_t nnz = (int64_t)p->rm->dim * p->rm->dim * p->nnz;
+    return with_host_buffers(c, p, nnz, coef, coef ? n_coef : 0, values,
+                             [&](double *coef_d, double *v_d) { return feddb200_assemble_stress_d(c, p, coef_const, coef ? coef_d : nullptr, v_d); });
 }
 extern "C" int feddb200_assemble_bdstab(feddb200_ctx *c, const feddb200_pat *p, double *values)
 {

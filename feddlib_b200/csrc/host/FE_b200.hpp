@@ -155,6 +155,44 @@ class FE_b200 {
         for (std::size_t k = 0; k < rhs.size(); k++) valuesRhs[k] += rhs[k];
     }
 
+    // FE::assemblyStress (FE_def.hpp:2407-2735): func is evaluated on the host at the physical quadrature points
+    // x_k = B q_k + p_1 of every element, where the reference evaluates it (:2479-2484, :2599-2608)
+    template <class CoeffFunc>   // the reference's CoeffFunc_Type = boost::function<double(double *x, int *parameters)>
+    void assemblyStress(int dim, std::string FEType, MatrixPtr_Type &A, CoeffFunc func, int *parameters,
+                        bool callFillComplete = true)
+    {
+        if (FEType == "P0") throw std::logic_error("Not implemented for P0");
+        const int loc = checkFE(dim, FEType);
+        feddb200_pat *p = pattern(loc, loc);
+        const auto &el = *slots_[loc].domain->getElementsC();
+        const auto &pts = *slots_[loc].domain->getPointsRepeated();
+        const int nloc = slots_[loc].nloc;
+        int nq = 0;
+        b200::check(feddb200_stress_quadrature(dim, nloc, &nq, nullptr, nullptr));
+        std::vector<double> q((std::size_t)nq * dim);
+        b200::check(feddb200_stress_quadrature(dim, nloc, &nq, q.data(), nullptr));
+        const std::size_t ne = el.numberElements();
+        std::vector<double> coef(ne * nq);
+        bool constant = true;
+        for (std::size_t T = 0; T < ne; T++) {
+            const std::vector<int> &nodes = el.getElement(T).getVectorNodeList();
+            const std::vector<double> &p1 = pts.at(nodes[0]);
+            for (int k = 0; k < nq; k++) {
+                double x[3] = {0., 0., 0.};
+                for (int r = 0; r < dim; r++)
+                    for (int c = 0; c < dim; c++) x[c] += (pts.at(nodes[r + 1])[c] - p1[c]) * q[(std::size_t)k * dim + r];
+                for (int c = 0; c < dim; c++) x[c] += p1[c];
+                coef[T * nq + k] = func(x, parameters);
+                constant = constant && coef[T * nq + k] == coef[0];
+            }
+        }
+        b200::LocalCsr<SC, LO, GO> csr;
+        expand(p, loc, dim, dim, FEDDB200_BLOCK_FULL, csr);
+        if (constant) b200::check(feddb200_assemble_stress(ctx_, p, ne ? coef[0] : 1.0, nullptr, 0, csr.values.data()));
+        else b200::check(feddb200_assemble_stress(ctx_, p, 1.0, coef.data(), (int64_t)coef.size(), csr.values.data()));
+        seat_csr(A, csr, MapConstPtr_Type(), MapConstPtr_Type(), callFillComplete);
+    }
+
     // FE::assemblyBDStabilization (FE_def.hpp:2151-2220): P1 only, like the reference (:2156)
     void assemblyBDStabilization(int dim, std::string FEType, MatrixPtr_Type &A, bool callFillComplete = true)
     {

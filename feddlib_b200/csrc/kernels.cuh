@@ -80,6 +80,7 @@ struct ElemArgs {
     const int32_t *elems;                    // nullable: element list of this launch (one colour)
     int64_t n_items;
     const double *u;
+    const double *coef;                      // nullable: per (element, quadrature point) coefficient (assemblyStress)
     double c0, c1, c2;                       // lambda,mu | rho*nu, rho, rho(newton)
     const OpTables *tab;
     double *values;
@@ -178,7 +179,8 @@ __global__ void __launch_bounds__(128) k_elem(const ElemArgs A)
         for (int q = 0; q < nq; q++) {
             double gi[DIM];
             push_grad<DIM>(&T.dphi[(q * NV + i) * DIM], Binv, gi);
-            const double w = T.w[q];
+            // assemblyStress (FE_def.hpp:2515-2518, 2654-2664): funcvalue * weight in front of the tensor product
+            const double w = A.coef ? A.coef[e * nq + q] * T.w[q] : T.w[q];
             double gia = 0.0;
 #pragma unroll
             for (int d = 0; d < DIM; d++) gia = (d == a) ? gi[d] : gia;

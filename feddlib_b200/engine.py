@@ -289,6 +289,40 @@ class Pattern:
     def assemble_mass_d(self, values, vec_field=False):
         check(self.ctx._L.feddb200_assemble_mass_d(self.ctx._h, self._h, int(bool(vec_field)), ptr(values)))
 
+    def stress_points(self, conn, coords):
+        """Physical quadrature points x_k = B q_k + p_1 of FE::assemblyStress for every element, [ne][nq][dim], summed in
+        the reference's order (FE_def.hpp:2479-2484, 2599-2608); conn / coords are the host arrays of the mesh."""
+        dim, nloc = self.dim, conn.shape[1]
+        nq = C.c_int(0)
+        check(self.ctx._L.feddb200_stress_quadrature(dim, nloc, C.byref(nq), None, None))
+        q = np.empty((nq.value, dim), dtype=np.float64)
+        check(self.ctx._L.feddb200_stress_quadrature(dim, nloc, C.byref(nq), ptr(q), None))
+        p = coords[conn[:, :dim + 1]]                                   # [ne][dim+1][dim]
+        B = np.stack([p[:, j + 1, :] - p[:, 0, :] for j in range(dim)], axis=2)   # B[e][i][j] = x_{j+1}[i] - x_0[i]
+        xyz = np.zeros((conn.shape[0], nq.value, dim))
+        for r in range(dim):
+            xyz += B[:, None, :, r] * q[None, :, r, None]
+        xyz += p[:, None, 0, :]
+        return xyz
+
+    def assemble_stress_d(self, values, coef=1.0):
+        """FE::assemblyStress; coef = the constant value of the coefficient function, or a CUDA tensor [ne * nq]."""
+        if hasattr(coef, "data_ptr"):
+            check(self.ctx._L.feddb200_assemble_stress_d(self.ctx._h, self._h, 1.0, ptr(coef), ptr(values)))
+        else:
+            check(self.ctx._L.feddb200_assemble_stress_d(self.ctx._h, self._h, float(coef), None, ptr(values)))
+
+    def assemble_stress(self, coef=1.0):
+        """Host variant: coef = constant or array [ne][nq] of func at the points of stress_points()."""
+        d = self.dim
+        out = np.empty(self.nnz(d, d, BLOCK_FULL), dtype=np.float64)
+        if np.ndim(coef) == 0:
+            check(self.ctx._L.feddb200_assemble_stress(self.ctx._h, self._h, float(coef), None, 0, ptr(out)))
+        else:
+            cf = np.ascontiguousarray(coef, dtype=np.float64).ravel()
+            check(self.ctx._L.feddb200_assemble_stress(self.ctx._h, self._h, 1.0, ptr(cf), cf.size, ptr(out)))
+        return out
+
     def assemble_bdstab_d(self, values):
         check(self.ctx._L.feddb200_assemble_bdstab_d(self.ctx._h, self._h, ptr(values)))
 

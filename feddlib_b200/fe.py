@@ -218,6 +218,24 @@ class FE:
         pat = self._pattern(d, d)
         a += pat.assemble_rhs(res, degFunc, fieldType == "Vector")
 
+    # ---- FE_def.hpp:2407-2735 ----
+    def assemblyStress(self, dim, FEType, A: Matrix, func, parameters=None, callFillComplete=True):
+        """func(x, parameters) -> float is the reference's CoeffFunc_Type; it is evaluated on the host at the physical
+        quadrature points of every element, exactly where the reference evaluates it."""
+        if FEType == "P0":
+            raise LogicError("Not implemented for P0")
+        d = self.domainVec_[self.checkFE(dim, FEType)]
+        pat = self._pattern(d, d)
+        xyz = pat.stress_points(d.elementsC_, d.pointsRep_)
+        f = np.array([[func(x, parameters) for x in el] for el in xyz], dtype=np.float64)
+        values = self.ctx.empty_values(pat.nnz(dim, dim, BLOCK_FULL))
+        if f.size == 0 or np.all(f == f.flat[0]):
+            pat.assemble_stress_d(values, float(f.flat[0]) if f.size else 1.0)
+        else:
+            import torch
+            pat.assemble_stress_d(values, torch.from_numpy(f.ravel()).to(values.device))
+        self._finish(A, d, d, pat, values, dim, dim, BLOCK_FULL, callFillComplete)
+
     # ---- FE_def.hpp:2151-2220 ----
     def assemblyBDStabilization(self, dim, FEType, A: Matrix, callFillComplete=True):
         if FEType != "P1":

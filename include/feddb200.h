@@ -139,6 +139,17 @@ int  feddb200_assemble_laplace_d(feddb200_ctx *ctx, const feddb200_pat *pat, int
 /* FE::assemblyMass (core/FE/FE_def.hpp:454-521): fieldType "Scalar" [vec_field=0, BLOCK_SCALAR] / "Vector"
  * [vec_field=1, BLOCK_DIAG with dim dofs] -- SURVEY.md 8(f) rank 2 */
 int  feddb200_assemble_mass_d(feddb200_ctx *ctx, const feddb200_pat *pat, int vec_field, double *values_d);
+/* FE::assemblyStress (core/FE/FE_def.hpp:2407-2735): the symmetric-gradient viscous block
+ *   K^{ab}_ij = |det B| sum_k func(x_k) w_k (delta_ab grad phi_i . grad phi_j + d_b phi_i d_a phi_j)
+ * on a BLOCK_FULL pattern (Stokes_def.hpp:69-70, NavierStokes_def.hpp:142-143 call it with func = 1).  The coefficient
+ * callback stays on the host: stress_quadrature gives the reference points of the rule (deg = Grad x Grad), the glue
+ * evaluates func at  x_k = B q_k + p_1  for every element (:2479-2484, :2599-2608) and passes either one constant
+ * (coef = NULL: all three scatter modes, row-gather kernels) or the array coef[ne][nq] (element-row kernels with the
+ * quadrature loop; gather mode is served by the coloured mode). */
+int  feddb200_stress_quadrature(int dim, int nloc, int *nq, double *ref_points /*[nq][dim] or NULL*/, double *weights /*[nq] or NULL*/);
+int  feddb200_assemble_stress_d(feddb200_ctx *ctx, const feddb200_pat *pat, double coef_const, const double *coef_d, double *values_d);
+int  feddb200_assemble_stress(feddb200_ctx *ctx, const feddb200_pat *pat, double coef_const, const double *coef, int64_t n_coef,
+                              double *values);
 /* FE::assemblyBDStabilization (core/FE/FE_def.hpp:2151-2220): the pressure stabilisation of the
  * P1-P1 Stokes / Navier-Stokes drivers (Stokes_def.hpp:97-104), C_ij = |det B| (sum_q w phi_i phi_j - size * scale) on a
  * P1 x P1 BLOCK_SCALAR pattern; any other FE type is the reference's logic_error "Only implemented for P1". */

@@ -722,6 +722,73 @@ int fo_assembly_linelas(int dim, const char *fe, int64_t ne, const int32_t *conn
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* FE_def.hpp:2407-2735 assemblyStress: the symmetric-gradient viscous block with a coefficient function,
+ *   v_ab += func(xyz_k) * weights[k] * (e_a(phi_i) : e_b(phi_j)),   v_ab = absDetB * v_ab,
+ * where e_a(phi_i) has the transformed gradient of phi_i in row a (:2496, :2511; 3D :2624-2626, :2636-2638, :2648-2650)
+ * and e_b(phi_j) is that row plus its transpose (:2485-2494, :2499-2509; 3D :2618-2622, :2629-2633, :2641-2645);
+ * innerProduct sums all entries row by row (SmallMatrix.hpp:164-190).  xyz_k = B * quadPts[k] + p1 (:2479-2484,
+ * :2599-2608).  func is evaluated once per (i, j, k) in the reference; it is a pure function of xyz.
+ * Insertion: one entry per call, for each column dof b the rows a = 0..dim-1 (:2547-2556, :2706-2723). */
+typedef double (*fo_coeff_func)(const double *xyz, void *user);
+int fo_assembly_stress(int dim, const char *fe, int64_t ne, const int32_t *conn, const double *coords,
+                       const int64_t *gid, fo_coeff_func func, void *user, fo_matrix *A)
+{
+    int nloc = fo_nloc(dim, fe);
+    if (nloc < 0) return -1;
+    double dphi[FO_MAXQ * FO_MAXN * 3], w[FO_MAXQ], dT[FO_MAXQ * FO_MAXN * 3], pts[FO_MAXQ * 3], wq[FO_MAXQ];
+    int deg = fo_determine_degree2(dim, fe, fe, FO_GRAD, FO_GRAD, 0);
+    int nq = fo_get_dphi(dim, fe, deg, dphi, w);
+    if (nq < 0 || fo_quadrature(dim, deg, pts, wq) != nq) return -1;
+    for (int64_t T = 0; T < ne; T++) {
+        const int32_t *el = conn + T * nloc;
+        double B[3][3];
+        fo_build_transformation(dim, el, coords, B);
+        double absDetB = fo_element_geometry(dim, nq, nloc, el, coords, dphi, dT);
+        const double *p1 = coords + (int64_t)el[0] * dim;
+        double fv[FO_MAXQ];
+        for (int k = 0; k < nq; k++) {
+            double xyz[3] = {0., 0., 0.};
+            for (int r = 0; r < dim; r++)
+                for (int c = 0; c < dim; c++) xyz[c] += B[c][r] * pts[k * dim + r];
+            for (int c = 0; c < dim; c++) xyz[c] += p1[c];
+            fv[k] = func(xyz, user);
+        }
+        for (int i = 0; i < nloc; i++) {
+            for (int j = 0; j < nloc; j++) {
+                double v[3][3] = {{0}};
+                for (int k = 0; k < nq; k++) {
+                    const double *gi = dT + (k * nloc + i) * dim, *gj = dT + (k * nloc + j) * dim;
+                    double ei[3][3][3], ej[3][3][3];
+                    memset(ei, 0, sizeof(ei)); memset(ej, 0, sizeof(ej));
+                    for (int a = 0; a < dim; a++)
+                        for (int c = 0; c < dim; c++) {
+                            ei[a][a][c] = gi[c];                         /* e_a i: row a = grad phi_i */
+                            if (dim == 2) {                              /* tmpRes1 + tmpRes2 (:2485-2509) */
+                                ej[a][a][c] += gj[c];
+                                ej[a][c][a] += gj[c];
+                            } else {                                     /* explicit entries (:2618-2645) */
+                                ej[a][a][c] = (c == a) ? 2. * gj[c] : gj[c];
+                                ej[a][c][a] = (c == a) ? 2. * gj[c] : gj[c];
+                            }
+                        }
+                    for (int a = 0; a < dim; a++)
+                        for (int b = 0; b < dim; b++) v[a][b] = v[a][b] + fv[k] * w[k] * fo_inner(dim, ei[a], ej[b]);
+                }
+                for (int a = 0; a < dim; a++)
+                    for (int b = 0; b < dim; b++) v[a][b] = absDetB * v[a][b];
+                int64_t glob_j = dim * gid[el[j]];
+                int64_t glob_i = dim * gid[el[i]];
+                for (int b = 0; b < dim; b++) {
+                    int64_t col = glob_j + b;
+                    for (int a = 0; a < dim; a++) fo_insert(A, glob_i + a, 1, &col, &v[a][b]);
+                }
+            }
+        }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* FE_def.hpp:1759-1832 assemblyAdvectionVecField (N); u is node-wise interleaved on the   */
 /* repeated map and indexed with LOCAL ids: u[dim*node + d]                                */
 /* ------------------------------------------------------------------------------------ */

@@ -25,6 +25,7 @@ def build(force: bool = False) -> str:
 _I32P = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
 _I64P = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
 _F64P = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+COEFF_FUNC = C.CFUNCTYPE(C.c_double, C.POINTER(C.c_double), C.c_void_p)
 
 
 def lib():
@@ -46,6 +47,7 @@ def lib():
         L.fo_assembly_laplace_vecfield.argtypes = common + [C.c_void_p]
         L.fo_assembly_mass.argtypes = common + [C.c_int, C.c_void_p]
         L.fo_assembly_bdstab.argtypes = common + [C.c_void_p]
+        L.fo_assembly_stress.argtypes = common + [COEFF_FUNC, C.c_void_p, C.c_void_p]
         L.fo_assembly_rhs.argtypes = [C.c_int, C.c_char_p, C.c_int64, _I32P, _F64P, C.c_int, C.c_int, _F64P, _F64P]
         L.fo_assembly_linelas.argtypes = common + [C.c_double, C.c_double, C.c_void_p]
         L.fo_assembly_advection.argtypes = common + [_F64P, C.c_void_p]
@@ -133,6 +135,13 @@ def assembly_rhs(dim, fe, conn, coords, value_func, deg_func=0, vec_field=False,
     rhs = np.zeros(n) if rhs is None else rhs
     _chk(lib().fo_assembly_rhs(dim, fe.encode(), conn.shape[0], conn, coords, int(bool(vec_field)), int(deg_func), f, rhs), "assemblyRHS")
     return rhs
+
+
+def assembly_stress(dim, fe, conn, coords, gid, func, A: Matrix):
+    """FE::assemblyStress (FE_def.hpp:2407-2735); func(xyz: np.ndarray[dim]) -> float is the CoeffFunc_Type callback."""
+    conn, coords, gid = _prep(conn, coords, gid)
+    cb = COEFF_FUNC(lambda x, _u: float(func(np.array([x[d] for d in range(dim)]))))
+    _chk(lib().fo_assembly_stress(dim, fe.encode(), conn.shape[0], conn, coords, gid, cb, None, A._h), "assemblyStress")
 
 
 def assembly_bdstab(dim, fe, conn, coords, gid, A: Matrix):

@@ -55,6 +55,27 @@ def _csr(L, h, nrows):
     return rp, ci, v
 
 
+def assemble_stress(dim, fe, conn, coords, func, gid=None, nrows_global=None):
+    """FE::assemblyStress of the reference with the Python callback func(xyz) -> float; returns CSR (rowptr, col gid, values)."""
+    L = lib()
+    conn = np.ascontiguousarray(conn, dtype=np.int32); coords = np.ascontiguousarray(coords, dtype=np.float64)
+    nn = coords.shape[0]
+    gid = np.arange(nn, dtype=np.int64) if gid is None else np.ascontiguousarray(gid, dtype=np.int64)
+    nglob = int(nrows_global if nrows_global is not None else gid.max() + 1)
+    cb = O.COEFF_FUNC(lambda x, _u: float(func(np.array([x[d] for d in range(dim)]))))
+    L.ref_assemble_stress.argtypes = [C.c_int, C.c_char_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
+                                      O.COEFF_FUNC, C.c_void_p, C.c_void_p]
+    h = L.fo_matrix_new(dim * nglob, 64)
+    try:
+        rc = L.ref_assemble_stress(dim, fe.encode(), conn.shape[0], _p(conn), conn.shape[1], _p(coords), nn, _p(gid), cb, None, h)
+        if rc != 0:
+            raise RuntimeError(L.ref_last_error().decode())
+        L.fo_fill_complete(h)
+        return _csr(L, h, dim * nglob)
+    finally:
+        L.fo_matrix_free(h)
+
+
 def assemble(op, dim, fe, conn, coords, gid=None, u=None, lam=0.0, mu=0.0, fe2=None, conn2=None, gid2=None,
              nrows_global=None):
     """Run the reference routine; returns CSR (rowptr, col gid, values) -- for div ops a pair (B, BT)."""

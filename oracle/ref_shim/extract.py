@@ -7,7 +7,7 @@ import sys
 
 src_path, out_path = sys.argv[1], sys.argv[2]
 src = open(src_path, encoding="utf-8", errors="replace").read()
-WANT = ["FE", "addFE", "applyBTinv", "assemblyMass", "assemblyBDStabilization", "assemblyRHS", "assemblyLaplace", "assemblyLaplaceVecField", "assemblyLinElasXDim",
+WANT = ["FE", "addFE", "applyBTinv", "assemblyMass", "assemblyBDStabilization", "assemblyStress", "assemblyRHS", "assemblyLaplace", "assemblyLaplaceVecField", "assemblyLinElasXDim",
         "assemblyAdvectionVecField", "assemblyAdvectionInUVecField", "assemblyDivAndDivT", "assemblyDivAndDivTFast",
         "epsilonTensor", "phi", "gradPhi", "buildTransformation", "determineDegree", "getQuadratureValues",
         "getPhi", "getPhiGlobal", "getDPhi", "checkFE"]

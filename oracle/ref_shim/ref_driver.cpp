@@ -83,6 +83,25 @@ extern "C" int ref_assemble(int op, int dim, const char *fe1, const char *fe2, i
     }
 }
 
+// FE::assemblyStress with the coefficient callback func(xyz, user) (CoeffFunc_Type = boost::function<double(double*, int*)>)
+extern "C" int ref_assemble_stress(int dim, const char *fe1, int64_t ne, const int32_t *conn1, int nloc1, const double *coords1,
+                                   int64_t nn1, const int64_t *gid1, double (*func)(const double *, void *), void *user, fo_matrix *A)
+{
+    try {
+        FE_t fe;
+        Teuchos::RCP<Domain_t> d1 = make_domain(dim, fe1, ne, conn1, nloc1, coords1, nn1, gid1);
+        fe.addFE(d1);
+        Teuchos::RCP<Matrix_t> mA(new Matrix_t(A));
+        CoeffFunc_Type f = [func, user](double *x, int *) { return func(x, user); };
+        int *dummy = nullptr;
+        fe.assemblyStress(dim, std::string(fe1), mA, f, dummy, true);
+        return 0;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -2;
+    }
+}
+
 // FE::assemblyRHS with a constant source: rhs[nn * dofs] (repeated vector, zero on entry)
 extern "C" int ref_assemble_rhs(int dim, const char *fe1, int64_t ne, const int32_t *conn1, int nloc1, const double *coords1,
                                 int64_t nn1, int vec_field, int deg_func, const double *value_func, double *rhs)

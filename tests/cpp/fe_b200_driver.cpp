@@ -31,7 +31,16 @@ int ref_assemble(int op, int dim, const char *fe1, const char *fe2, int64_t ne, 
                  const int64_t *gid2, const double *u, double lambda, double mu, fo_matrix *A, fo_matrix *B);
 int ref_assemble_rhs(int dim, const char *fe1, int64_t ne, const int32_t *conn1, int nloc1, const double *coords1, int64_t nn1,
                      int vec_field, int deg_func, const double *value_func, double *rhs);
+int ref_assemble_stress(int dim, const char *fe1, int64_t ne, const int32_t *conn1, int nloc1, const double *coords1, int64_t nn1,
+                        const int64_t *gid1, double (*func)(const double *, void *), void *user, fo_matrix *A);
 const char *ref_last_error(void);
+}
+
+// coefficient functions of the assemblyStress cases: user = dimension
+static double stress_one(const double *, void *) { return 1.0; }
+static double stress_varying(const double *x, void *user)
+{
+    return 1.0 + 0.5 * x[0] + 0.25 * x[1] * x[1] + (*static_cast<int *>(user) > 2 ? 0.125 * x[2] : 0.0);
 }
 
 using namespace FEDD;
@@ -140,11 +149,17 @@ int main(int argc, char **argv)
                               {"assemblyMass Scalar", 7, 1}, {"assemblyMass Vector", 8, dim}};
         std::vector<Case> todo(std::begin(cases), std::end(cases));
         if (std::string(fe1) == "P1") todo.push_back({"assemblyBDStabilization", 9, 1});
+        todo.push_back({"assemblyStress (func = 1)", 10, dim});
+        todo.push_back({"assemblyStress (func varies)", 11, dim});
         for (const Case &c : todo) {
             // reference
             fo_matrix *rA = fo_matrix_new(c.rowDofs * nglob1, 64), *rB = fo_matrix_new(1, 8);
-            if (ref_assemble(c.op, dim, fe1, fe1, ne, conn1.data(), nloc1, xyz.data(), nn1, gid1.data(), nullptr, 0, 0, nullptr, u.data(),
-                             lambda, mu, rA, rB) != 0) { std::printf("reference failed: %s\n", ref_last_error()); return 1; }
+            int dimv = dim;
+            const int rrc = c.op >= 10
+                ? ref_assemble_stress(dim, fe1, ne, conn1.data(), nloc1, xyz.data(), nn1, gid1.data(), c.op == 10 ? stress_one : stress_varying, &dimv, rA)
+                : ref_assemble(c.op, dim, fe1, fe1, ne, conn1.data(), nloc1, xyz.data(), nn1, gid1.data(), nullptr, 0, 0, nullptr, u.data(),
+                               lambda, mu, rA, rB);
+            if (rrc != 0) { std::printf("reference failed: %s\n", ref_last_error()); return 1; }
             RefCsr ref = ref_csr(rA, c.rowDofs * nglob1);
             fo_matrix_free(rA); fo_matrix_free(rB);
             // ours
@@ -158,6 +173,8 @@ int main(int argc, char **argv)
             case 7: fe.assemblyMass(dim, fe1, "Scalar", A); break;
             case 8: fe.assemblyMass(dim, fe1, "Vector", A); break;
             case 9: fe.assemblyBDStabilization(dim, fe1, A); break;
+            case 10: fe.assemblyStress(dim, fe1, A, [](double *x, int *) { return stress_one(x, nullptr); }, nullptr); break;
+            case 11: fe.assemblyStress(dim, fe1, A, [&dimv](double *x, int *) { return stress_varying(x, &dimv); }, nullptr); break;
             }
             all = compare(c.name, g_seated[A.get()], ref, gid1, c.rowDofs) && all;
             all = (A->fillCompleteCalls_ == 1) && all;

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "..", ".."))
 sys.path.insert(0, os.path.join(HERE, ".."))
 from oracle import ref as R  # noqa: E402
-from util import mesh_structured, random_u  # noqa: E402
+from util import mesh_structured, random_u, stress_coefficient  # noqa: E402
 
 CASES = {"2d_P1": (2, "P1", 3, False), "2d_P2": (2, "P2", 2, True), "3d_P1": (3, "P1", 2, True), "3d_P2": (3, "P2", 2, True)}
 
@@ -34,6 +34,8 @@ if __name__ == "__main__":
                        ("advection", dict(u=u)), ("advection_in_u", dict(u=u))):
             rp, ci, v = R.assemble(op, dim, fe, conn, coords, **kw)
             out[f"{name}/{op}/rowptr"], out[f"{name}/{op}/col"], out[f"{name}/{op}/val"] = rp, ci, v
+        rp, ci, v = R.assemble_stress(dim, fe, conn, coords, stress_coefficient)
+        out[f"{name}/stress/rowptr"], out[f"{name}/stress/col"], out[f"{name}/stress/val"] = rp, ci, v
         if fe == "P1":  # assemblyBDStabilization is P1 only (FE_def.hpp:2156)
             rp, ci, v = R.assemble("bdstab", dim, fe, conn, coords)
             out[f"{name}/bdstab/rowptr"], out[f"{name}/bdstab/col"], out[f"{name}/bdstab/val"] = rp, ci, v

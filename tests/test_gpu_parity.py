@@ -90,6 +90,21 @@ def test_mass(case, mode):
 
 
 @pytest.mark.parametrize("mode", MODES)
+def test_stress(case, mode):
+    """FE::assemblyStress (FE_def.hpp:2407-2735; SURVEY.md 8(f) rank 4): constant coefficient (all scatter modes, the
+    row-gather kernels in gather mode) and a coefficient that varies inside the elements (quadrature loop)."""
+    from feddlib_b200 import BLOCK_FULL
+    from util import stress_coefficient
+    case["ctx"].set_scatter_mode(mode)
+    d = case["dim"]
+    check(case, "stress", case["pat"].assemble_stress(1.0), d, d, BLOCK_FULL, func=lambda x: 1.0)
+    check(case, "stress", case["pat"].assemble_stress(2.5), d, d, BLOCK_FULL, func=lambda x: 2.5)
+    xyz = case["pat"].stress_points(case["conn"], case["coords"])
+    coef = np.array([[stress_coefficient(x) for x in el] for el in xyz])
+    check(case, "stress", case["pat"].assemble_stress(coef), d, d, BLOCK_FULL, func=stress_coefficient)
+
+
+@pytest.mark.parametrize("mode", MODES)
 def test_bd_stabilization(case, mode):
     """FE::assemblyBDStabilization (FE_def.hpp:2151-2220; SURVEY.md 8(f) rank 4): P1 only, logic_error otherwise."""
     from feddlib_b200 import BLOCK_SCALAR, LogicError

@@ -9,7 +9,7 @@ from oracle import mesh as OM
 from oracle import oracle as O
 from oracle import ref as R
 
-from util import mesh_dfg, mesh_structured, oracle_csr, random_u
+from util import mesh_dfg, mesh_structured, oracle_csr, random_u, stress_coefficient
 
 pytestmark = pytest.mark.skipif(not R.available(), reason="oracle/_ref not built (needs /root/reference)")
 
@@ -29,6 +29,10 @@ def test_restatement_is_bitwise_equal_to_reference_code(dim, fe, make):
         b = R.assemble(op, dim, fe, conn, coords, **kw)
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), op
         assert np.array_equal(a[2], b[2]), f"{op}: max abs diff {np.abs(a[2] - b[2]).max():.3e}"
+    for f in (lambda x: 1.0, stress_coefficient):   # assemblyStress (FE_def.hpp:2407-2735), constant and varying coefficient
+        a = oracle_csr("stress", dim, fe, conn, coords, func=f)
+        b = R.assemble_stress(dim, fe, conn, coords, f)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b)), "stress"
     if fe == "P1":  # assemblyBDStabilization (FE_def.hpp:2151-2220) is P1 only
         a = oracle_csr("bdstab", dim, fe, conn, coords)
         b = R.assemble("bdstab", dim, fe, conn, coords)

@@ -38,7 +38,7 @@ def mesh_dfg(fe="P2"):
     return np.ascontiguousarray(conn.astype(np.int32)), np.ascontiguousarray(coords)
 
 
-def oracle_csr(op, dim, fe, conn, coords, u=None, lam=None, mu=None, fe2=None, conn2=None):
+def oracle_csr(op, dim, fe, conn, coords, u=None, lam=None, mu=None, fe2=None, conn2=None, func=None):
     """CSR (rowptr, colind, values) of the oracle for a single rank with gid == lid."""
     nn = coords.shape[0]
     gid = np.arange(nn, dtype=np.int64)
@@ -46,6 +46,8 @@ def oracle_csr(op, dim, fe, conn, coords, u=None, lam=None, mu=None, fe2=None, c
         A = O.Matrix(nn); O.assembly_laplace(dim, fe, conn, coords, gid, A)
     elif op == "mass":
         A = O.Matrix(nn); O.assembly_mass(dim, fe, conn, coords, gid, A, False)
+    elif op == "stress":
+        A = O.Matrix(dim * nn, 64); O.assembly_stress(dim, fe, conn, coords, gid, func, A)
     elif op == "bdstab":
         A = O.Matrix(nn); O.assembly_bdstab(dim, fe, conn, coords, gid, A)
     elif op == "mass_vec":
@@ -67,6 +69,11 @@ def oracle_csr(op, dim, fe, conn, coords, u=None, lam=None, mu=None, fe2=None, c
     else:
         raise ValueError(op)
     return A.csr()
+
+
+def stress_coefficient(x, parameters=None):
+    """A smooth, non-constant CoeffFunc_Type for the assemblyStress tests."""
+    return 1.0 + 0.5 * x[0] + 0.25 * x[1] * x[1] + (0.125 * x[2] if len(x) > 2 else 0.0)
 
 
 def rel_frobenius(a, b):
