@@ -553,6 +553,117 @@ __device__ inline bool ring_order(int ninc, const int32_t *__restrict__ inc_row,
     return true;
 }
 
+// Chain order of the star of a VERTEX (3D P2 vertex-node rows, k_gather_s).  The tetrahedra around the row vertex I
+// are grouped into fans around its edges (I, J) -- greedily, the neighbour J shared by the most tetrahedra not yet
+// placed first -- and every fan is walked like an edge ring (ring_order above): canonical vertices (I, J, w_in, w_out),
+// consecutive tetrahedra share the face (I, J, w_out).  Along a chain the columns J and mid(I, J) accumulate in
+// registers and the contributions to the out-face group are carried to the next incidence, so an incidence costs 4
+// shared-memory updates instead of 9 (plus 5 where a chain ends).
+//   rflag[m]  0: the out-face group is carried to the next incidence;  1: the chain ends here (everything is flushed)
+// Any decomposition is valid for the kernel; fans the walk does not cover (a face shared by more than two tetrahedra,
+// duplicate elements) are emitted as chains of length one.
+__device__ inline void vchain_order(int ninc, const int32_t *__restrict__ inc_row, const int32_t *__restrict__ conn,
+                                    int *order, uint32_t *rperm, uint32_t *rflag)
+{
+    int8_t l0[RING_KMAX], lo[RING_KMAX][3];
+    int32_t go[RING_KMAX][3];
+    bool used[RING_KMAX];
+    for (int m = 0; m < ninc; m++) {
+        const int32_t code = inc_row[m];
+        const int64_t e = code >> 4;
+        const int i0 = code & 15;
+        l0[m] = (int8_t)i0;
+        int n = 0;
+        for (int v = 0; v < 4; v++)
+            if (v != i0) { lo[m][n] = (int8_t)v; go[m][n] = conn[e * 10 + v]; n++; }
+        used[m] = false;
+    }
+    int n_out = 0;
+    while (n_out < ninc) {
+        // the neighbour vertex shared by the most unplaced tetrahedra (ties: the smallest id)
+        int32_t J = -1;
+        int best = 0;
+        for (int m = 0; m < ninc; m++) {
+            if (used[m]) continue;
+            for (int x = 0; x < 3; x++) {
+                const int32_t g = go[m][x];
+                int c = 0;
+                for (int m2 = 0; m2 < ninc; m2++)
+                    if (!used[m2]) c += (go[m2][0] == g) + (go[m2][1] == g) + (go[m2][2] == g);
+                if (c > best || (c == best && g < J)) { best = c; J = g; }
+            }
+        }
+        // the fan around (I, J)
+        int mem[RING_KMAX], nm = 0;
+        int8_t lJ[RING_KMAX], la[RING_KMAX], lb[RING_KMAX];
+        int32_t wa[RING_KMAX], wb[RING_KMAX];
+        bool done[RING_KMAX];
+        for (int m = 0; m < ninc; m++) {
+            if (used[m]) continue;
+            int x = -1;
+            for (int t = 0; t < 3; t++)
+                if (go[m][t] == J) x = t;
+            if (x < 0) continue;
+            const int y = x == 0 ? 1 : 0, z = x == 2 ? 1 : 2;
+            mem[nm] = m; lJ[nm] = lo[m][x]; la[nm] = lo[m][y]; lb[nm] = lo[m][z]; wa[nm] = go[m][y]; wb[nm] = go[m][z];
+            done[nm] = false;
+            nm++;
+        }
+        auto count = [&](int32_t w) { int c = 0; for (int k = 0; k < nm; k++) c += (wa[k] == w) + (wb[k] == w); return c; };
+        bool ok = true;
+        for (int k = 0; k < nm && ok; k++) {
+            if (wa[k] == wb[k] || wa[k] == J || wb[k] == J || count(wa[k]) > 2 || count(wb[k]) > 2) ok = false;
+            for (int k2 = k + 1; k2 < nm && ok; k2++)
+                if ((wa[k] == wa[k2] && wb[k] == wb[k2]) || (wa[k] == wb[k2] && wb[k] == wa[k2])) ok = false;
+        }
+        auto emit = [&](int k, int l_in, int l_out, uint32_t mode) {
+            const int m = mem[k];
+            order[n_out] = m;
+            rperm[n_out] = (uint32_t)l0[m] | ((uint32_t)lJ[k] << 2) | ((uint32_t)l_in << 4) | ((uint32_t)l_out << 6);
+            rflag[n_out] = mode;
+            n_out++;
+            used[m] = true;
+            done[k] = true;
+        };
+        if (!ok) {
+            for (int k = 0; k < nm; k++) emit(k, la[k], lb[k], 1u);
+            continue;
+        }
+        int placed = 0;
+        while (placed < nm) {
+            // start at a tetrahedron with a face no other member shares (open fan), else anywhere (closed ring)
+            int start = -1, low = -1;
+            bool in_is_a = true;
+            for (int k = 0; k < nm && start < 0; k++) {
+                if (done[k]) continue;
+                if (low < 0) low = k;
+                int ca = 0, cb = 0;
+                for (int k2 = 0; k2 < nm; k2++)
+                    if (!done[k2]) { ca += (wa[k2] == wa[k]) + (wb[k2] == wa[k]); cb += (wa[k2] == wb[k]) + (wb[k2] == wb[k]); }
+                if (ca == 1) { start = k; in_is_a = true; }
+                else if (cb == 1) { start = k; in_is_a = false; }
+            }
+            if (start < 0) { start = low; in_is_a = true; }
+            int cur = start;
+            int32_t w_in = in_is_a ? wa[cur] : wb[cur];
+            for (;;) {
+                const bool cin_a = wa[cur] == w_in;
+                const int l_in = cin_a ? la[cur] : lb[cur], l_out = cin_a ? lb[cur] : la[cur];
+                const int32_t w_out = cin_a ? wb[cur] : wa[cur];
+                done[cur] = true;
+                int nxt = -1;
+                for (int k = 0; k < nm && nxt < 0; k++)
+                    if (!done[k] && (wa[k] == w_out || wb[k] == w_out)) nxt = k;
+                emit(cur, l_in, l_out, nxt >= 0 ? 0u : 1u);
+                placed++;
+                if (nxt < 0) break;
+                cur = nxt;
+                w_in = w_out;
+            }
+        }
+    }
+}
+
 // rtype[row] = 0 vertex-node row / 1 edge-node row in ring order (3D P2) / 2 edge-node row, generic;
 // sig[row] = hash of the row's stencil shape (row length, permutations, flags and positions of all
 // incidences, NOT the element indices): rows with equal signatures address their accumulators identically
@@ -571,26 +682,28 @@ __global__ void k_make_records(int64_t n_rows, const int64_t *__restrict__ inc_p
         const int ty = (ninc > 0 && (inc[kb] & 15) > DIM) ? 1 : 0;
         uint64_t h = 1469598103934665603ull;
         h = sig_mix(h, (uint32_t)(rowptr[r + 1] - rowptr[r]));
-        bool ring = false;
+        bool ring = false, vchain = false;   // edge row in ring order / vertex row in chain order
         uint64_t seen[4] = {0, 0, 0, 0}; // positions that receive a local contribution (rows of up to 256 nodes)
         int order[RING_KMAX];
         uint32_t rperm[RING_KMAX], rflag[RING_KMAX];
         if constexpr (DIM == 3 && NL == 10 && NLR == 10) {
             if (use_ring && ty == 1 && ninc <= RING_KMAX) ring = ring_order(ninc, inc + kb, conn, order, rperm, rflag);
+            if (ty == 0 && ninc > 0 && ninc <= RING_KMAX) { vchain_order(ninc, inc + kb, conn, order, rperm, rflag); vchain = true; }
         }
         for (int m = 0; m < ninc; m++) {
-            const int32_t code = inc[kb + (ring ? order[m] : m)];
+            const int32_t code = inc[kb + ((ring || vchain) ? order[m] : m)];
             const int64_t e = code >> 4;
             const int i = code & 15;
             int pi[DIM + 1];
             uint32_t bits = 0;
-            if (ring) {
+            if (ring || vchain) {
                 bits = rperm[m];
                 for (int v = 0; v <= DIM; v++) pi[v] = (int)((bits >> (2 * v)) & 3);
                 bits |= rflag[m] << 8;
             } else {
                 canon_perm<DIM>(i, pi);
                 for (int v = 0; v <= DIM; v++) bits |= (uint32_t)pi[v] << (2 * v);
+                if (DIM == 3 && NL == 10 && NLR == 10 && ty == 0) bits |= 1u << 8; // vertex row, not ordered: chains of length one
             }
             uint32_t w[RW];
             for (int x = 0; x < RW; x++) w[x] = 0;
@@ -1336,7 +1449,7 @@ __global__ void __launch_bounds__(64, FB_GS_MINBLOCKS) k_gather_s(const GatherAr
             cp_async_commit();
             gcount++;
         }
-        double dacc = 0.0;
+        double dacc = 0.0, accJ = 0.0, accIJ = 0.0, carry[3] = {0.0, 0.0, 0.0};
         int pdiag = 0;
         int cs = s0;
 #pragma unroll 1
@@ -1403,21 +1516,33 @@ __global__ void __launch_bounds__(64, FB_GS_MINBLOCKS) k_gather_s(const GatherAr
                     e[w] = x;
                 }
             }
-            dacc += A.R.r[0][0][0][0] * e[0];
-            // distinct canonical nodes hit distinct row positions: load all accumulators, add, store all
-            double *ptr[NL - 1];
-            double old[NL - 1];
-#pragma unroll
-            for (int jj = 0; jj < NL - 1; jj++) {
-                ptr[jj] = my + posof(jj + 1);
-                old[jj] = *ptr[jj];
-            }
-#pragma unroll
-            for (int jj = 0; jj < NL - 1; jj++) {
-                const int jc = jj + 1;
-                double v = old[jj] + A.R.r[0][jc][0][0] * e[canon_sv<DIM>(jc, 0)];
+            // chain order (vchain_order): canonical vertices (I, J, w_in, w_out).  J and mid(I, J) accumulate in
+            // registers along the chain, the out-face group {3, 7, 8} is carried to the next incidence, where it is
+            // the in-face group {2, 6, 5}; only that group and node 9 are updated in shared memory -- 4 updates
+            // per incidence instead of 9, plus 5 where the chain ends
+            auto contrib = [&](int jc) {
+                double v = A.R.r[0][jc][0][0] * e[canon_sv<DIM>(jc, 0)];
                 if (jc >= NVTX) v += A.R.r[0][jc][0][1] * e[canon_sv<DIM>(jc, 1)];
-                *ptr[jj] = v;
+                return v;
+            };
+            const uint32_t mode = (perm >> 8) & 3;
+            dacc += contrib(0);
+            accJ += contrib(1);
+            accIJ += contrib(4);
+            {
+                double *p2 = my + posof(2), *p6 = my + posof(6), *p5 = my + posof(5), *p9 = my + posof(9);
+                const double o2 = *p2, o6 = *p6, o5 = *p5, o9 = *p9;
+                *p2 = o2 + (carry[0] + contrib(2));
+                *p6 = o6 + (carry[1] + contrib(6));
+                *p5 = o5 + (carry[2] + contrib(5));
+                *p9 = o9 + contrib(9);
+            }
+            carry[0] = contrib(3); carry[1] = contrib(7); carry[2] = contrib(8);
+            if (mode != 0) {
+                double *p3 = my + posof(3), *p7 = my + posof(7), *p8 = my + posof(8), *p1 = my + posof(1), *p4 = my + posof(4);
+                const double o3 = *p3, o7 = *p7, o8 = *p8, o1 = *p1, o4 = *p4;
+                *p3 = o3 + carry[0]; *p7 = o7 + carry[1]; *p8 = o8 + carry[2]; *p1 = o1 + accJ; *p4 = o4 + accIJ;
+                carry[0] = carry[1] = carry[2] = accJ = accIJ = 0.0;
             }
             cs = wrap(cs + 1);
         }
