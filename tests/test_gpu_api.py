@@ -139,6 +139,35 @@ def test_ragged_mesh_with_unused_nodes(engine_ctx):
         assert rel_frobenius(pat.assemble_laplace(), vo) <= TOL
 
 
+@pytest.mark.parametrize("n", [12, 40])
+def test_large_vertex_and_edge_stars(engine_ctx, n):
+    """A double fan: 2n tetrahedra around the centre vertex, n around each of the edges (centre, top) and (centre, bottom).
+    n = 40 exceeds the 32 incidences the chain / ring ordering of the row-gather kernels handles (vertex star of 80,
+    edge rings of 40): those rows take the unordered records and the generic kernels; n = 12 keeps everything ordered
+    (closed rings of 12, a vertex star that decomposes into two closed fans)."""
+    from feddlib_b200 import BLOCK_FULL, BLOCK_SCALAR, Mesh, Pattern
+    from oracle import mesh as OM
+    ang = 2 * np.pi * np.arange(n) / n
+    ring = np.stack([np.cos(ang), np.sin(ang), 0.1 * np.sin(3 * ang)], axis=1)
+    pts = np.concatenate([[[0.0, 0.0, 0.0], [0.1, 0.0, 1.0], [0.0, -0.1, -1.2]], ring])   # centre, top, bottom, ring
+    c, t, b = 0, 1, 2
+    conn1 = np.array([[c, apex, 3 + i, 3 + (i + 1) % n] for apex in (t, b) for i in range(n)], dtype=np.int32)
+    conn, coords, _ = OM.p2_of_p1(conn1, pts)
+    conn = np.ascontiguousarray(conn.astype(np.int32)); coords = np.ascontiguousarray(coords)
+    pat = Pattern(engine_ctx, Mesh(engine_ctx, 3, conn, coords))
+    rp, ci = pat.expand(3, 3, BLOCK_FULL)
+    rpo, cio, vo = oracle_csr("linelas", 3, "P2", conn, coords, lam=3.0, mu=1.5)
+    assert np.array_equal(rp, rpo) and np.array_equal(ci, cio)
+    lo = oracle_csr("laplace", 3, "P2", conn, coords)[2]
+    for mode in ("gather", "coloured", "atomic"):
+        engine_ctx.set_scatter_mode(mode)
+        assert rel_frobenius(pat.assemble_linelas(3.0, 1.5), vo) <= TOL
+        assert rel_frobenius(pat.assemble_laplace(), lo) <= TOL
+    engine_ctx.set_scatter_mode("gather")
+    a, b2 = pat.assemble_linelas(3.0, 1.5), pat.assemble_linelas(3.0, 1.5)
+    assert np.array_equal(a, b2)           # write-once / fixed-order sums: bitwise reproducible
+
+
 def test_device_resident_path_and_launch_counter(engine_ctx):
     import torch
     from feddlib_b200 import BLOCK_FULL, Mesh, Pattern
