@@ -226,6 +226,8 @@ void canon_table(const OpTables &t, int dim, int nl, CanonR &R)
                 }
 }
 
+constexpr int64_t kSmallBucketRows = 4096;   // buckets up to this many rows run on the side stream (see launch_gather_t)
+
 template <int OPG, int DIM, int NL>
 int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
 {
@@ -242,9 +244,13 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
     int n_side = 0;
     if (const char *f = getenv("FEDDB200_SIDE_STREAMS")) n_side = std::max(0, std::min(feddb200_ctx::kSide, atoi(f))); // tuning aid
     if (p->buckets.size() < 2) n_side = 0;
-    if (n_side > 0) {
+    // ... except the SMALL buckets (boundary and corner rows: a handful of blocks that run for 5-50 us each on an
+    // otherwise empty GPU): they go to one side stream and run underneath the large launches
+    static const bool small_aside = [] { const char *f = getenv("FEDDB200_SMALL_ASIDE"); return !f || atoi(f) != 0; }(); // tuning aid
+    const bool aside = n_side == 0 && small_aside && p->buckets.size() >= 2;
+    if (n_side > 0 || aside) {
         FB_CUDA(cudaEventRecord(c->ev_fork, c->stream));
-        for (int i = 0; i < n_side; i++) FB_CUDA(cudaStreamWaitEvent(c->side[i], c->ev_fork, 0));
+        for (int i = 0; i < std::max(n_side, 1); i++) FB_CUDA(cudaStreamWaitEvent(c->side[i], c->ev_fork, 0));
     }
     std::vector<const Bucket *> order;
     for (const Bucket &b : p->buckets) order.push_back(&b);
@@ -253,7 +259,7 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
     for (const Bucket *bp : order) {
         const Bucket &b = *bp;
         if ((phase == FEDDB200_ROWS_GHOST && !b.ghost) || (phase == FEDDB200_ROWS_OWNED && b.ghost)) continue;
-        cudaStream_t st = n_side > 0 ? c->side[turn++ % n_side] : c->stream;
+        cudaStream_t st = n_side > 0 ? c->side[turn++ % n_side] : ((aside && b.count <= kSmallBucketRows) ? c->side[0] : c->stream);
         G.zero = 0;
         G.start = b.start; G.count = b.count;
         // ghost rows go straight into their owners' receive buffers (peer memory) when targets are set
@@ -337,7 +343,7 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
         }
         if (rc != FEDDB200_OK) return rc;
     }
-    for (int i = 0; i < n_side; i++) {
+    for (int i = 0; i < std::max(n_side, aside ? 1 : 0); i++) {
         FB_CUDA(cudaEventRecord(c->ev_join[i], c->side[i]));
         FB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join[i], 0));
     }
@@ -426,8 +432,20 @@ int launch_gatherx_t(feddb200_ctx *c, feddb200_pat *p, const feddb200_mesh *vm, 
     G.rowinfo = (const RowInfo *)p->rowinfo_d; G.rec = p->rec_d; G.geom = p->geom_d; G.uel = p->uel_d; G.dt = p->dt_d;
     G.values = values_d; G.vec_dim = vec_dim;
     const size_t budget = c->smem_optin - 1024;
-    for (const Bucket &b : p->buckets) {
+    // small buckets on a side stream, underneath the large launches (see launch_gather_t)
+    static const bool small_aside = [] { const char *f = getenv("FEDDB200_SMALL_ASIDE"); return !f || atoi(f) != 0; }(); // tuning aid
+    const bool aside = small_aside && p->buckets.size() >= 2;
+    if (aside) {
+        FB_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+        FB_CUDA(cudaStreamWaitEvent(c->side[0], c->ev_fork, 0));
+    }
+    std::vector<const Bucket *> order;
+    for (const Bucket &b : p->buckets) order.push_back(&b);
+    std::stable_sort(order.begin(), order.end(), [](const Bucket *x, const Bucket *y) { return x->count * (int64_t)x->lcap > y->count * (int64_t)y->lcap; });
+    for (const Bucket *bp : order) {
+        const Bucket &b = *bp;
         if ((c->row_phase == FEDDB200_ROWS_GHOST && !b.ghost) || (c->row_phase == FEDDB200_ROWS_OWNED && b.ghost)) continue;
+        cudaStream_t st = (aside && b.count <= kSmallBucketRows) ? c->side[0] : c->stream;
         G.start = b.start; G.count = b.count;
         G.pitch = (S::NB * b.lcap) | 1;
         int nt = 64;
@@ -437,7 +455,7 @@ int launch_gatherx_t(feddb200_ctx *c, feddb200_pat *p, const feddb200_mesh *vm, 
         const int64_t blocks = (b.count * S::RD + nt - 1) / nt;
         auto launch = [&](auto kernel) -> int {
             FB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
-            kernel<<<(unsigned)blocks, nt, smem, c->stream>>>(G);
+            kernel<<<(unsigned)blocks, nt, smem, st>>>(G);
             c->launches++;
             FB_CUDA(cudaGetLastError());
             return FEDDB200_OK;
@@ -449,6 +467,10 @@ int launch_gatherx_t(feddb200_ctx *c, feddb200_pat *p, const feddb200_mesh *vm, 
             else { set_error("edge-node row in a P1 row space"); rc = FEDDB200_ELOGIC; }
         }
         if (rc != FEDDB200_OK) return rc;
+    }
+    if (aside) {
+        FB_CUDA(cudaEventRecord(c->ev_join[0], c->side[0]));
+        FB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join[0], 0));
     }
     return FEDDB200_OK;
 }
