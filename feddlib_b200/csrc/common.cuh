@@ -104,7 +104,7 @@ struct feddb200_pat {
     int32_t *row_perm_d = nullptr; // rows ordered by bucket (built lazily with the gather maps)
     uint32_t *rec_d = nullptr;     // [n_inc][rec_words] per-incidence gather records (positions | element | permutation)
     void *rowinfo_d = nullptr;     // [n_rows] RowInfo records in bucket order
-    uint32_t *ahead_d = nullptr;   // [n_inc] ring rows: element of the incidence kRsAhead places further on (k_ring_s)
+    uint32_t *ahead_d = nullptr;   // [n_inc] 3D P2: element of the incidence kRsAhead places further along the same row (k_gather_s)
     int rec_words = 0;
     double *geom_d = nullptr;      // [ne][GS] per-element geometry cache, recomputed by every assembly
     double *uel_d = nullptr;       // [ne][nloc][4] nodal velocities of each element (operators with a velocity argument)
