@@ -258,6 +258,18 @@ def main():
     overlap = runner is not None and args.mode == "gather" and not args.no_overlap
 
     fused = overlap and args.exchange == "fused" and world <= 8
+    if fused:
+        # the peer-memory exchange needs CUDA IPC between the ranks of the box: set it up now (first assembly) and let
+        # every rank fall back to the NCCL exchange together if any of them cannot map its peers
+        ok = torch.ones(1, dtype=torch.int32, device=f"cuda:{local_rank}")
+        try:
+            runner.assemble_linelas_fused(values, LAM, MU)
+            ctx.synchronize()
+        except Exception as exc:  # noqa: BLE001
+            print(f"[bench] rank {rank}: peer-memory exchange unavailable ({exc}); using the NCCL exchange", file=sys.stderr)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        fused = bool(int(ok.item()))
 
     def step():
         if fused:        # ghost rows first, stored by their kernels into the owners' receive buffers (peer memory)
