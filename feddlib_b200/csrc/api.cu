@@ -181,8 +181,9 @@ int ensure_gather(feddb200_pat *p)
         FB_CUDA(cudaMalloc(&p->rowinfo_d, sizeof(RowInfo) * std::max<int64_t>(n_rows, 1)));
         FB_CUDA(cudaMemcpy(p->rowinfo_d, info.data(), sizeof(RowInfo) * n_rows, cudaMemcpyHostToDevice));
         if (dim == 3 && nl == 10 && nlc == 10 && n_rows > 0) { // 3D P2: look-ahead elements of k_gather_s
-            FB_CUDA(cudaMalloc(&p->ahead_d, sizeof(uint32_t) * std::max<int64_t>(p->n_inc, 1)));
-            FB_CUDA(cudaMemsetAsync(p->ahead_d, 0, sizeof(uint32_t) * std::max<int64_t>(p->n_inc, 1), c->stream));
+            // (+ 4: k_gather_s copies the aligned 16-byte chunk that holds ahead[k])
+            FB_CUDA(cudaMalloc(&p->ahead_d, sizeof(uint32_t) * (p->n_inc + 4)));
+            FB_CUDA(cudaMemsetAsync(p->ahead_d, 0, sizeof(uint32_t) * (p->n_inc + 4), c->stream));
             k_ring_ahead<<<(unsigned)std::min<int64_t>((n_rows + 127) / 128, 148 * 64), 128, 0, c->stream>>>(n_rows, (RowInfo *)p->rowinfo_d, p->rec_d, p->ahead_d);
             c->launches++;
             FB_CUDA(cudaGetLastError());

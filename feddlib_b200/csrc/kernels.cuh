@@ -1322,10 +1322,9 @@ __device__ __forceinline__ void cp_async16(void *sdst, const void *gsrc)
     const uint32_t s = (uint32_t)__cvta_generic_to_shared(sdst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void cp_async4(void *sdst, const void *gsrc)
+__device__ __forceinline__ void cp_async16_s(uint32_t sdst, const void *gsrc)   // destination as a shared-memory address
 {
-    const uint32_t s = (uint32_t)__cvta_generic_to_shared(sdst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gsrc) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -1383,13 +1382,20 @@ __global__ void __launch_bounds__(64, FB_GS_MINBLOCKS) k_gather_s(const GatherAr
 
     // this lane's share of the 11 chunks of a slot: chunk `comp` (record: 0, 1; geometry: 2..8), lane 0 also the
     // last geometry chunk, lane 1 the look-ahead word
+    // (per-lane constants: source array and offset of the lane's chunk, shared-memory address of its destination;
+    // the look-ahead word travels as the aligned 16-byte chunk of the `ahead` array that holds it)
+    const bool is_rec = comp < 2;
+    const char *const src0 = is_rec ? reinterpret_cast<const char *>(A.rec) + 16 * comp
+                                    : reinterpret_cast<const char *>(A.geom) + 16 * (comp - 2);
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+    const uint32_t dst0 = ring_s + 16 * comp, dst1 = ring_s + (comp == 0 ? 144 : 160);
     auto request = [&](int rs, int64_t k, uint32_t e) {
-        char *dst = ring + rs * kRsSlotB;
-        const char *rsrc = reinterpret_cast<const char *>(A.rec + k * 8);
-        const char *gsrc = reinterpret_cast<const char *>(A.geom + (int64_t)e * 16);
-        cp_async16(dst + 16 * comp, comp < 2 ? rsrc + 16 * comp : gsrc + 16 * (comp - 2));
-        if (comp == 0) cp_async16(dst + 144, gsrc + 112);
-        if (comp == 1) cp_async4(dst + 160, A.ahead + k);
+        const uint32_t so = rs * kRsSlotB;
+        const int64_t line = (int64_t)e * 128;
+        cp_async16_s(dst0 + so, src0 + (is_rec ? k * 32 : line));
+        if (is_rec)
+            cp_async16_s(dst1 + so, comp == 0 ? reinterpret_cast<const char *>(A.geom) + line + 112
+                                              : reinterpret_cast<const char *>(A.ahead + (k & ~(int64_t)3)));
     };
     auto wrap = [](int x) { return x >= kRsD ? x - kRsD : x; };
 
@@ -1462,7 +1468,7 @@ __global__ void __launch_bounds__(64, FB_GS_MINBLOCKS) k_gather_s(const GatherAr
                 const int j = m + kRsAhead;
                 if (j < ninc) {
                     const int rs = wrap(cs + kRsAhead);
-                    request(rs, k0 + j, *reinterpret_cast<const uint32_t *>(sl + 160));
+                    request(rs, k0 + j, *reinterpret_cast<const uint32_t *>(sl + 160 + 4 * (int)((k0 + m) & 3)));
                     note(rs);
                     nis = j + 1;
                 } else if (live_n) {
