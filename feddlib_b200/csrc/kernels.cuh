@@ -1300,10 +1300,9 @@ __global__ void __launch_bounds__(64, FB_RING_MINBLOCKS) k_ring(const GatherArgs
 // look-ahead word removes the record -> geometry dependence: the address of a geometry line is known kRsAhead
 // incidences early without a second level of prefetching.
 //
-// Bookkeeping per lane (identical in the lanes of a node): `gcount` cp.async groups committed so far and, per ring
-// slot, the group that filled it; before a slot is consumed the lane waits until at most (gcount - 1 - group) newer
-// groups are pending, which is kRsAhead - 1 in steady state and 0 right after a catch-up (first tile, rows with fewer
-// than kRsAhead incidences).
+// Completion: a lane commits one cp.async group per incidence it consumes, so the slot of an incidence was filled
+// kRsAhead groups earlier and `wait_group kRsAhead - 1` suffices; only where a row's first incidences were requested
+// late (first tile, or the previous row had fewer than kRsAhead incidences) the lane waits for everything.
 // -----------------------------------------------------------------------------------------
 #ifndef FB_RS_D
 #define FB_RS_D 3
@@ -1328,15 +1327,6 @@ __device__ __forceinline__ void cp_async16_s(uint32_t sdst, const void *gsrc)   
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-// wait until at most min(allowed, kRsAhead - 1) of this thread's newest groups are pending
-__device__ __forceinline__ void cp_async_wait_upto(int allowed)
-{
-    if constexpr (kRsAhead >= 4) { if (allowed >= 3) { cp_async_wait<3>(); return; } }
-    if constexpr (kRsAhead >= 3) { if (allowed >= 2) { cp_async_wait<2>(); return; } }
-    if constexpr (kRsAhead >= 2) { if (allowed >= 1) { cp_async_wait<1>(); return; } }
-    cp_async_wait<0>();
-}
-
 // one-time (pattern build): look-ahead elements of every row -- RowInfo::e (first incidences) and ahead[k]
 __global__ void k_ring_ahead(int64_t n_rows, RowInfo *__restrict__ info, const uint32_t *__restrict__ rec, uint32_t *__restrict__ ahead)
 {
@@ -1414,9 +1404,8 @@ __global__ void __launch_bounds__(64, FB_GS_MINBLOCKS) k_gather_s(const GatherAr
         const int64_t node = tile * NPT + slot;
         if (lane_used && node < A.count) ld_v4(reinterpret_cast<const double *>(A.rowinfo + A.start + node), raw);
     }
-    uint32_t gcount = 0, gis = 0;            // committed groups; the group that filled each slot (see above)
     int s0 = 0, nis = 0;
-    auto note = [&](int rs) { gis = (gis & ~(0xffu << (8 * rs))) | ((gcount & 0xffu) << (8 * rs)); };
+    bool careful = true;                     // the previous row was too short to request this row's first incidences in time
 
     for (;;) {
         const bool live = lane_used && tile * NPT + slot < A.count;
@@ -1449,11 +1438,10 @@ __global__ void __launch_bounds__(64, FB_GS_MINBLOCKS) k_gather_s(const GatherAr
                 if (j >= nis && j < ninc) {
                     const int rs = wrap(s0 + j);
                     request(rs, k0 + j, __ldg(A.rowinfo[A.start + tile * NPT + slot].e + j));
-                    note(rs);
                 }
             nis = ninc < kRsAhead ? ninc : kRsAhead;
             cp_async_commit();
-            gcount++;
+            careful = true;
         }
         double dacc = 0.0, accJ = 0.0, accIJ = 0.0, carry[3] = {0.0, 0.0, 0.0};
         int pdiag = 0;
@@ -1461,7 +1449,10 @@ __global__ void __launch_bounds__(64, FB_GS_MINBLOCKS) k_gather_s(const GatherAr
 #pragma unroll 1
         for (int m = 0; m < nmax; m++) {
             if (m >= ninc) continue;
-            cp_async_wait_upto((int)((gcount - 1u - (gis >> (8 * cs))) & 0xffu));
+            // one group per incidence: the slot of incidence m was requested kRsAhead groups ago, so kRsAhead - 1 newer
+            // groups may stay pending -- except at the start of a row whose first incidences were requested late
+            if (careful && m < kRsAhead) cp_async_wait<0>();
+            else cp_async_wait<kRsAhead - 1>();
             __syncwarp(nmask);
             const char *sl = ring + cs * kRsSlotB;
             {
@@ -1469,7 +1460,6 @@ __global__ void __launch_bounds__(64, FB_GS_MINBLOCKS) k_gather_s(const GatherAr
                 if (j < ninc) {
                     const int rs = wrap(cs + kRsAhead);
                     request(rs, k0 + j, *reinterpret_cast<const uint32_t *>(sl + 160 + 4 * (int)((k0 + m) & 3)));
-                    note(rs);
                     nis = j + 1;
                 } else if (live_n) {
                     const int jn = j - ninc;
@@ -1481,12 +1471,10 @@ __global__ void __launch_bounds__(64, FB_GS_MINBLOCKS) k_gather_s(const GatherAr
                         if (q >= nisn && q <= jn && q < lim) {
                             const int rs = wrap(sn0 + q);
                             request(rs, k0n + q, q == 0 ? en.x : (q == 1 ? en.y : (q == 2 ? en.z : en.w)));
-                            note(rs);
                         }
                     if (jn + 1 > nisn) nisn = jn + 1 < lim ? jn + 1 : lim;
                 }
                 cp_async_commit();
-                gcount++;
             }
             const uint4 w0 = *reinterpret_cast<const uint4 *>(sl);
             const uint4 w1 = *reinterpret_cast<const uint4 *>(sl + 16);
@@ -1575,6 +1563,7 @@ __global__ void __launch_bounds__(64, FB_GS_MINBLOCKS) k_gather_s(const GatherAr
         tile = tile_n;
         s0 = cs;
         nis = nisn;
+        careful = ninc < kRsAhead;
 #pragma unroll
         for (int x = 0; x < 4; x++) raw[x] = rawn[x];
     }
