@@ -901,12 +901,8 @@ extern "C" int feddb200_set_ghost_targets(feddb200_ctx *c, int nseg, const int64
         FB_LOGIC(seg_begin[i + 1] > seg_begin[i] && !seg_ptr_d[i], "set_ghost_targets: non-empty segment without a target");
     }
     c->n_ghost_seg = nseg;
-    for (int i = 0; i < kMaxGhostSeg; i++) {
-        c->ghost_seg_begin[i] = i <= nseg && nseg > 0 ? seg_begin[std::min(i, nseg)] : 0;
-        c->ghost_seg_ptr[i] = i < nseg ? static_cast<double *>(seg_ptr_d[i]) : nullptr;
-    }
-    c->ghost_seg_begin[kMaxGhostSeg] = nseg > 0 ? seg_begin[nseg] : 0;
-    for (int i = nseg + 1; i <= kMaxGhostSeg && nseg > 0; i++) c->ghost_seg_begin[i] = seg_begin[nseg];
+    for (int i = 0; i <= kMaxGhostSeg; i++) c->ghost_seg_begin[i] = nseg > 0 ? seg_begin[std::min(i, nseg)] : 0; // unused tail: empty
+    for (int i = 0; i < kMaxGhostSeg; i++) c->ghost_seg_ptr[i] = i < nseg ? static_cast<double *>(seg_ptr_d[i]) : nullptr;
     return FEDDB200_OK;
 }
 
