@@ -259,3 +259,34 @@ def test_bd_stabilization_known_answers(dim, M):
     assert D.min() >= 0 and D.max() > 0 and np.linalg.matrix_rank(D) <= conn.shape[0]
     with pytest.raises(ValueError):
         O.assembly_bdstab(dim, "P2", conn, coords, gid, O.Matrix(n, 64))
+
+
+@pytest.mark.parametrize("dim,fe,M", [(2, "P1", 4), (2, "P2", 3), (3, "P1", 3), (3, "P2", 2)])
+def test_stress_known_answers(dim, fe, M):
+    """assemblyStress (FE_def.hpp:2407-2735): K^{ab}_ij = int f (delta_ab grad phi_i . grad phi_j + d_b phi_i d_a phi_j).
+    With f = 1 it is the mu-part of assemblyLinElasXDim (lambda = 0, mu = 1); it is symmetric for any f, annihilates the
+    rigid translations and rotations (2 eps(u) = 0), and scales linearly with a constant f."""
+    from oracle import mesh as OM
+    conn, coords, gid = OM.structured(dim, fe, 1, M)
+    n = coords.shape[0]
+
+    def stress(func):
+        A = O.Matrix(dim * n, 64)
+        O.assembly_stress(dim, fe, conn, coords, gid, func, A)
+        return A.scipy().tocsr()
+
+    S1 = stress(lambda x: 1.0)
+    E = O.Matrix(dim * n, 64)
+    O.assembly_linelas(dim, fe, conn, coords, gid, 0.0, 1.0, E)
+    Es = E.scipy().tocsr()
+    assert abs(S1 - Es).max() <= 1e-14 * abs(Es).max()
+    Sf = stress(lambda x: 1.0 + 0.5 * x[0] + 0.25 * x[1] * x[1])
+    scale = abs(Sf).max()
+    assert abs(Sf - Sf.T).max() <= 1e-14 * scale
+    for d in range(dim):                                   # translations
+        t = np.zeros(dim * n); t[d::dim] = 1.0
+        assert abs(Sf @ t).max() <= 1e-13 * scale
+    rot = np.zeros(dim * n)                                # rotation about the last axis: u = (-y, x[, 0])
+    rot[0::dim], rot[1::dim] = -coords[:, 1], coords[:, 0]
+    assert abs(Sf @ rot).max() <= 1e-12 * scale
+    assert abs(stress(lambda x: 2.5) - 2.5 * S1).max() <= 1e-14 * abs(S1).max()
