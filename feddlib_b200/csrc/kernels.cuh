@@ -786,6 +786,33 @@ __device__ __forceinline__ void bulk_store(void *gptr, const void *sptr, int byt
     const uint32_t s = (uint32_t)__cvta_generic_to_shared(sptr);
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gptr), "r"(s), "r"(bytes) : "memory");
 }
+// L2 eviction policies (tuning aids FB_HINT_ST / FB_HINT_GEOM): the assembled values are written once and never read
+// again by the assembly (evict-first), the geometry lines are re-read by every row that touches the element (evict-last)
+__device__ __forceinline__ uint64_t policy_evict_first()
+{
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last()
+{
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_store_hint(void *gptr, const void *sptr, int bytes, uint64_t pol)
+{
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(sptr);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gptr), "r"(s), "r"(bytes), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_out(double *p, double v)
+{
+#ifdef FB_HINT_ST
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(policy_evict_first()) : "memory");
+#else
+    *p = v;
+#endif
+}
 __device__ __forceinline__ void bulk_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void bulk_commit_wait_read()
 {
@@ -796,6 +823,15 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 __device__ __forceinline__ void ld_v4(const double *p, double (&v)[4])
 {
     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+// geometry lines (re-read by every incident row)
+__device__ __forceinline__ void ld_v4g(const double *p, double (&v)[4])
+{
+#ifdef FB_HINT_GEOM
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p), "l"(policy_evict_last()));
+#else
+    ld_v4(p, v);
+#endif
 }
 __device__ __forceinline__ void ld_v8u(const uint32_t *p, uint32_t (&w)[8])
 {
@@ -843,7 +879,7 @@ __device__ __forceinline__ void load_geo(const GatherArgs &A, const IncRec<NL> &
     const double *g = A.geom + (int64_t)rec_elem<NL>(R.w) * GS;
     if constexpr (DIM == 3) {
 #pragma unroll
-        for (int v = 0; v < 4; v++) ld_v4(g + 4 * ((perm >> (2 * v)) & 3), D.G[v]);
+        for (int v = 0; v < 4; v++) ld_v4g(g + 4 * ((perm >> (2 * v)) & 3), D.G[v]);
     } else {
         const double ad = __ldg(g + 6);
 #pragma unroll
@@ -979,7 +1015,7 @@ __global__ void __launch_bounds__(GatherShape<OPG, DIM>::NT, FB_GATHER_MINBLOCKS
                 const double *gp = AA.geom + (int64_t)rec_elem<NL>(rn.w) * GeomStride<DIM>::value + dep;
                 if constexpr (DIM == 3) {
 #pragma unroll
-                    for (int v = 0; v < 4; v++) ld_v4(gp + 4 * ((perm >> (2 * v)) & 3), g.G[v]);
+                    for (int v = 0; v < 4; v++) ld_v4g(gp + 4 * ((perm >> (2 * v)) & 3), g.G[v]);
                 } else {
                     const double ad = __ldg(gp + 6);
 #pragma unroll
@@ -1033,7 +1069,7 @@ __global__ void __launch_bounds__(GatherShape<OPG, DIM>::NT, FB_GATHER_MINBLOCKS
         for (int d = 0; d < nrep; d++) {
             double *out = out_ptr(A, (int64_t)nrep * s_off[r]) + (int64_t)d * nr;
 #pragma unroll 4
-            for (int x = lane; x < nr; x += 32) out[x] = src[x];
+            for (int x = lane; x < nr; x += 32) st_out(out + x, src[x]);
         }
     }
 }
@@ -1186,7 +1222,7 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
                     const uint32_t perm = rec_perm<NL>(rn.w);
                     const double *gp = A.geom + (int64_t)rec_elem<NL>(rn.w) * GeomStride<DIM>::value + dep;
 #pragma unroll
-                    for (int v = 0; v < 4; v++) ld_v4(gp + 4 * ((perm >> (2 * v)) & 3), g.G[v]);
+                    for (int v = 0; v < 4; v++) ld_v4g(gp + 4 * ((perm >> (2 * v)) & 3), g.G[v]);
                     load_rec<NL>(A, k + 3 < kl ? k + 3 : kl, r3);
 #ifndef FB_NO_L2_PREFETCH
                     prefetch_l2(A.geom + (int64_t)rec_elem<NL>(r2.w) * GeomStride<DIM>::value);
@@ -1262,7 +1298,11 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
                 if (OPG == 1 || h == head) {
                     const int body_n = (total - h) & ~1;
                     if (h) out[0] = nodep[0];
+#ifdef FB_HINT_ST
+                    if (body_n > 0) bulk_store_hint(out + h, nodep + h, body_n * 8, policy_evict_first());
+#else
                     if (body_n > 0) bulk_store(out + h, nodep + h, body_n * 8);
+#endif
                     if (h + body_n < total) out[total - 1] = nodep[total - 1];
                 } else { // replicated scalar row whose copy has the other phase: plain stores
                     for (int x = 0; x < total; x++) out[x] = nodep[x];
@@ -1325,6 +1365,10 @@ __device__ __forceinline__ void cp_async16_s(uint32_t sdst, const void *gsrc)   
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async16_sh(uint32_t sdst, const void *gsrc, uint64_t pol)
+{
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(sdst), "l"(gsrc), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 // one-time (pattern build): look-ahead elements of every row -- RowInfo::e (first incidences) and ahead[k]
@@ -1382,10 +1426,19 @@ __global__ void __launch_bounds__(64, FB_GS_MINBLOCKS) k_gather_s(const GatherAr
     auto request = [&](int rs, int64_t k, uint32_t e) {
         const uint32_t so = rs * kRsSlotB;
         const int64_t line = (int64_t)e * 128;
+#ifdef FB_HINT_GEOM
+        // records and look-ahead words are read once (evict-first), geometry lines by every incident row (evict-last)
+        cp_async16_sh(dst0 + so, src0 + (is_rec ? k * 32 : line), is_rec ? policy_evict_first() : policy_evict_last());
+        if (is_rec)
+            cp_async16_sh(dst1 + so, comp == 0 ? reinterpret_cast<const char *>(A.geom) + line + 112
+                                               : reinterpret_cast<const char *>(A.ahead + (k & ~(int64_t)3)),
+                          comp == 0 ? policy_evict_last() : policy_evict_first());
+#else
         cp_async16_s(dst0 + so, src0 + (is_rec ? k * 32 : line));
         if (is_rec)
             cp_async16_s(dst1 + so, comp == 0 ? reinterpret_cast<const char *>(A.geom) + line + 112
                                               : reinterpret_cast<const char *>(A.ahead + (k & ~(int64_t)3)));
+#endif
     };
     auto wrap = [](int x) { return x >= kRsD ? x - kRsD : x; };
 
@@ -1555,7 +1608,7 @@ __global__ void __launch_bounds__(64, FB_GS_MINBLOCKS) k_gather_s(const GatherAr
 #pragma unroll
             for (int aa = 0; aa < DIM; aa++) {
                 const double *src = rows + (size_t)(sl * DIM + aa) * pitch;
-                for (int x = lane; x < n_s; x += 32) out[aa * n_s + x] = src[x];
+                for (int x = lane; x < n_s; x += 32) st_out(out + aa * n_s + x, src[x]);
             }
         }
         __syncwarp();

@@ -27,3 +27,16 @@ def engine_ctx():
         fb_build.build()
     from feddlib_b200 import Context
     return Context(0)
+
+
+@pytest.fixture(autouse=True)
+def _default_scatter_mode(request):
+    """Every GPU test starts and ends in the default scatter mode (gather): what a test covers must not depend on
+    the mode the previous test left in the session-scoped context."""
+    if request.node.get_closest_marker("gpu") is None:
+        yield
+        return
+    ctx = request.getfixturevalue("engine_ctx")
+    ctx.set_scatter_mode("gather")
+    yield
+    ctx.set_scatter_mode("gather")

@@ -124,7 +124,7 @@ def test_linear_elasticity(case, mode):
     check(case, "linelas", case["pat"].assemble_linelas(LAM, MU), d, d, BLOCK_FULL, lam=LAM, mu=MU)
 
 
-@pytest.mark.parametrize("mode", ["coloured", "atomic"])
+@pytest.mark.parametrize("mode", MODES)
 def test_advection_N_and_W(case, mode):
     from feddlib_b200 import BLOCK_DIAG, BLOCK_FULL
     case["ctx"].set_scatter_mode(mode)
@@ -134,7 +134,7 @@ def test_advection_N_and_W(case, mode):
     check(case, "advection_in_u", case["pat"].assemble_advection_in_u(u), d, d, BLOCK_FULL, u=u)
 
 
-@pytest.mark.parametrize("mode", ["coloured", "atomic"])
+@pytest.mark.parametrize("mode", MODES)
 def test_div_and_divT(case, mode):
     from feddlib_b200 import BLOCK_FULL, Mesh, Pattern, assemble_div_divT
     ctx = case["ctx"]
@@ -160,15 +160,17 @@ def test_div_and_divT(case, mode):
     rpT, ciT = patBT.expand(d, 1, BLOCK_FULL)
     B = sp.csr_matrix((vB, ciB, rpB), shape=(npres, d * case["coords"].shape[0]))
     BT = sp.csr_matrix((vBT, ciT, rpT), shape=(d * case["coords"].shape[0], npres))
-    if mode == "coloured":
+    if mode in ("coloured", "gather"):
         assert abs(B - BT.T).max() <= 1e-15 * abs(B).max()
 
 
-def test_ns_jacobian_fused_equals_sum_of_parts(case):
-    """rho*nu*A + rho*N + rho*W on the union pattern (NavierStokes_def.hpp:140-152, 297-313)."""
+@pytest.mark.parametrize("mode", MODES)
+def test_ns_jacobian_fused_equals_sum_of_parts(case, mode):
+    """rho*nu*A + rho*N + rho*W on the union pattern (NavierStokes_def.hpp:140-152, 297-313); gather mode is the
+    fused row-gather kernel k_gatherx<X_NSJ> that bench.py times."""
     from feddlib_b200 import BLOCK_FULL
     import scipy.sparse as sp
-    case["ctx"].set_scatter_mode("coloured")
+    case["ctx"].set_scatter_mode(mode)
     d = case["dim"]
     n = case["coords"].shape[0]
     u = random_u(d, n, seed=77)
