@@ -160,8 +160,10 @@ def test_div_and_divT(case, mode):
     rpT, ciT = patBT.expand(d, 1, BLOCK_FULL)
     B = sp.csr_matrix((vB, ciB, rpB), shape=(npres, d * case["coords"].shape[0]))
     BT = sp.csr_matrix((vBT, ciT, rpT), shape=(d * case["coords"].shape[0], npres))
-    if mode in ("coloured", "gather"):
+    if mode == "coloured":     # element-row kernels: the same expression on both sides
         assert abs(B - BT.T).max() <= 1e-15 * abs(B).max()
+    elif mode == "gather":     # row-gather kernels: B and B^T sum their incidences in different orders
+        assert abs(B - BT.T).max() <= 1e-13 * abs(B).max()
 
 
 @pytest.mark.parametrize("mode", MODES)
