@@ -5,6 +5,7 @@
 #include <cstdlib>
 
 #include "kernels.cuh"
+#include "star_kernels.cuh"
 
 using namespace fb;
 
@@ -97,6 +98,71 @@ int launch_elem_op(feddb200_ctx *c, int op, int dim, int nr, int nc, ElemArgs &A
 // gather path preparation (lazy, once per pattern): canonical position map, row types,
 // (type, length) buckets
 // ---------------------------------------------------------------------------------------
+// task programs of the block-task kernel (k_task): tiles of consecutive bucket rows, scheduled on the device
+int build_task_programs(feddb200_pat *p, const std::vector<RowInfo> &info)
+{
+    feddb200_ctx *c = p->ctx;
+    static const bool enabled = [] { const char *f = getenv("FEDDB200_TASK"); return !f || atoi(f) != 0; }(); // tuning aid
+    if (!enabled || !(p->rm->dim == 3 && p->rm->nloc == 10 && p->cm->nloc == 10)) return FEDDB200_OK;
+    std::vector<TaskTile> tiles;
+    for (Bucket &b : p->buckets) {
+        b.tile_start = 0; b.tile_count = 0; b.npt = 0;
+        if (b.type != 0 || b.lcap > kTaskMaxLen) continue;
+        int max_ninc = 0;
+        for (int64_t q = b.start; q < b.start + b.count; q++) max_ninc = std::max(max_ninc, info[q].ninc);
+        if (max_ninc > kTaskMaxTets) continue;
+        b.npt = std::max(1, std::min(kTaskMaxNodes, kTaskMaxTets / std::max(1, max_ninc)));
+        b.tile_start = (int64_t)tiles.size();
+        for (int64_t q = b.start; q < b.start + b.count;) {
+            TaskTile t;
+            std::memset(&t, 0, sizeof(t));
+            t.q0 = (uint32_t)q;
+            int n = 0, tets = 0;
+            while (q < b.start + b.count && n < b.npt && tets + info[q].ninc <= kTaskMaxTets) { tets += info[q].ninc; n++; q++; }
+            t.n_nodes = (uint8_t)n;
+            tiles.push_back(t);
+        }
+        b.tile_count = (int64_t)tiles.size() - b.tile_start;
+    }
+    const int64_t n_tiles = (int64_t)tiles.size();
+    if (n_tiles == 0) return FEDDB200_OK;
+    TaskBuildArgs A;
+    int *status_d = nullptr;
+    FB_CUDA(cudaMalloc(&p->task_tiles_d, sizeof(TaskTile) * n_tiles));
+    FB_CUDA(cudaMalloc(&status_d, sizeof(int)));
+    FB_CUDA(cudaMemsetAsync(status_d, 0, sizeof(int), c->stream));
+    FB_CUDA(cudaMemcpyAsync(p->task_tiles_d, tiles.data(), sizeof(TaskTile) * n_tiles, cudaMemcpyHostToDevice, c->stream));
+    A.rowinfo = (const RowInfo *)p->rowinfo_d; A.rec = p->rec_d; A.tiles = (TaskTile *)p->task_tiles_d; A.n_tiles = n_tiles;
+    A.tasks = nullptr; A.tiletet = nullptr; A.status = status_d;
+    const unsigned grid = (unsigned)std::min<int64_t>((n_tiles + 63) / 64, 148 * 32);
+    k_task_build<<<grid, 64, 0, c->stream>>>(A, 0);
+    c->launches++;
+    FB_CUDA(cudaGetLastError());
+    int status = 0;
+    FB_CUDA(cudaMemcpyAsync(tiles.data(), p->task_tiles_d, sizeof(TaskTile) * n_tiles, cudaMemcpyDeviceToHost, c->stream));
+    FB_CUDA(cudaMemcpyAsync(&status, status_d, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    FB_CUDA(cudaStreamSynchronize(c->stream));
+    int64_t passes = 0;
+    for (TaskTile &t : tiles) { t.task_off = (uint32_t)passes; passes += t.n_passes; }
+    if (status != 0 || passes >= (int64_t(1) << 32)) { // a tile outside the format limits: the buckets keep their other kernels
+        for (Bucket &b : p->buckets) b.tile_count = 0;
+        cudaFree(status_d);
+        return FEDDB200_OK;
+    }
+    FB_CUDA(cudaMalloc(&p->tasks_d, sizeof(uint64_t) * 32 * std::max<int64_t>(passes, 1)));
+    FB_CUDA(cudaMalloc(&p->tiletet_d, sizeof(uint2) * kTaskMaxTets * n_tiles));
+    FB_CUDA(cudaMemcpyAsync(p->task_tiles_d, tiles.data(), sizeof(TaskTile) * n_tiles, cudaMemcpyHostToDevice, c->stream));
+    A.tasks = p->tasks_d; A.tiletet = (uint2 *)p->tiletet_d;
+    k_task_build<<<grid, 64, 0, c->stream>>>(A, 1);
+    c->launches++;
+    FB_CUDA(cudaGetLastError());
+    FB_CUDA(cudaMemcpyAsync(&status, status_d, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    FB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(status_d);
+    FB_LOGIC(status != 0, "task programs: inconsistent schedule");
+    return FEDDB200_OK;
+}
+
 int ensure_gather(feddb200_pat *p)
 {
     if (p->gather_ready) return FEDDB200_OK;
@@ -189,6 +255,8 @@ int ensure_gather(feddb200_pat *p)
             FB_CUDA(cudaGetLastError());
             FB_CUDA(cudaStreamSynchronize(c->stream));
         }
+        const int rc_task = build_task_programs(p, info);
+        if (rc_task != FEDDB200_OK) return rc_task;
     }
     const int gs = dim == 3 ? 16 : 8;
     FB_CUDA(cudaMalloc(&p->geom_d, sizeof(double) * std::max<int64_t>(p->rm->ne * gs, 1)));
@@ -303,6 +371,29 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
                 rc = FEDDB200_OK;
             } else { set_error("ring rows exist for 3D P2 patterns only"); rc = FEDDB200_ELOGIC; }
         } else {
+            if constexpr (DIM == 3 && NL == 10) {
+                // vertex-node rows of 3D P2: block-task kernel (star_kernels.cuh), one warp per tile of row nodes
+                if (b.type == 0 && b.tile_count > 0 && p->tasks_d) {
+                    constexpr int TPRt = OPG == 1 ? DIM : 1, NBt = OPG == 1 ? DIM : 1;
+                    TaskArgs T;
+                    T.G = G;
+                    T.G.pitch = (TPRt * NBt * b.lcap + 2) & ~1;   // room for the phase shift, even (keeps the stage planes 16-byte aligned)
+                    T.tiles = (const TaskTile *)p->task_tiles_d + b.tile_start; T.n_tiles = b.tile_count;
+                    T.tasks = p->tasks_d; T.tiletet = (const uint2 *)p->tiletet_d + b.tile_start * kTaskMaxTets; T.npt = b.npt;
+                    const int ntk = 64;
+                    const size_t smem_t = ((size_t)b.npt * T.G.pitch * 8 + kTaskStageB) * (ntk / 32);
+                    if (smem_t <= budget) {
+                        FB_CUDA(cudaFuncSetAttribute(k_task<OPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+                        int per_sm = 1;
+                        FB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_task<OPG>, ntk, smem_t));
+                        const int64_t blocks_t = std::min<int64_t>((b.tile_count + ntk / 32 - 1) / (ntk / 32), (int64_t)std::max(per_sm, 1) * c->sm_count);
+                        k_task<OPG><<<(unsigned)blocks_t, ntk, smem_t, st>>>(T);
+                        c->launches++;
+                        FB_CUDA(cudaGetLastError());
+                        continue;
+                    }
+                }
+            }
             // accumulators: 32 rows of NBL*L doubles per block, `pitch` doubles apart with pitch == NBL (mod 16), see k_gather
             int pitch = S::NBL * b.lcap;
             while ((pitch & 15) != (S::NBL & 15)) pitch++;

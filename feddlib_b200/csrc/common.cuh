@@ -50,6 +50,9 @@ struct Bucket {            // rows of one type with node-row length <= lcap, pro
     int ghost;             // 1: rows owned by another rank (index >= n_owned); their values are shipped after the assembly
     int lcap;
     int64_t start, count;  // range in row_perm
+    // block-task kernel (star_kernels.cuh: k_task): tiles of this bucket in the pattern's tile array; count 0: not used
+    int64_t tile_start = 0, tile_count = 0;
+    int npt = 0;           // row nodes per tile at most
 };
 
 } // namespace fb
@@ -106,6 +109,9 @@ struct feddb200_pat {
     void *rowinfo_d = nullptr;     // [n_rows] RowInfo records in bucket order
     uint32_t *ahead_d = nullptr;   // [n_inc] 3D P2: element of the incidence kRsAhead places further along the same row (k_gather_s)
     int rec_words = 0;
+    void *task_tiles_d = nullptr;  // [n_tiles] TaskTile: tiles of the block-task kernel (3D P2 vertex-node rows)
+    uint64_t *tasks_d = nullptr;   // task programs of the tiles (tasks.cuh)
+    void *tiletet_d = nullptr;     // [n_tiles][32] (element, canonical permutation) of the tiles' incident elements
     double *geom_d = nullptr;      // [ne][GS] per-element geometry cache, recomputed by every assembly
     double *uel_d = nullptr;       // [ne][nloc][4] nodal velocities of each element (operators with a velocity argument)
     double *dt_d = nullptr;        // [ne][dim][dim][4] |det| * grad u at the element's vertices
