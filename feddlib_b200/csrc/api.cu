@@ -163,6 +163,37 @@ int build_task_programs(feddb200_pat *p, const std::vector<RowInfo> &info)
     return FEDDB200_OK;
 }
 
+// padded per-bucket records of the fan kernel (k_fan): ring-ordered edge-node rows of 3D P2
+int build_fan_records(feddb200_pat *p, const std::vector<RowInfo> &info)
+{
+    feddb200_ctx *c = p->ctx;
+    static const bool enabled = [] { const char *f = getenv("FEDDB200_FAN"); return !f || atoi(f) != 0; }(); // tuning aid
+    if (!enabled || !(p->rm->dim == 3 && p->rm->nloc == 10 && p->cm->nloc == 10)) return FEDDB200_OK;
+    int64_t total = 0;
+    for (Bucket &b : p->buckets) {
+        b.fan_off = 0; b.fan_W = 0; b.fan_npw = 0;
+        if (b.type != 1) continue;
+        int max_ninc = 0;
+        for (int64_t q = b.start; q < b.start + b.count; q++) max_ninc = std::max(max_ninc, info[q].ninc);
+        if (max_ninc > 32) continue;
+        b.fan_W = std::max(4, max_ninc);
+        b.fan_npw = 32 / b.fan_W;
+        b.fan_off = total;
+        total += b.count * b.fan_W;
+    }
+    if (total == 0) return FEDDB200_OK;
+    FB_CUDA(cudaMalloc(&p->fanrec_d, sizeof(uint32_t) * 8 * total));
+    for (const Bucket &b : p->buckets) {
+        if (b.fan_W == 0) continue;
+        k_fan_records<<<(unsigned)std::min<int64_t>((b.count + 127) / 128, 148 * 16), 128, 0, c->stream>>>(
+            (const RowInfo *)p->rowinfo_d, b.start, b.count, p->rec_d, b.fan_W, b.fan_npw, p->fanrec_d + b.fan_off * 8);
+        c->launches++;
+        FB_CUDA(cudaGetLastError());
+    }
+    FB_CUDA(cudaStreamSynchronize(c->stream));
+    return FEDDB200_OK;
+}
+
 int ensure_gather(feddb200_pat *p)
 {
     if (p->gather_ready) return FEDDB200_OK;
@@ -257,6 +288,8 @@ int ensure_gather(feddb200_pat *p)
         }
         const int rc_task = build_task_programs(p, info);
         if (rc_task != FEDDB200_OK) return rc_task;
+        const int rc_fan = build_fan_records(p, info);
+        if (rc_fan != FEDDB200_OK) return rc_fan;
     }
     const int gs = dim == 3 ? 16 : 8;
     FB_CUDA(cudaMalloc(&p->geom_d, sizeof(double) * std::max<int64_t>(p->rm->ne * gs, 1)));
@@ -341,6 +374,28 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
             if constexpr (DIM == 3 && NL == 10) {
                 constexpr int TPR = OPG == 1 ? DIM : 1;
                 constexpr int NBr = OPG == 1 ? DIM : 1;
+                if (b.fan_W > 0 && p->fanrec_d) {
+                    // fan kernel: one lane per incident element, fan_W lanes per row node (star_kernels.cuh)
+                    FanArgs F;
+                    F.G = G;
+                    F.G.pitch = (TPR * NBr * b.lcap + 2) & ~1;
+                    F.fanrec = p->fanrec_d + b.fan_off * 8; F.W = b.fan_W; F.npw = b.fan_npw;
+                    const int ntf = 64;
+                    size_t wd = std::max<size_t>((size_t)b.fan_npw * F.G.pitch, (size_t)3 * (OPG == 1 ? 9 : 1) * 33 + 1);
+                    wd = (wd + 1) & ~(size_t)1;
+                    const size_t smem_f = wd * 8 * (ntf / 32);
+                    if (smem_f <= budget) {
+                        FB_CUDA(cudaFuncSetAttribute(k_fan<OPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+                        int per_sm = 1;
+                        FB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fan<OPG>, ntf, smem_f));
+                        const int64_t tiles_f = (b.count + b.fan_npw - 1) / b.fan_npw;
+                        const int64_t blocks_f = std::min<int64_t>((tiles_f + ntf / 32 - 1) / (ntf / 32), (int64_t)std::max(per_sm, 1) * c->sm_count);
+                        k_fan<OPG><<<(unsigned)blocks_f, ntf, smem_f, st>>>(F);
+                        c->launches++;
+                        FB_CUDA(cudaGetLastError());
+                        continue;
+                    }
+                }
                 int nt = 64;
                 if (const char *f = getenv("FEDDB200_RING_NT")) nt = std::max(32, std::min(64, atoi(f) & ~31)); // tuning aid
                 const int npt = 32 / TPR;                       // row nodes per warp tile

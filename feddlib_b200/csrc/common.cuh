@@ -53,6 +53,10 @@ struct Bucket {            // rows of one type with node-row length <= lcap, pro
     // block-task kernel (star_kernels.cuh: k_task): tiles of this bucket in the pattern's tile array; count 0: not used
     int64_t tile_start = 0, tile_count = 0;
     int npt = 0;           // row nodes per tile at most
+    // fan kernel (star_kernels.cuh: k_fan): the bucket's padded records start at fan_off (in records) of the pattern's
+    // fan-record array, fan_W per row; fan_W 0: not used
+    int64_t fan_off = 0;
+    int fan_W = 0, fan_npw = 0;
 };
 
 } // namespace fb
@@ -111,6 +115,7 @@ struct feddb200_pat {
     int rec_words = 0;
     void *task_tiles_d = nullptr;  // [n_tiles] TaskTile: tiles of the block-task kernel (3D P2 vertex-node rows)
     uint64_t *tasks_d = nullptr;   // task programs of the tiles (tasks.cuh)
+    uint32_t *fanrec_d = nullptr;  // padded per-bucket records of the fan kernel (3D P2 ring-ordered edge-node rows)
     void *tiletet_d = nullptr;     // [n_tiles][32] (element, canonical permutation) of the tiles' incident elements
     double *geom_d = nullptr;      // [ne][GS] per-element geometry cache, recomputed by every assembly
     double *uel_d = nullptr;       // [ne][nloc][4] nodal velocities of each element (operators with a velocity argument)
