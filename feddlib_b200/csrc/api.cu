@@ -133,7 +133,7 @@ int build_task_programs(feddb200_pat *p, const std::vector<RowInfo> &info)
     FB_CUDA(cudaMemsetAsync(status_d, 0, sizeof(int), c->stream));
     FB_CUDA(cudaMemcpyAsync(p->task_tiles_d, tiles.data(), sizeof(TaskTile) * n_tiles, cudaMemcpyHostToDevice, c->stream));
     A.rowinfo = (const RowInfo *)p->rowinfo_d; A.rec = p->rec_d; A.tiles = (TaskTile *)p->task_tiles_d; A.n_tiles = n_tiles;
-    A.tasks = nullptr; A.tiletet = nullptr; A.status = status_d;
+    A.tasks = nullptr; A.tileblk = nullptr; A.status = status_d;
     const unsigned grid = (unsigned)std::min<int64_t>((n_tiles + 63) / 64, 148 * 32);
     k_task_build<<<grid, 64, 0, c->stream>>>(A, 0);
     c->launches++;
@@ -144,15 +144,22 @@ int build_task_programs(feddb200_pat *p, const std::vector<RowInfo> &info)
     FB_CUDA(cudaStreamSynchronize(c->stream));
     int64_t passes = 0;
     for (TaskTile &t : tiles) { t.task_off = (uint32_t)passes; passes += t.n_passes; }
+    for (Bucket &b : p->buckets) {
+        b.task_max_tets = 0; b.task_max_passes = 0;
+        for (int64_t t = b.tile_start; t < b.tile_start + b.tile_count; t++) {
+            b.task_max_tets = std::max<int>(b.task_max_tets, tiles[t].n_tets);
+            b.task_max_passes = std::max<int>(b.task_max_passes, tiles[t].n_passes);
+        }
+    }
     if (status != 0 || passes >= (int64_t(1) << 32)) { // a tile outside the format limits: the buckets keep their other kernels
         for (Bucket &b : p->buckets) b.tile_count = 0;
         cudaFree(status_d);
         return FEDDB200_OK;
     }
     FB_CUDA(cudaMalloc(&p->tasks_d, sizeof(uint64_t) * 32 * std::max<int64_t>(passes, 1)));
-    FB_CUDA(cudaMalloc(&p->tiletet_d, sizeof(uint2) * kTaskMaxTets * n_tiles));
+    FB_CUDA(cudaMalloc(&p->tiletet_d, (size_t)kTileBlkB * n_tiles));
     FB_CUDA(cudaMemcpyAsync(p->task_tiles_d, tiles.data(), sizeof(TaskTile) * n_tiles, cudaMemcpyHostToDevice, c->stream));
-    A.tasks = p->tasks_d; A.tiletet = (uint2 *)p->tiletet_d;
+    A.tasks = p->tasks_d; A.tileblk = (uint32_t *)p->tiletet_d;
     k_task_build<<<grid, 64, 0, c->stream>>>(A, 1);
     c->launches++;
     FB_CUDA(cudaGetLastError());
@@ -169,24 +176,26 @@ int build_fan_records(feddb200_pat *p, const std::vector<RowInfo> &info)
     feddb200_ctx *c = p->ctx;
     static const bool enabled = [] { const char *f = getenv("FEDDB200_FAN"); return !f || atoi(f) != 0; }(); // tuning aid
     if (!enabled || !(p->rm->dim == 3 && p->rm->nloc == 10 && p->cm->nloc == 10)) return FEDDB200_OK;
-    int64_t total = 0;
+    int64_t total = 0;   // in tiles
     for (Bucket &b : p->buckets) {
         b.fan_off = 0; b.fan_W = 0; b.fan_npw = 0;
-        if (b.type != 1) continue;
+        if (b.type != 1 || b.lcap > 255) continue;
         int max_ninc = 0;
         for (int64_t q = b.start; q < b.start + b.count; q++) max_ninc = std::max(max_ninc, info[q].ninc);
         if (max_ninc > 32) continue;
         b.fan_W = std::max(4, max_ninc);
         b.fan_npw = 32 / b.fan_W;
         b.fan_off = total;
-        total += b.count * b.fan_W;
+        total += (b.count + b.fan_npw - 1) / b.fan_npw;
     }
     if (total == 0) return FEDDB200_OK;
-    FB_CUDA(cudaMalloc(&p->fanrec_d, sizeof(uint32_t) * 8 * total));
+    FB_CUDA(cudaMalloc(&p->fanrec_d, sizeof(uint32_t) * 8 * 32 * total));
+    FB_CUDA(cudaMemsetAsync(p->fanrec_d, 0, sizeof(uint32_t) * 8 * 32 * total, c->stream));
     for (const Bucket &b : p->buckets) {
         if (b.fan_W == 0) continue;
-        k_fan_records<<<(unsigned)std::min<int64_t>((b.count + 127) / 128, 148 * 16), 128, 0, c->stream>>>(
-            (const RowInfo *)p->rowinfo_d, b.start, b.count, p->rec_d, b.fan_W, b.fan_npw, p->fanrec_d + b.fan_off * 8);
+        const int64_t ntiles = (b.count + b.fan_npw - 1) / b.fan_npw;
+        k_fan_records<<<(unsigned)std::min<int64_t>((ntiles * b.fan_npw + 127) / 128, 148 * 16), 128, 0, c->stream>>>(
+            (const RowInfo *)p->rowinfo_d, b.start, b.count, p->rec_d, b.fan_W, b.fan_npw, ntiles, p->fanrec_d + b.fan_off * 32 * 8);
         c->launches++;
         FB_CUDA(cudaGetLastError());
     }
@@ -379,20 +388,25 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
                     FanArgs F;
                     F.G = G;
                     F.G.pitch = (TPR * NBr * b.lcap + 2) & ~1;
-                    F.fanrec = p->fanrec_d + b.fan_off * 8; F.W = b.fan_W; F.npw = b.fan_npw;
+                    F.fanrec = reinterpret_cast<const uint4 *>(p->fanrec_d + b.fan_off * 32 * 8); F.W = b.fan_W; F.npw = b.fan_npw;
+                    F.ntiles = (b.count + b.fan_npw - 1) / b.fan_npw;
                     const int ntf = 64;
                     size_t wd = std::max<size_t>((size_t)b.fan_npw * F.G.pitch, (size_t)3 * (OPG == 1 ? 9 : 1) * 33 + 1);
                     wd = (wd + 1) & ~(size_t)1;
-                    const size_t smem_f = wd * 8 * (ntf / 32);
+                    const size_t smem_f = (wd * 8 + kFanStageB) * (ntf / 32);
                     if (smem_f <= budget) {
-                        FB_CUDA(cudaFuncSetAttribute(k_fan<OPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
-                        int per_sm = 1;
-                        FB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fan<OPG>, ntf, smem_f));
-                        const int64_t tiles_f = (b.count + b.fan_npw - 1) / b.fan_npw;
-                        const int64_t blocks_f = std::min<int64_t>((tiles_f + ntf / 32 - 1) / (ntf / 32), (int64_t)std::max(per_sm, 1) * c->sm_count);
-                        k_fan<OPG><<<(unsigned)blocks_f, ntf, smem_f, st>>>(F);
-                        c->launches++;
-                        FB_CUDA(cudaGetLastError());
+                        auto launch_fan = [&](auto kernel) -> int {
+                            FB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+                            int per_sm = 1;
+                            FB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, ntf, smem_f));
+                            const int64_t blocks_f = std::min<int64_t>((F.ntiles + ntf / 32 - 1) / (ntf / 32), (int64_t)std::max(per_sm, 1) * c->sm_count);
+                            kernel<<<(unsigned)blocks_f, ntf, smem_f, st>>>(F);
+                            c->launches++;
+                            FB_CUDA(cudaGetLastError());
+                            return FEDDB200_OK;
+                        };
+                        rc = b.fan_W == 4 ? launch_fan(k_fan<OPG, 4>) : (b.fan_W == 6 ? launch_fan(k_fan<OPG, 6>) : launch_fan(k_fan<OPG, 0>));
+                        if (rc != FEDDB200_OK) return rc;
                         continue;
                     }
                 }
@@ -433,10 +447,11 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
                     TaskArgs T;
                     T.G = G;
                     T.G.pitch = (TPRt * NBt * b.lcap + 2) & ~1;   // room for the phase shift, even (keeps the stage planes 16-byte aligned)
-                    T.tiles = (const TaskTile *)p->task_tiles_d + b.tile_start; T.n_tiles = b.tile_count;
-                    T.tasks = p->tasks_d; T.tiletet = (const uint2 *)p->tiletet_d + b.tile_start * kTaskMaxTets; T.npt = b.npt;
+                    T.tileblk = reinterpret_cast<const uint4 *>((const char *)p->tiletet_d + (size_t)b.tile_start * kTileBlkB); T.n_tiles = b.tile_count;
+                    T.tasks = p->tasks_d; T.npt = b.npt;
+                    T.max_tets = (std::max(1, b.task_max_tets) + 1) & ~1 /* even: keeps the areas 16-byte aligned */; T.max_passes = std::max(1, b.task_max_passes);
                     const int ntk = 64;
-                    const size_t smem_t = ((size_t)b.npt * T.G.pitch * 8 + kTaskStageB) * (ntk / 32);
+                    const size_t smem_t = task_warp_bytes(b.npt, T.G.pitch, T.max_tets, T.max_passes) * (ntk / 32);
                     if (smem_t <= budget) {
                         FB_CUDA(cudaFuncSetAttribute(k_task<OPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
                         int per_sm = 1;
@@ -557,7 +572,8 @@ void op_coefficients(const OpTables &t, int dim, int nl_vel, OpCoef &C, int what
 }
 
 template <int OPX, int DIM, int NLR, int NL>
-int launch_gatherx_t(feddb200_ctx *c, feddb200_pat *p, const feddb200_mesh *vm, const double *u_d, double *values_d, int vec_dim)
+int launch_gatherx_t(feddb200_ctx *c, feddb200_pat *p, const feddb200_mesh *vm, const double *u_d, double *values_d, int vec_dim,
+                     const OpCoef &C)
 {
     using S = OpXShape<OPX, DIM>;
     constexpr int NLV = OPX == X_BT ? NLR : NL; // nodes of the velocity space
@@ -577,7 +593,7 @@ int launch_gatherx_t(feddb200_ctx *c, feddb200_pat *p, const feddb200_mesh *vm, 
     }
     GatherXArgs G;
     G.rowinfo = (const RowInfo *)p->rowinfo_d; G.rec = p->rec_d; G.geom = p->geom_d; G.uel = p->uel_d; G.dt = p->dt_d;
-    G.values = values_d; G.vec_dim = vec_dim;
+    G.values = values_d; G.vec_dim = vec_dim; G.C = C;
     const size_t budget = c->smem_optin - 1024;
     // small buckets on a side stream, underneath the large launches (see launch_gather_t)
     static const bool small_aside = [] { const char *f = getenv("FEDDB200_SMALL_ASIDE"); return !f || atoi(f) != 0; }(); // tuning aid
@@ -635,7 +651,7 @@ int launch_gatherx(feddb200_ctx *c, feddb200_pat *p, int op, const feddb200_mesh
     if (op == OP_BT && !(combo == 20603 || combo == 31004 || combo == 20303 || combo == 30404)) return FEDDB200_OK;
     int rc = ensure_gather(p);
     if (rc != FEDDB200_OK) return rc;
-    // coefficient tensors -> constant memory (stream ordered)
+    // coefficient tensors: passed to the kernels by value (kernel parameter space)
     OpCoef C;
     std::memset(&C, 0, sizeof(C));
     OpTables t;
@@ -658,10 +674,8 @@ int launch_gatherx(feddb200_ctx *c, feddb200_pat *p, int op, const feddb200_mesh
         op_coefficients(t, dim, nvel, C, op == OP_B ? 1 : 2);
     }
     C.c0 = c0; C.c1 = c1; C.c2 = c2;
-    FB_CUDA(cudaMemcpyToSymbolAsync(g_coef, &C, sizeof(OpCoef), 0, cudaMemcpyHostToDevice, c->stream));
-    FB_CUDA(cudaStreamSynchronize(c->stream)); // C is a stack object
     *handled = 1;
-#define FB_GX(OPX, D, NR, NC) return launch_gatherx_t<OPX, D, NR, NC>(c, p, vm, u_d, values_d, vec_dim)
+#define FB_GX(OPX, D, NR, NC) return launch_gatherx_t<OPX, D, NR, NC>(c, p, vm, u_d, values_d, vec_dim, C)
     switch (op) {
     case OP_ADV:
         switch (combo) { case 20303: FB_GX(X_ADV, 2, 3, 3); case 20606: FB_GX(X_ADV, 2, 6, 6); case 30404: FB_GX(X_ADV, 3, 4, 4); case 31010: FB_GX(X_ADV, 3, 10, 10); }

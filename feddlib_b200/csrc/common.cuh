@@ -53,6 +53,7 @@ struct Bucket {            // rows of one type with node-row length <= lcap, pro
     // block-task kernel (star_kernels.cuh: k_task): tiles of this bucket in the pattern's tile array; count 0: not used
     int64_t tile_start = 0, tile_count = 0;
     int npt = 0;           // row nodes per tile at most
+    int task_max_tets = 0, task_max_passes = 0;   // per tile, over the bucket's tiles
     // fan kernel (star_kernels.cuh: k_fan): the bucket's padded records start at fan_off (in records) of the pattern's
     // fan-record array, fan_W per row; fan_W 0: not used
     int64_t fan_off = 0;
@@ -116,7 +117,7 @@ struct feddb200_pat {
     void *task_tiles_d = nullptr;  // [n_tiles] TaskTile: tiles of the block-task kernel (3D P2 vertex-node rows)
     uint64_t *tasks_d = nullptr;   // task programs of the tiles (tasks.cuh)
     uint32_t *fanrec_d = nullptr;  // padded per-bucket records of the fan kernel (3D P2 ring-ordered edge-node rows)
-    void *tiletet_d = nullptr;     // [n_tiles][32] (element, canonical permutation) of the tiles' incident elements
+    void *tiletet_d = nullptr;     // [n_tiles] tile blocks (400 bytes: header, row nodes, incident elements; star_kernels.cuh)
     double *geom_d = nullptr;      // [ne][GS] per-element geometry cache, recomputed by every assembly
     double *uel_d = nullptr;       // [ne][nloc][4] nodal velocities of each element (operators with a velocity argument)
     double *dt_d = nullptr;        // [ne][dim][dim][4] |det| * grad u at the element's vertices

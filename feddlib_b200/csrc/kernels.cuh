@@ -1643,7 +1643,6 @@ struct OpCoef {
     double MM[2][MAXN];           // mass: [row type][j']     sum_q w phi_i' phi_j'
     double c0, c1, c2;            // rho*nu, rho, rho (Newton) of the fused block
 };
-__constant__ OpCoef g_coef;
 
 // per-element velocity data (natural local order), written by k_udata after k_geom:
 //   uel[e][m]    = (u_m.x, u_m.y, u_m.z, 0)
@@ -1726,6 +1725,8 @@ struct GatherXArgs {
     double *values;
     int pitch;                // doubles per thread in shared memory (odd)
     int vec_dim;              // mass: 0 scalar, DIM = replicate to the DIM block-diagonal dof rows
+    OpCoef C;                 // coefficient tensors of the operator: kernel parameter (constant bank), so every launch carries
+                              // its own copy -- contexts, streams and host threads never share coefficient state
 };
 
 // the warp copies the 32 shared-memory rows of its threads to their CSR rows with coalesced stores
@@ -1820,8 +1821,8 @@ __global__ void __launch_bounds__(64, 4) k_gatherx(const GatherXArgs A)
                 }
 #pragma unroll
                 for (int j = 0; j < NL; j++) {
-                    vn[j] += g_coef.TN[TYPE][m][j][0] * s[canon_sv<DIM>(j, 0)];
-                    if (P2C && j >= NVTX) vn[j] += g_coef.TN[TYPE][m][j][1] * s[canon_sv<DIM>(j, 1)];
+                    vn[j] += A.C.TN[TYPE][m][j][0] * s[canon_sv<DIM>(j, 0)];
+                    if (P2C && j >= NVTX) vn[j] += A.C.TN[TYPE][m][j][1] * s[canon_sv<DIM>(j, 1)];
                 }
             }
             if constexpr (OPX == X_ADV) {
@@ -1844,10 +1845,10 @@ __global__ void __launch_bounds__(64, 4) k_gatherx(const GatherXArgs A)
                     double lap = 0.0;
 #pragma unroll
                     for (int s2 = 0; s2 < NS; s2++) {
-                        lap += g_coef.RL[TYPE][j][s2][0] * el[s2][canon_sv<DIM>(j, 0)];
-                        if (P2C && j >= NVTX) lap += g_coef.RL[TYPE][j][s2][1] * el[s2][canon_sv<DIM>(j, 1)];
+                        lap += A.C.RL[TYPE][j][s2][0] * el[s2][canon_sv<DIM>(j, 0)];
+                        if (P2C && j >= NVTX) lap += A.C.RL[TYPE][j][s2][1] * el[s2][canon_sv<DIM>(j, 1)];
                     }
-                    const double dg = g_coef.c0 * lap + g_coef.c1 * vn[j];
+                    const double dg = A.C.c0 * lap + A.C.c1 * vn[j];
 #pragma unroll
                     for (int b = 0; b < NB; b++) val[j][b] = (b == a) ? dg : 0.0;
                 }
@@ -1855,7 +1856,7 @@ __global__ void __launch_bounds__(64, 4) k_gatherx(const GatherXArgs A)
         }
         if constexpr (OPX == X_ADVU || OPX == X_NSJ) {
             // W^{ab}_{i'j'} = sum_{v'} MW[j'][v'] dt[a][b][pi(v')]
-            const double cw = OPX == X_NSJ ? g_coef.c2 : 1.0;
+            const double cw = OPX == X_NSJ ? A.C.c2 : 1.0;
 #pragma unroll
             for (int b = 0; b < DIM; b++) {
                 double dn[4], dv[NVTX];
@@ -1869,7 +1870,7 @@ __global__ void __launch_bounds__(64, 4) k_gatherx(const GatherXArgs A)
                 for (int j = 0; j < NL; j++) {
                     double x = 0.0;
 #pragma unroll
-                    for (int v = 0; v < NVTX; v++) x += g_coef.MW[TYPE][j][v] * dv[v];
+                    for (int v = 0; v < NVTX; v++) x += A.C.MW[TYPE][j][v] * dv[v];
                     val[j][b] += cw * x;
                 }
             }
@@ -1877,7 +1878,7 @@ __global__ void __launch_bounds__(64, 4) k_gatherx(const GatherXArgs A)
         if constexpr (OPX == X_MASS) {
             const double adet = g.G[0][3];
 #pragma unroll
-            for (int j = 0; j < NL; j++) val[j][0] = g_coef.MM[TYPE][j] * adet - g_coef.c0 * adet * g_coef.c1; // c0 = 0: mass; else BD stabilisation
+            for (int j = 0; j < NL; j++) val[j][0] = A.C.MM[TYPE][j] * adet - A.C.c0 * adet * A.C.c1; // c0 = 0: mass; else BD stabilisation
         }
         if constexpr (OPX == X_B) {
             // row = pressure vertex (canonical vertex 0); B_{i',(j',d)} = |det| sum_t' BC[j'][t'] G_{t'}[d]
@@ -1886,8 +1887,8 @@ __global__ void __launch_bounds__(64, 4) k_gatherx(const GatherXArgs A)
             for (int j = 0; j < NL; j++)
 #pragma unroll
                 for (int d = 0; d < DIM; d++) {
-                    double x = g_coef.BC[j][0] * g.G[canon_sv<DIM>(j, 0)][d];
-                    if (P2C && j >= NVTX) x += g_coef.BC[j][1] * g.G[canon_sv<DIM>(j, 1)][d];
+                    double x = A.C.BC[j][0] * g.G[canon_sv<DIM>(j, 0)][d];
+                    if (P2C && j >= NVTX) x += A.C.BC[j][1] * g.G[canon_sv<DIM>(j, 1)][d];
                     val[j][d] = x * adet;
                 }
         }
@@ -1900,7 +1901,7 @@ __global__ void __launch_bounds__(64, 4) k_gatherx(const GatherXArgs A)
 #pragma unroll
                 for (int s2 = 0; s2 < NS; s2++) {
                     const double ga = a == 0 ? g.G[s2][0] : (a == 1 ? g.G[s2][1] : g.G[s2][2]);
-                    x += g_coef.BTC[TYPE][j][s2] * ga;
+                    x += A.C.BTC[TYPE][j][s2] * ga;
                 }
                 val[j][0] = x * adet;
             }

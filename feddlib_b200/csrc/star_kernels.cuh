@@ -14,14 +14,20 @@
 
 namespace fb {
 
-// one-time: task programs.  pass 1 (count): passes per tile; pass 2 (emit): task words + the tile's element table
+// tile block of the block-task kernel (400 bytes = 25 chunks of 16 bytes, one contiguous record per tile):
+//   chunk 0      header: n_nodes | n_tets << 8 | n_passes << 16, first task (in units of 32 task words), 0, 0
+//   chunks 1-8   row nodes: rowptr of the node (int64), row length (u32), flags (bit 0: holes)
+//   chunks 9-24  incident elements, two per chunk: (element, canonical permutation)
+constexpr int kTileBlkB = 400, kTileBlkChunks = 25;
+
+// one-time: task programs.  pass 1 (count): passes per tile; pass 2 (emit): task words + the tile blocks
 struct TaskBuildArgs {
     const RowInfo *rowinfo;      // bucket-ordered row records
     const uint32_t *rec;         // incidence records (8 words)
     TaskTile *tiles;             // q0, n_nodes filled by the host; n_tets, n_passes by pass 1; task_off by the host before pass 2
     int64_t n_tiles;
     uint64_t *tasks;             // pass 2
-    uint2 *tiletet;              // pass 2: [tile][32] (element, canonical permutation)
+    uint32_t *tileblk;           // pass 2: [tile][100 words]
     int *status;                 // set to 1 if a tile violates the format limits
 };
 
@@ -40,29 +46,47 @@ __global__ void k_task_build(const TaskBuildArgs A, int emit)
         const int np = schedule_tile(T.n_nodes, len, ninc, k0, A.rec, 8, 10, emit ? A.tasks + (int64_t)T.task_off * 32 : nullptr);
         if (np < 0 || np > 255) { *A.status = 1; continue; }
         if (!emit) { T.n_tets = (uint8_t)ntet; T.n_passes = (uint8_t)np; continue; }
+        uint32_t *B = A.tileblk + t * (kTileBlkB / 4);
+        for (int x = 0; x < kTileBlkB / 4; x++) B[x] = 0;
+        B[0] = (uint32_t)T.n_nodes | (uint32_t)ntet << 8 | (uint32_t)np << 16;
+        B[1] = T.task_off;
         int m = 0;
-        for (int i = 0; i < T.n_nodes; i++)
+        for (int i = 0; i < T.n_nodes; i++) {
+            const RowInfo &R = A.rowinfo[T.q0 + i];
+            B[4 + 4 * i] = (uint32_t)((uint64_t)R.base & 0xffffffffu);
+            B[5 + 4 * i] = (uint32_t)((uint64_t)R.base >> 32);
+            B[6 + 4 * i] = (uint32_t)R.len;
+            B[7 + 4 * i] = (R.pad & 16) ? 1u : 0u;
             for (int j = 0; j < ninc[i]; j++, m++) {
                 const uint32_t *w = A.rec + (k0[i] + j) * 8;
-                A.tiletet[t * kTaskMaxTets + m] = make_uint2(w[5], w[6]);
+                B[36 + 2 * m] = w[5];
+                B[37 + 2 * m] = w[6] & 0xffu;
             }
-        for (; m < kTaskMaxTets; m++) A.tiletet[t * kTaskMaxTets + m] = make_uint2(0u, 0u);
+        }
     }
 }
 
 struct TaskArgs {
-    GatherArgs G;                // rowinfo, geom, values, c0/c1 (lambda, mu), R, pitch, vec_dim, ghost segments
-    const TaskTile *tiles;       // tiles of this launch
+    GatherArgs G;                // geom, values, c0/c1 (lambda, mu), R, pitch, vec_dim, ghost segments
+    const uint4 *tileblk;        // tile blocks of this launch
     int64_t n_tiles;
     const uint64_t *tasks;
-    const uint2 *tiletet;
     int npt;                     // row nodes per tile at most (shared-memory rows per warp)
+    int max_tets, max_passes;    // per tile, over the tiles of this launch (sizes of the staging areas)
 };
 
-constexpr int kTaskVec = 11;                                   // staged vectors per element: |det| G_0, q_0 .. q_9
-constexpr int kTaskStageB = kTaskMaxTets * kTaskVec * 24;      // bytes per warp: XY (double2) + Z (double) planes
+constexpr int kTaskVec = 11;     // staged vectors per element: |det| G_0, q_0 .. q_9
 
-// OPG 0: Laplace (one value per node block; vec_dim: replicated on the block diagonal), OPG 1: elasticity (3x3 blocks)
+// bytes of shared memory per warp
+__host__ __device__ inline size_t task_warp_bytes(int npt, int pitch, int max_tets, int max_passes)
+{
+    return (size_t)npt * pitch * 8 + (size_t)max_tets * kTaskVec * 24 + 2 * (size_t)kTileBlkChunks * 16 + (size_t)max_tets * 128 +
+           2 * (size_t)max_passes * 256;
+}
+
+// OPG 0: Laplace (one value per node block; vec_dim: replicated on the block diagonal), OPG 1: elasticity (3x3 blocks).
+// Inputs are streamed by cp.async: the tile block two tiles ahead, the geometry lines (canonical vertex order) and the task
+// words one tile ahead.
 template <int OPG>
 __global__ void __launch_bounds__(64, 8) k_task(const TaskArgs A)
 {
@@ -71,51 +95,77 @@ __global__ void __launch_bounds__(64, 8) k_task(const TaskArgs A)
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const int pitch = A.G.pitch;                                   // doubles per node row area (even)
-    const size_t warp_doubles = (size_t)A.npt * pitch + kTaskStageB / 8;
-    double *const rows = smem + (size_t)wib * warp_doubles;        // 16-byte aligned: pitch and the stage size are even
+    const int pitch = A.G.pitch, MT = A.max_tets;                  // pitch: doubles per node row area (even)
+    char *const wbase = reinterpret_cast<char *>(smem) + (size_t)wib * task_warp_bytes(A.npt, pitch, MT, A.max_passes);
+    double *const rows = reinterpret_cast<double *>(wbase);       // every area is a multiple of 16 bytes
     double2 *const XY = reinterpret_cast<double2 *>(rows + (size_t)A.npt * pitch);
-    double *const Z = reinterpret_cast<double *>(XY + kTaskMaxTets * kTaskVec);
+    double *const Z = reinterpret_cast<double *>(XY + MT * kTaskVec);
+    const uint4 *const blk = reinterpret_cast<const uint4 *>(Z + MT * kTaskVec);              // [2][25]
+    const uint4 *const geo = blk + 2 * kTileBlkChunks;                                         // [8][MT] chunk-major
+    const uint64_t *const tsk = reinterpret_cast<const uint64_t *>(geo + 8 * MT);              // [2][max_passes][32]
+    const uint32_t blk_s = (uint32_t)__cvta_generic_to_shared(blk), geo_s = (uint32_t)__cvta_generic_to_shared(geo),
+                   tsk_s = (uint32_t)__cvta_generic_to_shared(tsk);
     const double mu = A.G.c1, lam = A.G.c0;
     const int nrep = (OPG == 0 && A.G.vec_dim != 0) ? A.G.vec_dim : 1;
     const int64_t step = (int64_t)gridDim.x * wpb;
     int64_t tile = (int64_t)blockIdx.x * wpb + wib;
     if (tile >= A.n_tiles) return;
 
-    auto load_geo_lane = [&](uint2 et, double (&G)[4][4]) {
-        const double *g = A.G.geom + (int64_t)et.x * 16;
-#pragma unroll
-        for (int v = 0; v < 4; v++) ld_v4g(g + 4 * ((et.y >> (2 * v)) & 3), G[v]);
+    auto request_blk = [&](int64_t t, int b) {
+        if (lane < kTileBlkChunks) cp_async16_s(blk_s + (b * kTileBlkChunks + lane) * 16, A.tileblk + t * kTileBlkChunks + lane);
     };
-    // prologue: header, element table and geometry of the first tile
-    uint4 hdr = __ldg(reinterpret_cast<const uint4 *>(A.tiles + tile));
-    uint2 et = __ldg(A.tiletet + tile * kTaskMaxTets + lane);
-    double G[4][4];
-    if (lane < (int)((hdr.y >> 8) & 0xff)) load_geo_lane(et, G);
+    auto request_geo_tasks = [&](int b) {   // of the tile whose block is in buffer b
+        const uint4 h = blk[b * kTileBlkChunks];
+        const int nt = (h.x >> 8) & 0xff, np = (h.x >> 16) & 0xff;
+        if (lane < nt) {
+            const uint2 et = reinterpret_cast<const uint2 *>(blk + b * kTileBlkChunks + 9)[lane];
+            const char *g = reinterpret_cast<const char *>(A.G.geom) + (int64_t)et.x * 128;
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                const char *gv = g + 32 * ((et.y >> (2 * v)) & 3);
+                cp_async16_s(geo_s + ((2 * v) * MT + lane) * 16, gv);
+                cp_async16_s(geo_s + ((2 * v + 1) * MT + lane) * 16, gv + 16);
+            }
+        }
+        const char *tp = reinterpret_cast<const char *>(A.tasks + (int64_t)h.y * 32);
+        for (int x = lane; x < np * 16; x += 32) cp_async16_s(tsk_s + (b * A.max_passes * 16 + x) * 16, tp + x * 16);
+    };
+    request_blk(tile, 0);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+    request_geo_tasks(0);
+    if (tile + step < A.n_tiles) request_blk(tile + step, 1);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+    int buf = 0;
 
     for (;;) {
-        const int n_nodes = hdr.y & 0xff, n_tets = (hdr.y >> 8) & 0xff, n_passes = (hdr.y >> 16) & 0xff;
         const int64_t tile_n = tile + step;
         const bool more = tile_n < A.n_tiles;
-        uint4 hdr_n = make_uint4(0u, 0u, 0u, 0u);
-        uint2 et_n = make_uint2(0u, 0u);
-        if (more) {
-            hdr_n = __ldg(reinterpret_cast<const uint4 *>(A.tiles + tile_n));
-            et_n = __ldg(A.tiletet + tile_n * kTaskMaxTets + lane);
-        }
-        // row records of the tile's nodes (lane = node slot)
+        const uint4 hdr = blk[buf * kTileBlkChunks];
+        const int n_nodes = hdr.x & 0xff, n_tets = (hdr.x >> 8) & 0xff, n_passes = (hdr.x >> 16) & 0xff;
+        // row nodes of the tile (lane = node slot)
         int64_t base = 0;
         int L = 0;
         if (lane < n_nodes) {
-            double raw[4];
-            ld_v4(reinterpret_cast<const double *>(A.G.rowinfo + hdr.x + lane), raw);
-            base = __double_as_longlong(raw[0]);
-            L = (int)(__double_as_longlong(raw[2]) & 0xffffffff);
+            const uint4 nd = blk[buf * kTileBlkChunks + 1 + lane];
+            base = (int64_t)((uint64_t)nd.x | (uint64_t)nd.y << 32);
+            L = (int)nd.z;
         }
         // stage: lane m = element slot m.  vector 0: |det| G_0 (row function: canonical vertex 0), vector 1 + jc:
         // q_jc = R_jc^0 G_sv(jc,0) + R_jc^1 G_sv(jc,1)
         if (lane < n_tets) {
-            const double adet = G[0][3];
+            double G[4][3], adet = 0.0;
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                const uint4 a = geo[(2 * v) * MT + lane], b = geo[(2 * v + 1) * MT + lane];
+                G[v][0] = __hiloint2double((int)a.y, (int)a.x);
+                G[v][1] = __hiloint2double((int)a.w, (int)a.z);
+                G[v][2] = __hiloint2double((int)b.y, (int)b.x);
+                if (v == 0) adet = __hiloint2double((int)b.w, (int)b.z);
+            }
             XY[lane * kTaskVec] = make_double2(adet * G[0][0], adet * G[0][1]);
             Z[lane * kTaskVec] = adet * G[0][2];
 #pragma unroll
@@ -127,15 +177,18 @@ __global__ void __launch_bounds__(64, 8) k_task(const TaskArgs A)
                 if (jc >= NVTX) {
                     const double r1 = A.G.R.r[0][jc][0][1];
 #pragma unroll
-                    for (int d = 0; d < 3; d++) q[d] += r1 * G[canon_sv<DIM>(jc, 1)][d];
+                    for (int d = 0; d < 3; d++) q[d] = fma(r1, G[canon_sv<DIM>(jc, 1)][d], q[d]);
                 }
                 XY[lane * kTaskVec + 1 + jc] = make_double2(q[0], q[1]);
                 Z[lane * kTaskVec + 1 + jc] = q[2];
             }
         }
-        // the geometry registers are free: request the next tile's lines now, they land while this tile is processed
-        if (more && lane < (int)((hdr_n.y >> 8) & 0xff)) load_geo_lane(et_n, G);
+        // the geometry buffer is consumed: request the next tile's geometry and task words (its block arrived a tile ago)
+        // and the block of the tile after it; they land while this tile is processed
         __syncwarp();
+        if (more) request_geo_tasks(buf ^ 1);
+        if (tile_n + step < A.n_tiles) request_blk(tile_n + step, buf);
+        cp_async_commit();
 
         // node row of slot s: `pitch` doubles apart, shifted by one double where that gives the row the 16-byte phase of
         // its destination (the TMA bulk store needs both sides 16-byte aligned)
@@ -143,12 +196,11 @@ __global__ void __launch_bounds__(64, 8) k_task(const TaskArgs A)
         const int64_t off_node = (int64_t)TPR * NB * nrep * base;
         double *const outp = lane < n_nodes ? out_ptr(A.G, off_node) : nullptr;
         const int head = (int)((reinterpret_cast<uintptr_t>(outp) >> 3) & 1);
-        const int my_rowoff = lane * pitch + ((lane * pitch + head) & 1);   // lane = node slot
+        const int my_rowoff = lane * pitch + head;                    // lane = node slot; pitch is even
 
-        const uint64_t *tp = A.tasks + (int64_t)hdr.z * 32 + lane;
 #pragma unroll 1
-        for (int pass = 0; pass < n_passes; pass++, tp += 32) {
-            const uint64_t task = __ldg(reinterpret_cast<const unsigned long long *>(tp));
+        for (int pass = 0; pass < n_passes; pass++) {
+            const uint64_t task = tsk[(buf * A.max_passes + pass) * 32 + lane];
             const int np = (int)((task >> 36) & 7);
             const int nsteps = __reduce_max_sync(FULL, np);
             double X[NV];
@@ -162,11 +214,11 @@ __global__ void __launch_bounds__(64, 8) k_task(const TaskArgs A)
                     const double2 gxy = XY[m * kTaskVec], qxy = XY[m * kTaskVec + 1 + jc];
                     const double gz = Z[m * kTaskVec], qz = Z[m * kTaskVec + 1 + jc];
                     if constexpr (OPG == 1) {
-                        X[0] += gxy.x * qxy.x; X[1] += gxy.x * qxy.y; X[2] += gxy.x * qz;
-                        X[3] += gxy.y * qxy.x; X[4] += gxy.y * qxy.y; X[5] += gxy.y * qz;
-                        X[6] += gz * qxy.x;    X[7] += gz * qxy.y;    X[8] += gz * qz;
+                        X[0] = fma(gxy.x, qxy.x, X[0]); X[1] = fma(gxy.x, qxy.y, X[1]); X[2] = fma(gxy.x, qz, X[2]);
+                        X[3] = fma(gxy.y, qxy.x, X[3]); X[4] = fma(gxy.y, qxy.y, X[4]); X[5] = fma(gxy.y, qz, X[5]);
+                        X[6] = fma(gz, qxy.x, X[6]);    X[7] = fma(gz, qxy.y, X[7]);    X[8] = fma(gz, qz, X[8]);
                     } else {
-                        X[0] += gxy.x * qxy.x; X[0] += gxy.y * qxy.y; X[0] += gz * qz;
+                        X[0] = fma(gxy.x, qxy.x, X[0]); X[0] = fma(gxy.y, qxy.y, X[0]); X[0] = fma(gz, qz, X[0]);
                     }
                 }
             }
@@ -192,14 +244,14 @@ __global__ void __launch_bounds__(64, 8) k_task(const TaskArgs A)
 #pragma unroll
                     for (int a = 0; a < 3; a++)
 #pragma unroll
-                        for (int b = 0; b < 3; b++) p[a * ns + b] = mu * X[3 * b + a] + lam * X[3 * a + b] + (a == b ? mtr : 0.0);
+                        for (int b = 0; b < 3; b++) p[a * ns + b] = fma(mu, X[3 * b + a], fma(lam, X[3 * a + b], a == b ? mtr : 0.0));
                 } else p[0] = X[0];
             }
         }
+        __syncwarp();
 
         // write-out: ONE TMA bulk store per node (its TPR dof rows are one contiguous run); odd head / tail doubles and
         // replicated rows of the other phase by plain stores
-        __syncwarp();
         if (lane < n_nodes && n > 0) {
             bulk_fence();
             const int total = TPR * n;
@@ -219,11 +271,11 @@ __global__ void __launch_bounds__(64, 8) k_task(const TaskArgs A)
             }
         }
         bulk_commit_wait_read();   // the bulk stores read this warp's shared memory: wait before it is reused
+        cp_async_wait<0>();
         __syncwarp();
         if (!more) break;
         tile = tile_n;
-        hdr = hdr_n;
-        et = et_n;
+        buf ^= 1;
     }
 }
 
@@ -240,47 +292,71 @@ namespace fb {
 //    node's shared-memory row (closed rings: the last lane feeds the first); the three columns every element contributes
 //    to (v0, v1, the row node itself) are summed through a shared-memory scratch (aliased with the rows, fixed order).
 //    No read-modify-write, no atomics; one TMA bulk store per node.
+//
+//    Inputs are STREAMED: a lane's 32-byte fan record (positions, permutation, wiring, element, row base and length) and
+//    its element's geometry line enter shared memory by cp.async (LDGSTS) -- the record two tiles ahead, the geometry
+//    one tile ahead, in canonical vertex order -- so a warp never waits for global memory after its first tile and no
+//    register is held across the latency.
 // =========================================================================================
 struct FanArgs {
-    GatherArgs G;            // rowinfo, start/count (bucket rows), geom, values, c0/c1, R, pitch, vec_dim, ghost segments
-    const uint32_t *fanrec;  // [(row - start) * W + idx][8]: the bucket's records, W per row (w[5] = 0xffffffff: none)
+    GatherArgs G;            // geom, values, c0/c1, R, pitch, vec_dim, ghost segments
+    const uint4 *fanrec;     // [tile][32 lanes][2 x 16 bytes]: see k_fan_records
+    int64_t ntiles;
     int W, npw;              // lanes per row node, row nodes per warp
 };
 
-// one-time: the padded per-bucket record array of k_fan.  Word 7 (the natural-index word, unused by these operators)
-// carries the lane wiring: bits 0-4 lane whose out-face blocks are this lane's carry, bit 5 carry present, bit 6 the own
-// out-face blocks are final (the chain ends on a boundary face).
+// fan record of a lane (32 bytes):
+//   bytes 0-9 positions of the ten canonical column nodes | 10 canonical permutation | 11 wiring: bits 0-4 lane whose
+//   out-face blocks are this lane's carry, bit 5 carry present, bit 6 the own out-face blocks are final (the chain ends on
+//   a boundary face), bit 7 the lane has an element | 12-15 element | 16-23 rowptr of the row node | 24-25 row length |
+//   26 elements of the node | 27 flags: bit 0 the row has positions without a local contribution, bit 1 the node exists
 __global__ void k_fan_records(const RowInfo *__restrict__ info, int64_t start, int64_t count, const uint32_t *__restrict__ rec,
-                              int W, int npw, uint32_t *__restrict__ fanrec)
+                              int W, int npw, int64_t ntiles, uint32_t *__restrict__ fanrec)
 {
-    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < count; r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t nslots = ntiles * npw;
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nslots; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t tile = r / npw;
+        const int slot = (int)(r - tile * npw), lane0 = slot * W;
+        uint32_t *out = fanrec + (tile * 32 + lane0) * 8;
+        if (r >= count) {
+            for (int j = 0; j < W; j++)
+                for (int x = 0; x < 8; x++) out[j * 8 + x] = x == 3 ? 0xffffffffu : 0u;
+            continue;
+        }
         const RowInfo &R = info[start + r];
-        const int lane0 = (int)(r % npw) * W;
         uint32_t wire[32];
-        for (int j = 0; j < W && j < 32; j++) wire[j] = 0;
+        for (int j = 0; j < W; j++) wire[j] = 0;
         int chain_start = 0;
         for (int j = 0; j < R.ninc && j < W; j++) {
             const uint32_t mode = (rec[(R.k0 + j) * 8 + 6] >> 8) & 3;
+            wire[j] |= 128u;
             if (mode == 0) { if (j + 1 < W) wire[j + 1] |= 32u | (uint32_t)(lane0 + j); }
             else if (mode == 1) { wire[j] |= 64u; chain_start = j + 1; }
             else { wire[chain_start] |= 32u | (uint32_t)(lane0 + j); chain_start = j + 1; }
         }
+        const uint32_t flags = ((R.pad & 16) ? 1u : 0u) | 2u;
         for (int j = 0; j < W; j++) {
-            uint32_t *o = fanrec + (r * W + j) * 8;
+            uint32_t *o = out + j * 8;
+            uint32_t w0 = 0, w1 = 0, w2 = 0, e = 0xffffffffu;
             if (j < R.ninc) {
                 const uint32_t *w = rec + (R.k0 + j) * 8;
-                for (int x = 0; x < 7; x++) o[x] = w[x];
-                o[7] = wire[j];
-            } else {
-                for (int x = 0; x < 8; x++) o[x] = x == 5 ? 0xffffffffu : 0u;
+                uint32_t pos[10];
+                for (int jc = 0; jc < 10; jc++) pos[jc] = (w[jc >> 1] >> (16 * (jc & 1))) & 0xffu;
+                w0 = pos[0] | pos[1] << 8 | pos[2] << 16 | pos[3] << 24;
+                w1 = pos[4] | pos[5] << 8 | pos[6] << 16 | pos[7] << 24;
+                w2 = pos[8] | pos[9] << 8 | (w[6] & 0xffu) << 16;
+                e = w[5];
             }
+            o[0] = w0; o[1] = w1; o[2] = w2 | wire[j] << 24; o[3] = e;
+            o[4] = (uint32_t)((uint64_t)R.base & 0xffffffffu); o[5] = (uint32_t)((uint64_t)R.base >> 32);
+            o[6] = (uint32_t)R.len | (uint32_t)R.ninc << 16 | flags << 24; o[7] = 0;
         }
     }
 }
 
 // block of canonical column JC seen from an edge-node row (row support: canonical vertices 0, 1)
 template <int OPG, int JC>
-__device__ __forceinline__ void fan_block(const CanonR &R, const double (&G)[4][4], const double (&gs)[2][3], double mu, double lam,
+__device__ __forceinline__ void fan_block(const CanonR &R, const double (&G)[4][3], const double (&gs)[2][3], double mu, double lam,
                                           double (&out)[OPG == 1 ? 9 : 1])
 {
     constexpr int DIM = 3, NVTX = 4;
@@ -291,7 +367,7 @@ __device__ __forceinline__ void fan_block(const CanonR &R, const double (&G)[4][
         for (int d = 0; d < 3; d++) q[s][d] = R.r[1][JC][s][0] * G[canon_sv<DIM>(JC, 0)][d];
         if (JC >= NVTX) {
 #pragma unroll
-            for (int d = 0; d < 3; d++) q[s][d] += R.r[1][JC][s][1] * G[canon_sv<DIM>(JC, 1)][d];
+            for (int d = 0; d < 3; d++) q[s][d] = fma(R.r[1][JC][s][1], G[canon_sv<DIM>(JC, 1)][d], q[s][d]);
         }
     }
     if constexpr (OPG == 1) {
@@ -299,97 +375,117 @@ __device__ __forceinline__ void fan_block(const CanonR &R, const double (&G)[4][
 #pragma unroll
         for (int a = 0; a < 3; a++)
 #pragma unroll
-            for (int b = 0; b < 3; b++) X[a][b] = gs[0][a] * q[0][b] + gs[1][a] * q[1][b];
+            for (int b = 0; b < 3; b++) X[a][b] = fma(gs[1][a], q[1][b], gs[0][a] * q[0][b]);
         const double mtr = mu * (X[0][0] + X[1][1] + X[2][2]);
 #pragma unroll
         for (int a = 0; a < 3; a++)
 #pragma unroll
-            for (int b = 0; b < 3; b++) out[3 * a + b] = mu * X[b][a] + lam * X[a][b] + (a == b ? mtr : 0.0);
+            for (int b = 0; b < 3; b++) out[3 * a + b] = fma(mu, X[b][a], fma(lam, X[a][b], a == b ? mtr : 0.0));
     } else {
         double x = 0.0;
 #pragma unroll
         for (int s = 0; s < 2; s++)
 #pragma unroll
-            for (int d = 0; d < 3; d++) x += gs[s][d] * q[s][d];
+            for (int d = 0; d < 3; d++) x = fma(gs[s][d], q[s][d], x);
         out[0] = x;
     }
 }
 
-template <int OPG>
+constexpr int kFanStageB = 2 * 32 * 32 + 32 * 128;   // bytes per warp: two record buffers + one geometry buffer
+
+// WT > 0: lanes per node known at compile time (WT == A.W); WT == 0: run-time W
+template <int OPG, int WT>
 __global__ void __launch_bounds__(64, 8) k_fan(const FanArgs A)
 {
     constexpr int DIM = 3, NVTX = 4;
     constexpr int NB = OPG == 1 ? DIM : 1, TPR = OPG == 1 ? DIM : 1, NV = OPG == 1 ? 9 : 1;
     constexpr int SP = 33;                                  // scratch pitch (doubles per value row)
-    constexpr int MAXR = OPG == 1 ? 7 : 1;                  // heavy values per lane: ceil(3 * NV / W), W >= 4
+    constexpr int MAXR = OPG == 1 ? (WT > 0 ? (27 + WT - 1) / WT : 7) : 1;   // heavy values per lane (W >= 4)
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const int W = A.W, npw = A.npw, pitch = A.G.pitch;
+    const int W = WT > 0 ? WT : A.W, npw = WT > 0 ? 32 / WT : A.npw, pitch = A.G.pitch;
     size_t warp_doubles = (size_t)npw * pitch;
     if (warp_doubles < (size_t)3 * NV * SP + 1) warp_doubles = (size_t)3 * NV * SP + 1;
     warp_doubles = (warp_doubles + 1) & ~(size_t)1;
-    double *const rows = smem + (size_t)wib * warp_doubles;
+    double *const rows = smem + (size_t)wib * (warp_doubles + kFanStageB / 8);
+    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(rows + warp_doubles);   // 16-byte aligned
+    // staging layout (16-byte chunks, lane-minor: conflict-free): record buffer b chunk c at ((2 b + c) 32 + lane),
+    // geometry chunk c (canonical vertex c / 2, half c % 2) at (4 + c) 32 + lane
+    const uint4 *const stage = reinterpret_cast<const uint4 *>(rows + warp_doubles);
     const double mu = A.G.c1, lam = A.G.c0;
     const int nrep = (OPG == 0 && A.G.vec_dim != 0) ? A.G.vec_dim : 1;
     const int slot = lane / W;
     const bool lane_used = slot < npw;
     const int idx = lane - slot * W;
-    const int64_t ntiles = (A.G.count + npw - 1) / npw;
     const int64_t step = (int64_t)gridDim.x * wpb;
     int64_t tile = (int64_t)blockIdx.x * wpb + wib;
-    if (tile >= ntiles) return;
+    if (tile >= A.ntiles) return;
 
-    auto load_rec = [&](int64_t t, uint32_t (&w)[8], double (&raw)[4]) {
-        const int64_t node = t * npw + slot;
+    auto request_rec = [&](int64_t t, int b) {
+        const uint4 *src = A.fanrec + (t * 32 + lane) * 2;
+        cp_async16_s(stage_s + ((2 * b + 0) * 32 + lane) * 16, src);
+        cp_async16_s(stage_s + ((2 * b + 1) * 32 + lane) * 16, src + 1);
+    };
+    auto request_geo = [&](int b) {   // geometry line of the element in record buffer b, canonical vertex order
+        const uint4 r0 = stage[(2 * b + 0) * 32 + lane];
+        if (r0.w != 0xffffffffu) {
+            const char *g = reinterpret_cast<const char *>(A.G.geom) + (int64_t)r0.w * 128;
+            const uint32_t perm = (r0.z >> 16) & 0xffu;
 #pragma unroll
-        for (int x = 0; x < 8; x++) w[x] = 0u;
-        w[5] = 0xffffffffu;
-        raw[0] = raw[1] = raw[2] = raw[3] = 0.0;
-        if (lane_used && node < A.G.count) {
-            ld_v8u(A.fanrec + (node * W + idx) * 8, w);
-            ld_v4(reinterpret_cast<const double *>(A.G.rowinfo + A.G.start + node), raw);
+            for (int v = 0; v < 4; v++) {
+                const char *gv = g + 32 * ((perm >> (2 * v)) & 3);
+                cp_async16_s(stage_s + ((4 + 2 * v) * 32 + lane) * 16, gv);
+                cp_async16_s(stage_s + ((5 + 2 * v) * 32 + lane) * 16, gv + 16);
+            }
         }
     };
-    auto load_geo_lane = [&](const uint32_t (&w)[8], double (&G)[4][4]) {
-        if (w[5] != 0xffffffffu) {
-            const double *g = A.G.geom + (int64_t)w[5] * 16;
-#pragma unroll
-            for (int v = 0; v < 4; v++) ld_v4g(g + 4 * ((w[6] >> (2 * v)) & 3), G[v]);
-        } else {
-#pragma unroll
-            for (int v = 0; v < 4; v++)
-#pragma unroll
-                for (int d = 0; d < 4; d++) G[v][d] = 0.0;
-        }
-    };
-    uint32_t w[8];
-    double raw[4], G[4][4];
-    load_rec(tile, w, raw);
-    load_geo_lane(w, G);
+    // prologue: record of the first tile, then its geometry and the record of the second tile
+    request_rec(tile, 0);
+    cp_async_commit();
+    cp_async_wait<0>();
+    request_geo(0);
+    if (tile + step < A.ntiles) request_rec(tile + step, 1);
+    cp_async_commit();
+    cp_async_wait<0>();
+    int buf = 0;
 
     for (;;) {
         const int64_t tile_n = tile + step;
-        const bool more = tile_n < ntiles;
-        uint32_t wn[8];
-        double rawn[4];
-        if (more) load_rec(tile_n, wn, rawn);
+        const bool more = tile_n < A.ntiles;
+        // this tile's inputs: shared memory -> registers
+        const uint4 r0 = stage[(2 * buf + 0) * 32 + lane], r1 = stage[(2 * buf + 1) * 32 + lane];
+        const bool live = lane_used && r0.w != 0xffffffffu;
+        double G[4][3], adet = 0.0;
+        {
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                const uint4 a = stage[(4 + 2 * v) * 32 + lane], b = stage[(5 + 2 * v) * 32 + lane];
+                G[v][0] = live ? __hiloint2double((int)a.y, (int)a.x) : 0.0;
+                G[v][1] = live ? __hiloint2double((int)a.w, (int)a.z) : 0.0;
+                G[v][2] = live ? __hiloint2double((int)b.y, (int)b.x) : 0.0;
+                if (v == 0) adet = live ? __hiloint2double((int)b.w, (int)b.z) : 0.0;
+            }
+        }
+        // requests: the record two tiles ahead into the buffer just read, the geometry of the next tile
+        if (tile_n + step < A.ntiles) request_rec(tile_n + step, buf);
+        if (more) request_geo(buf ^ 1);
+        cp_async_commit();
 
-        const bool live = w[5] != 0xffffffffu;
-        const bool node_ok = lane_used && tile * npw + slot < A.G.count;
-        const int64_t base = __double_as_longlong(raw[0]);
-        const int L = node_ok ? (int)(__double_as_longlong(raw[2]) & 0xffffffff) : 0;
-        const int ninc = node_ok ? (int)(__double_as_longlong(raw[2]) >> 32) : 0;
-        const bool holes = node_ok && (__double_as_longlong(raw[3]) & 16) != 0;
+        const bool node_ok = lane_used && (r1.z >> 24 & 2u) != 0;
+        const int64_t base = (int64_t)((uint64_t)r1.x | (uint64_t)r1.y << 32);
+        const int L = node_ok ? (int)(r1.z & 0xffffu) : 0;
+        const int ninc = node_ok ? (int)((r1.z >> 16) & 0xffu) : 0;
+        const bool holes = node_ok && (r1.z >> 24 & 1u) != 0;
         const int n = NB * L;
         const int64_t off_node = (int64_t)TPR * NB * nrep * base;
         double *const outp = node_ok ? out_ptr(A.G, off_node) : nullptr;
         const int head = (int)((reinterpret_cast<uintptr_t>(outp) >> 3) & 1);
         double *const nodep = rows + (size_t)(lane_used ? slot : 0) * pitch + head;   // pitch is even
-        auto posof = [&](int jc) { return (int)((w[jc >> 1] >> (16 * (jc & 1))) & 0xffffu) * NB; };
+        const uint32_t pw[3] = {r0.x, r0.y, r0.z};
+        auto posof = [&](int jc) { return (int)((pw[jc >> 2] >> (8 * (jc & 3))) & 0xffu) * NB; };
 
         // row-side vectors |det| G_0, |det| G_1
-        const double adet = G[0][3];
         double gs[2][3];
 #pragma unroll
         for (int s = 0; s < 2; s++)
@@ -425,13 +521,19 @@ __global__ void __launch_bounds__(64, 8) k_fan(const FanArgs A)
             double s = 0.0;
             if (node_ok && v < 3 * NV) {
                 const double *src = rows + v * SP + slot * W;
-                for (int m = 0; m < ninc; m++) s += src[m];
+                if constexpr (WT > 0) {   // dead lanes wrote zeros
+#pragma unroll
+                    for (int m = 0; m < WT; m++) s += src[m];
+                } else {
+                    for (int m = 0; m < ninc; m++) s += src[m];
+                }
             }
             hv[r] = s;
         }
         // positions of the three heavy columns: the node's first lane has a record whenever the node has elements
         const int lane0 = (lane_used ? slot : 0) * W;
-        const int ph0 = __shfl_sync(FULL, posof(0), lane0), ph1 = __shfl_sync(FULL, posof(1), lane0), ph4 = __shfl_sync(FULL, posof(4), lane0);
+        const uint32_t pw0 = __shfl_sync(FULL, pw[0], lane0), pw1 = __shfl_sync(FULL, pw[1], lane0);
+        const int ph0 = (int)(pw0 & 0xffu) * NB, ph1 = (int)((pw0 >> 8) & 0xffu) * NB, ph4 = (int)(pw1 & 0xffu) * NB;
         __syncwarp();   // the scratch has been read: the rows may be written now
         if (__any_sync(FULL, holes)) { // rare: rows with positions no local element contributes to
             for (int x = lane; x < npw * pitch; x += 32) rows[x] = 0.0;
@@ -451,8 +553,9 @@ __global__ void __launch_bounds__(64, 8) k_fan(const FanArgs A)
         }
 
         // ---- out-face blocks (3, 7, 8) travel to the next element of the ring, whose in-face blocks (2, 6, 5) become final ----
-        const int src = (int)(w[7] & 31u);
-        const bool has_src = live && (w[7] & 32u) != 0, store_out = live && (w[7] & 64u) != 0;
+        const uint32_t wire = r0.z >> 24;
+        const int src = (int)(wire & 31u);
+        const bool has_src = live && (wire & 32u) != 0, store_out = live && (wire & 64u) != 0;
 #define FB_FAN_FACE(JO, JI)                                                                         \
         {                                                                                           \
             double bo[NV], bi[NV], cy[NV];                                                          \
@@ -474,8 +577,6 @@ __global__ void __launch_bounds__(64, 8) k_fan(const FanArgs A)
             fan_block<OPG, 9>(A.G.R, G, gs, mu, lam, b9);
             if (live) store_block(posof(9), b9);
         }
-        // the geometry registers are free: the next tile's lines
-        if (more) load_geo_lane(wn, G);
 
         // ---- write-out: ONE TMA bulk store per node ----
         __syncwarp();
@@ -497,13 +598,11 @@ __global__ void __launch_bounds__(64, 8) k_fan(const FanArgs A)
             }
         }
         bulk_commit_wait_read();
+        cp_async_wait<0>();     // the next tile's geometry and the record after it have landed (requested a tile ago)
         __syncwarp();
         if (!more) break;
         tile = tile_n;
-#pragma unroll
-        for (int x = 0; x < 8; x++) w[x] = wn[x];
-#pragma unroll
-        for (int x = 0; x < 4; x++) raw[x] = rawn[x];
+        buf ^= 1;
     }
 }
 
