@@ -120,19 +120,21 @@ def oracle_elasticity_time(M, repeat=1):
     return best, conn.shape[0]
 
 
-def ns_jacobian_numbers(ctx, M, peak):
-    """Times the (0,0) block (rho*nu*A + rho*N(u) + rho*W(u), fused), N, W and B/B^T on a structured P2-P1 cube."""
+def ns_block_numbers(ctx, conn, coords, n_vertices, label, peak):
+    """Times the (0,0) block (rho*nu*A + rho*N(u) + rho*W(u), fused), N, W and B/B^T on a P2-P1 mesh (velocity connectivity
+    conn [ne,10], P1 nodes first in the numbering or anywhere: the pressure mesh is the vertex sub-mesh)."""
     import torch
     from feddlib_b200 import BLOCK_DIAG, BLOCK_FULL, Mesh, Pattern
-    from feddlib_b200 import mesh as PM
     from feddlib_b200.engine import assemble_div_divT_d
     dim = 3
-    conn, coords, _ = PM.build_structured(dim, "P2", 1, M)
     verts = np.unique(conn[:, :4])
     lid = -np.ones(coords.shape[0], dtype=np.int64)
     lid[verts] = np.arange(verts.size)
+    t0 = time.perf_counter()
     mv, mp = Mesh(ctx, dim, conn, coords), Mesh(ctx, dim, lid[conn[:, :4]].astype(np.int32), coords[verts])
     pat, patB, patBT = Pattern(ctx, mv), Pattern(ctx, mp, mv), Pattern(ctx, mv, mp)
+    ctx.synchronize()
+    t_pat = time.perf_counter() - t0
     u = torch.from_numpy(np.random.default_rng(1234).uniform(-1, 1, dim * coords.shape[0])).cuda()
     vd, vf = ctx.empty_values(pat.nnz(dim, dim, BLOCK_DIAG)), ctx.empty_values(pat.nnz(dim, dim, BLOCK_FULL))
     vB, vBT = ctx.empty_values(patB.nnz(1, dim, BLOCK_FULL)), ctx.empty_values(patBT.nnz(dim, 1, BLOCK_FULL))
@@ -140,8 +142,10 @@ def ns_jacobian_numbers(ctx, M, peak):
     ops = {"ns_jacobian_00_block": (lambda: pat.assemble_ns_jacobian_d(vf, u, 1.0, 1e-3, True), vf.numel()),
            "advection_N": (lambda: pat.assemble_advection_d(vd, u), vd.numel()),
            "advection_in_u_W": (lambda: pat.assemble_advection_in_u_d(vf, u), vf.numel()),
+           "laplace_vec_A": (lambda: pat.assemble_laplace_d(vd, True), vd.numel()),
            "div_B_and_BT": (lambda: assemble_div_divT_d(ctx, patB, patBT, vB, vBT), vB.numel() + vBT.numel())}
-    out = {"workload": f"structured P2-P1 cube H/h={M}, {ne} tets, u ~ U(-1,1) seed 1234, rho=1, nu=1e-3, scatter mode gather"}
+    out = {"workload": f"{label}, {ne} tets, {coords.shape[0]} P2 nodes, u ~ U(-1,1) seed 1234, rho=1, nu=1e-3, scatter mode gather",
+           "pattern_build_s": t_pat}
     for name, (fn, nnz) in ops.items():
         for _ in range(3):
             fn()
@@ -153,9 +157,30 @@ def ns_jacobian_numbers(ctx, M, peak):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 5
-        alg = ne * 10 * 4 + (M + 1) ** 3 * dim * 8 + nnz * 8 + (0 if name.startswith("div") else dim * coords.shape[0] * 8)
-        out[name] = {"ms": ms, "elements_per_s": ne / (ms * 1e-3), "hbm_frac": alg / (ms * 1e-3) / 1e9 / peak}
+        needs_u = name in ("ns_jacobian_00_block", "advection_N", "advection_in_u_W")
+        alg = ne * 10 * 4 + n_vertices * dim * 8 + nnz * 8 + (dim * coords.shape[0] * 8 if needs_u else 0)
+        out[name] = {"ms": ms, "elements_per_s": ne / (ms * 1e-3), "hbm_frac": alg / (ms * 1e-3) / 1e9 / peak,
+                     "algorithmic_bytes": alg}
+    del vd, vf, vB, vBT, pat, patB, patBT, mv, mp
     return out
+
+
+def ns_jacobian_numbers(ctx, M, peak):
+    from feddlib_b200 import mesh as PM
+    conn, coords, _ = PM.build_structured(3, "P2", 1, M)
+    return ns_block_numbers(ctx, conn, coords, (M + 1) ** 3, f"structured P2-P1 cube H/h={M}", peak)
+
+
+def config4_numbers(ctx, levels, peak):
+    """BASELINE.json config 4: the Navier-Stokes blocks on meshes/DFG3DCylinder_6k.mesh (27 618 tets; committed as
+    tests/golden/dfg3d_6k.npz, the reference tree is absent on the GPU box) after `levels` regular refinements
+    (levels = 2: 1 767 552 tets), P2 velocity via edge midpoints (buildP2ofP1Domain), P1 pressure."""
+    from feddlib_b200 import mesh as PM
+    d = np.load(os.path.join(ROOT, "tests", "golden", "dfg3d_6k.npz"))
+    c1, x1 = PM.refine_regular(d["conn"], d["coords"], levels)
+    conn, coords = PM.build_p2_of_p1(c1, x1)
+    return ns_block_numbers(ctx, conn, coords, x1.shape[0],
+                            f"config 4: DFG3DCylinder_6k.mesh regular-refined k={levels}, P2-P1", peak)
 
 
 def _worker(M):
@@ -215,6 +240,7 @@ def main():
                          "ghost-row kernels; 'nccl' = all-to-all-v of the ghost values on a side stream")
     ap.add_argument("--no-ns", action="store_true", help="skip the secondary Navier-Stokes block timings")
     ap.add_argument("--ns-M", dest="ns_M", type=int, default=50, help="H/h of the P2-P1 cube of the secondary timings")
+    ap.add_argument("--cfg4-levels", dest="cfg4_levels", type=int, default=2, help="regular refinements of DFG3DCylinder_6k (config 4)")
     ap.add_argument("--all-modes", action="store_true", help="also time the other scatter modes (extra keys)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -364,9 +390,10 @@ def main():
         checksum = float(values[: min(nnz, 1 << 20)].sum().item())
 
     # secondary numbers (not the headline): the Navier-Stokes blocks of config 4 on a structured P2-P1 cube, same engine
-    ns_extra = None
+    ns_extra = cfg4 = None
     if world == 1 and not args.no_ns:
         ns_extra = ns_jacobian_numbers(ctx, args.ns_M, peak)
+        cfg4 = config4_numbers(ctx, args.cfg4_levels, peak)
 
     cpu_baseline = None
     if rank == 0:
@@ -397,6 +424,8 @@ def main():
             line["other_scatter_modes"] = extra
         if ns_extra:
             line["navier_stokes_blocks"] = ns_extra
+        if cfg4:
+            line["config4_navier_stokes_dfg3d"] = cfg4
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

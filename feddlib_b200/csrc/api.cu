@@ -174,7 +174,8 @@ int build_task_programs(feddb200_pat *p, const std::vector<RowInfo> &info)
 int build_fan_records(feddb200_pat *p, const std::vector<RowInfo> &info)
 {
     feddb200_ctx *c = p->ctx;
-    static const bool enabled = [] { const char *f = getenv("FEDDB200_FAN"); return !f || atoi(f) != 0; }(); // tuning aid
+    // off by default: measured equal to / slower than k_ring on B200; FEDDB200_FAN=1 selects it
+    static const bool enabled = [] { const char *f = getenv("FEDDB200_FAN"); return f && atoi(f) != 0; }();
     if (!enabled || !(p->rm->dim == 3 && p->rm->nloc == 10 && p->cm->nloc == 10)) return FEDDB200_OK;
     int64_t total = 0;   // in tiles
     for (Bucket &b : p->buckets) {
