@@ -98,6 +98,14 @@ int launch_elem_op(feddb200_ctx *c, int op, int dim, int nr, int nc, ElemArgs &A
 // gather path preparation (lazy, once per pattern): canonical position map, row types,
 // (type, length) buckets
 // ---------------------------------------------------------------------------------------
+// the star kernel (k_star: all fan and task tiles of an assembly in one address-ordered pass) is the default path of 3D P2;
+// FEDDB200_STAR=0 goes back to one launch per bucket (tuning aid)
+bool star_enabled()
+{
+    static const bool on = [] { const char *f = getenv("FEDDB200_STAR"); return !f || atoi(f) != 0; }();
+    return on;
+}
+
 // task programs of the block-task kernel (k_task): tiles of consecutive bucket rows, scheduled on the device
 int build_task_programs(feddb200_pat *p, const std::vector<RowInfo> &info)
 {
@@ -175,7 +183,7 @@ int build_fan_records(feddb200_pat *p, const std::vector<RowInfo> &info)
 {
     feddb200_ctx *c = p->ctx;
     // off by default: measured equal to / slower than k_ring on B200; FEDDB200_FAN=1 selects it
-    static const bool enabled = [] { const char *f = getenv("FEDDB200_FAN"); return f && atoi(f) != 0; }();
+    static const bool enabled = [] { const char *f = getenv("FEDDB200_FAN"); return f && atoi(f) != 0; }() || star_enabled();
     if (!enabled || !(p->rm->dim == 3 && p->rm->nloc == 10 && p->cm->nloc == 10)) return FEDDB200_OK;
     int64_t total = 0;   // in tiles
     for (Bucket &b : p->buckets) {
@@ -201,6 +209,42 @@ int build_fan_records(feddb200_pat *p, const std::vector<RowInfo> &info)
         FB_CUDA(cudaGetLastError());
     }
     FB_CUDA(cudaStreamSynchronize(c->stream));
+    return FEDDB200_OK;
+}
+
+// address-ordered tile lists of the star kernel: every fan tile and task tile of the pattern, sorted by the position of its
+// first row in the values array; owned and ghost rows separately (the ghost rows of a multi-GPU assembly run first)
+int build_star_tiles(feddb200_pat *p, const std::vector<RowInfo> &info)
+{
+    feddb200_ctx *c = p->ctx;
+    if (!star_enabled() || !(p->rm->dim == 3 && p->rm->nloc == 10 && p->cm->nloc == 10)) return FEDDB200_OK;
+    struct Item { int64_t key; uint32_t x, y, z; };
+    std::vector<Item> items[2];
+    for (Bucket &b : p->buckets) {
+        b.in_star = 0;
+        if (b.type == 0 && b.tile_count > 0 && p->tasks_d) {
+            std::vector<TaskTile> tiles((size_t)b.tile_count);
+            FB_CUDA(cudaMemcpy(tiles.data(), (const TaskTile *)p->task_tiles_d + b.tile_start, sizeof(TaskTile) * b.tile_count, cudaMemcpyDeviceToHost));
+            for (int64_t t = 0; t < b.tile_count; t++)
+                items[b.ghost].push_back({info[tiles[t].q0].base, 0u | (uint32_t)b.npt << 16, (uint32_t)(b.tile_start + t), (uint32_t)b.lcap});
+            b.in_star = 1;
+        } else if (b.type == 1 && b.fan_W > 0 && p->fanrec_d) {
+            const int64_t nt = (b.count + b.fan_npw - 1) / b.fan_npw;
+            for (int64_t t = 0; t < nt; t++)
+                items[b.ghost].push_back({info[b.start + t * b.fan_npw].base, 1u | (uint32_t)b.fan_W << 8, (uint32_t)(b.fan_off + t), (uint32_t)b.lcap});
+            b.in_star = 1;
+        }
+    }
+    for (int g = 0; g < 2; g++) {
+        p->star_n[g] = (int64_t)items[g].size();
+        if (items[g].empty()) continue;
+        std::sort(items[g].begin(), items[g].end(), [](const Item &a, const Item &b) { return a.key < b.key; });
+        std::vector<uint32_t> flat(items[g].size() * 4);
+        for (size_t i = 0; i < items[g].size(); i++) { flat[4 * i] = items[g][i].x; flat[4 * i + 1] = items[g][i].y; flat[4 * i + 2] = items[g][i].z; flat[4 * i + 3] = 0; }
+        FB_CUDA(cudaMalloc(&p->star_tiles_d[g], flat.size() * 4));
+        FB_CUDA(cudaMemcpy(p->star_tiles_d[g], flat.data(), flat.size() * 4, cudaMemcpyHostToDevice));
+    }
+    (void)c;
     return FEDDB200_OK;
 }
 
@@ -300,6 +344,8 @@ int ensure_gather(feddb200_pat *p)
         if (rc_task != FEDDB200_OK) return rc_task;
         const int rc_fan = build_fan_records(p, info);
         if (rc_fan != FEDDB200_OK) return rc_fan;
+        const int rc_star = build_star_tiles(p, info);
+        if (rc_star != FEDDB200_OK) return rc_star;
     }
     const int gs = dim == 3 ? 16 : 8;
     FB_CUDA(cudaMalloc(&p->geom_d, sizeof(double) * std::max<int64_t>(p->rm->ne * gs, 1)));
@@ -367,10 +413,53 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
     std::vector<const Bucket *> order;
     for (const Bucket &b : p->buckets) order.push_back(&b);
     std::stable_sort(order.begin(), order.end(), [](const Bucket *x, const Bucket *y) { return x->count * (int64_t)x->lcap > y->count * (int64_t)y->lcap; });
+    // star kernel: all fan / task tiles of the phase in one address-ordered persistent launch (star_kernels.cuh)
+    bool star_done = false;
+    if constexpr (DIM == 3 && NL == 10) {
+        if (star_enabled() && (p->star_n[0] > 0 || p->star_n[1] > 0)) {
+            constexpr int TPRs = OPG == 1 ? DIM : 1, NBs = OPG == 1 ? DIM : 1, NVs = OPG == 1 ? 9 : 1;
+            size_t wb = 0;
+            for (const Bucket &b : p->buckets) {
+                if (!b.in_star) continue;
+                const size_t pitch = (size_t)((TPRs * NBs * b.lcap + 2) & ~1);
+                size_t need;
+                if (b.type == 0) need = (size_t)b.npt * pitch * 8 + (size_t)kTaskMaxTets * kTaskVec * 24;
+                else need = (std::max<size_t>((size_t)b.fan_npw * pitch, (size_t)3 * NVs * 33 + 1) + 1 & ~(size_t)1) * 8;
+                wb = std::max(wb, need);
+            }
+            wb = (wb + 15) & ~(size_t)15;
+            const int nts = 64;
+            const size_t smem_s = wb * (nts / 32);
+            if (smem_s <= budget) {
+                FB_CUDA(cudaFuncSetAttribute(k_star<OPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+                int per_sm = 1;
+                FB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_star<OPG>, nts, smem_s));
+                for (int g = 1; g >= 0; g--) {   // ghost rows first
+                    if (p->star_n[g] == 0) continue;
+                    if ((phase == FEDDB200_ROWS_GHOST && g == 0) || (phase == FEDDB200_ROWS_OWNED && g == 1)) continue;
+                    StarArgs SA;
+                    SA.G = G;
+                    SA.G.zero = 0;
+                    SA.G.nseg = g ? c->n_ghost_seg : 0;
+                    for (int i = 0; i < kMaxGhostSeg; i++) { SA.G.seg_begin[i] = c->ghost_seg_begin[i]; SA.G.seg_ptr[i] = c->ghost_seg_ptr[i]; }
+                    SA.G.seg_begin[kMaxGhostSeg] = c->ghost_seg_begin[kMaxGhostSeg];
+                    SA.tiles = (const uint4 *)p->star_tiles_d[g]; SA.n_tiles = p->star_n[g];
+                    SA.fanrec = (const uint4 *)p->fanrec_d; SA.tileblk = (const uint4 *)p->tiletet_d; SA.tasks = p->tasks_d;
+                    SA.warp_bytes = (int)wb;
+                    const int64_t blocks_s = std::min<int64_t>((SA.n_tiles + nts / 32 - 1) / (nts / 32), (int64_t)std::max(per_sm, 1) * c->sm_count);
+                    k_star<OPG><<<(unsigned)blocks_s, nts, smem_s, c->stream>>>(SA);
+                    c->launches++;
+                    FB_CUDA(cudaGetLastError());
+                }
+                star_done = true;
+            }
+        }
+    }
     int turn = 0;
     for (const Bucket *bp : order) {
         const Bucket &b = *bp;
         if ((phase == FEDDB200_ROWS_GHOST && !b.ghost) || (phase == FEDDB200_ROWS_OWNED && b.ghost)) continue;
+        if (star_done && b.in_star) continue;
         cudaStream_t st = n_side > 0 ? c->side[turn++ % n_side] : ((aside && b.count <= kSmallBucketRows) ? c->side[0] : c->stream);
         G.zero = 0;
         G.start = b.start; G.count = b.count;

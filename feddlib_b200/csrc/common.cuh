@@ -58,6 +58,7 @@ struct Bucket {            // rows of one type with node-row length <= lcap, pro
     // fan-record array, fan_W per row; fan_W 0: not used
     int64_t fan_off = 0;
     int fan_W = 0, fan_npw = 0;
+    int in_star = 0;       // the bucket's rows are tiles of the star kernel's address-ordered tile list (k_star)
 };
 
 } // namespace fb
@@ -116,6 +117,8 @@ struct feddb200_pat {
     int rec_words = 0;
     void *task_tiles_d = nullptr;  // [n_tiles] TaskTile: tiles of the block-task kernel (3D P2 vertex-node rows)
     uint64_t *tasks_d = nullptr;   // task programs of the tiles (tasks.cuh)
+    void *star_tiles_d[2] = {nullptr, nullptr};   // address-ordered tile lists of k_star: owned rows, ghost rows
+    int64_t star_n[2] = {0, 0};
     uint32_t *fanrec_d = nullptr;  // padded per-bucket records of the fan kernel (3D P2 ring-ordered edge-node rows)
     void *tiletet_d = nullptr;     // [n_tiles] tile blocks (400 bytes: header, row nodes, incident elements; star_kernels.cuh)
     double *geom_d = nullptr;      // [ne][GS] per-element geometry cache, recomputed by every assembly

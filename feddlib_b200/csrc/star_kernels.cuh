@@ -607,3 +607,337 @@ __global__ void __launch_bounds__(64, 8) k_fan(const FanArgs A)
 }
 
 } // namespace fb
+
+namespace fb {
+
+// =========================================================================================
+//  * k_star -- ONE persistent kernel for all star tiles of an assembly (fan tiles of the edge-node rows, task tiles of the
+//    vertex-node rows), walked in the ADDRESS ORDER of their CSR rows.  The type-bucketed launches write ~2 KB row runs
+//    scattered over the whole values array (row types interleave node by node in the CSR): measured on B200
+//    (tools/microbench_write.cu) 2 KB runs reach 3.2-3.6 TB/s in scattered order against 4.1-5.6 TB/s in address order
+//    and 6.9 TB/s for a flat fill -- the row kernels were sitting on the scattered-write ceiling.  Here the warps of the
+//    grid work at any moment on one contiguous window of the matrix (all row types), so DRAM pages fill while they are
+//    open and the geometry lines of the window's elements are reused from L2 by every row type.
+// =========================================================================================
+struct StarArgs {
+    GatherArgs G;            // geom, values, c0/c1, R, vec_dim, ghost segments
+    const uint4 *tiles;      // [n_tiles] x = kind | W << 8 | npt << 16, y = index of the tile in its array, z = node pitch (doubles)
+    int64_t n_tiles;
+    const uint4 *fanrec;     // fan tiles: [index][32 lanes][2 x 16 bytes]   (k_fan_records)
+    const uint4 *tileblk;    // task tiles: [index][25 x 16 bytes]           (k_task_build)
+    const uint64_t *tasks;
+    int warp_bytes;          // shared memory per warp
+};
+
+// the warp copies the rows of its tile's nodes to their place in the values array.  Lane s < n_nodes holds the node's
+// destination, the offset of its row in the warp's shared memory and its length (all dof rows, contiguous); 16-byte
+// stores where source and destination have the same 16-byte phase (arranged by the callers), 8-byte stores otherwise
+__device__ __forceinline__ void star_write_out(const double *rows, int n_nodes, double *outp, int rowoff, int total, int nrep, int lane)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+#pragma unroll 1
+    for (int s = 0; s < n_nodes; s++) {
+        double *const op = reinterpret_cast<double *>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(outp), s));
+        const int ro = __shfl_sync(FULL, rowoff, s), tot = __shfl_sync(FULL, total, s);
+        if (tot == 0) continue;
+        const double *src = rows + ro;
+        const int hs = (int)((reinterpret_cast<uintptr_t>(src) >> 3) & 1);
+#pragma unroll 1
+        for (int d = 0; d < nrep; d++) {
+            double *out = op + (int64_t)d * tot;
+            const int h = (int)((reinterpret_cast<uintptr_t>(out) >> 3) & 1);
+            if (h == hs) {
+                const int body = (tot - h) & ~1;
+                if (lane == 0 && h) out[0] = src[0];
+                if (lane == 1 && h + body < tot) out[tot - 1] = src[tot - 1];
+                const double2 *s2 = reinterpret_cast<const double2 *>(src + h);
+                double2 *o2 = reinterpret_cast<double2 *>(out + h);
+                for (int x = lane; x < (body >> 1); x += 32) o2[x] = s2[x];
+            } else {
+                for (int x = lane; x < tot; x += 32) out[x] = src[x];
+            }
+        }
+    }
+}
+
+// one fan tile: 32 / W ring-ordered edge-node rows, one lane per incident element (see k_fan)
+template <int OPG, int WT>
+__device__ __forceinline__ void star_fan_tile(const StarArgs &A, const uint4 *__restrict__ fr, double *rows, int pitch, int W_rt)
+{
+    constexpr int DIM = 3, NVTX = 4;
+    constexpr int NB = OPG == 1 ? DIM : 1, TPR = OPG == 1 ? DIM : 1, NV = OPG == 1 ? 9 : 1;
+    constexpr int SP = 33;
+    constexpr int MAXR = OPG == 1 ? (WT > 0 ? (27 + WT - 1) / WT : 7) : 1;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int W = WT > 0 ? WT : W_rt, npw = 32 / W;
+    const double mu = A.G.c1, lam = A.G.c0;
+    const int nrep = (OPG == 0 && A.G.vec_dim != 0) ? A.G.vec_dim : 1;
+    const int slot = lane / W;
+    const bool lane_used = slot < npw;
+    const int idx = lane - slot * W;
+
+    const uint4 r0 = __ldg(fr + 2 * lane), r1 = __ldg(fr + 2 * lane + 1);
+    const bool live = lane_used && r0.w != 0xffffffffu;
+    double G[4][3], adet = 0.0;
+#pragma unroll
+    for (int v = 0; v < 4; v++) G[v][0] = G[v][1] = G[v][2] = 0.0;
+    if (live) {
+        const double *g = A.G.geom + (int64_t)r0.w * 16;
+        const uint32_t perm = (r0.z >> 16) & 0xffu;
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            double t[4];
+            ld_v4g(g + 4 * ((perm >> (2 * v)) & 3), t);
+            G[v][0] = t[0]; G[v][1] = t[1]; G[v][2] = t[2];
+            if (v == 0) adet = t[3];
+        }
+    }
+    const bool node_ok = lane_used && (r1.z >> 24 & 2u) != 0;
+    const int64_t base = (int64_t)((uint64_t)r1.x | (uint64_t)r1.y << 32);
+    const int L = node_ok ? (int)(r1.z & 0xffffu) : 0;
+    const int ninc = node_ok ? (int)((r1.z >> 16) & 0xffu) : 0;
+    const bool holes = node_ok && (r1.z >> 24 & 1u) != 0;
+    const int n = NB * L;
+    const int64_t off_node = (int64_t)TPR * NB * nrep * base;
+    double *const outp = node_ok ? out_ptr(A.G, off_node) : nullptr;
+    const int head = (int)((reinterpret_cast<uintptr_t>(outp) >> 3) & 1);
+    const int rowoff = (lane_used ? slot : 0) * pitch + head;          // pitch is even, rows is 16-byte aligned
+    double *const nodep = rows + rowoff;
+    const uint32_t pw[3] = {r0.x, r0.y, r0.z};
+    auto posof = [&](int jc) { return (int)((pw[jc >> 2] >> (8 * (jc & 3))) & 0xffu) * NB; };
+
+    double gs[2][3];
+#pragma unroll
+    for (int s = 0; s < 2; s++)
+#pragma unroll
+        for (int d = 0; d < 3; d++) gs[s][d] = adet * G[s][d];
+    auto store_block = [&](int p, const double (&v)[NV]) {
+        if constexpr (OPG == 1) {
+#pragma unroll
+            for (int a = 0; a < 3; a++)
+#pragma unroll
+                for (int b = 0; b < 3; b++) nodep[a * n + p + b] = v[3 * a + b];
+        } else nodep[p] = v[0];
+    };
+    {
+        double hb[NV];
+        fan_block<OPG, 0>(A.G.R, G, gs, mu, lam, hb);
+#pragma unroll
+        for (int v = 0; v < NV; v++) rows[(0 * NV + v) * SP + lane] = hb[v];
+        fan_block<OPG, 1>(A.G.R, G, gs, mu, lam, hb);
+#pragma unroll
+        for (int v = 0; v < NV; v++) rows[(1 * NV + v) * SP + lane] = hb[v];
+        fan_block<OPG, 4>(A.G.R, G, gs, mu, lam, hb);
+#pragma unroll
+        for (int v = 0; v < NV; v++) rows[(2 * NV + v) * SP + lane] = hb[v];
+    }
+    __syncwarp();
+    double hv[MAXR];
+#pragma unroll
+    for (int r = 0; r < MAXR; r++) {
+        const int v = idx + r * W;
+        double s = 0.0;
+        if (node_ok && v < 3 * NV) {
+            const double *src = rows + v * SP + slot * W;
+            if constexpr (WT > 0) {
+#pragma unroll
+                for (int m = 0; m < WT; m++) s += src[m];
+            } else {
+                for (int m = 0; m < ninc; m++) s += src[m];
+            }
+        }
+        hv[r] = s;
+    }
+    const int lane0 = (lane_used ? slot : 0) * W;
+    const uint32_t pw0 = __shfl_sync(FULL, pw[0], lane0), pw1 = __shfl_sync(FULL, pw[1], lane0);
+    const int ph0 = (int)(pw0 & 0xffu) * NB, ph1 = (int)((pw0 >> 8) & 0xffu) * NB, ph4 = (int)(pw1 & 0xffu) * NB;
+    __syncwarp();
+    if (__any_sync(FULL, holes)) {
+        for (int x = lane; x < npw * pitch; x += 32) rows[x] = 0.0;
+        __syncwarp();
+    }
+    if (node_ok && ninc > 0) {
+#pragma unroll
+        for (int r = 0; r < MAXR; r++) {
+            const int v = idx + r * W;
+            if (v < 3 * NV) {
+                const int ci = v / NV, ab = v - ci * NV;
+                const int p = ci == 0 ? ph0 : (ci == 1 ? ph1 : ph4);
+                if constexpr (OPG == 1) nodep[(ab / 3) * n + p + (ab % 3)] = hv[r];
+                else nodep[p] = hv[r];
+            }
+        }
+    }
+    const uint32_t wire = r0.z >> 24;
+    const int src = (int)(wire & 31u);
+    const bool has_src = live && (wire & 32u) != 0, store_out = live && (wire & 64u) != 0;
+#define FB_FAN_FACE(JO, JI)                                                                         \
+    {                                                                                               \
+        double bo[NV], bi[NV], cy[NV];                                                              \
+        fan_block<OPG, JO>(A.G.R, G, gs, mu, lam, bo);                                               \
+        _Pragma("unroll") for (int v = 0; v < NV; v++) cy[v] = __shfl_sync(FULL, bo[v], src);       \
+        fan_block<OPG, JI>(A.G.R, G, gs, mu, lam, bi);                                               \
+        if (live) {                                                                                 \
+            _Pragma("unroll") for (int v = 0; v < NV; v++) bi[v] += has_src ? cy[v] : 0.0;          \
+            store_block(posof(JI), bi);                                                             \
+            if (store_out) store_block(posof(JO), bo);                                              \
+        }                                                                                           \
+    }
+    FB_FAN_FACE(3, 2)
+    FB_FAN_FACE(7, 6)
+    FB_FAN_FACE(8, 5)
+#undef FB_FAN_FACE
+    {
+        double b9[NV];
+        fan_block<OPG, 9>(A.G.R, G, gs, mu, lam, b9);
+        if (live) store_block(posof(9), b9);
+    }
+    __syncwarp();
+    // lane s (< npw) publishes node s: its values live in lane s * W
+    {
+        const int sl = lane < npw ? lane * W : 0;
+        double *const op = reinterpret_cast<double *>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(outp), sl));
+        const int ro = __shfl_sync(FULL, rowoff, sl), tot = __shfl_sync(FULL, TPR * n, sl);
+        star_write_out(rows, npw, op, ro, lane < npw ? tot : 0, nrep, lane);
+    }
+    __syncwarp();
+}
+
+// one task tile: a few vertex-node rows, lanes = node blocks (see k_task)
+template <int OPG>
+__device__ __forceinline__ void star_task_tile(const StarArgs &A, const uint4 *__restrict__ blk, double *rows, int pitch, int npt)
+{
+    constexpr int DIM = 3, NVTX = 4, NL = 10;
+    constexpr int NB = OPG == 1 ? DIM : 1, TPR = OPG == 1 ? DIM : 1, NV = OPG == 1 ? 9 : 1;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    double2 *const XY = reinterpret_cast<double2 *>(rows + (size_t)npt * pitch);
+    double *const Z = reinterpret_cast<double *>(XY + kTaskMaxTets * kTaskVec);
+    const double mu = A.G.c1, lam = A.G.c0;
+    const int nrep = (OPG == 0 && A.G.vec_dim != 0) ? A.G.vec_dim : 1;
+
+    const uint4 hdr = __ldg(blk);
+    const int n_nodes = hdr.x & 0xff, n_tets = (hdr.x >> 8) & 0xff, n_passes = (hdr.x >> 16) & 0xff;
+    const uint2 et = __ldg(reinterpret_cast<const uint2 *>(blk + 9) + lane);
+    int64_t base = 0;
+    int L = 0;
+    if (lane < n_nodes) {
+        const uint4 nd = __ldg(blk + 1 + lane);
+        base = (int64_t)((uint64_t)nd.x | (uint64_t)nd.y << 32);
+        L = (int)nd.z;
+    }
+    const uint64_t *tp = A.tasks + (int64_t)hdr.y * 32 + lane;
+    uint64_t tw0 = 0, tw1 = 0, tw2 = 0;   // the first three passes' task words travel with the geometry
+    if (n_passes > 0) tw0 = __ldg(reinterpret_cast<const unsigned long long *>(tp));
+    if (n_passes > 1) tw1 = __ldg(reinterpret_cast<const unsigned long long *>(tp + 32));
+    if (n_passes > 2) tw2 = __ldg(reinterpret_cast<const unsigned long long *>(tp + 64));
+    if (lane < n_tets) {
+        double G[4][4];
+        const double *g = A.G.geom + (int64_t)et.x * 16;
+#pragma unroll
+        for (int v = 0; v < 4; v++) ld_v4g(g + 4 * ((et.y >> (2 * v)) & 3), G[v]);
+        const double adet = G[0][3];
+        XY[lane * kTaskVec] = make_double2(adet * G[0][0], adet * G[0][1]);
+        Z[lane * kTaskVec] = adet * G[0][2];
+#pragma unroll
+        for (int jc = 0; jc < NL; jc++) {
+            const double r0 = A.G.R.r[0][jc][0][0];
+            double q[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++) q[d] = r0 * G[canon_sv<DIM>(jc, 0)][d];
+            if (jc >= NVTX) {
+                const double r1 = A.G.R.r[0][jc][0][1];
+#pragma unroll
+                for (int d = 0; d < 3; d++) q[d] = fma(r1, G[canon_sv<DIM>(jc, 1)][d], q[d]);
+            }
+            XY[lane * kTaskVec + 1 + jc] = make_double2(q[0], q[1]);
+            Z[lane * kTaskVec + 1 + jc] = q[2];
+        }
+    }
+    __syncwarp();
+    const int n = NB * L;
+    const int64_t off_node = (int64_t)TPR * NB * nrep * base;
+    double *const outp = lane < n_nodes ? out_ptr(A.G, off_node) : nullptr;
+    const int head = (int)((reinterpret_cast<uintptr_t>(outp) >> 3) & 1);
+    const int my_rowoff = lane * pitch + head;
+
+#pragma unroll 1
+    for (int pass = 0; pass < n_passes; pass++) {
+        const uint64_t task = pass == 0 ? tw0 : (pass == 1 ? tw1 : (pass == 2 ? tw2 : __ldg(reinterpret_cast<const unsigned long long *>(tp + 32 * pass))));
+        const int np = (int)((task >> 36) & 7);
+        const int nsteps = __reduce_max_sync(FULL, np);
+        double X[NV];
+#pragma unroll
+        for (int i = 0; i < NV; i++) X[i] = 0.0;
+#pragma unroll 1
+        for (int s = 0; s < nsteps; s++) {
+            if (s < np) {
+                const uint32_t pr = (uint32_t)(task >> (9 * s)) & 0x1ffu;
+                const int m = pr & 31, jc = pr >> 5;
+                const double2 gxy = XY[m * kTaskVec], qxy = XY[m * kTaskVec + 1 + jc];
+                const double gz = Z[m * kTaskVec], qz = Z[m * kTaskVec + 1 + jc];
+                if constexpr (OPG == 1) {
+                    X[0] = fma(gxy.x, qxy.x, X[0]); X[1] = fma(gxy.x, qxy.y, X[1]); X[2] = fma(gxy.x, qz, X[2]);
+                    X[3] = fma(gxy.y, qxy.x, X[3]); X[4] = fma(gxy.y, qxy.y, X[4]); X[5] = fma(gxy.y, qz, X[5]);
+                    X[6] = fma(gz, qxy.x, X[6]);    X[7] = fma(gz, qxy.y, X[7]);    X[8] = fma(gz, qz, X[8]);
+                } else {
+                    X[0] = fma(gxy.x, qxy.x, X[0]); X[0] = fma(gxy.y, qxy.y, X[0]); X[0] = fma(gz, qz, X[0]);
+                }
+            }
+        }
+        const int rem = (int)((task >> 50) & 7);
+        if (__any_sync(FULL, rem != 0)) {
+#pragma unroll
+            for (int d = 1; d <= 4; d <<= 1) {
+#pragma unroll
+                for (int i = 0; i < NV; i++) {
+                    const double t = __shfl_down_sync(FULL, X[i], d);
+                    if (d <= rem) X[i] += t;
+                }
+            }
+        }
+        const int slot = (int)((task >> 47) & 7), pos = (int)((task >> 39) & 255);
+        const int rowoff = __shfl_sync(FULL, my_rowoff, slot), ns = __shfl_sync(FULL, n, slot);
+        if ((task >> 53) & 1) {
+            double *p = rows + rowoff + NB * pos;
+            if constexpr (OPG == 1) {
+                const double mtr = mu * (X[0] + X[4] + X[8]);
+#pragma unroll
+                for (int a = 0; a < 3; a++)
+#pragma unroll
+                    for (int b = 0; b < 3; b++) p[a * ns + b] = fma(mu, X[3 * b + a], fma(lam, X[3 * a + b], a == b ? mtr : 0.0));
+            } else p[0] = X[0];
+        }
+    }
+    __syncwarp();
+    star_write_out(rows, n_nodes, outp, my_rowoff, lane < n_nodes ? TPR * n : 0, nrep, lane);
+    __syncwarp();
+}
+
+template <int OPG>
+__global__ void __launch_bounds__(64, 8) k_star(const StarArgs A)
+{
+    extern __shared__ double smem[];
+    const int wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    double *const rows = reinterpret_cast<double *>(reinterpret_cast<char *>(smem) + (size_t)wib * A.warp_bytes);
+    const int64_t step = (int64_t)gridDim.x * wpb;
+    int64_t i = (int64_t)blockIdx.x * wpb + wib;
+    if (i >= A.n_tiles) return;
+    uint4 e = __ldg(A.tiles + i);
+    for (;;) {
+        const int64_t i_n = i + step;
+        uint4 e_n = make_uint4(0u, 0u, 0u, 0u);
+        if (i_n < A.n_tiles) e_n = __ldg(A.tiles + i_n);
+        const int kind = e.x & 0xff, w = (e.x >> 8) & 0xff, npt = (e.x >> 16) & 0xff, pitch = (int)e.z;
+        if (kind == 0) star_task_tile<OPG>(A, A.tileblk + (int64_t)e.y * kTileBlkChunks, rows, pitch, npt);
+        else if (w == 6) star_fan_tile<OPG, 6>(A, A.fanrec + (int64_t)e.y * 64, rows, pitch, w);
+        else if (w == 4) star_fan_tile<OPG, 4>(A, A.fanrec + (int64_t)e.y * 64, rows, pitch, w);
+        else star_fan_tile<OPG, 0>(A, A.fanrec + (int64_t)e.y * 64, rows, pitch, w);
+        if (i_n >= A.n_tiles) break;
+        i = i_n;
+        e = e_n;
+    }
+}
+
+} // namespace fb
