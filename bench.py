@@ -386,6 +386,23 @@ def main():
                "d2h_bytes_per_step": int(nnz * 8), "ms_per_step": dt * 1e3, "steps": args.e2e_steps}
         checksum = float(out_np[: min(nnz, 1 << 20)].sum())
         del pinned_vals
+        # the same end-to-end step through the compiled C++ host layer (FEDD::FE_b200 over the C ABI: host containers in,
+        # fill-complete host CSR in a pooled page-locked buffer out); N = 1 only, the binary is built by build()
+        exe = os.path.join(ROOT, "feddlib_b200", "bench_fe_b200")
+        if world == 1 and os.path.exists(exe):
+            del values
+            torch.cuda.empty_cache()
+            try:
+                r = subprocess.run([exe, str(M), str(max(2, args.e2e_steps)), str(local_rank)], capture_output=True, text=True, timeout=600)
+                cpp = json.loads(r.stdout.strip().splitlines()[-1])
+                e2e["cpp_host"] = {"value": ne / (cpp["ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": cpp["ms_per_step"],
+                                   "ms_best": cpp["ms_best"], "first_call_s": cpp["first_call_s"], "addFE_s": cpp["addFE_s"],
+                                   "checksum_first_1Mi_values": cpp["checksum_first_1Mi_values"],
+                                   "what": "FEDD::FE_b200::assemblyLinElasXDim (C++), points H2D from pageable host memory + "
+                                           "assembly + CSR values D2H into a pooled page-locked buffer owned by the returned matrix"}
+            except Exception as exc:  # noqa: BLE001
+                e2e["cpp_host"] = {"error": str(exc)[:200]}
+            values = ctx.empty_values(nnz)
     else:
         checksum = float(values[: min(nnz, 1 << 20)].sum().item())
 

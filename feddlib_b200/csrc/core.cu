@@ -135,6 +135,18 @@ extern "C" int feddb200_dev_free(feddb200_ctx *c, void *p)
     FB_CUDA(cudaFree(p));
     return FEDDB200_OK;
 }
+extern "C" int feddb200_host_alloc(feddb200_ctx *c, void **p, int64_t bytes)
+{
+    FB_LOGIC(!c || !p || bytes < 0, "feddb200_host_alloc: bad arguments");
+    FB_CUDA(cudaSetDevice(c->device));
+    FB_CUDA(cudaHostAlloc(p, (size_t)std::max<int64_t>(bytes, 8), cudaHostAllocDefault));
+    return FEDDB200_OK;
+}
+extern "C" int feddb200_host_free(feddb200_ctx *, void *p)
+{
+    FB_CUDA(cudaFreeHost(p));
+    return FEDDB200_OK;
+}
 extern "C" int feddb200_copy_h2d(feddb200_ctx *c, void *dst, const void *src, int64_t bytes)
 {
     FB_LOGIC(!c, "null context");

@@ -15,8 +15,11 @@
 // (FE_def.hpp:610, 676, 2746, 6950), std::runtime_error for engine failures.  There is no CPU fallback.
 #pragma once
 
+#include <algorithm>
 #include <cstdint>
 #include <map>
+#include <memory>
+#include <tuple>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -35,17 +38,80 @@ inline void check(int rc)
     throw std::runtime_error(msg);
 }
 
-// CSR of one assembled matrix, as handed to the seat step: local rows in row-map order, local column
-// indices into `colmap` (global dof ids of the column map, owned first), values on the host.
-template <class SC, class LO, class GO>
-struct LocalCsr {
+// Structure of one assembled matrix: local rows in row-map order, local column indices into `colmap` (global dof ids of
+// the column map, owned first).  Built ONCE per (pattern, dof layout) and shared by every matrix assembled on it.
+template <class GO>
+struct CsrStructure {
     std::vector<std::int64_t> rowptr;
     std::vector<std::int32_t> colind;
     std::vector<GO> colmap;
-    std::vector<SC> values;
+};
+
+// Page-locked value buffers (feddb200_host_alloc) are expensive to create, so they are pooled: a buffer belongs to the
+// matrix it was handed to (shared ownership) and returns to the pool when the last owner lets go of it.  In a Newton or
+// time loop the previous Jacobian is released before or right after the next assembly, so the pool settles at one or
+// two buffers and every device-to-host copy of the values runs at the PCIe rate.
+class PinnedPool : public std::enable_shared_from_this<PinnedPool> {
+  public:
+    explicit PinnedPool(feddb200_ctx *ctx) : ctx_(ctx) {}
+    ~PinnedPool() { retire(); }
+    std::shared_ptr<double> take(std::size_t n)
+    {
+        std::size_t best = free_.size();
+        for (std::size_t k = 0; k < free_.size(); k++)
+            if (free_[k].second >= n && (best == free_.size() || free_[k].second < free_[best].second)) best = k;
+        double *p = nullptr;
+        std::size_t cap = n;
+        if (best < free_.size()) {
+            p = free_[best].first; cap = free_[best].second;
+            free_.erase(free_.begin() + (std::ptrdiff_t)best);
+        } else {
+            void *raw = nullptr;
+            check_(feddb200_host_alloc(ctx_, &raw, (std::int64_t)(sizeof(double) * std::max<std::size_t>(n, 1))));
+            p = static_cast<double *>(raw);
+        }
+        std::weak_ptr<PinnedPool> home = shared_from_this();
+        return std::shared_ptr<double>(p, [home, cap](double *q) {
+            if (std::shared_ptr<PinnedPool> h = home.lock()) { if (h->ctx_) { h->free_.push_back(std::make_pair(q, cap)); return; } }
+            feddb200_host_free(nullptr, q);
+        });
+    }
+    // called before the engine context goes away: buffers still held by matrices free themselves later
+    void retire()
+    {
+        for (auto &f : free_) feddb200_host_free(nullptr, f.first);
+        free_.clear();
+        ctx_ = nullptr;
+    }
+    std::size_t idle() const { return free_.size(); }
+
+  private:
+    static void check_(int rc)
+    {
+        if (rc != FEDDB200_OK) throw std::runtime_error(feddb200_last_error());
+    }
+    feddb200_ctx *ctx_;
+    std::vector<std::pair<double *, std::size_t> > free_;
+};
+
+// CSR of one assembled matrix, as handed to the seat step: the shared structure + this matrix's values on the host
+template <class SC, class LO, class GO>
+struct LocalCsr {
+    std::shared_ptr<const CsrStructure<GO> > pattern;
+    std::shared_ptr<double> values;   // page-locked, pooled
+    std::size_t nnz = 0;
 };
 
 #ifdef FEDD_B200_TRILINOS
+// Teuchos deallocator that only holds a shared owner of the memory an ArrayRCP views
+template <class T, class Owner>
+struct KeepAlive {
+    typedef T ptr_t;
+    explicit KeepAlive(const std::shared_ptr<Owner> &o) : owner(o) {}
+    void free(T *) { owner.reset(); }
+    std::shared_ptr<Owner> owner;
+};
+
 // Seat step for the real containers: wrap the CSR in a Tpetra::CrsMatrix on the caller's row map and re-seat
 // `A` (passed as MatrixPtr_Type&, as in the reference).  domain/range default to the row map, like
 // Matrix::fillComplete() (Matrix_def.hpp:192-194); B / B^T pass (map1,map2) / (map2,map1) (FE_def.hpp:2052-2055).
@@ -59,14 +125,18 @@ void seat_csr(Teuchos::RCP<Matrix<SC, LO, GO, NO> > &A, LocalCsr<SC, LO, GO> &cs
     Teuchos::RCP<const Map<LO, GO, NO> > rowMapF = A->getMap();
     Teuchos::RCP<const TMap> rowMap = Xpetra::toTpetra(rowMapF->getXpetraMap());
     Teuchos::RCP<const TMap> colMap = Teuchos::rcp(new TMap(Teuchos::OrdinalTraits<Tpetra::global_size_t>::invalid(),
-                                                              Teuchos::ArrayView<const GO>(csr.colmap.data(), csr.colmap.size()),
+                                                              Teuchos::ArrayView<const GO>(csr.pattern->colmap.data(), csr.pattern->colmap.size()),
                                                               rowMap->getIndexBase(), rowMap->getComm()));
-    Teuchos::ArrayRCP<std::size_t> rp(csr.rowptr.size());
-    for (std::size_t k = 0; k < csr.rowptr.size(); k++) rp[k] = (std::size_t)csr.rowptr[k];
-    Teuchos::ArrayRCP<LO> ci(csr.colind.size());
-    for (std::size_t k = 0; k < csr.colind.size(); k++) ci[k] = (LO)csr.colind[k];
-    Teuchos::ArrayRCP<SC> va(csr.values.size());
-    for (std::size_t k = 0; k < csr.values.size(); k++) va[k] = csr.values[k];
+    // no copies: Tpetra's arrays are views of the shared structure and of this matrix's pooled value buffer; each view
+    // keeps its owner alive (Teuchos deallocator) and lets go of it when Tpetra releases the array
+    static_assert(sizeof(std::size_t) == sizeof(std::int64_t) && sizeof(LO) == sizeof(std::int32_t), "index types");
+    const CsrStructure<GO> &P = *csr.pattern;
+    Teuchos::ArrayRCP<std::size_t> rp = Teuchos::arcp(reinterpret_cast<std::size_t *>(const_cast<std::int64_t *>(P.rowptr.data())), 0,
+                                                     (Teuchos::Ordinal)P.rowptr.size(), KeepAlive<std::size_t, const CsrStructure<GO> >(csr.pattern), true);
+    Teuchos::ArrayRCP<LO> ci = Teuchos::arcp(reinterpret_cast<LO *>(const_cast<std::int32_t *>(P.colind.data())), 0,
+                                             (Teuchos::Ordinal)P.colind.size(), KeepAlive<LO, const CsrStructure<GO> >(csr.pattern), true);
+    Teuchos::ArrayRCP<SC> va = Teuchos::arcp(reinterpret_cast<SC *>(csr.values.get()), 0, (Teuchos::Ordinal)csr.nnz,
+                                             KeepAlive<SC, double>(csr.values), true);
     Teuchos::RCP<TCrs> T = Teuchos::rcp(new TCrs(rowMap, colMap, rp, ci, va));
     if (callFillComplete) {
         Teuchos::RCP<const TMap> dom = domainMap.is_null() ? rowMap : Xpetra::toTpetra(domainMap->getXpetraMap());
@@ -96,9 +166,11 @@ class FE_b200 {
     explicit FE_b200(bool /*saveAssembly*/ = false, int device = 0) : ctx_(nullptr)
     {
         b200::check(feddb200_create(&ctx_, device));
+        pool_ = std::make_shared<b200::PinnedPool>(ctx_);
     }
     ~FE_b200()
     {
+        pool_->retire();
         for (auto &kv : pats_) feddb200_pat_free(kv.second);
         for (auto &s : slots_) feddb200_mesh_free(s.mesh);
         feddb200_destroy(ctx_);
@@ -128,6 +200,18 @@ class FE_b200 {
             for (int c = 0; c < s.dim; c++) xyz[(std::size_t)k * s.dim + c] = (*points)[k][c];
         b200::check(feddb200_mesh_upload(ctx_, &s.mesh, s.dim, s.nloc, s.ne, conn.data(), s.nn, xyz.data()));
         slots_.push_back(s);
+    }
+
+    // re-reads the points of a registered domain and uploads them (moving meshes: the Geometry / FSI problems displace the
+    // mesh between assemblies, problems/specific/FSI_def.hpp; connectivity and pattern stay)
+    void updatePoints(int loc)
+    {
+        Slot &s = slots_.at((std::size_t)loc);
+        auto points = s.domain->getPointsRepeated();
+        std::vector<double> xyz((std::size_t)s.nn * s.dim);
+        for (std::int64_t k = 0; k < s.nn; k++)
+            for (int c = 0; c < s.dim; c++) xyz[(std::size_t)k * s.dim + c] = (*points)[k][c];
+        b200::check(feddb200_mesh_update_coords(ctx_, s.mesh, xyz.data()));
     }
 
     void setScatterMode(int mode) { b200::check(feddb200_set_scatter_mode(ctx_, mode)); }
@@ -188,8 +272,8 @@ class FE_b200 {
         }
         b200::LocalCsr<SC, LO, GO> csr;
         expand(p, loc, dim, dim, FEDDB200_BLOCK_FULL, csr);
-        if (constant) b200::check(feddb200_assemble_stress(ctx_, p, ne ? coef[0] : 1.0, nullptr, 0, csr.values.data()));
-        else b200::check(feddb200_assemble_stress(ctx_, p, 1.0, coef.data(), (int64_t)coef.size(), csr.values.data()));
+        if (constant) b200::check(feddb200_assemble_stress(ctx_, p, ne ? coef[0] : 1.0, nullptr, 0, csr.values.get()));
+        else b200::check(feddb200_assemble_stress(ctx_, p, 1.0, coef.data(), (int64_t)coef.size(), csr.values.get()));
         seat_csr(A, csr, MapConstPtr_Type(), MapConstPtr_Type(), callFillComplete);
     }
 
@@ -202,7 +286,7 @@ class FE_b200 {
         feddb200_pat *p = pattern(loc, loc);
         b200::LocalCsr<SC, LO, GO> csr;
         expand(p, loc, 1, 1, FEDDB200_BLOCK_SCALAR, csr);
-        b200::check(feddb200_assemble_bdstab(ctx_, p, csr.values.data()));
+        b200::check(feddb200_assemble_bdstab(ctx_, p, csr.values.get()));
         seat_csr(A, csr, MapConstPtr_Type(), MapConstPtr_Type(), callFillComplete);
     }
 
@@ -217,7 +301,7 @@ class FE_b200 {
         b200::LocalCsr<SC, LO, GO> csr;
         if (vec) expand(p, loc, dim, dim, FEDDB200_BLOCK_DIAG, csr);
         else expand(p, loc, 1, 1, FEDDB200_BLOCK_SCALAR, csr);
-        b200::check(feddb200_assemble_mass(ctx_, p, vec ? 1 : 0, csr.values.data()));
+        b200::check(feddb200_assemble_mass(ctx_, p, vec ? 1 : 0, csr.values.get()));
         seat_csr(A, csr, MapConstPtr_Type(), MapConstPtr_Type(), callFillComplete);
     }
 
@@ -230,7 +314,7 @@ class FE_b200 {
         feddb200_pat *p = pattern(loc, loc);
         b200::LocalCsr<SC, LO, GO> csr;
         expand(p, loc, 1, 1, FEDDB200_BLOCK_SCALAR, csr);
-        b200::check(feddb200_assemble_laplace(ctx_, p, 0, csr.values.data()));
+        b200::check(feddb200_assemble_laplace(ctx_, p, 0, csr.values.get()));
         seat_csr(A, csr, MapConstPtr_Type(), MapConstPtr_Type(), callFillComplete);
     }
 
@@ -242,7 +326,7 @@ class FE_b200 {
         feddb200_pat *p = pattern(loc, loc);
         b200::LocalCsr<SC, LO, GO> csr;
         expand(p, loc, dim, dim, FEDDB200_BLOCK_DIAG, csr);
-        b200::check(feddb200_assemble_laplace(ctx_, p, 1, csr.values.data()));
+        b200::check(feddb200_assemble_laplace(ctx_, p, 1, csr.values.get()));
         seat_csr(A, csr, MapConstPtr_Type(), MapConstPtr_Type(), callFillComplete);
     }
 
@@ -254,7 +338,7 @@ class FE_b200 {
         feddb200_pat *p = pattern(loc, loc);
         b200::LocalCsr<SC, LO, GO> csr;
         expand(p, loc, dim, dim, FEDDB200_BLOCK_FULL, csr);
-        b200::check(feddb200_assemble_linelas(ctx_, p, lambda, mu, csr.values.data()));
+        b200::check(feddb200_assemble_linelas(ctx_, p, lambda, mu, csr.values.get()));
         seat_csr(A, csr, MapConstPtr_Type(), MapConstPtr_Type(), callFillComplete);
     }
 
@@ -268,7 +352,7 @@ class FE_b200 {
         b200::LocalCsr<SC, LO, GO> csr;
         expand(p, loc, dim, dim, FEDDB200_BLOCK_DIAG, csr);
         Teuchos::ArrayRCP<const SC> uArray = u->getData(0);
-        b200::check(feddb200_assemble_advection(ctx_, p, (uArray.size() ? &uArray[0] : nullptr), csr.values.data()));
+        b200::check(feddb200_assemble_advection(ctx_, p, (uArray.size() ? &uArray[0] : nullptr), csr.values.get()));
         seat_csr(A, csr, MapConstPtr_Type(), MapConstPtr_Type(), callFillComplete);
     }
 
@@ -281,7 +365,7 @@ class FE_b200 {
         b200::LocalCsr<SC, LO, GO> csr;
         expand(p, loc, dim, dim, FEDDB200_BLOCK_FULL, csr);
         Teuchos::ArrayRCP<const SC> uArray = u->getData(0);
-        b200::check(feddb200_assemble_advection_in_u(ctx_, p, (uArray.size() ? &uArray[0] : nullptr), csr.values.data()));
+        b200::check(feddb200_assemble_advection_in_u(ctx_, p, (uArray.size() ? &uArray[0] : nullptr), csr.values.get()));
         seat_csr(A, csr, MapConstPtr_Type(), MapConstPtr_Type(), callFillComplete);
     }
 
@@ -297,7 +381,7 @@ class FE_b200 {
         b200::LocalCsr<SC, LO, GO> cB, cBT;
         expand(pB, loc1, 1, dim, FEDDB200_BLOCK_FULL, cB);
         expand(pBT, loc2, dim, 1, FEDDB200_BLOCK_FULL, cBT);
-        b200::check(feddb200_assemble_div_divT(ctx_, pB, pBT, cB.values.data(), cBT.values.data()));
+        b200::check(feddb200_assemble_div_divT(ctx_, pB, pBT, cB.values.get(), cBT.values.get()));
         seat_csr(Bmat, cB, map1, map2, callFillComplete);
         seat_csr(BTmat, cBT, map2, map1, callFillComplete);
     }
@@ -319,7 +403,7 @@ class FE_b200 {
         b200::LocalCsr<SC, LO, GO> csr;
         expand(p, loc, dim, dim, FEDDB200_BLOCK_FULL, csr);
         Teuchos::ArrayRCP<const SC> uArray = u->getData(0);
-        b200::check(feddb200_assemble_ns_jacobian(ctx_, p, rho, nu, (uArray.size() ? &uArray[0] : nullptr), newton ? 1 : 0, csr.values.data()));
+        b200::check(feddb200_assemble_ns_jacobian(ctx_, p, rho, nu, (uArray.size() ? &uArray[0] : nullptr), newton ? 1 : 0, csr.values.get()));
         seat_csr(A, csr, MapConstPtr_Type(), MapConstPtr_Type(), callFillComplete);
     }
 
@@ -366,26 +450,37 @@ class FE_b200 {
         return p;
     }
 
-    // dof-level CSR + column map of global dof ids (node-wise numbering dofs*g + d, Map_def.hpp:95-108)
+    // dof-level CSR + column map of global dof ids (node-wise numbering dofs*g + d, Map_def.hpp:95-108): expanded and
+    // downloaded once per (pattern, layout), then shared; the values come from the pinned pool
     void expand(feddb200_pat *p, int colLoc, int rowDofs, int colDofs, int mode, b200::LocalCsr<SC, LO, GO> &csr)
     {
-        std::int64_t nRows = 0, nCols = 0;
-        b200::check(feddb200_pattern_info(p, &nRows, nullptr, &nCols, nullptr, nullptr, nullptr, nullptr));
         const std::int64_t nnz = feddb200_pattern_nnz(p, rowDofs, colDofs, mode);
-        csr.rowptr.resize((std::size_t)nRows * rowDofs + 1);
-        csr.colind.resize((std::size_t)nnz);
-        csr.values.resize((std::size_t)nnz);
-        b200::check(feddb200_pattern_expand(ctx_, p, rowDofs, colDofs, mode, csr.rowptr.data(), csr.colind.data()));
-        MapConstPtr_Type mapRep = slots_[colLoc].domain->getMapRepeated();
-        csr.colmap.resize((std::size_t)nCols * colDofs);
-        for (std::int64_t j = 0; j < nCols; j++)
-            for (int d = 0; d < colDofs; d++)
-                csr.colmap[(std::size_t)j * colDofs + d] = (GO)colDofs * mapRep->getGlobalElement((LO)j) + d;
+        const std::tuple<feddb200_pat *, int, int, int> key(p, rowDofs, colDofs, mode);
+        auto it = structures_.find(key);
+        if (it == structures_.end()) {
+            std::int64_t nRows = 0, nCols = 0;
+            b200::check(feddb200_pattern_info(p, &nRows, nullptr, &nCols, nullptr, nullptr, nullptr, nullptr));
+            std::shared_ptr<b200::CsrStructure<GO> > st = std::make_shared<b200::CsrStructure<GO> >();
+            st->rowptr.resize((std::size_t)nRows * rowDofs + 1);
+            st->colind.resize((std::size_t)nnz);
+            b200::check(feddb200_pattern_expand(ctx_, p, rowDofs, colDofs, mode, st->rowptr.data(), st->colind.data()));
+            MapConstPtr_Type mapRep = slots_[colLoc].domain->getMapRepeated();
+            st->colmap.resize((std::size_t)nCols * colDofs);
+            for (std::int64_t j = 0; j < nCols; j++)
+                for (int d = 0; d < colDofs; d++)
+                    st->colmap[(std::size_t)j * colDofs + d] = (GO)colDofs * mapRep->getGlobalElement((LO)j) + d;
+            it = structures_.insert(std::make_pair(key, std::shared_ptr<const b200::CsrStructure<GO> >(st))).first;
+        }
+        csr.pattern = it->second;
+        csr.nnz = (std::size_t)nnz;
+        csr.values = pool_->take(csr.nnz);
     }
 
     feddb200_ctx *ctx_;
     std::vector<Slot> slots_;
     std::map<std::pair<int, int>, feddb200_pat *> pats_;
+    std::map<std::tuple<feddb200_pat *, int, int, int>, std::shared_ptr<const b200::CsrStructure<GO> > > structures_;
+    std::shared_ptr<b200::PinnedPool> pool_;
 };
 
 } // namespace FEDD

@@ -79,6 +79,11 @@ int  feddb200_dev_alloc(feddb200_ctx *ctx, void **ptr_d, int64_t bytes);
 int  feddb200_dev_free(feddb200_ctx *ctx, void *ptr_d);
 int  feddb200_copy_h2d(feddb200_ctx *ctx, void *dst_d, const void *src, int64_t bytes);
 int  feddb200_copy_d2h(feddb200_ctx *ctx, void *dst, const void *src_d, int64_t bytes);
+/* page-locked host memory for the buffers the host-pointer entry points fill (the CSR values that the seat step hands to
+ * Tpetra: core/LinearAlgebra/Matrix_def.hpp:46-51 allocates them inside Tpetra in the reference): a device-to-host copy
+ * into pageable memory runs at a fraction of the PCIe rate.  ctx may be NULL for feddb200_host_free. */
+int  feddb200_host_alloc(feddb200_ctx *ctx, void **ptr, int64_t bytes);
+int  feddb200_host_free(feddb200_ctx *ctx, void *ptr);
 
 /* ---- mesh ------------------------------------------------------------------------------
  * Replaces the per-call reads of Domain::getElementsC / getPointsRepeated

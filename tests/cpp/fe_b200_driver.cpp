@@ -90,14 +90,18 @@ static RefCsr ref_csr(fo_matrix *A, int64_t nrows)
 static bool compare(const char *name, const Csr_t &ours, const RefCsr &ref, const std::vector<int64_t> &gidRow, int rowDofs)
 {
     double num = 0.0, den = 0.0;
-    const int64_t nLocalRows = (int64_t)ours.rowptr.size() - 1;
+    const std::vector<std::int64_t> &rowptr = ours.pattern->rowptr;
+    const std::vector<std::int32_t> &colind = ours.pattern->colind;
+    const std::vector<GOx> &colmap = ours.pattern->colmap;
+    const double *values = ours.values.get();
+    const int64_t nLocalRows = (int64_t)rowptr.size() - 1;
     bool pattern_ok = nLocalRows == (int64_t)gidRow.size() * rowDofs;
     for (int64_t lr = 0; lr < nLocalRows && pattern_ok; lr++) {
         const int64_t gr = rowDofs * gidRow[lr / rowDofs] + lr % rowDofs;
-        const int64_t a0 = ours.rowptr[lr], a1 = ours.rowptr[lr + 1], b0 = ref.rowptr[gr], b1 = ref.rowptr[gr + 1];
+        const int64_t a0 = rowptr[lr], a1 = rowptr[lr + 1], b0 = ref.rowptr[gr], b1 = ref.rowptr[gr + 1];
         if (a1 - a0 != b1 - b0) { pattern_ok = false; break; }
         std::vector<std::pair<GOx, double> > row;
-        for (int64_t k = a0; k < a1; k++) row.push_back(std::make_pair(ours.colmap[ours.colind[k]], ours.values[k]));
+        for (int64_t k = a0; k < a1; k++) row.push_back(std::make_pair(colmap[colind[k]], values[k]));
         std::sort(row.begin(), row.end());
         for (int64_t k = 0; k < a1 - a0; k++) {
             if (row[k].first != ref.col[b0 + k]) { pattern_ok = false; break; }
@@ -107,7 +111,7 @@ static bool compare(const char *name, const Csr_t &ours, const RefCsr &ref, cons
     }
     const double err = std::sqrt(num) / (den > 0 ? std::sqrt(den) : 1.0);
     const bool ok = pattern_ok && err <= 1e-12;
-    std::printf("%-28s nnz %10lld  pattern %s  rel.Frobenius %.3e  %s\n", name, (long long)ours.values.size(),
+    std::printf("%-28s nnz %10lld  pattern %s  rel.Frobenius %.3e  %s\n", name, (long long)ours.nnz,
                 pattern_ok ? "exact" : "MISMATCH", err, ok ? "PASS" : "FAIL");
     return ok;
 }
