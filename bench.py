@@ -171,6 +171,46 @@ def ns_jacobian_numbers(ctx, M, peak):
     return ns_block_numbers(ctx, conn, coords, (M + 1) ** 3, f"structured P2-P1 cube H/h={M}", peak)
 
 
+def laplace_numbers(ctx, dim, fe, M, label, peak, steps=10):
+    """BASELINE.json configs 1 and 2: scalar Laplace (FE::assemblyLaplace) on the built-in structured mesh; config 1 (P1 square,
+    ~1e5 triangles) is the launch-latency case, config 2 (P2 cube, 6M tets) the bandwidth case."""
+    import torch
+    from feddlib_b200 import BLOCK_SCALAR, Mesh, Pattern
+    from feddlib_b200 import mesh as PM
+    conn, coords, _ = PM.build_structured(dim, fe, 1, M)
+    t0 = time.perf_counter()
+    mesh = Mesh(ctx, dim, conn, coords)
+    pat = Pattern(ctx, mesh)
+    ctx.synchronize()
+    t_pat = time.perf_counter() - t0
+    nnz = pat.nnz(1, 1, BLOCK_SCALAR)
+    v = ctx.empty_values(nnz)
+    for _ in range(3):
+        pat.assemble_laplace_d(v, False)
+    torch.cuda.synchronize()
+    l0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        pat.assemble_laplace_d(v, False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        pat.assemble_laplace_d(v, False)
+    torch.cuda.synchronize()
+    wall_us = (time.perf_counter() - t0) / steps * 1e6
+    ne = conn.shape[0]
+    alg = ne * conn.shape[1] * 4 + (M + 1) ** dim * dim * 8 + nnz * 8
+    out = {"workload": f"{label}: Laplace {fe} on the structured {'square' if dim == 2 else 'cube'} H/h={M}, {ne} elements, nnz {nnz}",
+           "ms": ms, "us_per_assembly_wall": wall_us, "elements_per_s": ne / (ms * 1e-3), "hbm_frac": alg / (ms * 1e-3) / 1e9 / peak,
+           "algorithmic_bytes": alg, "launches": (ctx.launches - l0) // steps, "pattern_build_s": t_pat,
+           "checksum": float(v[: min(nnz, 1 << 20)].sum().item())}
+    del v, pat, mesh
+    return out
+
+
 def config4_numbers(ctx, levels, peak):
     """BASELINE.json config 4: the Navier-Stokes blocks on meshes/DFG3DCylinder_6k.mesh (27 618 tets; committed as
     tests/golden/dfg3d_6k.npz, the reference tree is absent on the GPU box) after `levels` regular refinements
@@ -390,8 +430,6 @@ def main():
         # fill-complete host CSR in a pooled page-locked buffer out); N = 1 only, the binary is built by build()
         exe = os.path.join(ROOT, "feddlib_b200", "bench_fe_b200")
         if world == 1 and os.path.exists(exe):
-            del values
-            torch.cuda.empty_cache()
             try:
                 r = subprocess.run([exe, str(M), str(max(2, args.e2e_steps)), str(local_rank)], capture_output=True, text=True, timeout=600)
                 cpp = json.loads(r.stdout.strip().splitlines()[-1])
@@ -402,15 +440,16 @@ def main():
                                            "assembly + CSR values D2H into a pooled page-locked buffer owned by the returned matrix"}
             except Exception as exc:  # noqa: BLE001
                 e2e["cpp_host"] = {"error": str(exc)[:200]}
-            values = ctx.empty_values(nnz)
     else:
         checksum = float(values[: min(nnz, 1 << 20)].sum().item())
 
     # secondary numbers (not the headline): the Navier-Stokes blocks of config 4 on a structured P2-P1 cube, same engine
-    ns_extra = cfg4 = None
+    ns_extra = cfg4 = cfg12 = None
     if world == 1 and not args.no_ns:
         ns_extra = ns_jacobian_numbers(ctx, args.ns_M, peak)
         cfg4 = config4_numbers(ctx, args.cfg4_levels, peak)
+        cfg12 = {"config1": laplace_numbers(ctx, 2, "P1", 224, "config 1", peak, steps=50),
+                 "config2": laplace_numbers(ctx, 3, "P2", 100, "config 2", peak)}
 
     cpu_baseline = None
     if rank == 0:
@@ -443,6 +482,8 @@ def main():
             line["navier_stokes_blocks"] = ns_extra
         if cfg4:
             line["config4_navier_stokes_dfg3d"] = cfg4
+        if cfg12:
+            line["laplace_configs_1_2"] = cfg12
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
