@@ -18,6 +18,25 @@ int elem_index(int dim, int nloc)
     return -1;
 }
 
+// raises the dynamic shared-memory limit of a kernel and asks for its residency once per (kernel, block size, shared memory)
+// and context; per_sm may be null (attribute only)
+template <class K>
+int kernel_cfg(feddb200_ctx *c, K kernel, int nt, size_t smem, size_t budget, int *per_sm)
+{
+    const void *f = reinterpret_cast<const void *>(kernel);
+    const size_t key_smem = per_sm ? smem : (size_t)-1;
+    for (const feddb200_ctx::OccEntry &e : c->occ_cache)
+        if (e.f == f && e.nt == nt && e.smem == key_smem) { if (per_sm) *per_sm = e.per_sm; return FEDDB200_OK; }
+    FB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+    int v = 1;
+    if (per_sm) { FB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, nt, smem)); *per_sm = v; }
+    c->occ_cache.push_back({f, nt, key_smem, v});
+    return FEDDB200_OK;
+}
+
+// tuning knob from the environment, read once per call site
+#define FB_ENV_INT(NAME, DEFAULT) ([] { static const int v = [] { const char *f = getenv(NAME); return f ? atoi(f) : (DEFAULT); }(); return v; }())
+
 // device copy of the operator tables, cached per context slot
 int get_tables(feddb200_ctx *c, int op, int dim, int nv, int np, const OpTables **out_d, OpTables *out_h = nullptr)
 {
@@ -316,6 +335,10 @@ int ensure_gather(feddb200_pat *p)
         p->buckets.push_back({(int)(rtype[perm[s]] & 3), perm[s] >= p->n_owned ? 1 : 0, cap(perm[s]), s, e - s});
         s = e;
     }
+    p->bucket_order.resize(p->buckets.size());
+    for (size_t i = 0; i < p->buckets.size(); i++) p->bucket_order[i] = (int)i;
+    std::stable_sort(p->bucket_order.begin(), p->bucket_order.end(), [&](int x, int y) {
+        return p->buckets[x].count * (int64_t)p->buckets[x].lcap > p->buckets[y].count * (int64_t)p->buckets[y].lcap; });
     {
         std::vector<int64_t> inc_ptr(n_rows + 1);
         FB_CUDA(cudaMemcpy(inc_ptr.data(), p->inc_ptr_d, sizeof(int64_t) * (n_rows + 1), cudaMemcpyDeviceToHost));
@@ -399,8 +422,7 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
     const size_t budget = c->smem_optin - 1024;
     // the bucket launches are independent of one another and can be forked over the side streams (measured on
     // B200: slower than back-to-back launches -- concurrent sweeps of the mesh compete for L2 -- so off by default)
-    int n_side = 0;
-    if (const char *f = getenv("FEDDB200_SIDE_STREAMS")) n_side = std::max(0, std::min(feddb200_ctx::kSide, atoi(f))); // tuning aid
+    int n_side = std::max(0, std::min(feddb200_ctx::kSide, FB_ENV_INT("FEDDB200_SIDE_STREAMS", 0))); // tuning aid
     if (p->buckets.size() < 2) n_side = 0;
     // ... except the SMALL buckets (boundary and corner rows: a handful of blocks that run for 5-50 us each on an
     // otherwise empty GPU): they go to one side stream and run underneath the large launches
@@ -410,9 +432,6 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
         FB_CUDA(cudaEventRecord(c->ev_fork, c->stream));
         for (int i = 0; i < std::max(n_side, 1); i++) FB_CUDA(cudaStreamWaitEvent(c->side[i], c->ev_fork, 0));
     }
-    std::vector<const Bucket *> order;
-    for (const Bucket &b : p->buckets) order.push_back(&b);
-    std::stable_sort(order.begin(), order.end(), [](const Bucket *x, const Bucket *y) { return x->count * (int64_t)x->lcap > y->count * (int64_t)y->lcap; });
     // star kernel: all fan / task tiles of the phase in one address-ordered persistent launch (star_kernels.cuh)
     bool star_done = false;
     if constexpr (DIM == 3 && NL == 10) {
@@ -431,9 +450,8 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
             const int nts = 64;
             const size_t smem_s = wb * (nts / 32);
             if (smem_s <= budget) {
-                FB_CUDA(cudaFuncSetAttribute(k_star<OPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
                 int per_sm = 1;
-                FB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_star<OPG>, nts, smem_s));
+                { const int rc_k = kernel_cfg(c, k_star<OPG>, nts, smem_s, budget, &per_sm); if (rc_k != FEDDB200_OK) return rc_k; }
                 for (int g = 1; g >= 0; g--) {   // ghost rows first
                     if (p->star_n[g] == 0) continue;
                     if ((phase == FEDDB200_ROWS_GHOST && g == 0) || (phase == FEDDB200_ROWS_OWNED && g == 1)) continue;
@@ -456,8 +474,8 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
         }
     }
     int turn = 0;
-    for (const Bucket *bp : order) {
-        const Bucket &b = *bp;
+    for (const int bi : p->bucket_order) {
+        const Bucket &b = p->buckets[bi];
         if ((phase == FEDDB200_ROWS_GHOST && !b.ghost) || (phase == FEDDB200_ROWS_OWNED && b.ghost)) continue;
         if (star_done && b.in_star) continue;
         cudaStream_t st = n_side > 0 ? c->side[turn++ % n_side] : ((aside && b.count <= kSmallBucketRows) ? c->side[0] : c->stream);
@@ -486,9 +504,8 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
                     const size_t smem_f = (wd * 8 + kFanStageB) * (ntf / 32);
                     if (smem_f <= budget) {
                         auto launch_fan = [&](auto kernel) -> int {
-                            FB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
                             int per_sm = 1;
-                            FB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, ntf, smem_f));
+                            { const int rc_k = kernel_cfg(c, kernel, ntf, smem_f, budget, &per_sm); if (rc_k != FEDDB200_OK) return rc_k; }
                             const int64_t blocks_f = std::min<int64_t>((F.ntiles + ntf / 32 - 1) / (ntf / 32), (int64_t)std::max(per_sm, 1) * c->sm_count);
                             kernel<<<(unsigned)blocks_f, ntf, smem_f, st>>>(F);
                             c->launches++;
@@ -500,8 +517,7 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
                         continue;
                     }
                 }
-                int nt = 64;
-                if (const char *f = getenv("FEDDB200_RING_NT")) nt = std::max(32, std::min(64, atoi(f) & ~31)); // tuning aid
+                const int nt = std::max(32, std::min(64, FB_ENV_INT("FEDDB200_RING_NT", 64) & ~31)); // tuning aid
                 const int npt = 32 / TPR;                       // row nodes per warp tile
                 // node pitch: room for the TPR dof rows + the phase shift; among the next candidates the one with the fewest
                 // bank conflicts when the threads of a half-warp store to the same position of their rows
@@ -517,12 +533,10 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
                 G.pitch = pitch;
                 const int64_t tiles = ((b.count + npt - 1) / npt + nt / 32 - 1) / (nt / 32); // in blocks
                 FB_LOGIC(smem > budget, "row too long for the gather path's shared-memory rows; use the coloured or atomic mode");
-                FB_CUDA(cudaFuncSetAttribute(k_ring<OPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
                 // persistent blocks: as many as are resident at once (times a small factor that evens out the tail)
                 int per_sm = 1;
-                FB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ring<OPG>, nt, smem));
-                int waves = 1;
-                if (const char *f = getenv("FEDDB200_RING_WAVES")) waves = std::max(1, atoi(f)); // tuning aid
+                { const int rc_k = kernel_cfg(c, k_ring<OPG>, nt, smem, budget, &per_sm); if (rc_k != FEDDB200_OK) return rc_k; }
+                const int waves = std::max(1, FB_ENV_INT("FEDDB200_RING_WAVES", 1)); // tuning aid
                 const int64_t blocks = std::min<int64_t>(tiles, (int64_t)std::max(per_sm, 1) * c->sm_count * waves);
                 k_ring<OPG><<<(unsigned)blocks, nt, smem, st>>>(G);
                 c->launches++;
@@ -543,9 +557,8 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
                     const int ntk = 64;
                     const size_t smem_t = task_warp_bytes(b.npt, T.G.pitch, T.max_tets, T.max_passes) * (ntk / 32);
                     if (smem_t <= budget) {
-                        FB_CUDA(cudaFuncSetAttribute(k_task<OPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
                         int per_sm = 1;
-                        FB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_task<OPG>, ntk, smem_t));
+                        { const int rc_k = kernel_cfg(c, k_task<OPG>, ntk, smem_t, budget, &per_sm); if (rc_k != FEDDB200_OK) return rc_k; }
                         const int64_t blocks_t = std::min<int64_t>((b.tile_count + ntk / 32 - 1) / (ntk / 32), (int64_t)std::max(per_sm, 1) * c->sm_count);
                         k_task<OPG><<<(unsigned)blocks_t, ntk, smem_t, st>>>(T);
                         c->launches++;
@@ -564,13 +577,11 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
             if constexpr (OPG == 1 && DIM == 3 && NL == 10) {
                 // vertex-node rows of 3D P2 elasticity: streamed inputs (k_gather_s), 3 row nodes per warp
                 static const bool stream_ok = [] { const char *f = getenv("FEDDB200_GATHER_STREAM"); return !f || atoi(f) != 0; }(); // tuning aid
-                int nts = 64;
-                if (const char *f = getenv("FEDDB200_GATHER_NT")) nts = std::max(32, std::min(128, atoi(f) & ~31)); // tuning aid
+                const int nts = std::max(32, std::min(128, FB_ENV_INT("FEDDB200_GATHER_NT", 64) & ~31)); // tuning aid
                 const size_t smem_s = ((((size_t)pitch * 8 * 9 + 15) & ~(size_t)15) + 3 * kRsNodeB) * (nts / 32);
                 if (stream_ok && b.type == 0 && p->ahead_d && smem_s <= budget) {
-                    FB_CUDA(cudaFuncSetAttribute(k_gather_s, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
                     int per_sm = 1;
-                    FB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gather_s, nts, smem_s));
+                    { const int rc_k = kernel_cfg(c, k_gather_s, nts, smem_s, budget, &per_sm); if (rc_k != FEDDB200_OK) return rc_k; }
                     const int64_t tiles = ((b.count + 2) / 3 + nts / 32 - 1) / (nts / 32); // in blocks
                     const int64_t blocks_s = std::min<int64_t>(tiles, (int64_t)std::max(per_sm, 1) * c->sm_count);
                     k_gather_s<<<(unsigned)blocks_s, nts, smem_s, st>>>(G);
@@ -581,7 +592,7 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
             }
             const int64_t blocks = (b.count * S::CPR + nt - 1) / nt;
             auto launch = [&](auto kernel) -> int {
-                FB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+                { const int rc_k = kernel_cfg(c, kernel, 0, 0, budget, nullptr); if (rc_k != FEDDB200_OK) return rc_k; }
                 kernel<<<(unsigned)blocks, nt, smem, st>>>(G);
                 c->launches++;
                 FB_CUDA(cudaGetLastError());
@@ -692,11 +703,8 @@ int launch_gatherx_t(feddb200_ctx *c, feddb200_pat *p, const feddb200_mesh *vm, 
         FB_CUDA(cudaEventRecord(c->ev_fork, c->stream));
         FB_CUDA(cudaStreamWaitEvent(c->side[0], c->ev_fork, 0));
     }
-    std::vector<const Bucket *> order;
-    for (const Bucket &b : p->buckets) order.push_back(&b);
-    std::stable_sort(order.begin(), order.end(), [](const Bucket *x, const Bucket *y) { return x->count * (int64_t)x->lcap > y->count * (int64_t)y->lcap; });
-    for (const Bucket *bp : order) {
-        const Bucket &b = *bp;
+    for (const int bi : p->bucket_order) {
+        const Bucket &b = p->buckets[bi];
         if ((c->row_phase == FEDDB200_ROWS_GHOST && !b.ghost) || (c->row_phase == FEDDB200_ROWS_OWNED && b.ghost)) continue;
         cudaStream_t st = (aside && b.count <= kSmallBucketRows) ? c->side[0] : c->stream;
         G.start = b.start; G.count = b.count;
@@ -707,7 +715,7 @@ int launch_gatherx_t(feddb200_ctx *c, feddb200_pat *p, const feddb200_mesh *vm, 
         FB_LOGIC(smem > budget, "row too long for the gather path's shared-memory accumulators; use the coloured or atomic mode");
         const int64_t blocks = (b.count * S::RD + nt - 1) / nt;
         auto launch = [&](auto kernel) -> int {
-            FB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+            { const int rc_k = kernel_cfg(c, kernel, 0, 0, budget, nullptr); if (rc_k != FEDDB200_OK) return rc_k; }
             kernel<<<(unsigned)blocks, nt, smem, st>>>(G);
             c->launches++;
             FB_CUDA(cudaGetLastError());
@@ -828,7 +836,7 @@ int run_op(feddb200_ctx *c, const feddb200_pat *pc, int op, const double *u_d, d
     if (coef_d && mode == FEDDB200_SCATTER_GATHER) mode = FEDDB200_SCATTER_COLOURED;
     if (mode == FEDDB200_SCATTER_GATHER && !(op == OP_LAP || op == OP_ELAS)) {
         int handled = 0;
-        if (getenv("FEDDB200_NO_GATHERX") == nullptr) { // tuning aid
+        if (FB_ENV_INT("FEDDB200_NO_GATHERX", 0) == 0) { // tuning aid
             rc = launch_gatherx(c, p, op, vm, u_d, c0, c1, c2, values_d, (op == OP_MASS && vec_field) ? dim : 0, &handled);
             if (rc != FEDDB200_OK || handled) return rc;
         }

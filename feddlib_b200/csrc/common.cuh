@@ -85,6 +85,10 @@ struct feddb200_ctx {
     int64_t ghost_seg_begin[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     double *ghost_seg_ptr[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t scratch_bytes[2] = {0, 0};
+    // kernels whose shared-memory attribute has been raised / whose occupancy has been queried on this context (per call
+    // these driver queries cost more than a small assembly)
+    struct OccEntry { const void *f; int nt; size_t smem; int per_sm; };
+    std::vector<OccEntry> occ_cache;
 };
 
 struct feddb200_mesh {
@@ -126,6 +130,7 @@ struct feddb200_pat {
     double *dt_d = nullptr;        // [ne][dim][dim][4] |det| * grad u at the element's vertices
     bool gather_ready = false;
     std::vector<fb::Bucket> buckets;
+    std::vector<int> bucket_order;   // launch order of the buckets (largest first), fixed with the gather maps
     // element colouring (lazy)
     int n_colours = 0;
     std::vector<int64_t> colour_ptr;

@@ -621,7 +621,7 @@ namespace fb {
 // =========================================================================================
 struct StarArgs {
     GatherArgs G;            // geom, values, c0/c1, R, vec_dim, ghost segments
-    const uint4 *tiles;      // [n_tiles] x = kind | W << 8 | npt << 16, y = index of the tile in its array, z = node pitch (doubles)
+    const uint4 *tiles;      // [n_tiles] x = kind | W << 8 | npt << 16, y = index of the tile in its array, z = row capacity (nodes) of its bucket
     int64_t n_tiles;
     const uint4 *fanrec;     // fan tiles: [index][32 lanes][2 x 16 bytes]   (k_fan_records)
     const uint4 *tileblk;    // task tiles: [index][25 x 16 bytes]           (k_task_build)
@@ -929,7 +929,9 @@ __global__ void __launch_bounds__(64, 8) k_star(const StarArgs A)
         const int64_t i_n = i + step;
         uint4 e_n = make_uint4(0u, 0u, 0u, 0u);
         if (i_n < A.n_tiles) e_n = __ldg(A.tiles + i_n);
-        const int kind = e.x & 0xff, w = (e.x >> 8) & 0xff, npt = (e.x >> 16) & 0xff, pitch = (int)e.z;
+        constexpr int BS = OPG == 1 ? 9 : 1;                       // values per node block
+        const int kind = e.x & 0xff, w = (e.x >> 8) & 0xff, npt = (e.x >> 16) & 0xff;
+        const int pitch = (BS * (int)e.z + 2) & ~1;              // e.z: row capacity of the tile's bucket (nodes); even pitch
         if (kind == 0) star_task_tile<OPG>(A, A.tileblk + (int64_t)e.y * kTileBlkChunks, rows, pitch, npt);
         else if (w == 6) star_fan_tile<OPG, 6>(A, A.fanrec + (int64_t)e.y * 64, rows, pitch, w);
         else if (w == 4) star_fan_tile<OPG, 4>(A, A.fanrec + (int64_t)e.y * 64, rows, pitch, w);
