@@ -138,7 +138,10 @@ int build_task_programs(feddb200_pat *p, const std::vector<RowInfo> &info)
         int max_ninc = 0;
         for (int64_t q = b.start; q < b.start + b.count; q++) max_ninc = std::max(max_ninc, info[q].ninc);
         if (max_ninc > kTaskMaxTets) continue;
-        b.npt = std::max(1, std::min(kTaskMaxNodes, kTaskMaxTets / std::max(1, max_ninc)));
+        // row nodes per tile: as many as the element slots allow, but the tile's shared-memory rows (elasticity: 9 lcap + 2
+        // doubles per node) stay within the ~5 KB of the interior vertex rows, so small boundary buckets do not set the
+        // shared memory per warp (and with it the residency) of the star kernel
+        b.npt = std::max(1, std::min({kTaskMaxNodes, kTaskMaxTets / std::max(1, max_ninc), 5120 / (72 * b.lcap + 16)}));
         b.tile_start = (int64_t)tiles.size();
         for (int64_t q = b.start; q < b.start + b.count;) {
             TaskTile t;
