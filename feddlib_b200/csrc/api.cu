@@ -117,11 +117,13 @@ int launch_elem_op(feddb200_ctx *c, int op, int dim, int nr, int nc, ElemArgs &A
 // gather path preparation (lazy, once per pattern): canonical position map, row types,
 // (type, length) buckets
 // ---------------------------------------------------------------------------------------
-// the star kernel (k_star: all fan and task tiles of an assembly in one address-ordered pass) is the default path of 3D P2;
-// FEDDB200_STAR=0 goes back to one launch per bucket (tuning aid)
+// the star kernel (k_star: all fan and task tiles of an assembly in one address-ordered pass) is an alternative path of 3D P2,
+// selected with FEDDB200_STAR=1.  Measured on B200 (config 3): 3.4 ms against 2.49 ms for one launch per bucket -- the three
+// tile bodies do not fit the instruction caches together (ncu: 3.3 no-instruction stall cycles per issue), which costs more
+// than the address-ordered writes gain.
 bool star_enabled()
 {
-    static const bool on = [] { const char *f = getenv("FEDDB200_STAR"); return !f || atoi(f) != 0; }();
+    static const bool on = [] { const char *f = getenv("FEDDB200_STAR"); return f && atoi(f) != 0; }();
     return on;
 }
 
@@ -315,7 +317,18 @@ int ensure_gather(feddb200_pat *p)
     // signature) are adjacent, so the threads of a warp address their accumulator rows identically
     std::vector<int32_t> perm(n_rows);
     for (int64_t r = 0; r < n_rows; r++) perm[r] = (int32_t)r;
-    auto cap = [&](int64_t r) { const int l = (int)(p->rowptr_h[r + 1] - p->rowptr_h[r]); return std::max(4, (l + 3) & ~3); };
+    // FEDDB200_MERGE_RING=1 (tuning aid): all ring-ordered edge rows in ONE bucket, so one launch sweeps 72 % of the matrix in
+    // address order instead of one launch per row length
+    const bool merge_ring = FB_ENV_INT("FEDDB200_MERGE_RING", 0) != 0;
+    int ring_cap = 4;
+    if (merge_ring)
+        for (int64_t r = 0; r < n_rows; r++)
+            if ((rtype[r] & 3) == 1) ring_cap = std::max(ring_cap, ((int)(p->rowptr_h[r + 1] - p->rowptr_h[r]) + 3) & ~3);
+    auto cap = [&](int64_t r) {
+        if (merge_ring && (rtype[r] & 3) == 1) return ring_cap;
+        const int l = (int)(p->rowptr_h[r + 1] - p->rowptr_h[r]);
+        return std::max(4, (l + 3) & ~3);
+    };
     auto key = [&](int32_t r) { return (int64_t)(r >= p->n_owned ? 0 : 1) * 1000000 + (int64_t)(rtype[r] & 3) * 100000 + cap(r); };
     // ... but only inside chunks of consecutive rows, so that a launch still sweeps the mesh (and the geometry
     // lines in L2) once instead of once per stencil class

@@ -289,7 +289,7 @@ extern "C" int feddb200_halo_split_sizes(const feddb200_halo *H, int rd, int cd,
 // element (a, q, b) to  f * base_I + a * per * L_I + per * p + b  (per = values per column node in a dof row).
 extern "C" int feddb200_halo_recv_slots(const feddb200_halo *H, int rd, int cd, int mode, int64_t *slots)
 {
-    HL_LOGIC(!H || !slots, "feddb200_halo_recv_slots: null argument");
+    HL_LOGIC(!H || (!slots && !H->recv_row.empty()), "feddb200_halo_recv_slots: null argument");
     const int f = factor_of(rd, cd, mode);
     const int per = mode == FEDDB200_BLOCK_FULL ? cd : 1;
     const int nrow_dofs = mode == FEDDB200_BLOCK_SCALAR ? 1 : rd;

@@ -198,3 +198,35 @@ def test_multi_gpu_exchange_if_available():
                           "--master-addr", "127.0.0.1", "--master-port", "29561",
                           os.path.join(root, "tests", "dist_gpu_check.py")], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+def test_alternative_star_kernels_in_a_subprocess():
+    """k_fan (FEDDB200_FAN=1) and k_star (FEDDB200_STAR=1) are alternative row kernels of 3D P2 that are off by default (their
+    knobs are read once per process): the same parity check as the default path, in a child process per setting."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from util import TOL, mesh_structured, mesh_dfg, oracle_csr, rel_frobenius
+from feddlib_b200 import BLOCK_FULL, BLOCK_SCALAR, Context, Mesh, Pattern
+ctx = Context(0)
+for name, make in (("cube", lambda: mesh_structured(3, "P2", 4)), ("warp", lambda: mesh_structured(3, "P2", 3, warp=True, shuffle=True, seed=5)),
+                   ("dfg", lambda: mesh_dfg("P2"))):
+    conn, coords = make()
+    pat = Pattern(ctx, Mesh(ctx, 3, conn, coords))
+    l0 = ctx.launches
+    for op, vals, rd, mode, kw in (("linelas", pat.assemble_linelas(8e6, 2e6), 3, BLOCK_FULL, dict(lam=8e6, mu=2e6)),
+                                   ("laplace", pat.assemble_laplace(False), 1, BLOCK_SCALAR, {})):
+        rp_o, ci_o, v_o = oracle_csr(op, 3, "P2", conn, coords, **kw)
+        rp, ci = pat.expand(rd, rd, mode)
+        assert np.array_equal(rp, rp_o) and np.array_equal(ci, ci_o), (name, op)
+        err = rel_frobenius(vals, v_o)
+        assert err <= TOL, (name, op, err)
+print("ok")
+''' % (root, os.path.join(root, "tests"))
+    for env in ({"FEDDB200_FAN": "1"}, {"FEDDB200_STAR": "1"}, {"FEDDB200_TASK": "0"}):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0 and "ok" in r.stdout, (env, r.stdout[-500:], r.stderr[-1500:])
