@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "feddb200.h"
+#include "feddb200_halo.h"
 
 namespace FEDD {
 namespace b200 {
@@ -171,6 +172,7 @@ class FE_b200 {
     ~FE_b200()
     {
         pool_->retire();
+        for (auto &kv : plans_) feddb200_halo_free(kv.second->halo);
         for (auto &kv : pats_) feddb200_pat_free(kv.second);
         for (auto &s : slots_) feddb200_mesh_free(s.mesh);
         feddb200_destroy(ctx_);
@@ -201,6 +203,22 @@ class FE_b200 {
         b200::check(feddb200_mesh_upload(ctx_, &s.mesh, s.dim, s.nloc, s.ne, conn.data(), s.nn, xyz.data()));
         slots_.push_back(s);
     }
+
+    // Multi-rank use (one FE_b200 per rank / GPU).  The communicator is two callbacks (include/feddb200_halo.h): an MPI build
+    // passes MPI_Alltoallv on the problem's Teuchos communicator, the tests an in-process one.  Set it BEFORE addFE, and
+    // register every domain with the rank that owns each repeated node (the unique map of the reference:
+    // Map::buildUniqueMap, core/LinearAlgebra/Map_def.hpp:184-212; with Trilinos: mapUnique->getRemoteIndexList).
+    // Rows then live on the unique map, columns on the Tpetra column map (owned, then remotes by (owner, gid)), and every
+    // assembly ends with the host-side globalAssemble of Matrix::fillComplete (Matrix_def.hpp:192-199): the entries this
+    // rank computed for rows of other ranks travel to their owners and are added there.
+    void setCommunicator(const feddb200_comm &comm) { comm_ = comm; }
+    void addFE(DomainConstPtr_Type domain, const std::vector<int> &ownerRanks)
+    {
+        addFE(domain);
+        if ((std::int64_t)ownerRanks.size() != slots_.back().nn) throw std::logic_error("addFE: one owner rank per repeated node");
+        slots_.back().owner.assign(ownerRanks.begin(), ownerRanks.end());
+    }
+    int numRanks() const { return comm_.size; }
 
     // re-reads the points of a registered domain and uploads them (moving meshes: the Geometry / FSI problems displace the
     // mesh between assemblies, problems/specific/FSI_def.hpp; connectivity and pattern stay)
@@ -274,6 +292,7 @@ class FE_b200 {
         expand(p, loc, dim, dim, FEDDB200_BLOCK_FULL, csr);
         if (constant) b200::check(feddb200_assemble_stress(ctx_, p, ne ? coef[0] : 1.0, nullptr, 0, csr.values.get()));
         else b200::check(feddb200_assemble_stress(ctx_, p, 1.0, coef.data(), (int64_t)coef.size(), csr.values.get()));
+        globalAssemble(p, dim, dim, FEDDB200_BLOCK_FULL, csr);
         seat_csr(A, csr, MapConstPtr_Type(), MapConstPtr_Type(), callFillComplete);
     }
 
@@ -287,6 +306,7 @@ class FE_b200 {
         b200::LocalCsr<SC, LO, GO> csr;
         expand(p, loc, 1, 1, FEDDB200_BLOCK_SCALAR, csr);
         b200::check(feddb200_assemble_bdstab(ctx_, p, csr.values.get()));
+        globalAssemble(p, 1, 1, FEDDB200_BLOCK_SCALAR, csr);
         seat_csr(A, csr, MapConstPtr_Type(), MapConstPtr_Type(), callFillComplete);
     }
 
@@ -302,6 +322,8 @@ class FE_b200 {
         if (vec) expand(p, loc, dim, dim, FEDDB200_BLOCK_DIAG, csr);
         else expand(p, loc, 1, 1, FEDDB200_BLOCK_SCALAR, csr);
         b200::check(feddb200_assemble_mass(ctx_, p, vec ? 1 : 0, csr.values.get()));
+        if (vec) globalAssemble(p, dim, dim, FEDDB200_BLOCK_DIAG, csr);
+        else globalAssemble(p, 1, 1, FEDDB200_BLOCK_SCALAR, csr);
         seat_csr(A, csr, MapConstPtr_Type(), MapConstPtr_Type(), callFillComplete);
     }
 
@@ -315,6 +337,7 @@ class FE_b200 {
         b200::LocalCsr<SC, LO, GO> csr;
         expand(p, loc, 1, 1, FEDDB200_BLOCK_SCALAR, csr);
         b200::check(feddb200_assemble_laplace(ctx_, p, 0, csr.values.get()));
+        globalAssemble(p, 1, 1, FEDDB200_BLOCK_SCALAR, csr);
         seat_csr(A, csr, MapConstPtr_Type(), MapConstPtr_Type(), callFillComplete);
     }
 
@@ -327,6 +350,7 @@ class FE_b200 {
         b200::LocalCsr<SC, LO, GO> csr;
         expand(p, loc, dim, dim, FEDDB200_BLOCK_DIAG, csr);
         b200::check(feddb200_assemble_laplace(ctx_, p, 1, csr.values.get()));
+        globalAssemble(p, dim, dim, FEDDB200_BLOCK_DIAG, csr);
         seat_csr(A, csr, MapConstPtr_Type(), MapConstPtr_Type(), callFillComplete);
     }
 
@@ -339,6 +363,7 @@ class FE_b200 {
         b200::LocalCsr<SC, LO, GO> csr;
         expand(p, loc, dim, dim, FEDDB200_BLOCK_FULL, csr);
         b200::check(feddb200_assemble_linelas(ctx_, p, lambda, mu, csr.values.get()));
+        globalAssemble(p, dim, dim, FEDDB200_BLOCK_FULL, csr);
         seat_csr(A, csr, MapConstPtr_Type(), MapConstPtr_Type(), callFillComplete);
     }
 
@@ -353,6 +378,7 @@ class FE_b200 {
         expand(p, loc, dim, dim, FEDDB200_BLOCK_DIAG, csr);
         Teuchos::ArrayRCP<const SC> uArray = u->getData(0);
         b200::check(feddb200_assemble_advection(ctx_, p, (uArray.size() ? &uArray[0] : nullptr), csr.values.get()));
+        globalAssemble(p, dim, dim, FEDDB200_BLOCK_DIAG, csr);
         seat_csr(A, csr, MapConstPtr_Type(), MapConstPtr_Type(), callFillComplete);
     }
 
@@ -366,6 +392,7 @@ class FE_b200 {
         expand(p, loc, dim, dim, FEDDB200_BLOCK_FULL, csr);
         Teuchos::ArrayRCP<const SC> uArray = u->getData(0);
         b200::check(feddb200_assemble_advection_in_u(ctx_, p, (uArray.size() ? &uArray[0] : nullptr), csr.values.get()));
+        globalAssemble(p, dim, dim, FEDDB200_BLOCK_FULL, csr);
         seat_csr(A, csr, MapConstPtr_Type(), MapConstPtr_Type(), callFillComplete);
     }
 
@@ -404,6 +431,7 @@ class FE_b200 {
         expand(p, loc, dim, dim, FEDDB200_BLOCK_FULL, csr);
         Teuchos::ArrayRCP<const SC> uArray = u->getData(0);
         b200::check(feddb200_assemble_ns_jacobian(ctx_, p, rho, nu, (uArray.size() ? &uArray[0] : nullptr), newton ? 1 : 0, csr.values.get()));
+        globalAssemble(p, dim, dim, FEDDB200_BLOCK_FULL, csr);
         seat_csr(A, csr, MapConstPtr_Type(), MapConstPtr_Type(), callFillComplete);
     }
 
@@ -427,7 +455,38 @@ class FE_b200 {
         int dim = 0, nloc = 0;
         std::int64_t ne = 0, nn = 0;
         std::string FEType;
+        std::vector<std::int32_t> owner;   // multi-rank: owning rank of every repeated node
     };
+
+    // multi-rank plan of one pattern + the state of its node-pattern callback
+    struct Plan {
+        FE_b200 *self = nullptr;
+        int loc = 0;
+        feddb200_halo *halo = nullptr;
+        feddb200_pat *pat = nullptr;          // pattern of the last callback (the final one stays)
+        std::vector<std::int64_t> rowptr;
+        std::vector<std::int32_t> colind;
+    };
+    static int pattern_callback(void *user, const std::int32_t *row_lid, std::int64_t n_rows, std::int64_t n_owned, const std::int32_t *col_lid,
+                                std::int64_t n_cols, const std::int32_t *extra_row, const std::int32_t *extra_col, std::int64_t n_extra,
+                                const std::int64_t **rowptr, const std::int32_t **colind)
+    {
+        Plan &P = *static_cast<Plan *>(user);
+        FE_b200 &F = *P.self;
+        if (P.pat) { feddb200_pat_free(P.pat); P.pat = nullptr; }
+        const feddb200_mesh *m = F.slots_[(std::size_t)P.loc].mesh;
+        int rc = feddb200_pattern_build(F.ctx_, &P.pat, m, m, n_rows, n_owned, row_lid, n_cols, col_lid, n_extra, extra_row, extra_col);
+        if (rc != FEDDB200_OK) return rc;
+        std::int64_t nnz = 0;
+        rc = feddb200_pattern_info(P.pat, nullptr, nullptr, nullptr, &nnz, nullptr, nullptr, nullptr);
+        if (rc != FEDDB200_OK) return rc;
+        P.rowptr.resize((std::size_t)n_rows + 1);
+        P.colind.resize((std::size_t)std::max<std::int64_t>(nnz, 1));
+        rc = feddb200_pattern_get_nodes(F.ctx_, P.pat, P.rowptr.data(), P.colind.data());
+        *rowptr = P.rowptr.data();
+        *colind = P.colind.data();
+        return rc;
+    }
 
     static int nloc_of(int dim, const std::string &fe)
     {
@@ -444,6 +503,20 @@ class FE_b200 {
         auto it = pats_.find(key);
         if (it != pats_.end()) return it->second;
         feddb200_pat *p = nullptr;
+        if (comm_.size > 1) {
+            if (rowLoc != colLoc)
+                throw std::logic_error("FE_b200: patterns over two FE spaces (B, B^T) are single-rank in this version");
+            Slot &s = slots_[(std::size_t)rowLoc];
+            if ((std::int64_t)s.owner.size() != s.nn) throw std::logic_error("FE_b200: multi-rank use needs addFE(domain, ownerRanks)");
+            std::unique_ptr<Plan> P(new Plan());
+            P->self = this; P->loc = rowLoc;
+            MapConstPtr_Type mapRep = s.domain->getMapRepeated();
+            std::vector<std::int64_t> gid((std::size_t)s.nn);
+            for (std::int64_t k = 0; k < s.nn; k++) gid[(std::size_t)k] = (std::int64_t)mapRep->getGlobalElement((LO)k);
+            b200::check(feddb200_halo_create(&P->halo, &comm_, s.nn, gid.data(), s.owner.data(), &FE_b200::pattern_callback, P.get()));
+            p = P->pat;
+            plans_[p] = std::move(P);
+        } else
         b200::check(feddb200_pattern_build(ctx_, &p, slots_[rowLoc].mesh, slots_[colLoc].mesh, 0, 0, nullptr, 0, nullptr, 0,
                                            nullptr, nullptr));
         pats_[key] = p;
@@ -457,23 +530,45 @@ class FE_b200 {
         const std::int64_t nnz = feddb200_pattern_nnz(p, rowDofs, colDofs, mode);
         const std::tuple<feddb200_pat *, int, int, int> key(p, rowDofs, colDofs, mode);
         auto it = structures_.find(key);
+        auto pl = plans_.find(p);
         if (it == structures_.end()) {
-            std::int64_t nRows = 0, nCols = 0;
-            b200::check(feddb200_pattern_info(p, &nRows, nullptr, &nCols, nullptr, nullptr, nullptr, nullptr));
+            std::int64_t nRows = 0, nCols = 0, nOwned = 0;
+            b200::check(feddb200_pattern_info(p, &nRows, &nOwned, &nCols, nullptr, nullptr, nullptr, nullptr));
             std::shared_ptr<b200::CsrStructure<GO> > st = std::make_shared<b200::CsrStructure<GO> >();
             st->rowptr.resize((std::size_t)nRows * rowDofs + 1);
             st->colind.resize((std::size_t)nnz);
             b200::check(feddb200_pattern_expand(ctx_, p, rowDofs, colDofs, mode, st->rowptr.data(), st->colind.data()));
-            MapConstPtr_Type mapRep = slots_[colLoc].domain->getMapRepeated();
-            st->colmap.resize((std::size_t)nCols * colDofs);
-            for (std::int64_t j = 0; j < nCols; j++)
-                for (int d = 0; d < colDofs; d++)
-                    st->colmap[(std::size_t)j * colDofs + d] = (GO)colDofs * mapRep->getGlobalElement((LO)j) + d;
+            if (pl == plans_.end()) {
+                MapConstPtr_Type mapRep = slots_[colLoc].domain->getMapRepeated();
+                st->colmap.resize((std::size_t)nCols * colDofs);
+                for (std::int64_t j = 0; j < nCols; j++)
+                    for (int d = 0; d < colDofs; d++)
+                        st->colmap[(std::size_t)j * colDofs + d] = (GO)colDofs * mapRep->getGlobalElement((LO)j) + d;
+            } else {
+                // multi-rank: the matrix has the OWNED rows (unique map) and the columns of the Tpetra column map; the ghost
+                // rows behind them only exist in the value buffer until the globalAssemble step has shipped them
+                const std::int64_t nnzOwned = feddb200_pattern_nnz_owned(p, rowDofs, colDofs, mode);
+                st->rowptr.resize((std::size_t)nOwned * rowDofs + 1);
+                st->colind.resize((std::size_t)nnzOwned);
+                std::int64_t nColmap = 0;
+                const std::int64_t *cg = static_cast<const std::int64_t *>(feddb200_halo_array(pl->second->halo, 4, &nColmap));
+                st->colmap.resize((std::size_t)nColmap * colDofs);
+                for (std::int64_t j = 0; j < nColmap; j++)
+                    for (int d = 0; d < colDofs; d++) st->colmap[(std::size_t)j * colDofs + d] = (GO)colDofs * (GO)cg[j] + d;
+            }
             it = structures_.insert(std::make_pair(key, std::shared_ptr<const b200::CsrStructure<GO> >(st))).first;
         }
         csr.pattern = it->second;
-        csr.nnz = (std::size_t)nnz;
-        csr.values = pool_->take(csr.nnz);
+        csr.values = pool_->take((std::size_t)nnz);     // owned + ghost values
+        csr.nnz = pl == plans_.end() ? (std::size_t)nnz : (std::size_t)feddb200_pattern_nnz_owned(p, rowDofs, colDofs, mode);
+    }
+
+    // the globalAssemble step of Matrix::fillComplete (multi-rank): ghost-row values to their owners, added there
+    void globalAssemble(feddb200_pat *p, int rowDofs, int colDofs, int mode, b200::LocalCsr<SC, LO, GO> &csr)
+    {
+        auto pl = plans_.find(p);
+        if (pl == plans_.end()) return;
+        b200::check(feddb200_halo_export_add(pl->second->halo, &comm_, rowDofs, colDofs, mode, (std::int64_t)csr.nnz, csr.values.get()));
     }
 
     feddb200_ctx *ctx_;
@@ -481,6 +576,8 @@ class FE_b200 {
     std::map<std::pair<int, int>, feddb200_pat *> pats_;
     std::map<std::tuple<feddb200_pat *, int, int, int>, std::shared_ptr<const b200::CsrStructure<GO> > > structures_;
     std::shared_ptr<b200::PinnedPool> pool_;
+    feddb200_comm comm_ = {nullptr, 0, 1, nullptr};
+    std::map<feddb200_pat *, std::unique_ptr<Plan> > plans_;
 };
 
 } // namespace FEDD
