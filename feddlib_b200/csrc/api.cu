@@ -850,6 +850,13 @@ int run_op(feddb200_ctx *c, const feddb200_pat *pc, int op, const double *u_d, d
     int mode = c->mode;
     // a coefficient that varies inside the elements needs the quadrature loop of the element-row kernels
     if (coef_d && mode == FEDDB200_SCATTER_GATHER) mode = FEDDB200_SCATTER_COLOURED;
+    // ghost targets (feddb200_set_ghost_targets): only the row-gather kernels of the Laplace / elasticity operators store their
+    // ghost rows through out_ptr into the owners' buffers; every other path would leave those buffers untouched and the owners
+    // would add stale data -- refuse instead of assembling a wrong matrix
+    FB_LOGIC(c->n_ghost_seg > 0 && c->row_phase != FEDDB200_ROWS_OWNED &&
+                 !(mode == FEDDB200_SCATTER_GATHER && (op == OP_LAP || op == OP_ELAS) && !coef_d && rm->nloc == cm->nloc),
+             "assembly: ghost targets are set, but this operator / scatter mode does not store ghost rows to peer memory; "
+             "use the NCCL exchange (assemble_overlapped) for it");
     if (mode == FEDDB200_SCATTER_GATHER && !(op == OP_LAP || op == OP_ELAS)) {
         int handled = 0;
         if (FB_ENV_INT("FEDDB200_NO_GATHERX", 0) == 0) { // tuning aid

@@ -269,6 +269,9 @@ extern "C" const void *feddb200_halo_array(const feddb200_halo *H, int which, in
     case 13: HL_ARR(H->recv_pos);
     case 14: HL_ARR(H->recv_len_sender);
     case 15: HL_ARR(H->recv_q);
+    case 16: HL_ARR(H->imp_send_rows);
+    case 17: HL_ARR(H->imp_send_counts);
+    case 18: HL_ARR(H->rep_of_row);
     }
 #undef HL_ARR
     return nullptr;

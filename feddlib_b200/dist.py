@@ -292,13 +292,47 @@ class DistributedMatrixAssembler:
             return pat.nodes()
 
         dev = torch.device(f"cuda:{ctx.device}")
-        self.plan = HaloPlan(Comm(rank, size, dev), gid_rep, owner, pattern_fn)
+        # the plan is built by the C++ host code a FEDDLib build links (halo.cpp); HaloPlan (numpy) is its executable
+        # specification in the CPU tests
+        from .halo import NativeHaloPlan
+        self.plan = NativeHaloPlan(Comm(rank, size, dev), gid_rep, owner, pattern_fn)
         self.pat = self._pats[-1]
         for p in self._pats[:-1]:
             p.close()
         self._dev = dev
         self._slot_t = {}
         self._recv_buf = {}
+
+    def _main_stream(self):
+        """The stream the engine launches on (bound in Context.__init__): the exchange is ordered against IT, not against whatever
+        torch's current stream happens to be when the call is made."""
+        import torch
+        s = getattr(self.ctx, "torch_stream", None)
+        return s if s is not None else torch.cuda.current_stream(self._dev)
+
+    def import_vector(self, u_unique, dofs):
+        """MultiVector::importFromVector (core/LinearAlgebra/MultiVector_def.hpp:258-294), unique -> repeated, on the device: the
+        velocity of the advection operators lives on the unique map between Newton steps and is read on the repeated map
+        (problems/specific/NavierStokes_def.hpp:294).  u_unique: [dofs * n_owned] device tensor in unique-map order; returns the
+        [dofs * nn] repeated vector.  One all-to-all-v of dofs * 8 bytes per ghost node."""
+        import torch
+        import torch.distributed as dist
+        plan = self.plan
+        nn = plan.gid_rep.size
+        if not hasattr(self, "_imp"):
+            rep = torch.from_numpy(np.asarray(plan.rep_of_row, dtype=np.int64)).to(self._dev)
+            self._imp = {"rep": rep, "send_rows": torch.from_numpy(np.asarray(plan.import_send_rows, dtype=np.int64)).to(self._dev)}
+        u2 = u_unique.reshape(-1, dofs)
+        out = torch.empty((nn, dofs), dtype=torch.float64, device=self._dev)
+        out[self._imp["rep"][: plan.n_owned]] = u2
+        if self.size > 1:
+            send = u2[self._imp["send_rows"]].contiguous()
+            ssz = [int(x) for x in plan.import_send_counts]
+            rsz = [int((plan.ghost_row_owner == d).sum()) for d in range(self.size)]
+            recv = torch.empty((plan.n_ghost, dofs), dtype=torch.float64, device=self._dev)
+            dist.all_to_all_single(recv, send, rsz, ssz)
+            out[self._imp["rep"][plan.n_owned:]] = recv
+        return out.reshape(-1)
 
     def _exchange_buffers(self, rd, cd, mode):
         import torch
@@ -321,7 +355,7 @@ class DistributedMatrixAssembler:
             self._side = torch.cuda.Stream(device=self._dev)
         ssz, rsz = self.plan.split_sizes(rd, cd, mode)
         send, recv = values[self.pat.nnz_owned(rd, cd, mode):], self._recv_buf[key]
-        main = torch.cuda.current_stream(self._dev)
+        main = self._main_stream()
         self.ctx.set_row_phase(1)
         try:
             assemble()                      # geometry pre-pass + ghost rows
@@ -383,7 +417,7 @@ class DistributedMatrixAssembler:
         if getattr(self, "_side", None) is None:
             self._side = torch.cuda.Stream(device=self._dev)
         _, rsz = self.plan.split_sizes(rd, cd, mode)
-        main = torch.cuda.current_stream(self._dev)
+        main = self._main_stream()
         self.ctx.set_ghost_targets(P["seg_begin"], P["seg_ptr"][par])
         self.ctx.set_row_phase(1)
         try:

@@ -32,8 +32,8 @@ class Context:
     def bind_torch_stream(self):
         """Run the engine's kernels on torch's current CUDA stream so torch events time them."""
         import torch
-        s = torch.cuda.current_stream(self.device).cuda_stream
-        check(self._L.feddb200_set_stream(self._h, C.c_void_p(s)))
+        self.torch_stream = torch.cuda.current_stream(self.device)   # the stream the engine launches on, as a torch object
+        check(self._L.feddb200_set_stream(self._h, C.c_void_p(self.torch_stream.cuda_stream)))
 
     def close(self):
         if getattr(self, "_h", None):

@@ -39,7 +39,8 @@ HALO_SIGNATURES = {
 _ARRAYS = {"row_lid": (0, np.int32), "col_lid": (1, np.int32), "extra_row": (2, np.int32), "extra_col": (3, np.int32),
            "colmap_gids": (4, np.int64), "unique_gids": (5, np.int64), "ghost_row_gids": (6, np.int64), "ghost_row_owner": (7, np.int64),
            "rowptr": (8, np.int64), "colind": (9, np.int32), "send_counts_nodes": (10, np.int64), "recv_counts_nodes": (11, np.int64),
-           "recv_row": (12, np.int64), "recv_pos": (13, np.int64), "recv_len_sender": (14, np.int64), "recv_q": (15, np.int64)}
+           "recv_row": (12, np.int64), "recv_pos": (13, np.int64), "recv_len_sender": (14, np.int64), "recv_q": (15, np.int64),
+           "import_send_rows": (16, np.int64), "import_send_counts": (17, np.int64), "rep_of_row": (18, np.int64)}
 
 
 def _load():

@@ -52,7 +52,9 @@ int  feddb200_halo_sizes(const feddb200_halo *plan, int64_t *n_owned, int64_t *n
 /* arrays (owned by the plan): which = 0 row_lid[nn] i32, 1 col_lid[nn] i32, 2 extra_row i32, 3 extra_col i32,
  * 4 colmap_gids[n_colmap] i64, 5 unique_gids[n_owned] i64, 6 ghost_row_gids[n_ghost] i64, 7 ghost_row_owner[n_ghost] i64,
  * 8 rowptr[n_rows+1] i64, 9 colind[nnz_nodes] i32, 10 send_counts_nodes[size] i64, 11 recv_counts_nodes[size] i64,
- * 12 recv_row i64, 13 recv_pos i64, 14 recv_len_sender i64, 15 recv_q i64 (12-15: [n_recv]) */
+ * 12 recv_row i64, 13 recv_pos i64, 14 recv_len_sender i64, 15 recv_q i64 (12-15: [n_recv]),
+ * 16 import_send_rows i64 (owned rows the other ranks hold as ghosts, grouped by requesting rank, in their ghost order),
+ * 17 import_send_counts[size] i64, 18 rep_of_row[n_rows] i64 (repeated node of every pattern row) */
 const void *feddb200_halo_array(const feddb200_halo *plan, int which, int64_t *count);
 
 /* value slots (into this rank's dof-level CSR values) of every received value, in arrival order; block_mode as in

@@ -97,6 +97,45 @@ def main():
                     np.add.at(glob, (dofs * g2[:, None] + np.arange(dofs)[None, :]).ravel(), O.assembly_rhs(dim, fe, c2, x2, f, 1, vec_field))
                 want = glob[(dofs * plan.unique_gids[:, None] + np.arange(dofs)[None, :]).ravel()]
                 assert np.abs(got - want).max() <= 1e-13 * np.abs(want).max(), f"rank {rank}: load vector export/ADD"
+        if mode == "gather":
+            # Navier-Stokes (0,0) block on several GPUs: the velocity lives on the unique map, is imported to the repeated map on
+            # the device (MultiVector::importFromVector before the advection assemblies, NavierStokes_def.hpp:294), the fused block
+            # rho*nu*A + rho*N(u) + rho*W(u) is assembled with the NCCL ghost-row exchange overlapped; N(u) alone as well
+            import scipy.sparse as sp
+            rho, nu = 1.3, 1.0e-3
+            ufun = lambda x: np.stack([np.sin(2 * x[:, 1]) + x[:, 2], -x[:, 0] ** 2, 0.3 + x[:, 0] * x[:, 1]], axis=1).ravel()
+            owned = plan.rep_of_row[: plan.n_owned]
+            u_unique = torch.from_numpy(ufun(run.coords[owned])).cuda()
+            u_rep = run.import_vector(u_unique, dim)
+            assert np.array_equal(u_rep.cpu().numpy(), ufun(run.coords)), f"rank {rank}: unique -> repeated import"
+            vN = ctx.empty_values(pat.nnz(dim, dim, BLOCK_FULL))
+            run.assemble_overlapped(vN, dim, dim, BLOCK_FULL, lambda: pat.assemble_ns_jacobian_d(vN, u_rep, rho, nu, True))
+            ctx.synchronize()
+            GA, GN, GW = O.Matrix(dim * nglob, 64), O.Matrix(dim * nglob, 64), O.Matrix(dim * nglob, 64)
+            for r in range(world):
+                c2, x2, g2, _ = PM.build_structured_box(dim, fe, dims, M, r)
+                O.assembly_laplace_vecfield(dim, fe, c2, x2, g2, GA)
+                O.assembly_advection(dim, fe, c2, x2, g2, ufun(x2), GN)
+                O.assembly_advection_in_u(dim, fe, c2, x2, g2, ufun(x2), GW)
+            J = (rho * nu * GA.scipy() + rho * GN.scipy() + rho * GW.scipy()).tocsr()
+            rows = (dim * plan.unique_gids[:, None] + np.arange(dim)[None, :]).ravel()
+            got = sp.csr_matrix((vN.cpu().numpy()[: pat.nnz_owned(dim, dim, BLOCK_FULL)], col_gid_dof[cid[: rpd[n_owned_dofs]]], rpd[: n_owned_dofs + 1]),
+                                shape=(n_owned_dofs, dim * nglob))
+            diff = got - J[rows]
+            relJ = float(np.sqrt(diff.multiply(diff).sum() / J[rows].multiply(J[rows]).sum()))
+            assert relJ <= 1e-12, f"rank {rank}: multi-GPU Navier-Stokes block, relative Frobenius error {relJ:.3e}"
+            # the peer-memory path must refuse operators whose kernels do not store ghost rows through it
+            from feddlib_b200 import LogicError
+            try:
+                run.assemble_fused(vN, dim, dim, BLOCK_FULL, lambda: pat.assemble_ns_jacobian_d(vN, u_rep, rho, nu, True))
+                refused = world == 1
+            except LogicError:
+                refused = True
+            ctx.synchronize()
+            dist.barrier()
+            run.close_peer()
+            assert refused, f"rank {rank}: assemble_fused accepted an operator without peer-memory ghost rows"
+            print(f"[dist_gpu_check] rank {rank}/{world}: Navier-Stokes block on {world} GPUs rel. error {relJ:.2e} OK", flush=True)
         print(f"[dist_gpu_check] rank {rank}/{world} mode {mode}: owned rows {plan.n_owned}, ghost rows {plan.n_ghost}, "
               f"rel. error {rel:.2e} OK (overlapped exchange equal)", flush=True)
     dist.destroy_process_group()
