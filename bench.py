@@ -473,7 +473,7 @@ def main():
                                "peer memory (CUDA IPC), one-element all-reduce as barrier under the owned rows, unpack-add"
                                if fused else "; ghost rows assembled first, NCCL ghost-row exchange overlapped with the owned rows"
                                if overlap else ("; NCCL ghost-row exchange after the assembly" if world > 1 else "")),
-                           "pattern_build_s": t_pattern},
+                           "pattern_build_s": t_pattern, "pattern_build_breakdown": getattr(runner, "timing", None)},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
                 "clocks": clocks, "checksum_first_1Mi_values": checksum}
         if extra:

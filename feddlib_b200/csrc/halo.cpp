@@ -27,8 +27,13 @@ struct feddb200_halo {
     int rank = 0, size = 1;
     int64_t nn = 0, n_owned = 0, n_ghost = 0, n_rows = 0, n_colmap = 0, n_cols = 0;
     std::vector<int64_t> gid_rep, owner;
-    std::vector<int32_t> row_lid, col_lid, extra_row, extra_col, colind;
-    std::vector<int64_t> unique_gids, ghost_row_gids, ghost_row_owner, colmap_gids, rowptr, rep_of_row;
+    std::vector<int32_t> row_lid, col_lid, extra_row, extra_col;
+    // final node pattern: the arrays of the pattern callback's last call (valid as long as the caller keeps them, see
+    // feddb200_node_pattern_fn); not copied -- they are the largest arrays of the plan
+    const int64_t *rowptr = nullptr;
+    const int32_t *colind = nullptr;
+    int64_t nnz_nodes = 0;
+    std::vector<int64_t> unique_gids, ghost_row_gids, ghost_row_owner, colmap_gids, rep_of_row;
     std::vector<int64_t> send_counts_nodes, recv_counts_nodes;
     std::vector<int64_t> recv_row, recv_pos, recv_len_sender, recv_q;
     // import plan: owned rows each peer needs (in the peer's ghost order), my ghost rows per owner are contiguous
@@ -170,8 +175,7 @@ extern "C" int feddb200_halo_create(feddb200_halo **out, const feddb200_comm *co
     rc = pattern_fn(pattern_user, H->row_lid.data(), H->n_rows, H->n_owned, H->col_lid.data(), H->n_cols, H->extra_row.data(), H->extra_col.data(),
                     n_rec, &rp, &ci);
     if (rc != 0) return fail(rc);
-    H->rowptr.assign(rp, rp + H->n_rows + 1);
-    H->colind.assign(ci, ci + rp[H->n_rows]);
+    H->rowptr = rp; H->colind = ci; H->nnz_nodes = rp[H->n_rows];
 
     // 5. ghost rows in final CSR order -> the owners resolve every entry to (row, position)
     {
@@ -181,10 +185,10 @@ extern "C" int feddb200_halo_create(feddb200_halo **out, const feddb200_comm *co
         std::vector<std::vector<int64_t>> send((size_t)size);
         H->send_counts_nodes.assign((size_t)size, 0);
         for (int64_t r = H->n_owned; r < H->n_rows; r++) {
-            const int64_t rep = H->rep_of_row[(size_t)r], len = H->rowptr[(size_t)r + 1] - H->rowptr[(size_t)r];
+            const int64_t rep = H->rep_of_row[(size_t)r], len = H->rowptr[r + 1] - H->rowptr[r];
             std::vector<int64_t> &s = send[(size_t)owner[rep]];
             for (int64_t q = 0; q < len; q++) {
-                s.push_back(gid_rep[rep]); s.push_back(gid_of_col[(size_t)H->colind[(size_t)(H->rowptr[(size_t)r] + q)]]); s.push_back(len); s.push_back(q);
+                s.push_back(gid_rep[rep]); s.push_back(gid_of_col[(size_t)H->colind[H->rowptr[r] + q]]); s.push_back(len); s.push_back(q);
             }
             H->send_counts_nodes[(size_t)owner[rep]] += len;
         }
@@ -200,7 +204,7 @@ extern "C" int feddb200_halo_create(feddb200_halo **out, const feddb200_comm *co
             const int64_t c = colmap_index.find(rec4[(size_t)(4 * k + 1)]);
             if (rep < 0 || c < 0) { fb::set_error("halo plan: received entry with an unknown row or column"); return fail(FEDDB200_ELOGIC); }
             const int64_t I = H->row_lid[(size_t)rep];
-            const int32_t *b = H->colind.data() + H->rowptr[(size_t)I], *e = H->colind.data() + H->rowptr[(size_t)I + 1];
+            const int32_t *b = H->colind + H->rowptr[I], *e = H->colind + H->rowptr[I + 1];
             const int32_t *it = std::lower_bound(b, e, (int32_t)c);
             if (it == e || *it != (int32_t)c) { fb::set_error("halo plan: received entry missing from the owner's pattern"); return fail(FEDDB200_ELOGIC); }
             H->recv_row[(size_t)k] = I; H->recv_pos[(size_t)k] = it - b;
@@ -242,8 +246,8 @@ extern "C" int feddb200_halo_sizes(const feddb200_halo *H, int64_t *n_owned, int
     if (n_colmap) *n_colmap = H->n_colmap;
     if (n_cols) *n_cols = H->n_cols;
     if (n_extra) *n_extra = (int64_t)H->extra_row.size();
-    if (nnz_owned_nodes) *nnz_owned_nodes = H->rowptr[(size_t)H->n_owned];
-    if (nnz_nodes) *nnz_nodes = H->rowptr[(size_t)H->n_rows];
+    if (nnz_owned_nodes) *nnz_owned_nodes = H->rowptr[H->n_owned];
+    if (nnz_nodes) *nnz_nodes = H->nnz_nodes;
     if (n_recv) *n_recv = (int64_t)H->recv_row.size();
     return FEDDB200_OK;
 }
@@ -261,8 +265,8 @@ extern "C" const void *feddb200_halo_array(const feddb200_halo *H, int which, in
     case 5: HL_ARR(H->unique_gids);
     case 6: HL_ARR(H->ghost_row_gids);
     case 7: HL_ARR(H->ghost_row_owner);
-    case 8: HL_ARR(H->rowptr);
-    case 9: HL_ARR(H->colind);
+    case 8: if (count) *count = H->n_rows + 1; return H->rowptr;
+    case 9: if (count) *count = H->nnz_nodes; return H->colind;
     case 10: HL_ARR(H->send_counts_nodes);
     case 11: HL_ARR(H->recv_counts_nodes);
     case 12: HL_ARR(H->recv_row);
@@ -302,7 +306,7 @@ extern "C" int feddb200_halo_recv_slots(const feddb200_halo *H, int rd, int cd, 
         const int64_t Ls = H->recv_len_sender[(size_t)k], q = H->recv_q[(size_t)k];
         if (q == 0) { block_start = next_start; next_start += f * Ls; }
         const int64_t I = H->recv_row[(size_t)k], p = H->recv_pos[(size_t)k];
-        const int64_t base = H->rowptr[(size_t)I], L = H->rowptr[(size_t)I + 1] - base;
+        const int64_t base = H->rowptr[I], L = H->rowptr[I + 1] - base;
         for (int a = 0; a < nrow_dofs; a++)
             for (int b = 0; b < per; b++) slots[block_start + a * per * Ls + per * q + b] = f * base + a * per * L + per * p + b;
     }

@@ -279,29 +279,43 @@ class DistributedMatrixAssembler:
     """Device-side driver: per-rank mesh + pattern from a HaloPlan, assembly + ghost exchange."""
 
     def __init__(self, ctx, dim, conn, coords, gid_rep, owner, rank, size):
+        import os
+        import time
         import torch
         from .engine import Mesh, Pattern
         self.ctx, self.dim, self.rank, self.size = ctx, dim, rank, size
         self.conn, self.coords = conn, coords
+        t0 = time.perf_counter()
         self.mesh = Mesh(ctx, dim, conn, coords)
         self._pats = []
+        self.timing = {"mesh_upload_s": time.perf_counter() - t0, "pattern_calls_s": 0.0}
 
         def pattern_fn(row_lid, n_rows, n_owned, col_lid, n_cols, er, ec):
+            t1 = time.perf_counter()
+            for p in self._pats:            # the preliminary pattern is not needed once the next one is built
+                p.close()
             pat = Pattern(ctx, self.mesh, None, row_lid, n_rows, n_owned, col_lid, n_cols, er, ec)
             self._pats.append(pat)
-            return pat.nodes()
+            out = pat.nodes()
+            self.timing["pattern_calls_s"] += time.perf_counter() - t1
+            return out
 
         dev = torch.device(f"cuda:{ctx.device}")
         # the plan is built by the C++ host code a FEDDLib build links (halo.cpp); HaloPlan (numpy) is its executable
         # specification in the CPU tests
         from .halo import NativeHaloPlan
+        t0 = time.perf_counter()
         self.plan = NativeHaloPlan(Comm(rank, size, dev), gid_rep, owner, pattern_fn)
+        self.timing["plan_total_s"] = time.perf_counter() - t0
         self.pat = self._pats[-1]
         for p in self._pats[:-1]:
             p.close()
         self._dev = dev
         self._slot_t = {}
         self._recv_buf = {}
+        if os.environ.get("FEDDB200_TIMING"):
+            import sys
+            print(f"[feddb200 timing] rank {rank}: {self.timing}", file=sys.stderr, flush=True)
 
     def _main_stream(self):
         """The stream the engine launches on (bound in Context.__init__): the exchange is ordered against IT, not against whatever
@@ -525,9 +539,13 @@ class DistributedElasticity(DistributedMatrixAssembler):
 
     def __init__(self, ctx, dim, fe, M, rank, world):
         from . import mesh as PM
+        import time
         dims = box_dims(world)
+        t0 = time.perf_counter()
         conn, coords, gid, owner = PM.build_structured_box(dim, fe, dims, M, rank)
+        t_mesh = time.perf_counter() - t0
         super().__init__(ctx, dim, conn, coords, gid, owner, rank, world)
+        self.timing["mesh_generation_s"] = t_mesh
         self.dims = dims
 
     def exchange(self, values):

@@ -115,12 +115,21 @@ class NativeHaloPlan:
         check(self._L.feddb200_halo_sizes(self._h, *[C.byref(x) for x in v]))
         (self.n_owned, self.n_ghost, self.n_rows, self.n_colmap, self.n_cols, self.n_extra, self.nnz_owned_nodes, self.nnz_nodes,
          self.n_recv) = [int(x.value) for x in v]
-        for name, (which, dt) in _ARRAYS.items():
+        # the final node pattern stays what the callback returned (the plan references those arrays)
+        self.rowptr, self.colind = self._keep["rp"], self._keep["ci"][: self.nnz_nodes]
+        self._slots = {}
+
+    def __getattr__(self, name):
+        # plan arrays are fetched on first use (several are as large as the mesh)
+        if name in _ARRAYS and name not in ("rowptr", "colind") and self.__dict__.get("_h"):
+            which, dt = _ARRAYS[name]
             n = C.c_int64()
             ptr = self._L.feddb200_halo_array(self._h, which, C.byref(n))
-            arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(n.value,)).copy() if n.value else np.zeros(0, dtype=dt)
-            setattr(self, name, arr)
-        self._slots = {}
+            arr = (np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(n.value,)).copy()
+                   if n.value else np.zeros(0, dtype=dt))
+            self.__dict__[name] = arr
+            return arr
+        raise AttributeError(name)
 
     def close(self):
         if getattr(self, "_h", None):

@@ -32,7 +32,8 @@ typedef struct feddb200_comm {
 
 /* node pattern of this rank's elements for a given row / column numbering (the semantics of feddb200_pattern_build):
  * rows row_lid[node] (n_rows, the first n_owned owned), columns col_lid[node] (NULL: repeated ids, n_cols = nodes) plus
- * the extra entries (row, col); returns rowptr[n_rows+1] / colind[nnz], valid until the next call with the same user. */
+ * the extra entries (row, col); returns rowptr[n_rows+1] / colind[nnz], valid until the next call with the same user -- the
+ * arrays of the LAST call (the final pattern) are referenced by the plan, not copied, and must outlive it. */
 typedef int (*feddb200_node_pattern_fn)(void *user, const int32_t *row_lid, int64_t n_rows, int64_t n_owned, const int32_t *col_lid,
                                         int64_t n_cols, const int32_t *extra_row, const int32_t *extra_col, int64_t n_extra,
                                         const int64_t **rowptr, const int32_t **colind);
