@@ -729,7 +729,7 @@ int launch_gatherx_t(feddb200_ctx *c, feddb200_pat *p, const feddb200_mesh *vm, 
         while (nt > 32 && (size_t)G.pitch * 8 * nt > budget) nt -= 32;
         const size_t smem = (size_t)G.pitch * 8 * nt;
         FB_LOGIC(smem > budget, "row too long for the gather path's shared-memory accumulators; use the coloured or atomic mode");
-        const int64_t blocks = (b.count + (32 / S::RD) * (nt / 32) - 1) / ((32 / S::RD) * (nt / 32));   // 32 / RD row nodes per warp
+        const int64_t blocks = (b.count * S::RD + nt - 1) / nt;
         auto launch = [&](auto kernel) -> int {
             { const int rc_k = kernel_cfg(c, kernel, 0, 0, budget, nullptr); if (rc_k != FEDDB200_OK) return rc_k; }
             kernel<<<(unsigned)blocks, nt, smem, st>>>(G);

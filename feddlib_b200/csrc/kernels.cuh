@@ -1760,15 +1760,10 @@ __global__ void __launch_bounds__(64, 4) k_gatherx(const GatherXArgs A)
     constexpr bool P2C = NL > NVTX;                                // P2 column space
     extern __shared__ double acc[];                                // [blockDim.x][pitch]
     const int NT = blockDim.x, tid = threadIdx.x, lane = tid & 31, pitch = A.pitch;
-    // the RD dof rows of a row node are threads of ONE warp (32 / RD nodes per warp, the remaining lanes idle): they share
-    // the node-level part of the work (fused Navier-Stokes block: the advection sums, see below) through shuffles
-    constexpr int NPWX = 32 / RD;
-    const int slot = lane / RD;
-    const int a = lane - slot * RD;
-    const int64_t rloc_ = ((int64_t)blockIdx.x * (NT >> 5) + (tid >> 5)) * NPWX + slot;
-    const bool live = slot < NPWX && rloc_ < A.count;
-    const int64_t rloc = live ? rloc_ : 0;
-    const unsigned node_mask = ((RD == 32 ? 0xffffffffu : ((1u << RD) - 1u)) << (slot * RD));
+    const int64_t t = blockIdx.x * (int64_t)NT + tid;
+    const bool live = t < A.count * RD;
+    const int64_t rloc = live ? t / RD : 0;
+    const int a = live ? (int)(t - rloc * RD) : 0;
     int64_t base = 0, k0 = 0;
     int L = 0, ninc = 0;
     if (live) {
@@ -1812,11 +1807,8 @@ __global__ void __launch_bounds__(64, 4) k_gatherx(const GatherXArgs A)
             double vn[NL];
 #pragma unroll
             for (int j = 0; j < NL; j++) vn[j] = 0.0;
-            // N_{i'j'} does not depend on the row dof: with RD dof threads per node each thread sums the nodes m' = a, a + RD, ...
-            // of the element and the RD partial sums are combined in a fixed order (every dof row gets the same bits)
 #pragma unroll
             for (int m = 0; m < NL; m++) {
-                if (RD > 1 && (m % RD) != a) continue;
                 double um[4];
                 ld_v4(A.uel + (e * NL + rec_natidx<NL>(rc.w, m)) * 4, um);
                 double s[NVTX];
@@ -1831,16 +1823,6 @@ __global__ void __launch_bounds__(64, 4) k_gatherx(const GatherXArgs A)
                 for (int j = 0; j < NL; j++) {
                     vn[j] += A.C.TN[TYPE][m][j][0] * s[canon_sv<DIM>(j, 0)];
                     if (P2C && j >= NVTX) vn[j] += A.C.TN[TYPE][m][j][1] * s[canon_sv<DIM>(j, 1)];
-                }
-            }
-            if constexpr (RD > 1) {
-                const int lane0 = slot * RD;
-#pragma unroll
-                for (int j = 0; j < NL; j++) {
-                    double tot = 0.0;
-#pragma unroll
-                    for (int r = 0; r < RD; r++) tot += __shfl_sync(node_mask, vn[j], lane0 + r);
-                    vn[j] = tot;
                 }
             }
             if constexpr (OPX == X_ADV) {
