@@ -229,8 +229,9 @@ def determine_degree1(dim, fe, t):
 def set_dirichlet_rows(rowptr, colgid, values, row_gid_of_dof, dof_is_dirichlet, diagonal_block=True):
     """BCBuilder::setLocalRowOne / setLocalRowZero (core/General/BCBuilder_def.hpp:653-709) on a dof-level CSR:
     every Dirichlet dof row is replaced by zeros (:672, :704) and, on a diagonal block, the entry whose column gid
-    equals the row gid by one (:674-679).  Parity unpinned: BCBuilder needs the full Trilinos stack, so this
-    restatement is checked by review only.  Returns a new values array."""
+    equals the row gid by one (:674-679).  Pinned: tests/test_bc_vs_ref.py runs the reference's own members (compiled where
+    they lie against CSR mocks, oracle/ref_bc.py) on the same systems and compares bitwise; golden vectors in
+    tests/golden/bc_vectors.npz.  Returns a new values array."""
     out = np.array(values, dtype=np.float64, copy=True)
     for r in np.nonzero(dof_is_dirichlet)[0]:
         a, b = rowptr[r], rowptr[r + 1]
@@ -239,4 +240,43 @@ def set_dirichlet_rows(rowptr, colgid, values, row_gid_of_dof, dof_is_dirichlet,
             hit = np.nonzero(colgid[a:b] == row_gid_of_dof[r])[0]
             if hit.size:
                 out[a + hit[0]] = 1.0
+    return out
+
+
+DIRICHLET_MASKS = {"Dirichlet": 0b111, "Dirichlet_X": 0b001, "Dirichlet_Y": 0b010, "Dirichlet_Z": 0b100, "Dirichlet_X_Y": 0b011,
+                   "Dirichlet_X_Z": 0b101, "Dirichlet_Y_Z": 0b110}
+
+
+def dirichlet_dof_masks(node_flags, bcs, block, dofs):
+    """Per node, the bit mask of the dofs of block `block` that carry a Dirichlet condition: BCBuilder::findFlag picks the FIRST
+    entry of the BC table with the node's flag and this block (BCBuilder_def.hpp:561-586); its type selects the dofs
+    (:662-669).  bcs: list of (flag, block, type, dofs) in addBC order.  Also returns the index of the matching entry (-1: none)."""
+    node_flags = np.asarray(node_flags)
+    mask = np.zeros(node_flags.size, dtype=np.uint8)
+    which = -np.ones(node_flags.size, dtype=np.int64)
+    for i, fl in enumerate(node_flags):
+        for k, (flag, blk, typ, _d) in enumerate(bcs):
+            if flag == fl and blk == block:
+                if typ in DIRICHLET_MASKS:
+                    mask[i] = DIRICHLET_MASKS[typ] & ((1 << dofs) - 1)
+                    which[i] = k
+                break
+    return mask, which
+
+
+def set_dirichlet_rhs(rhs, node_flags, points, bcs, block, dofs, func, params, t=0.0):
+    """BCBuilder::setRHS, Dirichlet part (core/General/BCBuilder_def.hpp:93-166): at every node whose flag has a Dirichlet entry
+    for this block, result starts as the node's coordinates (:131-133), the boundary function overwrites it (:134) and the dofs
+    selected by the type are written into the right-hand side (:138-163).  Returns a new vector."""
+    out = np.array(rhs, dtype=np.float64, copy=True)
+    mask, which = dirichlet_dof_masks(node_flags, bcs, block, dofs)
+    dim = points.shape[1]
+    for i in np.nonzero(which >= 0)[0]:
+        res = [points[i][d] if d < dim else 0.0 for d in range(dofs)]
+        got = func(np.array(points[i]), t, np.asarray(params))
+        for d, v in enumerate(got):
+            res[d] = v
+        for d in range(dofs):
+            if (mask[i] >> d) & 1:
+                out[dofs * i + d] = res[d]
     return out

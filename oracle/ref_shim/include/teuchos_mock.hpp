@@ -51,7 +51,9 @@ template <class T, class U> RCP<T> rcp_dynamic_cast(const RCP<U> &p) { return RC
 template <class T>
 class ArrayView {
   public:
+    ArrayView() : p_(nullptr), n_(0) {}
     ArrayView(const T *p, std::size_t n) : p_(p), n_(n) {}
+    const ArrayView &operator()() const { return *this; }
     std::size_t size() const { return n_; }
     const T &operator[](std::size_t i) const { return p_[i]; }
     const T *getRawPtr() const { return p_; }
@@ -79,6 +81,7 @@ template <class T>
 class ArrayRCP {
   public:
     ArrayRCP() : p_(nullptr), n_(0) {}
+    ArrayRCP(ENull) : p_(nullptr), n_(0) {}
     ArrayRCP(T *p, std::size_t n) : p_(p), n_(n) {}
     T &operator[](std::size_t i) const { return p_[i]; }
     std::size_t size() const { return n_; }
@@ -92,7 +95,12 @@ template <class T> struct OrdinalTraits { static T invalid() { return T(-1); } }
 
 class ParameterList { };
 class Time { };
-class TimeMonitor { };
+class TimeMonitor {
+  public:
+    TimeMonitor() {}
+    explicit TimeMonitor(Time &) {}
+    static RCP<Time> getNewCounter(const std::string &) { return RCP<Time>(new Time()); }
+};
 class CommandLineProcessor { };
 template <class O, class S> class BLAS { };
 
