@@ -223,6 +223,105 @@ def config4_numbers(ctx, levels, peak):
                             f"config 4: DFG3DCylinder_6k.mesh regular-refined k={levels}, P2-P1", peak)
 
 
+def parity_check(values, pat, M, dims, rank, plan, n_sample=800):
+    """Sampled rows of the FULL-SIZE matrix against the reference's own assembly loop (oracle/_ref; the oracle restatement where it is
+    not built): for every sampled owned row node -- interior nodes, nodes on the faces / edges / corners of the global box and on
+    the planes between ranks (rows that receive ghost contributions) -- the elements of its star are regenerated from the global
+    lattice (any rank's elements), assembled by the checker, and the node's dof rows are compared: pattern exactly, values to 1e-12
+    (relative Frobenius norm over all sampled rows).  Checker only: never inside a timed region."""
+    from feddlib_b200 import mesh as PM
+    from oracle import oracle as O
+    from oracle import ref as R
+    dim = 3
+    dims = tuple(dims) + (1,) * (3 - len(dims))
+    n = 2 * M                                                   # lattice intervals per rank and direction
+    ng = [dims[d] * n + 1 for d in range(3)]
+    if plan is None:
+        ugid, colmap, n_owned = None, None, pat.n_owned_rows
+    else:
+        ugid, colmap, n_owned = plan.unique_gids, plan.colmap_gids, plan.n_owned
+    rng = np.random.default_rng(1234 + rank)
+    rows_all = np.arange(n_owned, dtype=np.int64)
+    g_all = rows_all if ugid is None else ugid
+    X = np.stack([g_all % ng[0], (g_all // ng[0]) % ng[1], g_all // (ng[0] * ng[1])], axis=1)
+    on_plane = (X % n == 0).sum(axis=1)                          # 0 interior ... 3 corner of a sub-cube
+    pick = []
+    for k in range(4):
+        cand = rows_all[on_plane == k]
+        if cand.size:
+            pick.append(rng.choice(cand, size=min(cand.size, n_sample // 4), replace=False))
+    rows = np.unique(np.concatenate(pick))
+    # star meshes from the global lattice: the cells around the node, every Kuhn tetrahedron of them, isolated numbering per star
+    tets, mids = np.array(PM._TET), np.array(PM._MID[3])
+    conn_l, coord_l, gid_l, base = [], [], [], 0
+    row_gid, row_loc = [], []
+    h2 = 0.5 / M
+    for I in rows:
+        x = X[I]
+        lo = [max(0, (x[d] - 1) // 2) for d in range(3)]
+        hi = [min(dims[d] * M - 1, x[d] // 2) for d in range(3)]
+        cells = np.array([[cx, cy, cz] for cz in range(lo[2], hi[2] + 1) for cy in range(lo[1], hi[1] + 1) for cx in range(lo[0], hi[0] + 1)])
+        corner = np.stack([(tets >> d) & 1 for d in range(3)], axis=-1)              # [6, 4, 3]
+        v = 2 * (cells[:, None, None, :] + corner[None])                             # [nc, 6, 4, 3] lattice coordinates
+        m = (v[:, :, mids[:, 0]] + v[:, :, mids[:, 1]]) // 2
+        lat = np.concatenate([v, m], axis=2).reshape(-1, 10, 3)                      # [ne, 10, 3]
+        lat = lat[(lat == x).all(axis=2).any(axis=1)]                                # tetrahedra that contain the node
+        g = lat[..., 0] + ng[0] * (lat[..., 1] + ng[1] * lat[..., 2])
+        ug, inv = np.unique(g, return_inverse=True)
+        conn_l.append(inv.reshape(-1, 10) + base)
+        latu = np.stack([ug % ng[0], (ug // ng[0]) % ng[1], ug // (ng[0] * ng[1])], axis=1)
+        coord_l.append(latu * h2)
+        gid_l.append(ug)
+        row_gid.append(g_all[I]); row_loc.append(base + int(np.searchsorted(ug, g_all[I])))
+        base += ug.size
+    conn_s = np.concatenate(conn_l).astype(np.int32)
+    coords_s = np.concatenate(coord_l).astype(np.float64)
+    gid_true = np.concatenate(gid_l)
+    if R.available():
+        rp, ci, va = R.assemble("linelas", dim, "P2", conn_s, coords_s, lam=LAM, mu=MU)
+        kind = "reference"
+    else:
+        A = O.Matrix(dim * coords_s.shape[0], 240)
+        O.assembly_linelas(dim, "P2", conn_s, coords_s, np.arange(coords_s.shape[0]), LAM, MU, A)
+        rp, ci, va = A.csr()
+        kind = "port"
+    # our rows
+    nrp, nci = pat.nodes()
+    vals_rows = []
+    num = den = 0.0
+    ok = True
+    import torch
+    idx = []
+    meta = []
+    for I, rl in zip(rows, row_loc):
+        b0, L = int(nrp[I]), int(nrp[I + 1] - nrp[I])
+        cols = nci[b0:b0 + L].astype(np.int64)
+        cg = cols if colmap is None else colmap[cols]
+        meta.append((rl, b0, L, cg))
+        idx.append(np.arange(9 * b0, 9 * (b0 + L), dtype=np.int64))
+    got_all = values[torch.from_numpy(np.concatenate(idx)).to(values.device)].cpu().numpy()
+    at = 0
+    for rl, b0, L, cg in meta:
+        blk = got_all[at:at + 9 * L].reshape(3, L, 3)            # (a, p, b)
+        at += 9 * L
+        for a in range(3):
+            r = dim * rl + a
+            seg = slice(rp[r], rp[r + 1])
+            ref_cols = dim * gid_true[ci[seg] // dim] + ci[seg] % dim
+            mine_cols = (dim * cg[:, None] + np.arange(3)[None, :]).ravel()
+            order = np.argsort(mine_cols)
+            o2 = np.argsort(ref_cols)
+            if mine_cols.size != ref_cols.size or not np.array_equal(mine_cols[order], ref_cols[o2]):
+                ok = False
+                continue
+            d = blk[a].ravel()[order] - va[seg][o2]
+            num += float((d * d).sum()); den += float((va[seg][o2] ** 2).sum())
+    rel = float(np.sqrt(num / den)) if den > 0 else float("nan")
+    return {"rows_checked": int(rows.size) * 3, "by_position": {str(k): int((on_plane[rows] == k).sum()) for k in range(4)},
+            "pattern": "identical" if ok else "DIFFERS", "rel_frobenius": rel, "tolerance": 1e-12, "checker": kind,
+            "result": "pass" if ok and rel <= 1e-12 else "FAIL"}
+
+
 def _worker(M):
     return oracle_elasticity_time(M)
 
@@ -278,6 +377,7 @@ def main():
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
                     help="multi-GPU ghost rows: 'fused' = stored straight into the owners' buffers over NVLink peer memory by the "
                          "ghost-row kernels; 'nccl' = all-to-all-v of the ghost values on a side stream")
+    ap.add_argument("--no-parity", dest="no_parity", action="store_true", help="skip the sampled-row parity check of the full-size matrix")
     ap.add_argument("--no-ns", action="store_true", help="skip the secondary Navier-Stokes block timings")
     ap.add_argument("--ns-M", dest="ns_M", type=int, default=50, help="H/h of the P2-P1 cube of the secondary timings")
     ap.add_argument("--cfg4-levels", dest="cfg4_levels", type=int, default=2, help="regular refinements of DFG3DCylinder_6k (config 4)")
@@ -370,6 +470,23 @@ def main():
             ms = float(t.item())
         return ms, (ctx.launches - l0) // steps
 
+    # parity of the full-size workload (outside every timed region): sampled rows against the reference on their element stars; on
+    # several GPUs also the peer-memory exchange against the NCCL exchange, bitwise, on every rank
+    parity = None
+    if args.mode == "gather" and not args.no_parity:
+        step()
+        ctx.synchronize()
+        parity = parity_check(values, pat, M, runner.dims if runner is not None else (1, 1, 1), rank, runner.plan if runner is not None else None)
+        if runner is not None:
+            n_owned_vals = pat.nnz_owned(dim, dim, BLOCK_FULL)
+            v_nccl = values.clone()
+            runner.assemble_linelas_overlapped(v_nccl, LAM, MU)
+            ctx.synchronize()
+            parity["nccl_exchange_equals_timed_path_bitwise"] = bool(torch.equal(v_nccl[:n_owned_vals], values[:n_owned_vals]))
+            del v_nccl
+            flags = torch.tensor([1 if parity["result"] == "pass" and parity["nccl_exchange_equals_timed_path_bitwise"] else 0], device="cuda")
+            dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+            parity["all_ranks"] = "pass" if int(flags.item()) == 1 else "FAIL"
     with ClockSampler(local_rank) as clk:
         ms, launches = timed(step, args.steps, args.warmup)
     clocks = clk.summary()
@@ -475,7 +592,7 @@ def main():
                                if overlap else ("; NCCL ghost-row exchange after the assembly" if world > 1 else "")),
                            "pattern_build_s": t_pattern, "pattern_build_breakdown": getattr(runner, "timing", None)},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
-                "clocks": clocks, "checksum_first_1Mi_values": checksum}
+                "clocks": clocks, "checksum_first_1Mi_values": checksum, "parity_check": parity}
         if extra:
             line["other_scatter_modes"] = extra
         if ns_extra:

@@ -88,6 +88,7 @@ SIGNATURES = {
     "feddb200_assemble_rhs_d": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp]),
     "feddb200_assemble_rhs": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp]),
     "feddb200_set_dirichlet_rows_d": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp]),
+    "feddb200_set_dirichlet_rhs_d": (C.c_int, [_vp, _i64, C.c_int, _vp, _vp, _vp]),
     "feddb200_scale_d": (C.c_int, [_vp, _vp, _i64, C.c_double]),
     "feddb200_csr_add_symbolic_d": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_int64)]),
     "feddb200_csr_add_numeric_d": (C.c_int, [_vp, _i64, C.c_double, _vp, _vp, _vp, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp]),

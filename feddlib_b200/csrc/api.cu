@@ -1267,6 +1267,27 @@ extern "C" int feddb200_set_dirichlet_rows_d(feddb200_ctx *c, const feddb200_pat
     return FEDDB200_OK;
 }
 
+__global__ void k_dirichlet_rhs(int64_t n, int dofs, const uint8_t *__restrict__ mask, const double *__restrict__ bc, double *__restrict__ rhs)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n * dofs; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t node = t / dofs;
+        const int a = (int)(t - node * dofs);
+        if ((mask[node] >> a) & 1) rhs[t] = bc[t];
+    }
+}
+
+extern "C" int feddb200_set_dirichlet_rhs_d(feddb200_ctx *c, int64_t n_nodes, int dofs, const uint8_t *node_mask_d, const double *bc_values_d,
+                                            double *rhs_d)
+{
+    FB_LOGIC(!c || n_nodes < 0 || dofs < 1 || dofs > 3 || (n_nodes > 0 && (!node_mask_d || !bc_values_d || !rhs_d)), "set_dirichlet_rhs: bad arguments");
+    if (n_nodes == 0) return FEDDB200_OK;
+    FB_CUDA(cudaSetDevice(c->device));
+    k_dirichlet_rhs<<<(unsigned)std::min<int64_t>((n_nodes * dofs + 255) / 256, 148 * 16), 256, 0, c->stream>>>(n_nodes, dofs, node_mask_d, bc_values_d, rhs_d);
+    c->launches++;
+    FB_CUDA(cudaGetLastError());
+    return FEDDB200_OK;
+}
+
 extern "C" int feddb200_scale_d(feddb200_ctx *c, double *values_d, int64_t n, double alpha)
 {
     FB_LOGIC(!c || (n > 0 && !values_d) || n < 0, "scale: bad arguments");

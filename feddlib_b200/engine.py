@@ -359,6 +359,11 @@ class Pattern:
         check(self.ctx._L.feddb200_set_dirichlet_rows_d(self.ctx._h, self._h, int(row_dofs), int(col_dofs), int(mode),
                                                        ptr(node_mask), int(bool(diagonal_block)), ptr(values)))
 
+    def set_dirichlet_rhs_d(self, rhs, node_mask, bc_values, dofs=1):
+        """BCBuilder::setRHS, Dirichlet part, on a resident right-hand side (BCBuilder_def.hpp:93-166): rhs[dofs*I + a] =
+        bc_values[dofs*I + a] where bit a of node_mask[I] is set (CUDA tensors; bc_values = the boundary function at the nodes)."""
+        check(self.ctx._L.feddb200_set_dirichlet_rhs_d(self.ctx._h, int(node_mask.numel()), int(dofs), ptr(node_mask), ptr(bc_values), ptr(rhs)))
+
     # ---- host-buffer forms (H2D / D2H inside the call) ----
     def assemble_laplace(self, vec_field=False):
         out = np.empty(self.nnz(self.dim, self.dim, BLOCK_DIAG) if vec_field else self.nnz(), dtype=np.float64)

@@ -227,6 +227,12 @@ int  feddb200_assemble_rhs(feddb200_ctx *ctx, const feddb200_pat *pat, int vec_f
  * Every selected dof row is zeroed; on a diagonal block (diagonal_block != 0) its diagonal entry becomes 1. */
 int  feddb200_set_dirichlet_rows_d(feddb200_ctx *ctx, const feddb200_pat *pat, int row_dofs, int col_dofs, int block_mode,
                                    const uint8_t *node_mask_d, int diagonal_block, double *values_d);
+/* BCBuilder::setRHS, Dirichlet part (core/General/BCBuilder_def.hpp:93-166) on a resident right-hand side: rhs_d[dofs * I + a] =
+ * bc_values_d[dofs * I + a] for every owned node I and dof a with bit a of node_mask_d[I] set.  bc_values holds the boundary
+ * function evaluated by the host glue at the node's coordinates (the reference calls the user's boost::function per node, :134);
+ * entries of dofs without a condition are ignored. */
+int  feddb200_set_dirichlet_rhs_d(feddb200_ctx *ctx, int64_t n_nodes, int dofs, const uint8_t *node_mask_d, const double *bc_values_d,
+                                  double *rhs_d);
 /* Matrix::scale (core/LinearAlgebra/Matrix_def.hpp:257) on resident values */
 int  feddb200_scale_d(feddb200_ctx *ctx, double *values_d, int64_t n, double alpha);
 

@@ -38,3 +38,28 @@ def test_dirichlet_rows(engine_ctx, dim, fe, M, layout, diagonal_block):
     got = v_d.cpu().numpy()
     assert np.array_equal(got, want)
     assert (got != vals).any()
+
+
+@pytest.mark.parametrize("dofs", [1, 3])
+def test_dirichlet_rhs(engine_ctx, dofs):
+    """feddb200_set_dirichlet_rhs_d against the restatement of BCBuilder::setRHS (pinned by the reference's own routine in
+    tests/test_bc_vs_ref.py): flags by position, a table of Dirichlet types, a boundary function of the coordinates."""
+    from feddlib_b200 import Mesh, Pattern
+    conn, coords = mesh_structured(3, "P2", 3, warp=True)
+    nn = coords.shape[0]
+    pat = Pattern(engine_ctx, Mesh(engine_ctx, 3, conn, coords))
+    flags = np.zeros(nn, dtype=np.int32)
+    flags[np.abs(coords[:, 0]) < 1e-12] = 1
+    flags[np.abs(coords[:, 1] - 1) < 1e-12] = 2
+    flags[np.abs(coords[:, 2]) < 1e-12] = 3
+    bcs = [(1, 0, "Dirichlet", dofs), (2, 0, "Dirichlet_X_Z" if dofs == 3 else "Dirichlet", dofs), (3, 0, "Dirichlet_Y" if dofs == 3 else "Neumann", dofs)]
+    func = (lambda x, t, par: [par[0] * x[0] + t, par[1] - x[1] * x[2], 2.0 + x[2]][:dofs])
+    par, t = np.array([1.5, -0.25]), 0.75
+    rhs = np.random.default_rng(3).uniform(-1, 1, nn * dofs)
+    want = O.set_dirichlet_rhs(rhs, flags, coords, bcs, 0, dofs, func, par, t)
+    mask, _ = O.dirichlet_dof_masks(flags, bcs, 0, dofs)
+    bc_values = np.array([func(x, t, par) for x in coords]).reshape(-1)      # the host glue evaluates the user's function per node
+    r_d = torch.from_numpy(rhs).cuda()
+    pat.set_dirichlet_rhs_d(r_d, torch.from_numpy(mask).cuda(), torch.from_numpy(bc_values).cuda(), dofs)
+    got = r_d.cpu().numpy()
+    assert np.array_equal(got, want) and (got != rhs).any()
