@@ -562,7 +562,8 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
         } else {
             if constexpr (DIM == 3 && NL == 10) {
                 // vertex-node rows of 3D P2: block-task kernel (star_kernels.cuh), one warp per tile of row nodes
-                if (b.type == 0 && b.tile_count > 0 && p->tasks_d) {
+                // (elasticity only: for the scalar Laplace operator the task kernel measured slower than k_gather, 1.81 vs 1.63 ms at M = 80)
+                if (OPG == 1 && b.type == 0 && b.tile_count > 0 && p->tasks_d) {
                     constexpr int TPRt = OPG == 1 ? DIM : 1, NBt = OPG == 1 ? DIM : 1;
                     TaskArgs T;
                     T.G = G;

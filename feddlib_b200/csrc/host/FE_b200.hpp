@@ -22,6 +22,7 @@
 #include <tuple>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -152,6 +153,27 @@ void seat_csr(Teuchos::RCP<Matrix<SC, LO, GO, NO> > &A, LocalCsr<SC, LO, GO> &cs
 
 } // namespace b200
 
+namespace b200 {
+// vec2D_dbl_Type (one std::vector per point) -> flat array; the pointer chase over millions of small vectors is the slowest
+// host step of a re-upload of the mesh points, so it runs on a few threads
+template <class Points>
+inline void flatten_points(const Points &points, std::int64_t nn, int dim, std::vector<double> &xyz)
+{
+    xyz.resize((std::size_t)nn * dim);
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int nt = nn < (1 << 16) ? 1 : (int)std::max(1u, std::min(8u, hw ? hw : 1u));
+    auto part = [&](int t) {
+        const std::int64_t k0 = nn * t / nt, k1 = nn * (t + 1) / nt;
+        for (std::int64_t k = k0; k < k1; k++)
+            for (int c = 0; c < dim; c++) xyz[(std::size_t)k * dim + c] = points[(std::size_t)k][(std::size_t)c];
+    };
+    if (nt == 1) { part(0); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) th.emplace_back(part, t);
+    for (std::thread &t : th) t.join();
+}
+} // namespace b200
+
 template <class SC = double, class LO = int, class GO = long long, class NO = int>
 class FE_b200 {
   public:
@@ -197,9 +219,8 @@ class FE_b200 {
             const std::vector<int> &nodes = elements->getElement((int)T).getVectorNodeList();
             for (int i = 0; i < s.nloc; i++) conn[(std::size_t)T * s.nloc + i] = nodes[i];
         }
-        std::vector<double> xyz((std::size_t)s.nn * s.dim);
-        for (std::int64_t k = 0; k < s.nn; k++)
-            for (int c = 0; c < s.dim; c++) xyz[(std::size_t)k * s.dim + c] = (*points)[k][c];
+        std::vector<double> xyz;
+        b200::flatten_points(*points, s.nn, s.dim, xyz);
         b200::check(feddb200_mesh_upload(ctx_, &s.mesh, s.dim, s.nloc, s.ne, conn.data(), s.nn, xyz.data()));
         slots_.push_back(s);
     }
@@ -226,9 +247,8 @@ class FE_b200 {
     {
         Slot &s = slots_.at((std::size_t)loc);
         auto points = s.domain->getPointsRepeated();
-        std::vector<double> xyz((std::size_t)s.nn * s.dim);
-        for (std::int64_t k = 0; k < s.nn; k++)
-            for (int c = 0; c < s.dim; c++) xyz[(std::size_t)k * s.dim + c] = (*points)[k][c];
+        std::vector<double> xyz;
+        b200::flatten_points(*points, s.nn, s.dim, xyz);
         b200::check(feddb200_mesh_update_coords(ctx_, s.mesh, xyz.data()));
     }
 
