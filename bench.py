@@ -401,6 +401,7 @@ def main():
 
     dim, fe, M = 3, "P2", args.M
     ctx = Context(local_rank)
+    numa_node = ctx.bind_host_numa()      # pinned staging buffers next to this rank's GPU (e2e at N > 1)
     ctx.set_scatter_mode(args.mode)
     if world == 1:
         conn, coords, gid = PM.build_structured(dim, fe, 1, M)
@@ -540,7 +541,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {"value": ne_total / dt, "unit": UNIT, "h2d_bytes_per_step": int(coords.nbytes),
-               "d2h_bytes_per_step": int(nnz * 8), "ms_per_step": dt * 1e3, "steps": args.e2e_steps}
+               "d2h_bytes_per_step": int(nnz * 8), "ms_per_step": dt * 1e3, "steps": args.e2e_steps, "host_numa_node": numa_node}
         checksum = float(out_np[: min(nnz, 1 << 20)].sum())
         del pinned_vals
         # the same end-to-end step through the compiled C++ host layer (FEDD::FE_b200 over the C ABI: host containers in,

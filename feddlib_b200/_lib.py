@@ -49,6 +49,7 @@ SIGNATURES = {
     "feddb200_dev_free": (C.c_int, [_vp, _vp]),
     "feddb200_copy_h2d": (C.c_int, [_vp, _vp, _vp, _i64]),
     "feddb200_copy_d2h": (C.c_int, [_vp, _vp, _vp, _i64]),
+    "feddb200_bind_host_numa": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "feddb200_host_alloc": (C.c_int, [_vp, C.POINTER(_vp), _i64]),
     "feddb200_host_free": (C.c_int, [_vp, _vp]),
     "feddb200_mesh_upload": (C.c_int, [_vp, C.POINTER(_vp), C.c_int, C.c_int, _i64, _vp, _i64, _vp]),

@@ -13,6 +13,13 @@
 #include <cstring>
 #include <mutex>
 
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE
+#endif
+#include <sched.h>
+#include <cctype>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace fb {
@@ -133,6 +140,45 @@ extern "C" int feddb200_dev_free(feddb200_ctx *c, void *p)
     FB_LOGIC(!c, "null context");
     FB_CUDA(cudaSetDevice(c->device));
     FB_CUDA(cudaFree(p));
+    return FEDDB200_OK;
+}
+extern "C" int feddb200_bind_host_numa(feddb200_ctx *c, int *numa_node)
+{
+    FB_LOGIC(!c, "feddb200_bind_host_numa: null context");
+    if (numa_node) *numa_node = -1;
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), c->device) != cudaSuccess) { cudaGetLastError(); return FEDDB200_OK; }
+    for (char *q = bus; *q; q++) *q = (char)tolower(*q);
+    std::string base = std::string("/sys/bus/pci/devices/") + bus;
+    int node = -1;
+    if (FILE *f = fopen((base + "/numa_node").c_str(), "r")) { if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f); }
+    if (node < 0) return FEDDB200_OK;
+    char list[4096] = {0};
+    FILE *f = fopen(("/sys/devices/system/node/node" + std::to_string(node) + "/cpulist").c_str(), "r");
+    if (!f) return FEDDB200_OK;
+    const bool got = fgets(list, sizeof(list), f) != nullptr;
+    fclose(f);
+    if (!got) return FEDDB200_OK;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int n_cpus = 0;
+    for (char *tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {   // "0-31,64-95"
+        int a = -1, b = -1;
+        const int k = sscanf(tok, "%d-%d", &a, &b);
+        if (k == 1) b = a;
+        if (k >= 1)
+            for (int x = a; x <= b && x < CPU_SETSIZE; x++) { CPU_SET(x, &set); n_cpus++; }
+    }
+    if (n_cpus == 0) return FEDDB200_OK;
+    cpu_set_t cur;   // keep only CPUs this process may use (cgroup / taskset limits)
+    if (sched_getaffinity(0, sizeof(cur), &cur) == 0) {
+        cpu_set_t both;
+        CPU_AND(&both, &set, &cur);
+        if (CPU_COUNT(&both) == 0) return FEDDB200_OK;
+        set = both;
+    }
+    if (sched_setaffinity(0, sizeof(set), &set) != 0) return FEDDB200_OK;
+    if (numa_node) *numa_node = node;
     return FEDDB200_OK;
 }
 extern "C" int feddb200_host_alloc(feddb200_ctx *c, void **p, int64_t bytes)

@@ -189,6 +189,7 @@ class FE_b200 {
     explicit FE_b200(bool /*saveAssembly*/ = false, int device = 0) : ctx_(nullptr)
     {
         b200::check(feddb200_create(&ctx_, device));
+        feddb200_bind_host_numa(ctx_, nullptr);   // this rank's thread and its page-locked buffers next to its GPU
         pool_ = std::make_shared<b200::PinnedPool>(ctx_);
     }
     ~FE_b200()

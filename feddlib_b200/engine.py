@@ -35,6 +35,13 @@ class Context:
         self.torch_stream = torch.cuda.current_stream(self.device)   # the stream the engine launches on, as a torch object
         check(self._L.feddb200_set_stream(self._h, C.c_void_p(self.torch_stream.cuda_stream)))
 
+    def bind_host_numa(self) -> int:
+        """Bind this thread to the CPUs next to the GPU (feddb200_bind_host_numa): page-locked buffers allocated afterwards
+        are NUMA-local.  Returns the node or -1."""
+        node = C.c_int(-1)
+        check(self._L.feddb200_bind_host_numa(self._h, C.byref(node)))
+        return int(node.value)
+
     def close(self):
         if getattr(self, "_h", None):
             self._L.feddb200_destroy(self._h)

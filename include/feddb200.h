@@ -82,6 +82,12 @@ int  feddb200_copy_d2h(feddb200_ctx *ctx, void *dst, const void *src_d, int64_t 
 /* page-locked host memory for the buffers the host-pointer entry points fill (the CSR values that the seat step hands to
  * Tpetra: core/LinearAlgebra/Matrix_def.hpp:46-51 allocates them inside Tpetra in the reference): a device-to-host copy
  * into pageable memory runs at a fraction of the PCIe rate.  ctx may be NULL for feddb200_host_free. */
+/* Binds the CALLING thread to the CPUs of the NUMA node the context's GPU hangs off (PCI bus id -> /sys/bus/pci/devices/.../
+ * numa_node -> cpulist), so that page-locked buffers allocated afterwards are node-local and the device-to-host copies of the
+ * CSR values do not cross the socket interconnect (8 ranks on a two-socket box otherwise share one socket's memory and links).
+ * *numa_node = the node, or -1 when the platform does not tell (nothing is changed then).  Optional; call it once per rank before
+ * feddb200_host_alloc / the first host-pointer assembly. */
+int  feddb200_bind_host_numa(feddb200_ctx *ctx, int *numa_node);
 int  feddb200_host_alloc(feddb200_ctx *ctx, void **ptr, int64_t bytes);
 int  feddb200_host_free(feddb200_ctx *ctx, void *ptr);
 
