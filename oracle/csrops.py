@@ -1,6 +1,8 @@
 """Test infrastructure: numpy/scipy restatement of the two matrix passes SURVEY.md 8(f) rank 3 names.  Their arithmetic
-lives in Trilinos (Tpetra insertGlobalValues / fillComplete, Xpetra TwoMatrixAdd), which is absent from /root/reference,
-so this restatement is REVIEWED against the cited call sites, not pinned by reference code ("parity unpinned" for this row).
+lives in Trilinos (Tpetra insertGlobalValues / fillComplete, Xpetra TwoMatrixAdd), which is absent from /root/reference.
+block_merge is PINNED: tests/test_csrops_vs_ref.py runs the reference's own BlockMatrix::merge / BlockMap::merge (compiled where
+they lie against mock containers, oracle/ref_bm.py) and compares bitwise, golden vectors in tests/golden/bm_vectors.npz.
+add_matrix is a reviewed restatement ("parity unpinned"): the reference routine is a two-line wrapper around Xpetra's TwoMatrixAdd.
 
   add_matrix   Matrix::addMatrix(alpha, B, beta): B := alpha*A + beta*B via TwoMatrixAdd on a resumed-fill B
                (core/LinearAlgebra/Matrix_def.hpp:281-287): every entry of A is summed into B; entries new to B are
