@@ -44,8 +44,9 @@ def peaks():
 
 def ncu_traffic(M):
     """dram__bytes_read.sum + dram__bytes_write.sum of one assembly pass (all its launches) from the committed
-    `ncu --set full` capture of this command (profiles/r01_step_traffic.json); None for other sizes."""
-    p = os.path.join(ROOT, "profiles", "r01_step_traffic.json")
+    `ncu --set full` capture of this command and this build (profiles/r02_step_traffic.json, written by tools/ncu_step_traffic.py
+    from the capture of tools/make_profiles.sh); None for other sizes."""
+    p = os.path.join(ROOT, "profiles", "r02_step_traffic.json")
     if os.path.exists(p):
         d = json.load(open(p))
         if int(d.get("M", -1)) == int(M):
@@ -503,8 +504,8 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(M) if args.mode == "gather" and world == 1 else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_step": alg_bytes,
-                "kernel": f"assembly pass = k_geom + k_ring (edge-node rows, ring order, TMA bulk stores) + k_gather "
-                          f"(vertex-node rows) bucket launches ({launches} launches/step); time = whole pass, CUDA events"
+                "kernel": f"assembly pass = k_geom + k_ring (edge-node rows, ring order, TMA bulk stores) + k_task "
+                          f"(vertex-node rows, block tasks) bucket launches ({launches} launches/step); time = whole pass, CUDA events"
                 if args.mode == "gather" else f"{args.mode} scatter pass ({launches} launches/step)"}
 
     extra = {}
@@ -582,7 +583,8 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"config {3 if M == 70 else (5 if M == 101 else '3-like')}: linear elasticity P2 3D cube H/h={M} per GPU, {ne} tets/GPU, "
+                "config": {"workload": f"{'config 3' if M == 70 else ('config 5' if M == 101 else 'config 3-like')}{' per GPU (weak-scaling box of sub-cubes)' if world > 1 else ''}: "
+                                       f"linear elasticity P2 3D cube H/h={M} per GPU, {ne} tets/GPU, "
                                        f"{nnz} CSR values/GPU (30x30 local blocks)",
                            "lambda": LAM, "mu": MU, "scatter_mode": args.mode,
                            "l2_policy": "outputs (5.7 GB at M=70) exceed the 126 MB L2; no flush needed",

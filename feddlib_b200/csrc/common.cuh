@@ -126,6 +126,9 @@ struct feddb200_pat {
     uint32_t *fanrec_d = nullptr;  // padded per-bucket records of the fan kernel (3D P2 ring-ordered edge-node rows)
     void *tiletet_d = nullptr;     // [n_tiles] tile blocks (400 bytes: header, row nodes, incident elements; star_kernels.cuh)
     double *geom_d = nullptr;      // [ne][GS] per-element geometry cache, recomputed by every assembly
+    // boundary-sector fragments of the row-gather path (kernels.cuh: "fragment protocol"): two 32-byte slots per node row
+    // (head, tail); null if some node row is too short for the protocol
+    double *frag_d = nullptr;
     double *uel_d = nullptr;       // [ne][nloc][4] nodal velocities of each element (operators with a velocity argument)
     double *dt_d = nullptr;        // [ne][dim][dim][4] |det| * grad u at the element's vertices
     bool gather_ready = false;

@@ -743,7 +743,8 @@ struct RowInfo {
     int64_t k0;     // first incidence
     int32_t len;    // node-row length
     int32_t ninc;   // number of incidences
-    int64_t pad;
+    int64_t pad;    // bits 0-1 row type, bit 4 the row has positions without a local contribution, bit 5 the row's tail goes
+                    // straight to the values array (last row of the fragment protocol), bits 32-63 the row (index in the pattern)
     uint32_t e[8];  // elements of the row's first incidences -- lets k_gather_s request the geometry lines of a
                     // row's first incidences from the row record alone (second 32-byte half)
 };
@@ -767,8 +768,55 @@ struct GatherArgs {
     int64_t seg_begin[kMaxGhostSeg + 1];
     double *seg_ptr[kMaxGhostSeg];
     const uint32_t *ahead;    // k_gather_s: element of the incidence kRsAhead places further along the same row
+    double *frag;             // fragment protocol (below): two 32-byte slots per node row; null: plain stores
     CanonR R;
 };
+
+// Fragment protocol of the write-out.  The values of a row node (all its dof rows) are one contiguous RUN of the values
+// array, 8-byte aligned, so its first and last 32-byte sector are shared with the neighbouring runs -- rows of another type,
+// written by another launch milliseconds later.  A sector that reaches DRAM partially written costs a read-modify-write
+// there: measured on B200 (tools/microbench_frag.cu, microbench_chunk.cu) runs of 1944 bytes written in an order in which
+// neighbours are not written together reach 3.6 TB/s, the same runs 32-byte aligned 5.4 TB/s, in address order 5.7 TB/s.
+// So every launch writes only the WHOLE sectors of its runs; the doubles in front of the first / behind the last sector
+// boundary go, as whole 32-byte stores, into the run's head / tail slot of a side buffer (frag[2 row], frag[2 row + 1],
+// values at their position inside the sector), and k_stitch composes every shared sector from the tail slot of the left
+// run and the head slot of the right run after the last launch (4.5 TB/s for the three passes together).
+// Rows flagged with bit 5 of RowInfo::pad (the last row of the protocol: nothing behind it completes the sector) store
+// their tail doubles directly.  Runs are at least 8 doubles long (checked when the maps are built).
+__device__ __forceinline__ void st_v4(double *p, double a, double b, double c, double d);
+struct RunSplit {
+    int hc, tc;      // doubles in front of the first / behind the last sector boundary
+};
+__device__ __forceinline__ RunSplit run_split(const double *outp, int total)
+{
+    const int mis = (int)((reinterpret_cast<uintptr_t>(outp) >> 3) & 3);
+    RunSplit s;
+    s.hc = (4 - mis) & 3;
+    s.tc = (mis + total) & 3;
+    return s;
+}
+// head / tail doubles of the run [src, src + total) (shared or generic memory) into the slots of `row`
+__device__ __forceinline__ void frag_head(double *frag, int64_t row, const double *src, int hc)
+{
+    const int mis = 4 - hc;   // hc in 1..3
+    st_v4(frag + 8 * row, 0.0, mis <= 1 ? src[1 - mis] : 0.0, mis <= 2 ? src[2 - mis] : 0.0, src[3 - mis]);
+}
+__device__ __forceinline__ void frag_tail(double *frag, int64_t row, const double *src_tail, int tc)
+{
+    st_v4(frag + 8 * row + 4, src_tail[0], tc > 1 ? src_tail[1] : 0.0, tc > 2 ? src_tail[2] : 0.0, 0.0);
+}
+// one thread per boundary between the runs of rows r and r + 1 (r + 1 < n_rows_protocol)
+__global__ void __launch_bounds__(256) k_stitch(int64_t n_bound, const int64_t *__restrict__ rowptr, int mult, double *__restrict__ values,
+                                                const double *__restrict__ frag)
+{
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_bound; r += (int64_t)gridDim.x * blockDim.x) {
+        double *e = values + (int64_t)mult * rowptr[r + 1];
+        const int t = (int)((reinterpret_cast<uintptr_t>(e) >> 3) & 3);
+        if (t == 0) continue;
+        const double4 a = *reinterpret_cast<const double4 *>(frag + 8 * r + 4), b = *reinterpret_cast<const double4 *>(frag + 8 * (r + 1));
+        st_v4(e - t, a.x, t > 1 ? a.y : b.y, t > 2 ? a.z : b.z, b.w);
+    }
+}
 
 // destination of the values at offset `off` of the values array (see GatherArgs::nseg)
 __device__ __forceinline__ double *out_ptr(const GatherArgs &A, int64_t off)
@@ -820,6 +868,12 @@ __device__ __forceinline__ void bulk_commit_wait_read()
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// prefetch.global.L2 brings in ONE 32-byte sector (ncu: 12 sectors per warp-wide prefetch of ten 128-byte lines); whole
+// lines / spans go through the bulk (TMA) prefetch: address 16-byte aligned, size a multiple of 16
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void ld_v4(const double *p, double (&v)[4])
 {
     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
@@ -930,6 +984,7 @@ __global__ void __launch_bounds__(GatherShape<OPG, DIM>::NT, FB_GATHER_MINBLOCKS
     constexpr int ROWS = 32;                 // accumulator rows per block
     extern __shared__ double acc[];          // [ROWS][pitch]
     __shared__ int64_t s_off[ROWS];
+    __shared__ int64_t s_flags[ROWS];
     __shared__ int s_n[ROWS];
     const int tid = threadIdx.x;
     const int pitch = A.pitch;
@@ -938,7 +993,7 @@ __global__ void __launch_bounds__(GatherShape<OPG, DIM>::NT, FB_GATHER_MINBLOCKS
     const int64_t rloc = live ? t / CPR : 0;
     const int comp = live ? (int)(t - rloc * CPR) : 0;
     const int a = comp / NBL, b = comp - a * NBL;
-    int64_t base = 0, k0 = 0;
+    int64_t base = 0, k0 = 0, rflags = 0;
     int L = 0, ninc = 0;
     if (live) {
         double raw[4];
@@ -948,6 +1003,7 @@ __global__ void __launch_bounds__(GatherShape<OPG, DIM>::NT, FB_GATHER_MINBLOCKS
         const int64_t ln = __double_as_longlong(raw[2]);
         L = (int)(ln & 0xffffffff);
         ninc = (int)(ln >> 32);
+        rflags = __double_as_longlong(raw[3]);
     }
     const int64_t k1 = k0 + ninc, kl = k1 - 1;
     IncRec<NL> rc, rn, r2;
@@ -964,6 +1020,7 @@ __global__ void __launch_bounds__(GatherShape<OPG, DIM>::NT, FB_GATHER_MINBLOCKS
     if (b == 0) {
         s_n[row] = live ? NBL * L : 0;
         s_off[row] = OPG == 1 ? (int64_t)CPR * base + (int64_t)a * NBL * L : base;
+        s_flags[row] = rflags;
     }
     __syncthreads();
     double *my = acc + (size_t)row * pitch + b;
@@ -1066,6 +1123,23 @@ __global__ void __launch_bounds__(GatherShape<OPG, DIM>::NT, FB_GATHER_MINBLOCKS
     for (int r = tid >> 5; r < ROWS; r += NT / 32) {
         const int nr = s_n[r];
         const double *src = acc + (size_t)r * pitch;
+        if (A.frag != nullptr && A.nseg == 0) {
+            // fragment protocol: this accumulator row is dof row a = r % NBL of its node; the node's run starts with
+            // dof row 0 and ends with dof row NBL - 1 (the boundaries between them are written by this block together)
+            if (nr == 0) continue;
+            double *out = A.values + s_off[r];
+            const int64_t fl = s_flags[r];
+            const int a_r = r % NBL;
+            const RunSplit sp = run_split(out, nr);
+            const int lo = a_r == 0 ? sp.hc : 0;
+            const bool tail_frag = a_r == NBL - 1 && sp.tc != 0 && (fl & 32) == 0;
+            const int hi = tail_frag ? nr - sp.tc : nr;
+#pragma unroll 4
+            for (int x = lo + lane; x < hi; x += 32) st_out(out + x, src[x]);
+            if (lane == 0 && lo != 0) frag_head(A.frag, fl >> 32, src, sp.hc);
+            if (lane == 1 && tail_frag) frag_tail(A.frag, fl >> 32, src + hi, sp.tc);
+            continue;
+        }
         for (int d = 0; d < nrep; d++) {
             double *out = out_ptr(A, (int64_t)nrep * s_off[r]) + (int64_t)d * nr;
 #pragma unroll 4
@@ -1091,10 +1165,27 @@ __global__ void __launch_bounds__(GatherShape<OPG, DIM>::NT, FB_GATHER_MINBLOCKS
 #ifndef FB_RING_UNROLL
 #define FB_RING_UNROLL 1
 #endif
+#ifndef FB_RING_PF_AT
+#define FB_RING_PF_AT 1      // main-loop iteration after which the next tile's lines are requested into L2
+#endif
+// L2 prefetch of k_ring (tuning aid).  0: one sector of the geometry line two incidences ahead (default), 1: that whole line
+// (bulk prefetch), 2: everything the next tile reads, a tile ahead (bulk prefetches), 3: 1 + 2.  Measured on B200, config 3:
+// 2.49 / 2.71 / 2.65 / 2.91 ms per assembly -- every additional prefetched byte makes the step SLOWER: the ring launches move
+// 3.5-3.8 TB/s of DRAM traffic (writes + reads), the ceiling of this write pattern (tools/microbench_window.cu), so they are
+// bound by DRAM traffic, not by the latency their long-scoreboard stalls suggest.
+#ifndef FB_RING_PF_MODE
+#define FB_RING_PF_MODE 0
+#endif
 constexpr int kRingUnroll = FB_RING_UNROLL;
+__device__ __forceinline__ void cp_async16(void *sdst, const void *gsrc);
+__device__ __forceinline__ void cp_async_commit();
+template <int N> __device__ __forceinline__ void cp_async_wait();
 template <int OPG>
 __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
 {
+#if FB_RING_PF_MODE >= 2
+    __shared__ uint4 s_en[2][64];   // elements of the next tile's rows (second half of their row records), per lane
+#endif
     constexpr int DIM = 3, NL = 10, NVTX = 4;
     constexpr int TPR = OPG == 1 ? DIM : 1;
     constexpr int NB = OPG == 1 ? DIM : 1;
@@ -1154,7 +1245,36 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
         const bool live_n = lane_used && tile_n < ntiles && node_n < A.count;
         double rawn[4] = {0.0, 0.0, 0.0, 0.0};
         if (live_n) ld_v4(reinterpret_cast<const double *>(A.rowinfo + A.start + node_n), rawn);
-
+#if FB_RING_PF_MODE >= 2
+        // ... and the elements of its rows (second half of the row record): their geometry lines, the rows' incidence
+        // records and the row records of the tile after the next are requested into L2 a whole tile ahead (do_prefetch
+        // below, issued by the node's first lane from inside the main loop, once this load has landed).  These lines are
+        // streamed (no reuse): without the request every tile waits for DRAM three times in a row -- row record, first
+        // incidence records, first geometry line (ncu source page: 10 %, 12 % and 31 % of the kernel's stall samples).
+        // (the element list waits in shared memory, not in registers: the main loop has none to spare)
+        const bool pf_lane = live_n && lane == slot * TPR;
+        if (pf_lane) {
+            const char *src = reinterpret_cast<const char *>(A.rowinfo + A.start + node_n) + 32;
+            cp_async16(&s_en[0][tid], src);
+            cp_async16(&s_en[1][tid], src + 16);
+        }
+        cp_async_commit();
+        bool pf_done = !pf_lane;
+        auto do_prefetch = [&]() {
+            const int64_t k0p = __double_as_longlong(rawn[1]);
+            const int nincp = (int)(__double_as_longlong(rawn[2]) >> 32);
+            cp_async_wait<0>();
+            const uint4 e0 = s_en[0][tid], e1 = s_en[1][tid];
+            const uint32_t en[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (j < nincp) prefetch_l2_bulk(A.geom + (int64_t)en[j] * GeomStride<DIM>::value, GeomStride<DIM>::value * 8);
+            if (nincp > 0) prefetch_l2_bulk(A.rec + k0p * RecWords<NL>::value, (uint32_t)nincp * RecWords<NL>::value * 4);
+            const int64_t node_nn = node_n + tile_step * NPT;
+            if (node_nn < A.count) prefetch_l2_bulk(A.rowinfo + A.start + node_nn, (uint32_t)sizeof(RowInfo));
+            pf_done = true;
+        };
+#endif
         const int n = NB * L;                         // values of this thread's dof row
         const int64_t off_node = (int64_t)TPR * NB * nrep * base; // first value of the node's TPR dof rows (contiguous)
         // the node's rows are stored back to back in shared memory (node pitch A.pitch), shifted by one double where
@@ -1220,12 +1340,23 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
                 {
                     const int dep = __double2hiint(E[0][0][0]) & A.zero;
                     const uint32_t perm = rec_perm<NL>(rn.w);
+#ifdef FB_WHATIF_GEOM0   // timing experiment only (wrong values): every geometry load hits L1
+                    const double *gp = A.geom + (int64_t)(rec_elem<NL>(rn.w) & 63) * GeomStride<DIM>::value + dep;
+#else
                     const double *gp = A.geom + (int64_t)rec_elem<NL>(rn.w) * GeomStride<DIM>::value + dep;
+#endif
 #pragma unroll
                     for (int v = 0; v < 4; v++) ld_v4g(gp + 4 * ((perm >> (2 * v)) & 3), g.G[v]);
+#ifdef FB_WHATIF_REC0    // timing experiment only (wrong values): every record load hits L1
+                    load_rec<NL>(A, k0 + ((k + 3 - k0) & 1), r3);
+#else
                     load_rec<NL>(A, k + 3 < kl ? k + 3 : kl, r3);
-#ifndef FB_NO_L2_PREFETCH
+#endif
+#if FB_RING_PF_MODE == 0
                     prefetch_l2(A.geom + (int64_t)rec_elem<NL>(r2.w) * GeomStride<DIM>::value);
+#elif FB_RING_PF_MODE == 1 || FB_RING_PF_MODE == 3
+                    // the whole geometry line of the incidence two places on (one request per node)
+                    if (lane == slot * TPR) prefetch_l2_bulk(A.geom + (int64_t)rec_elem<NL>(r2.w) * GeomStride<DIM>::value, GeomStride<DIM>::value * 8);
 #endif
                 }
                 auto contrib = [&](int jc, int b) {
@@ -1269,10 +1400,16 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
                     }
                 }
                 rc = rn; rn = r2; r2 = r3;
+#if FB_RING_PF_MODE >= 2
+                if (!pf_done && k >= k0 + FB_RING_PF_AT) do_prefetch();
+#endif
             }
 #pragma unroll
             for (int b = 0; b < NB; b++) { my[p_v0 + b] = accE[0][b]; my[p_v1 + b] = accE[1][b]; my[p_self + b] = accE[2][b]; }
         }
+#if FB_RING_PF_MODE >= 2
+        if (!pf_done) do_prefetch();
+#endif
 
         // first incidence records of the next tile (their addresses come from the row record fetched above)
         const int64_t k0n = __double_as_longlong(rawn[1]);
@@ -1288,6 +1425,23 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
         // bulk store per node (SASS UBLKCP) moves the 16-byte aligned interior; the at most two odd doubles go by plain
         // stores.  (One store per dof row is limited by the rate of bulk operations: 45 cycles per SM each.)
         __syncwarp();
+        if (a == 0 && n > 0 && A.frag != nullptr && A.nseg == 0) {
+            // fragment protocol: whole sectors by one bulk store, the head / tail doubles into the row's slots
+            bulk_fence();
+            const int total = TPR * n;
+            const int64_t fl = __double_as_longlong(raw[3]);
+            const RunSplit sp = run_split(outp, total);
+            const bool tail_plain = (fl & 32) != 0;
+            const int body_n = total - sp.hc - sp.tc;
+#ifndef FB_WHATIF_NOSTORE   // timing experiment only: no write-out
+            if (body_n > 0) bulk_store(outp + sp.hc, nodep + sp.hc, body_n * 8);
+#endif
+            if (sp.hc) frag_head(A.frag, fl >> 32, nodep, sp.hc);
+            if (sp.tc) {
+                if (tail_plain) { for (int x = total - sp.tc; x < total; x++) outp[x] = nodep[x]; }
+                else frag_tail(A.frag, fl >> 32, nodep + total - sp.tc, sp.tc);
+            }
+        } else
         if (a == 0 && n > 0) {
             bulk_fence(); // make the generic-proxy shared-memory writes visible to the async proxy
             const int total = TPR * n;

@@ -56,7 +56,7 @@ __global__ void k_task_build(const TaskBuildArgs A, int emit)
             B[4 + 4 * i] = (uint32_t)((uint64_t)R.base & 0xffffffffu);
             B[5 + 4 * i] = (uint32_t)((uint64_t)R.base >> 32);
             B[6 + 4 * i] = (uint32_t)R.len;
-            B[7 + 4 * i] = (R.pad & 16) ? 1u : 0u;
+            B[7 + 4 * i] = ((R.pad & 16) ? 1u : 0u) | ((R.pad & 32) ? 2u : 0u) | (uint32_t)((uint64_t)R.pad >> 32) << 2;   // holes | tail plain | row
             for (int j = 0; j < ninc[i]; j++, m++) {
                 const uint32_t *w = A.rec + (k0[i] + j) * 8;
                 B[36 + 2 * m] = w[5];
@@ -149,10 +149,12 @@ __global__ void __launch_bounds__(64, 8) k_task(const TaskArgs A)
         // row nodes of the tile (lane = node slot)
         int64_t base = 0;
         int L = 0;
+        uint32_t nflags = 0;
         if (lane < n_nodes) {
             const uint4 nd = blk[buf * kTileBlkChunks + 1 + lane];
             base = (int64_t)((uint64_t)nd.x | (uint64_t)nd.y << 32);
             L = (int)nd.z;
+            nflags = nd.w;
         }
         // stage: lane m = element slot m.  vector 0: |det| G_0 (row function: canonical vertex 0), vector 1 + jc:
         // q_jc = R_jc^0 G_sv(jc,0) + R_jc^1 G_sv(jc,1)
@@ -252,6 +254,20 @@ __global__ void __launch_bounds__(64, 8) k_task(const TaskArgs A)
 
         // write-out: ONE TMA bulk store per node (its TPR dof rows are one contiguous run); odd head / tail doubles and
         // replicated rows of the other phase by plain stores
+        if (lane < n_nodes && n > 0 && A.G.frag != nullptr && A.G.nseg == 0) {
+            // fragment protocol (kernels.cuh): whole sectors by one bulk store, head / tail doubles into the row's slots
+            bulk_fence();
+            const int total = TPR * n;
+            const double *nodep = rows + my_rowoff;
+            const RunSplit sp = run_split(outp, total);
+            const int body_n = total - sp.hc - sp.tc;
+            if (body_n > 0) bulk_store(outp + sp.hc, nodep + sp.hc, body_n * 8);
+            if (sp.hc) frag_head(A.G.frag, nflags >> 2, nodep, sp.hc);
+            if (sp.tc) {
+                if (nflags & 2u) { for (int x = total - sp.tc; x < total; x++) outp[x] = nodep[x]; }
+                else frag_tail(A.G.frag, nflags >> 2, nodep + total - sp.tc, sp.tc);
+            }
+        } else
         if (lane < n_nodes && n > 0) {
             bulk_fence();
             const int total = TPR * n;

@@ -8,5 +8,5 @@ for f in core tables api csrops; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr "$@" -c $f.cu -o /tmp/fbv_$N/$f.o &
 done
 wait
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../variants/lib_$N.so /tmp/fbv_$N/core.o /tmp/fbv_$N/tables.o /tmp/fbv_$N/api.o /tmp/fbv_$N/csrops.o -lcudart
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../variants/lib_$N.so /tmp/fbv_$N/core.o /tmp/fbv_$N/tables.o /tmp/fbv_$N/api.o /tmp/fbv_$N/csrops.o _build/halo.o -lcudart
 echo built variants/lib_$N.so
