@@ -695,11 +695,8 @@ void op_coefficients(const OpTables &t, int dim, int nl_vel, OpCoef &C, int what
             const double *phi = &t.phi[q * t.np];
             for (int type = 0; type < ntypes; type++) {
                 const int ir = type == 0 ? 0 : nv;
-                for (int j = 0; j < nl_vel; j++) {
-                    for (int m = 0; m < nl_vel; m++)
-                        for (int tt = 0; tt < (j < nv ? 1 : 2); tt++) C.TN[type][m][j][tt] += w * phi[ir] * phi[m] * cgrad(lam, j, tt);
+                for (int j = 0; j < nl_vel; j++)
                     for (int v = 0; v < nv; v++) C.MW[type][j][v] += w * lam[v] * phi[ir] * phi[j];
-                }
             }
         } else if (what == 3) {
             const double *phi = &t.phi[q * t.np];
@@ -719,6 +716,42 @@ void op_coefficients(const OpTables &t, int dim, int nl_vel, OpCoef &C, int what
     }
 }
 
+// coefficient tensors of k_sloc (kernels.cuh), natural local order, from the operators' own quadrature rules:
+//   TNF[i][m][j][t] = sum_q w phi_i phi_m c_{jt}   (advection rule)      RLF[i][j][s][t] = sum_q w c_{is} c_{jt}   (Grad-Grad rule)
+// with c_{jt} the coefficient of G_sv(j,t) in grad phi_j (P2 vertex v: 4 lambda_v - 1; edge (p,q): 4 lambda_q on p, 4 lambda_p
+// on q; P1: 1).  Layout: TNF[nl][nl][nl][2] | RLF[nl][nl][2][2].
+void sloc_tables(const OpTables &ta, const OpTables *tl, int dim, int nl, std::vector<double> &out)
+{
+    const int nv = dim + 1;
+    const bool p2 = nl > nv;
+    static const int E2[3][2] = {{0, 1}, {1, 2}, {0, 2}};
+    static const int E3[6][2] = {{0, 1}, {1, 2}, {0, 2}, {0, 3}, {1, 3}, {2, 3}};
+    auto sv = [&](int j, int k) { return j < nv ? j : (dim == 2 ? E2[j - nv][k] : E3[j - nv][k]); };
+    auto cgrad = [&](const double *lam, int j, int tt) {
+        if (!p2) return 1.0;
+        return j < nv ? 4.0 * lam[j] - 1.0 : 4.0 * lam[sv(j, 1 - tt)];
+    };
+    const size_t ntn = (size_t)nl * nl * nl * 2, nrl = (size_t)nl * nl * 4;
+    out.assign(ntn + nrl, 0.0);
+    for (int q = 0; q < ta.nq; q++) {
+        const double *lam = &ta.lam[q * 4], *phi = &ta.phi[q * ta.np];
+        for (int i = 0; i < nl; i++)
+            for (int m = 0; m < nl; m++)
+                for (int j = 0; j < nl; j++)
+                    for (int tt = 0; tt < (j < nv ? 1 : 2); tt++)
+                        out[(((size_t)i * nl + m) * nl + j) * 2 + tt] += ta.w[q] * phi[i] * phi[m] * cgrad(lam, j, tt);
+    }
+    if (tl)
+        for (int q = 0; q < tl->nq; q++) {
+            const double *lam = &tl->lam[q * 4];
+            for (int i = 0; i < nl; i++)
+                for (int j = 0; j < nl; j++)
+                    for (int ss = 0; ss < (i < nv ? 1 : 2); ss++)
+                        for (int tt = 0; tt < (j < nv ? 1 : 2); tt++)
+                            out[ntn + (((size_t)i * nl + j) * 2 + ss) * 2 + tt] += tl->w[q] * cgrad(lam, i, ss) * cgrad(lam, j, tt);
+        }
+}
+
 template <int OPX, int DIM, int NLR, int NL>
 int launch_gatherx_t(feddb200_ctx *c, feddb200_pat *p, const feddb200_mesh *vm, const double *u_d, double *values_d, int vec_dim,
                      const OpCoef &C)
@@ -730,17 +763,32 @@ int launch_gatherx_t(feddb200_ctx *c, feddb200_pat *p, const feddb200_mesh *vm, 
         k_geom<DIM, NLV><<<(unsigned)((ne + 255) / 256), 256, 0, c->stream>>>(ne, vm->conn_d, vm->coords_d, p->geom_d);
         c->launches++;
         if constexpr (S::NEEDS_U) {
-            if (!p->uel_d) {
-                FB_CUDA(cudaMalloc(&p->uel_d, sizeof(double) * 4 * NLV * ne));
-                FB_CUDA(cudaMalloc(&p->dt_d, sizeof(double) * 4 * DIM * DIM * ne));
+            if (!p->dt_d) FB_CUDA(cudaMalloc(&p->dt_d, sizeof(double) * 4 * DIM * DIM * ne));
+            if constexpr (OPX != X_ADV) {   // |det| grad u at the vertices: W(u)
+                k_udata<DIM, NLV><<<(unsigned)((ne + 255) / 256), 256, 0, c->stream>>>(ne, vm->conn_d, p->geom_d, u_d, nullptr, p->dt_d, 1);
+                c->launches++;
             }
-            k_udata<DIM, NLV><<<(unsigned)((ne + 255) / 256), 256, 0, c->stream>>>(ne, vm->conn_d, p->geom_d, u_d, p->uel_d, p->dt_d,
-                                                                                   OPX != X_ADV);
-            c->launches++;
+            if constexpr (OPX != X_ADVU) {  // scalar local matrices: N(u) [+ the viscous term]
+                if (!p->sloc_d) FB_CUDA(cudaMalloc(&p->sloc_d, sizeof(double) * NLV * NLV * ne));
+                if (!p->sloc_tab_d) {       // once per pattern
+                    OpTables ta, tl;
+                    if (build_tables(ta, OP_ADV, DIM, NLV, NLV) != 0 || build_tables(tl, OP_LAP, DIM, NLV, NLV) != 0) { set_error("no tables"); return FEDDB200_ELOGIC; }
+                    std::vector<double> tab;
+                    sloc_tables(ta, &tl, DIM, NLV, tab);
+                    FB_CUDA(cudaMalloc(&p->sloc_tab_d, sizeof(double) * tab.size()));
+                    FB_CUDA(cudaMemcpy(p->sloc_tab_d, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
+                }
+                const int nts = 128;
+                const size_t smem_s = sizeof(double) * ((size_t)NLV * NLV * NLV * 2 + (size_t)NLV * NLV * 4 + (size_t)16 * nts);
+                k_sloc<DIM, NLV><<<(unsigned)((ne + nts - 1) / nts), nts, smem_s, c->stream>>>(
+                    ne, vm->conn_d, p->geom_d, u_d, p->sloc_tab_d, OPX == X_NSJ ? C.c0 : 0.0, OPX == X_NSJ ? C.c1 : 1.0, p->sloc_d);
+                c->launches++;
+            }
+            FB_CUDA(cudaGetLastError());
         }
     }
     GatherXArgs G;
-    G.rowinfo = (const RowInfo *)p->rowinfo_d; G.rec = p->rec_d; G.geom = p->geom_d; G.uel = p->uel_d; G.dt = p->dt_d;
+    G.rowinfo = (const RowInfo *)p->rowinfo_d; G.rec = p->rec_d; G.geom = p->geom_d; G.sloc = p->sloc_d; G.dt = p->dt_d;
     G.values = values_d; G.vec_dim = vec_dim; G.C = C;
     const size_t budget = c->smem_optin - 1024;
     // small buckets on a side stream, underneath the large launches (see launch_gather_t)
@@ -806,13 +854,6 @@ int launch_gatherx(feddb200_ctx *c, feddb200_pat *p, int op, const feddb200_mesh
     } else if (square) {
         if (build_tables(t, OP_ADV, dim, nr, nr) != 0) { set_error("no tables"); return FEDDB200_ELOGIC; }
         op_coefficients(t, dim, nr, C, 0);
-        if (op == OP_NSJ) {
-            OpTables tl;
-            if (build_tables(tl, OP_LAP, dim, nr, nr) != 0) { set_error("no tables"); return FEDDB200_ELOGIC; }
-            CanonR R;
-            canon_table(tl, dim, nr, R);
-            std::memcpy(C.RL, R.r, sizeof(C.RL));
-        }
     } else {
         const int nvel = op == OP_B ? nc : nr, npre = op == OP_B ? nr : nc;
         if (build_tables(t, op, dim, nvel, npre) != 0) { set_error("no tables"); return FEDDB200_ELOGIC; }

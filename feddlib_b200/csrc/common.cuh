@@ -129,7 +129,8 @@ struct feddb200_pat {
     // boundary-sector fragments of the row-gather path (kernels.cuh: "fragment protocol"): two 32-byte slots per node row
     // (head, tail); null if some node row is too short for the protocol
     double *frag_d = nullptr;
-    double *uel_d = nullptr;       // [ne][nloc][4] nodal velocities of each element (operators with a velocity argument)
+    double *sloc_d = nullptr;      // [ne][nloc][nloc] scalar local matrices of N(u) / the fused Navier-Stokes block (k_sloc)
+    double *sloc_tab_d = nullptr;  // coefficient tensors of k_sloc (uploaded once per pattern)
     double *dt_d = nullptr;        // [ne][dim][dim][4] |det| * grad u at the element's vertices
     bool gather_ready = false;
     std::vector<fb::Bucket> buckets;

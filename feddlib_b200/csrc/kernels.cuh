@@ -1787,11 +1787,16 @@ __global__ void __launch_bounds__(64, FB_GS_MINBLOCKS) k_gather_s(const GatherAr
 //   W_ij^ab  = |det| sum_v     MW[i][j][v] D^(v)[b][a]              (D = sum_m u_m (x) grad phi_m is affine)
 //   B_i,(j,d)= |det| sum_t     BC[j][t] G_t[d]
 // One thread per CSR dof row (I, a); accumulators in a shared-memory row laid out like the CSR row.
+//
+// The SCALAR part of N(u) and of the fused Navier-Stokes block -- the same number on the three diagonal entries of a node
+// block -- is evaluated ONCE PER ELEMENT by k_sloc (element-stationary, one thread per element):
+//   S_e[i][j] = c0 |det| sum_{s,t} RLF[i][j][s][t] G_sv(i,s).G_sv(j,t)  +  c1 |det| sum_{m,t} TNF[i][m][j][t] (u_m . G_sv(j,t))
+// (natural local order, 800 bytes per P2 tetrahedron), and the row kernels read their row of it (ten 8-byte loads per
+// incidence) instead of contracting the 160-term tensor in every one of the 3 x 10 dof-row threads that meet the element:
+// k_gatherx<X_NSJ> went from 246 registers / 900 instructions per incidence to the W(u) contraction alone.
 // =========================================================================================
 struct OpCoef {
-    double TN[2][MAXN][MAXN][2];  // [row type][m'][j'][t']   sum_q w phi_i' phi_m' c_{j' t'}
     double MW[2][MAXN][4];        // [row type][j'][v']       sum_q w lambda_v' phi_i' phi_j'
-    double RL[2][MAXN][2][2];     // Laplace part of the fused block, as CanonR
     double BC[MAXN][2];           // B:   [j'][t']            sum_q w psi_0 c_{j' t'}
     double BTC[2][4][2];          // B^T: [row type][j'][s']  sum_q w psi_j' c_{i' s'}
     double MM[2][MAXN];           // mass: [row type][j']     sum_q w phi_i' phi_j'
@@ -1813,10 +1818,9 @@ __global__ void __launch_bounds__(256) k_udata(int64_t ne, const int32_t *__rest
 #pragma unroll
     for (int m = 0; m < NL; m++) {
         const int64_t n = conn[e * NL + m];
-        double *o = uel + (e * NL + m) * 4;
 #pragma unroll
         for (int d = 0; d < DIM; d++) U[m][d] = u[n * DIM + d];
-        st_v4(o, U[m][0], U[m][1], DIM == 3 ? U[m][DIM - 1] : 0.0, 0.0);
+        if (uel != nullptr) st_v4(uel + (e * NL + m) * 4, U[m][0], U[m][1], DIM == 3 ? U[m][DIM - 1] : 0.0, 0.0);
     }
     if (!want_dt) return;
     const double *g = geom + e * GS;
@@ -1863,6 +1867,112 @@ __global__ void __launch_bounds__(256) k_udata(int64_t ne, const int32_t *__rest
         }
 }
 
+// natural vertex support of local node i (run-time index): vertex functions sit on one vertex, edge functions on two
+template <int DIM>
+__device__ __forceinline__ int sv_rt(int i, int t)
+{
+    constexpr int NVTX = DIM + 1;
+    // packed 2-bit fields of canon_sv's edge tables
+    constexpr uint32_t P0 = DIM == 2 ? (0u | 1u << 2 | 0u << 4) : (0u | 1u << 2 | 0u << 4 | 0u << 6 | 1u << 8 | 2u << 10);
+    constexpr uint32_t P1 = DIM == 2 ? (1u | 2u << 2 | 2u << 4) : (1u | 2u << 2 | 2u << 4 | 3u << 6 | 3u << 8 | 3u << 10);
+    if (i < NVTX) return i;
+    return (int)(((t == 0 ? P0 : P1) >> (2 * (i - NVTX))) & 3u);
+}
+
+// Element-stationary pre-pass of N(u) and of the fused Navier-Stokes block: the scalar local matrix S_e (see the header of
+// this section), one thread per element, after k_geom.  tab = TNF[NL][NL][NL][2] | RLF[NL][NL][2][2] (api.cu: sloc_tables),
+// staged in shared memory and read with warp-uniform addresses; the element's Gram matrix |det| G_a.G_b sits in a
+// per-thread shared-memory column because the row loop indexes it at run time.
+template <int DIM, int NL>
+__global__ void __launch_bounds__(128) k_sloc(int64_t ne, const int32_t *__restrict__ conn, const double *__restrict__ geom,
+                                              const double *__restrict__ u, const double *__restrict__ tab, double c0, double c1,
+                                              double *__restrict__ sloc)
+{
+    constexpr int NVTX = DIM + 1, GS = GeomStride<DIM>::value;
+    constexpr int NTN = NL * NL * NL * 2, NRL = NL * NL * 4;
+    constexpr bool P2 = NL > NVTX;
+    extern __shared__ double sm_sloc[];
+    double *const tn = sm_sloc, *const rl = sm_sloc + NTN, *const gmall = rl + NRL;
+    const int NT = blockDim.x, tid = threadIdx.x;
+    for (int x = tid; x < NTN + NRL; x += NT) sm_sloc[x] = tab[x];
+    __syncthreads();
+    const int64_t e = blockIdx.x * (int64_t)NT + tid;
+    if (e >= ne) return;
+    double G[NVTX][DIM], adet;
+    {
+        const double *g = geom + e * GS;
+        if constexpr (DIM == 3) {
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                double t4[4];
+                ld_v4(g + 4 * v, t4);
+                G[v][0] = t4[0]; G[v][1] = t4[1]; G[v][2] = t4[2];
+                if (v == 0) adet = t4[3];
+            }
+        } else {
+#pragma unroll
+            for (int v = 0; v < 3; v++) { G[v][0] = g[2 * v]; G[v][1] = g[2 * v + 1]; }
+            adet = g[6];
+        }
+    }
+    double *const gm = gmall + tid;   // gm[(a * 4 + b) * NT]
+#pragma unroll
+    for (int a = 0; a < NVTX; a++)
+#pragma unroll
+        for (int b = 0; b < NVTX; b++) {
+            double x = 0.0;
+#pragma unroll
+            for (int d = 0; d < DIM; d++) x += G[a][d] * G[b][d];
+            gm[(a * 4 + b) * NT] = x * adet;
+        }
+    double s[NL][NVTX];   // |det| u_m . G_t
+#pragma unroll
+    for (int m = 0; m < NL; m++) {
+        const int64_t n = conn[e * NL + m];
+        double um[DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; d++) um[d] = u != nullptr ? u[n * DIM + d] : 0.0;
+#pragma unroll
+        for (int t = 0; t < NVTX; t++) {
+            double x = 0.0;
+#pragma unroll
+            for (int d = 0; d < DIM; d++) x += um[d] * G[t][d];
+            s[m][t] = x * adet;
+        }
+    }
+    double *out = sloc + e * (int64_t)(NL * NL);
+#pragma unroll 1
+    for (int i = 0; i < NL; i++) {
+        double acc[NL];
+#pragma unroll
+        for (int j = 0; j < NL; j++) acc[j] = 0.0;
+        const double *T = tn + i * (NL * NL * 2);
+#pragma unroll
+        for (int m = 0; m < NL; m++)
+#pragma unroll
+            for (int j = 0; j < NL; j++) {
+                const double2 c = *reinterpret_cast<const double2 *>(T + (m * NL + j) * 2);
+                acc[j] = fma(c.x, s[m][canon_sv<DIM>(j, 0)], acc[j]);
+                if (P2 && j >= NVTX) acc[j] = fma(c.y, s[m][canon_sv<DIM>(j, 1)], acc[j]);
+            }
+        const int i0 = sv_rt<DIM>(i, 0), i1 = sv_rt<DIM>(i, 1);
+        const double *R = rl + i * (NL * 4);
+#pragma unroll
+        for (int j = 0; j < NL; j++) {
+            const double2 r0 = *reinterpret_cast<const double2 *>(R + j * 4), r1 = *reinterpret_cast<const double2 *>(R + j * 4 + 2);
+            double lap = r0.x * gm[(i0 * 4 + canon_sv<DIM>(j, 0)) * NT];
+            lap = fma(r1.x, gm[(i1 * 4 + canon_sv<DIM>(j, 0)) * NT], lap);      // zero coefficient for a vertex row function
+            if (P2 && j >= NVTX) {
+                lap = fma(r0.y, gm[(i0 * 4 + canon_sv<DIM>(j, 1)) * NT], lap);
+                lap = fma(r1.y, gm[(i1 * 4 + canon_sv<DIM>(j, 1)) * NT], lap);
+            }
+            acc[j] = c0 * lap + c1 * acc[j];
+        }
+#pragma unroll
+        for (int j = 0; j < NL; j++) out[i * NL + j] = acc[j];
+    }
+}
+
 enum OpX { X_ADV = 0, X_ADVU = 1, X_NSJ = 2, X_B = 3, X_BT = 4, X_MASS = 5 };
 template <int OPX, int DIM> struct OpXShape {
     static constexpr int RD = (OPX == X_ADV || OPX == X_B || OPX == X_MASS) ? 1 : DIM;   // threads (row dofs) per row node
@@ -1875,7 +1985,7 @@ struct GatherXArgs {
     const RowInfo *rowinfo;
     int64_t start, count;
     const uint32_t *rec;
-    const double *geom, *uel, *dt;
+    const double *geom, *sloc, *dt;   // geometry lines, scalar local matrices of k_sloc, |det| grad u of k_udata
     double *values;
     int pitch;                // doubles per thread in shared memory (odd)
     int vec_dim;              // mass: 0 scalar, DIM = replicate to the DIM block-diagonal dof rows
@@ -1948,7 +2058,7 @@ __global__ void __launch_bounds__(64, 4) k_gatherx(const GatherXArgs A)
         const int64_t e = rec_elem<NL>(rc.w);
         IncGeo<DIM> g;
         if constexpr (OPX == X_MASS) g.G[0][3] = __ldg(RA.geom + e * GS + (DIM == 3 ? 3 : 6)); // only |det| is needed
-        else if constexpr (OPX != X_ADVU) load_geo<DIM, NL>(RA, rc, g);
+        else if constexpr (OPX == X_B || OPX == X_BT) load_geo<DIM, NL>(RA, rc, g);
         double val[NL][NB];
 #pragma unroll
         for (int j = 0; j < NL; j++)
@@ -1956,55 +2066,15 @@ __global__ void __launch_bounds__(64, 4) k_gatherx(const GatherXArgs A)
             for (int b = 0; b < NB; b++) val[j][b] = 0.0;
 
         if constexpr (OPX == X_ADV || OPX == X_NSJ) {
-            // N_{i'j'} = sum_{m',t'} TN[m'][j'][t'] s[m'][t'],  s = |det| u_{m'} . G_{t'}   (added to column dof b = a only)
-            const double adet = g.G[0][3];
-            double vn[NL];
+            // scalar part: the row of the element's scalar local matrix (k_sloc) that belongs to the row node, natural order
+            const double *srow = A.sloc + (e * NL + rec_natidx<NL>(rc.w, JD)) * NL;
 #pragma unroll
-            for (int j = 0; j < NL; j++) vn[j] = 0.0;
+            for (int j = 0; j < NL; j++) {
+                const double sv = __ldg(srow + rec_natidx<NL>(rc.w, j));
+                if constexpr (OPX == X_ADV) val[j][0] = sv;
+                else {
 #pragma unroll
-            for (int m = 0; m < NL; m++) {
-                double um[4];
-                ld_v4(A.uel + (e * NL + rec_natidx<NL>(rc.w, m)) * 4, um);
-                double s[NVTX];
-#pragma unroll
-                for (int w = 0; w < NVTX; w++) {
-                    double x = 0.0;
-#pragma unroll
-                    for (int d = 0; d < DIM; d++) x += um[d] * g.G[w][d];
-                    s[w] = x * adet;
-                }
-#pragma unroll
-                for (int j = 0; j < NL; j++) {
-                    vn[j] += A.C.TN[TYPE][m][j][0] * s[canon_sv<DIM>(j, 0)];
-                    if (P2C && j >= NVTX) vn[j] += A.C.TN[TYPE][m][j][1] * s[canon_sv<DIM>(j, 1)];
-                }
-            }
-            if constexpr (OPX == X_ADV) {
-#pragma unroll
-                for (int j = 0; j < NL; j++) val[j][0] = vn[j];
-            } else {
-                // Laplace part: e[s][w] = |det| G_s . G_w
-                double el[NS][NVTX];
-#pragma unroll
-                for (int s2 = 0; s2 < NS; s2++)
-#pragma unroll
-                    for (int w = 0; w < NVTX; w++) {
-                        double x = 0.0;
-#pragma unroll
-                        for (int d = 0; d < DIM; d++) x += g.G[s2][d] * g.G[w][d];
-                        el[s2][w] = x * adet;
-                    }
-#pragma unroll
-                for (int j = 0; j < NL; j++) {
-                    double lap = 0.0;
-#pragma unroll
-                    for (int s2 = 0; s2 < NS; s2++) {
-                        lap += A.C.RL[TYPE][j][s2][0] * el[s2][canon_sv<DIM>(j, 0)];
-                        if (P2C && j >= NVTX) lap += A.C.RL[TYPE][j][s2][1] * el[s2][canon_sv<DIM>(j, 1)];
-                    }
-                    const double dg = A.C.c0 * lap + A.C.c1 * vn[j];
-#pragma unroll
-                    for (int b = 0; b < NB; b++) val[j][b] = (b == a) ? dg : 0.0;
+                    for (int b = 0; b < NB; b++) val[j][b] = (b == a) ? sv : 0.0;
                 }
             }
         }
