@@ -798,11 +798,38 @@ int launch_gatherx_t(feddb200_ctx *c, feddb200_pat *p, const feddb200_mesh *vm, 
         FB_CUDA(cudaEventRecord(c->ev_fork, c->stream));
         FB_CUDA(cudaStreamWaitEvent(c->side[0], c->ev_fork, 0));
     }
+    static const bool percomp = [] { const char *f = getenv("FEDDB200_GATHERW"); return !f || atoi(f) != 0; }(); // tuning aid
     for (const int bi : p->bucket_order) {
         const Bucket &b = p->buckets[bi];
         if ((c->row_phase == FEDDB200_ROWS_GHOST && !b.ghost) || (c->row_phase == FEDDB200_ROWS_OWNED && b.ghost)) continue;
         cudaStream_t st = (aside && b.count <= kSmallBucketRows) ? c->side[0] : c->stream;
         G.start = b.start; G.count = b.count;
+        if constexpr (OPX == X_ADVU || OPX == X_NSJ) {
+            // W(u) / Navier-Stokes block: per-component threads (k_gatherw), 32 dof rows per block
+            int pitch = DIM * b.lcap;
+            while ((pitch & 15) != (DIM & 15)) pitch++;
+            const size_t smem_w = (size_t)pitch * 8 * 32;
+            if (percomp && smem_w <= budget) {
+                G.pitch = pitch;
+                const int ntw = 32 * DIM;
+                const int64_t blocks_w = (b.count * DIM * DIM + ntw - 1) / ntw;
+                auto launch_w = [&](auto kernel) -> int {
+                    { const int rc_k = kernel_cfg(c, kernel, 0, 0, budget, nullptr); if (rc_k != FEDDB200_OK) return rc_k; }
+                    kernel<<<(unsigned)blocks_w, ntw, smem_w, st>>>(G);
+                    c->launches++;
+                    FB_CUDA(cudaGetLastError());
+                    return FEDDB200_OK;
+                };
+                int rc_w;
+                if (b.type == 0) rc_w = launch_w(k_gatherw<OPX, DIM, NL, 0>);
+                else {
+                    if constexpr (NLR > DIM + 1) rc_w = launch_w(k_gatherw<OPX, DIM, NL, 1>);
+                    else { set_error("edge-node row in a P1 row space"); rc_w = FEDDB200_ELOGIC; }
+                }
+                if (rc_w != FEDDB200_OK) return rc_w;
+                continue;
+            }
+        }
         G.pitch = (S::NB * b.lcap) | 1;
         int nt = 64;
         while (nt > 32 && (size_t)G.pitch * 8 * nt > budget) nt -= 32;

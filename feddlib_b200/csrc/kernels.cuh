@@ -1883,8 +1883,13 @@ __device__ __forceinline__ int sv_rt(int i, int t)
 // this section), one thread per element, after k_geom.  tab = TNF[NL][NL][NL][2] | RLF[NL][NL][2][2] (api.cu: sloc_tables),
 // staged in shared memory and read with warp-uniform addresses; the element's Gram matrix |det| G_a.G_b sits in a
 // per-thread shared-memory column because the row loop indexes it at run time.
+// (Tried: the tensors as immediate constant-bank operands with every loop unrolled -- no loads at all, but 58 KB of
+// straight-line code: 0.83 ms instead of 0.50 ms for 750 k elements, instruction-cache bound.)
+#ifndef FB_SLOC_MINBLOCKS
+#define FB_SLOC_MINBLOCKS 3
+#endif
 template <int DIM, int NL>
-__global__ void __launch_bounds__(128) k_sloc(int64_t ne, const int32_t *__restrict__ conn, const double *__restrict__ geom,
+__global__ void __launch_bounds__(128, FB_SLOC_MINBLOCKS) k_sloc(int64_t ne, const int32_t *__restrict__ conn, const double *__restrict__ geom,
                                               const double *__restrict__ u, const double *__restrict__ tab, double c0, double c1,
                                               double *__restrict__ sloc)
 {
@@ -2154,6 +2159,112 @@ __global__ void __launch_bounds__(64, 4) k_gatherx(const GatherXArgs A)
     const int nrep = OPX == X_ADV ? DIM : ((OPX == X_MASS && A.vec_dim != 0) ? A.vec_dim : 1);
     const int64_t off = (OPX == X_ADV || OPX == X_MASS) ? (int64_t)nrep * base : (int64_t)RD * NB * base + (int64_t)a * n;
     warp_write_rows(wbase, pitch, lane, n, off, nrep, A.values);
+}
+
+// Per-component variant of the row-gather kernel for W(u) and the fused Navier-Stokes block (3 x 3 node blocks): one thread
+// per COMPONENT row (I, a, b), DIM * DIM threads per row node -- it contracts one row of |det| grad u (one 32-byte sector)
+// with MW for the NL column nodes (4 FMA each) and owns the entries NB p + b of the shared-memory row of dof row (I, a),
+// which is laid out like the CSR row (pitch == NB (mod 16): the threads of a node never collide, see k_gather).  A third of
+// the registers and of the shared memory per thread of k_gatherx: 12 instead of 4 resident warps on the vertex-node rows
+// (config 4 Navier-Stokes block 9.1 -> 5.8 ms).
+template <int OPX, int DIM, int NL, int TYPE>
+__global__ void __launch_bounds__(32 * DIM, 4) k_gatherw(const GatherXArgs A)
+{
+    static_assert(OPX == X_ADVU || OPX == X_NSJ, "W(u) / Navier-Stokes block only");
+    constexpr int NB = DIM, CPR = DIM * DIM, NT = 32 * NB, ROWS = 32, NVTX = DIM + 1;
+    constexpr int JD = TYPE == 0 ? 0 : NVTX;
+    extern __shared__ double acc[];                  // [ROWS][pitch]
+    __shared__ int64_t s_off[ROWS];
+    __shared__ int s_n[ROWS];
+    const int tid = threadIdx.x, pitch = A.pitch;
+    const int64_t t = blockIdx.x * (int64_t)NT + tid;
+    const bool live = t < A.count * CPR;
+    const int64_t rloc = live ? t / CPR : 0;
+    const int comp = live ? (int)(t - rloc * CPR) : 0;
+    const int a = comp / NB, b = comp - a * NB;
+    int64_t base = 0, k0 = 0;
+    int L = 0, ninc = 0;
+    if (live) {
+        double raw[4];
+        ld_v4(reinterpret_cast<const double *>(A.rowinfo + A.start + rloc), raw);
+        base = __double_as_longlong(raw[0]);
+        k0 = __double_as_longlong(raw[1]);
+        const int64_t ln = __double_as_longlong(raw[2]);
+        L = (int)(ln & 0xffffffff);
+        ninc = (int)(ln >> 32);
+    }
+    GatherArgs RA; // only .rec is used by the shared load helper
+    RA.rec = A.rec;
+    IncRec<NL> rc, rn;
+    if (ninc > 0) load_rec<NL>(RA, k0, rc);
+    for (int x = tid; x < ROWS * pitch; x += NT) acc[x] = 0.0;
+    const int row = tid / NB;
+    if (b == 0) {
+        s_n[row] = live ? NB * L : 0;
+        s_off[row] = (int64_t)CPR * base + (int64_t)a * NB * L;
+    }
+    __syncthreads();
+    double *my = acc + (size_t)row * pitch + b;
+    const double cw = OPX == X_NSJ ? A.C.c2 : 1.0;
+    double dacc = 0.0;
+    int pdiag = 0;
+    for (int k = 0; k < ninc; k++) {
+        if (k + 1 < ninc) load_rec<NL>(RA, k0 + k + 1, rn);
+        const uint32_t perm = rec_perm<NL>(rc.w);
+        const int64_t e = rec_elem<NL>(rc.w);
+        // |det| grad u (component a, b) at the canonical vertices: four 8-byte loads of one sector, addressed through the
+        // permutation (a 32-byte load + register selects costs 24 instructions more)
+        double dv[NVTX];
+        {
+            const double *dp = A.dt + ((e * DIM + a) * DIM + b) * 4;
+#pragma unroll
+            for (int v = 0; v < NVTX; v++) dv[v] = cw * __ldg(dp + ((perm >> (2 * v)) & 3));
+        }
+        double val[NL];
+        if (OPX == X_NSJ && a == b) {   // scalar part (k_sloc): the diagonal components only
+            const double *srow = A.sloc + (e * NL + rec_natidx<NL>(rc.w, JD)) * NL;
+#pragma unroll
+            for (int j = 0; j < NL; j++) val[j] = __ldg(srow + rec_natidx<NL>(rc.w, j));
+        } else {
+#pragma unroll
+            for (int j = 0; j < NL; j++) val[j] = 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < NL; j++) {
+            double x = val[j];
+#pragma unroll
+            for (int v = 0; v < NVTX; v++) x = fma(A.C.MW[TYPE][j][v], dv[v], x);
+            val[j] = x;
+        }
+        if (k == 0) pdiag = (int)((rc.w[JD >> 1] >> (16 * (JD & 1))) & 0xffffu) * NB;
+        dacc += val[JD];
+        // distinct canonical nodes hit distinct row positions: load all, add, store all
+        constexpr int NO = NL - 1;
+        double *ptr[NO];
+        double old[NO];
+#pragma unroll
+        for (int jj = 0; jj < NO; jj++) {
+            const int jc = jj + (jj >= JD ? 1 : 0);
+            ptr[jj] = my + ((rc.w[jc >> 1] >> (16 * (jc & 1))) & 0xffffu) * NB;
+            old[jj] = *ptr[jj];
+        }
+#pragma unroll
+        for (int jj = 0; jj < NO; jj++) {
+            const int jc = jj + (jj >= JD ? 1 : 0);
+            *ptr[jj] = old[jj] + val[jc];
+        }
+        rc = rn;
+    }
+    if (ninc > 0) my[pdiag] = dacc;
+    __syncthreads();
+    const int lane = tid & 31;
+    for (int r = tid >> 5; r < ROWS; r += NT / 32) {
+        const int nr = s_n[r];
+        const double *src = acc + (size_t)r * pitch;
+        double *out = A.values + s_off[r];
+#pragma unroll 4
+        for (int x = lane; x < nr; x += 32) out[x] = src[x];
+    }
 }
 
 } // namespace fb
