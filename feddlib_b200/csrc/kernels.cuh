@@ -1884,12 +1884,10 @@ __device__ __forceinline__ int sv_rt(int i, int t)
 // staged in shared memory and read with warp-uniform addresses; the element's Gram matrix |det| G_a.G_b sits in a
 // per-thread shared-memory column because the row loop indexes it at run time.
 // (Tried: the tensors as immediate constant-bank operands with every loop unrolled -- no loads at all, but 58 KB of
-// straight-line code: 0.83 ms instead of 0.50 ms for 750 k elements, instruction-cache bound.)
-#ifndef FB_SLOC_MINBLOCKS
-#define FB_SLOC_MINBLOCKS 3
-#endif
+// straight-line code: 0.83 ms instead of 0.50 ms for 750 k elements, instruction-cache bound.  Register caps through
+// __launch_bounds__(128, 3 | 4): 168 / 128 registers, both slower than the 134 the compiler picks on its own.)
 template <int DIM, int NL>
-__global__ void __launch_bounds__(128, FB_SLOC_MINBLOCKS) k_sloc(int64_t ne, const int32_t *__restrict__ conn, const double *__restrict__ geom,
+__global__ void __launch_bounds__(128) k_sloc(int64_t ne, const int32_t *__restrict__ conn, const double *__restrict__ geom,
                                               const double *__restrict__ u, const double *__restrict__ tab, double c0, double c1,
                                               double *__restrict__ sloc)
 {
