@@ -493,6 +493,23 @@ def main():
         ms, launches = timed(step, args.steps, args.warmup)
     clocks = clk.summary()
 
+    # several GPUs: where a step's time goes (outside the timed region: three more steps with events around the phases, max over ranks)
+    phases = None
+    if fused:
+        runner.phase_timing = True
+        acc = None
+        for _ in range(3):
+            step()
+            ctx.synchronize()
+            pm = runner.phase_ms()
+            acc = pm if acc is None else {k: acc[k] + pm[k] for k in pm}
+        runner.phase_timing = False
+        keys = sorted(acc)
+        t = torch.tensor([acc[k] / 3 for k in keys], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        phases = {k: float(v) for k, v in zip(keys, t.tolist())}
+        phases["what"] = "device ms per phase of one step, max over ranks; the barrier runs under the owned rows"
+
     ne_total = ne * world
     value = ne_total / (ms * 1e-3)
 
@@ -596,6 +613,8 @@ def main():
                            "pattern_build_s": t_pattern, "pattern_build_breakdown": getattr(runner, "timing", None)},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
                 "clocks": clocks, "checksum_first_1Mi_values": checksum, "parity_check": parity}
+        if phases:
+            line["multi_gpu_phase_ms"] = phases
         if extra:
             line["other_scatter_modes"] = extra
         if ns_extra:

@@ -432,19 +432,25 @@ class DistributedMatrixAssembler:
             self._side = torch.cuda.Stream(device=self._dev)
         _, rsz = self.plan.split_sizes(rd, cd, mode)
         main = self._main_stream()
+        # optional per-phase device times (self.phase_timing = True; read with phase_ms() after a synchronize)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)] if getattr(self, "phase_timing", False) else None
+        if ev: ev[0].record(main)
         self.ctx.set_ghost_targets(P["seg_begin"], P["seg_ptr"][par])
         self.ctx.set_row_phase(1)
         try:
             assemble()                      # geometry pre-pass + ghost rows -> peer memory
             self.ctx.set_ghost_targets()
+            if ev: ev[1].record(main)
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
                 dist.all_reduce(self._flag)  # barrier: every rank's ghost rows have been stored
+                if ev: ev[4].record(self._side)
             self.ctx.set_row_phase(2)
             assemble()                      # owned rows
         finally:
             self.ctx.set_ghost_targets()
             self.ctx.set_row_phase(0)
+        if ev: ev[2].record(main)
         main.wait_stream(self._side)
         slots = self._slot_t[key]
         off = 0
@@ -452,6 +458,20 @@ class DistributedMatrixAssembler:
             if n:
                 self.ctx.unpack_add_d(values, P["recv"][par] + 8 * off, slots[off:off + n], n)
             off += n
+        if ev:
+            ev[3].record(main)
+            self._phase_ev = ev
+
+    def phase_ms(self):
+        """Device times of the last assemble_fused call (phase_timing = True): geometry + ghost rows, owned rows, the
+        cross-rank barrier measured from the end of the ghost rows (it runs under the owned rows), the wait for it after the
+        owned rows plus the unpack-add launches, and the whole call."""
+        ev = getattr(self, "_phase_ev", None)
+        if ev is None:
+            return None
+        return {"geometry_and_ghost_rows": ev[0].elapsed_time(ev[1]), "owned_rows": ev[1].elapsed_time(ev[2]),
+                "barrier_after_ghost_rows": ev[1].elapsed_time(ev[4]), "barrier_wait_and_unpack_add": ev[2].elapsed_time(ev[3]),
+                "total": ev[0].elapsed_time(ev[3])}
 
     def close_peer(self):
         for P in getattr(self, "_peer", {}).values():
