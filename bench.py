@@ -411,9 +411,15 @@ def main():
         pat = Pattern(ctx, mesh)
         ctx.synchronize()
         t_pattern = time.perf_counter() - t0
-        runner = None
+        runner, t_nccl_warm = None, None
     else:
         from feddlib_b200 import dist as fdist
+        # NCCL sets its peer-to-peer channels up on the first all-to-all (seconds at 8 ranks): do that before the plan is timed
+        t0 = time.perf_counter()
+        w = torch.zeros(world, dtype=torch.int64, device="cuda")
+        dist.all_to_all_single(torch.empty_like(w), w)
+        torch.cuda.synchronize()
+        t_nccl_warm = time.perf_counter() - t0
         t0 = time.perf_counter()
         runner = fdist.DistributedElasticity(ctx, dim, fe, M, rank, world)
         mesh, pat, conn, coords = runner.mesh, runner.pat, runner.conn, runner.coords
@@ -558,8 +564,22 @@ def main():
             t = torch.tensor([dt], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
+        # the device->host copy of the CSR values alone (all ranks at the same time): what the platform gives for that copy
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            pinned_vals.copy_(values, non_blocking=True)
+            torch.cuda.synchronize()
+        barrier()
+        d2h = (time.perf_counter() - t0) / 2
+        if world > 1:
+            t = torch.tensor([d2h], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            d2h = float(t.item())
         e2e = {"value": ne_total / dt, "unit": UNIT, "h2d_bytes_per_step": int(coords.nbytes),
-               "d2h_bytes_per_step": int(nnz * 8), "ms_per_step": dt * 1e3, "steps": args.e2e_steps, "host_numa_node": numa_node}
+               "d2h_bytes_per_step": int(nnz * 8), "ms_per_step": dt * 1e3, "steps": args.e2e_steps, "host_numa_node": numa_node,
+               "d2h_copy_alone_ms": d2h * 1e3, "d2h_copy_alone_GBs_per_gpu": nnz * 8 / d2h / 1e9,
+               "d2h_copy_alone_GBs_all_gpus": world * nnz * 8 / d2h / 1e9}
         checksum = float(out_np[: min(nnz, 1 << 20)].sum())
         del pinned_vals
         # the same end-to-end step through the compiled C++ host layer (FEDD::FE_b200 over the C ABI: host containers in,
@@ -610,7 +630,8 @@ def main():
                                "peer memory (CUDA IPC), one-element all-reduce as barrier under the owned rows, unpack-add"
                                if fused else "; ghost rows assembled first, NCCL ghost-row exchange overlapped with the owned rows"
                                if overlap else ("; NCCL ghost-row exchange after the assembly" if world > 1 else "")),
-                           "pattern_build_s": t_pattern, "pattern_build_breakdown": getattr(runner, "timing", None)},
+                           "pattern_build_s": t_pattern, "pattern_build_breakdown": getattr(runner, "timing", None),
+                           "nccl_first_alltoall_s": t_nccl_warm if world > 1 else None},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
                 "clocks": clocks, "checksum_first_1Mi_values": checksum, "parity_check": parity}
         if phases:
