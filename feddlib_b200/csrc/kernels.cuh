@@ -1454,7 +1454,7 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
                     if (h) out[0] = nodep[0];
 #ifdef FB_HINT_ST
                     if (body_n > 0) bulk_store_hint(out + h, nodep + h, body_n * 8, policy_evict_first());
-#else
+#elif !defined(FB_WHATIF_NOSTORE)
                     if (body_n > 0) bulk_store(out + h, nodep + h, body_n * 8);
 #endif
                     if (h + body_n < total) out[total - 1] = nodep[total - 1];
