@@ -441,10 +441,13 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
     using S = GatherShape<OPG, DIM>;
     const int64_t blocks_geom = (p->rm->ne + 255) / 256;
     const int phase = c->row_phase;
-    if (p->rm->ne > 0 && phase != FEDDB200_ROWS_OWNED) {
+    const bool want_ghost = phase == FEDDB200_ROWS_ALL || phase == FEDDB200_ROWS_GHOST || phase == FEDDB200_ROWS_GHOST_ONLY;
+    const bool want_owned = phase == FEDDB200_ROWS_ALL || phase == FEDDB200_ROWS_OWNED;
+    if (p->rm->ne > 0 && phase != FEDDB200_ROWS_OWNED && phase != FEDDB200_ROWS_GHOST_ONLY) {
         k_geom<DIM, NL><<<(unsigned)blocks_geom, 256, 0, c->stream>>>(p->rm->ne, p->rm->conn_d, p->rm->coords_d, p->geom_d);
         c->launches++;
     }
+    if (phase == FEDDB200_ROWS_GEOM) { FB_CUDA(cudaGetLastError()); return FEDDB200_OK; }
     const size_t budget = c->smem_optin - 1024;
     // the bucket launches are independent of one another and can be forked over the side streams (measured on
     // B200: slower than back-to-back launches -- concurrent sweeps of the mesh compete for L2 -- so off by default)
@@ -480,7 +483,7 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
                 { const int rc_k = kernel_cfg(c, k_star<OPG>, nts, smem_s, budget, &per_sm); if (rc_k != FEDDB200_OK) return rc_k; }
                 for (int g = 1; g >= 0; g--) {   // ghost rows first
                     if (p->star_n[g] == 0) continue;
-                    if ((phase == FEDDB200_ROWS_GHOST && g == 0) || (phase == FEDDB200_ROWS_OWNED && g == 1)) continue;
+                    if ((g == 0 && !want_owned) || (g == 1 && !want_ghost)) continue;
                     StarArgs SA;
                     SA.G = G;
                     SA.G.zero = 0;
@@ -514,7 +517,7 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
     int turn = 0;
     for (const int bi : p->bucket_order) {
         const Bucket &b = p->buckets[bi];
-        if ((phase == FEDDB200_ROWS_GHOST && !b.ghost) || (phase == FEDDB200_ROWS_OWNED && b.ghost)) continue;
+        if ((!b.ghost && !want_owned) || (b.ghost && !want_ghost)) continue;
         if (star_done && b.in_star) continue;
         G.frag = (frag_on && !b.ghost) ? p->frag_d : nullptr;
         cudaStream_t st = n_side > 0 ? c->side[turn++ % n_side] : ((aside && b.count <= kSmallBucketRows) ? c->side[0] : c->stream);
@@ -650,7 +653,7 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
         FB_CUDA(cudaEventRecord(c->ev_join[i], c->side[i]));
         FB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join[i], 0));
     }
-    if (frag_on && phase != FEDDB200_ROWS_GHOST) {
+    if (frag_on && want_owned) {
         const int64_t n_bound = p->n_owned - 1;
         k_stitch<<<(unsigned)std::min<int64_t>((n_bound + 255) / 256, (int64_t)c->sm_count * 8), 256, 0, c->stream>>>(
             n_bound, p->rowptr_d, OPG == 1 ? DIM * DIM : 1, G.values, p->frag_d);
@@ -759,7 +762,11 @@ int launch_gatherx_t(feddb200_ctx *c, feddb200_pat *p, const feddb200_mesh *vm, 
     using S = OpXShape<OPX, DIM>;
     constexpr int NLV = OPX == X_BT ? NLR : NL; // nodes of the velocity space
     const int64_t ne = p->rm->ne;
-    if (ne > 0) {
+    const int phase = c->row_phase;
+    const bool want_ghost = phase == FEDDB200_ROWS_ALL || phase == FEDDB200_ROWS_GHOST || phase == FEDDB200_ROWS_GHOST_ONLY;
+    const bool want_owned = phase == FEDDB200_ROWS_ALL || phase == FEDDB200_ROWS_OWNED;
+    // element pre-passes (geometry, |det| grad u, scalar local matrices): once per assembly, in its first phase
+    if (ne > 0 && phase != FEDDB200_ROWS_OWNED && phase != FEDDB200_ROWS_GHOST_ONLY) {
         k_geom<DIM, NLV><<<(unsigned)((ne + 255) / 256), 256, 0, c->stream>>>(ne, vm->conn_d, vm->coords_d, p->geom_d);
         c->launches++;
         if constexpr (S::NEEDS_U) {
@@ -787,6 +794,7 @@ int launch_gatherx_t(feddb200_ctx *c, feddb200_pat *p, const feddb200_mesh *vm, 
             FB_CUDA(cudaGetLastError());
         }
     }
+    if (phase == FEDDB200_ROWS_GEOM) return FEDDB200_OK;
     GatherXArgs G;
     G.rowinfo = (const RowInfo *)p->rowinfo_d; G.rec = p->rec_d; G.geom = p->geom_d; G.sloc = p->sloc_d; G.dt = p->dt_d;
     G.values = values_d; G.vec_dim = vec_dim; G.C = C;
@@ -801,7 +809,7 @@ int launch_gatherx_t(feddb200_ctx *c, feddb200_pat *p, const feddb200_mesh *vm, 
     static const bool percomp = [] { const char *f = getenv("FEDDB200_GATHERW"); return !f || atoi(f) != 0; }(); // tuning aid
     for (const int bi : p->bucket_order) {
         const Bucket &b = p->buckets[bi];
-        if ((c->row_phase == FEDDB200_ROWS_GHOST && !b.ghost) || (c->row_phase == FEDDB200_ROWS_OWNED && b.ghost)) continue;
+        if ((!b.ghost && !want_owned) || (b.ghost && !want_ghost)) continue;
         cudaStream_t st = (aside && b.count <= kSmallBucketRows) ? c->side[0] : c->stream;
         G.start = b.start; G.count = b.count;
         if constexpr (OPX == X_ADVU || OPX == X_NSJ) {
@@ -976,7 +984,7 @@ int run_op(feddb200_ctx *c, const feddb200_pat *pc, int op, const double *u_d, d
         return op == OP_LAP ? launch_gather<0>(c, p, G) : launch_gather<1>(c, p, G);
     }
 
-    if (c->row_phase == FEDDB200_ROWS_OWNED) return FEDDB200_OK; // element-wise modes did everything in the ROWS_GHOST call
+    if (c->row_phase == FEDDB200_ROWS_OWNED || c->row_phase == FEDDB200_ROWS_GEOM) return FEDDB200_OK; // element-wise modes do everything in the ROWS_GHOST[_ONLY] call
     ElemArgs A;
     A.conn_r = rm->conn_d; A.conn_c = cm->conn_d; A.conn_v = vm->conn_d; A.coords = vm->coords_d;
     A.row_lid = p->row_lid_d; A.rowptr = p->rowptr_d; A.pos = p->pos_d; A.pos_stride = p->pos_stride;

@@ -114,7 +114,7 @@ extern "C" int feddb200_get_scatter_mode(const feddb200_ctx *c) { return c ? c->
 extern "C" int feddb200_set_row_phase(feddb200_ctx *c, int phase)
 {
     FB_LOGIC(!c, "null context");
-    FB_LOGIC(phase < 0 || phase > 2, "feddb200_set_row_phase: phase must be 0 (all), 1 (ghost rows) or 2 (owned rows)");
+    FB_LOGIC(phase < 0 || phase > 4, "feddb200_set_row_phase: phase must be 0 (all), 1 (ghost rows), 2 (owned rows), 3 (geometry) or 4 (ghost rows only)");
     c->row_phase = phase;
     return FEDDB200_OK;
 }

@@ -35,6 +35,10 @@ class Context:
         self.torch_stream = torch.cuda.current_stream(self.device)   # the stream the engine launches on, as a torch object
         check(self._L.feddb200_set_stream(self._h, C.c_void_p(self.torch_stream.cuda_stream)))
 
+    def set_stream(self, stream):
+        """Launch the following calls on `stream` (a torch.cuda.Stream); bind_torch_stream's stream stays the main one."""
+        check(self._L.feddb200_set_stream(self._h, C.c_void_p(stream.cuda_stream)))
+
     def bind_host_numa(self) -> int:
         """Bind this thread to the CPUs next to the GPU (feddb200_bind_host_numa): page-locked buffers allocated afterwards
         are NUMA-local.  Returns the node or -1."""
@@ -61,7 +65,7 @@ class Context:
         return self._L.feddb200_get_scatter_mode(self._h)
 
     def set_row_phase(self, phase: int):
-        """0 all rows, 1 geometry + ghost rows, 2 owned rows (feddb200_set_row_phase)."""
+        """0 all rows, 1 geometry + ghost rows, 2 owned rows, 3 geometry only, 4 ghost rows only (feddb200_set_row_phase)."""
         check(self._L.feddb200_set_row_phase(self._h, int(phase)))
 
     def synchronize(self):

@@ -69,6 +69,12 @@ int  feddb200_get_scatter_mode(const feddb200_ctx *ctx);
 #define FEDDB200_ROWS_ALL   0
 #define FEDDB200_ROWS_GHOST 1
 #define FEDDB200_ROWS_OWNED 2
+/* the ROWS_GHOST call in two parts, so that the ghost rows can run on another stream NEXT TO the owned rows (only the
+ * geometry pre-pass is a true dependency of both): ROWS_GEOM = the geometry pre-pass alone, ROWS_GHOST_ONLY = the rows
+ * owned by other ranks, using the geometry of a preceding ROWS_GEOM call (gather mode; the element-wise modes treat
+ * ROWS_GEOM as a no-op and ROWS_GHOST_ONLY like ROWS_GHOST) */
+#define FEDDB200_ROWS_GEOM       3
+#define FEDDB200_ROWS_GHOST_ONLY 4
 int  feddb200_set_row_phase(feddb200_ctx *ctx, int phase);
 int  feddb200_synchronize(feddb200_ctx *ctx);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
