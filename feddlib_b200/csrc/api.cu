@@ -443,10 +443,34 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
     const int phase = c->row_phase;
     const bool want_ghost = phase == FEDDB200_ROWS_ALL || phase == FEDDB200_ROWS_GHOST || phase == FEDDB200_ROWS_GHOST_ONLY;
     const bool want_owned = phase == FEDDB200_ROWS_ALL || phase == FEDDB200_ROWS_OWNED;
+    // points path of the scalar Laplace rows of 3D P2 patterns (kernels.cuh: geo_from_points): no geometry lines at all, unless
+    // one of the alternative row kernels (tuning aids, they read geometry lines) is switched on
+    bool use_pts = false;
+    if constexpr (OPG == 0 && DIM == 3 && NL == 10) {
+        // OFF by default: parity-green (the GPU suite ran with it), but config 2 measured 3.19 ms with it against 3.08 ms with the
+        // geometry lines -- 70 % fewer DRAM reads buy nothing, the Laplace rows are not bandwidth-bound either
+        static const bool pts_env = [] { const char *f = getenv("FEDDB200_LAPLACE_POINTS"); return f && atoi(f) != 0; }(); // tuning aid
+        use_pts = pts_env && !star_enabled() && p->n_inc > 0 && p->rm->nn < ((int64_t)1 << 32);
+        for (const Bucket &b : p->buckets)
+            if (b.fan_W > 0 && p->fanrec_d) use_pts = false;
+        if (use_pts && !p->vtx_d) {   // once per pattern
+            feddb200_pat *pm = const_cast<feddb200_pat *>(p);
+            FB_CUDA(cudaMalloc(&pm->vtx_d, sizeof(uint4) * p->n_inc));
+            FB_CUDA(cudaMalloc(&pm->coords4_d, sizeof(double) * 4 * std::max<int64_t>(p->rm->nn, 1)));
+            k_make_vtx<<<(unsigned)std::min<int64_t>((p->n_inc + 255) / 256, (int64_t)c->sm_count * 16), 256, 0, c->stream>>>(
+                p->n_inc, p->rec_d, p->rm->conn_d, (uint4 *)p->vtx_d);
+            c->launches++;
+        }
+    }
     if (p->rm->ne > 0 && phase != FEDDB200_ROWS_OWNED && phase != FEDDB200_ROWS_GHOST_ONLY) {
-        k_geom<DIM, NL><<<(unsigned)blocks_geom, 256, 0, c->stream>>>(p->rm->ne, p->rm->conn_d, p->rm->coords_d, p->geom_d);
+        if (use_pts)
+            k_coords4<<<(unsigned)std::min<int64_t>((p->rm->nn + 255) / 256, (int64_t)c->sm_count * 16), 256, 0, c->stream>>>(p->rm->nn, p->rm->coords_d, p->coords4_d);
+        else
+            k_geom<DIM, NL><<<(unsigned)blocks_geom, 256, 0, c->stream>>>(p->rm->ne, p->rm->conn_d, p->rm->coords_d, p->geom_d);
         c->launches++;
     }
+    G.vtx = use_pts ? (const uint4 *)p->vtx_d : nullptr;
+    G.coords4 = use_pts ? p->coords4_d : nullptr;
     if (phase == FEDDB200_ROWS_GEOM) { FB_CUDA(cudaGetLastError()); return FEDDB200_OK; }
     const size_t budget = c->smem_optin - 1024;
     // the bucket launches are independent of one another and can be forked over the side streams (measured on
@@ -576,14 +600,18 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
                 const int64_t tiles = ((b.count + npt - 1) / npt + nt / 32 - 1) / (nt / 32); // in blocks
                 FB_LOGIC(smem > budget, "row too long for the gather path's shared-memory rows; use the coloured or atomic mode");
                 // persistent blocks: as many as are resident at once (times a small factor that evens out the tail)
-                int per_sm = 1;
-                { const int rc_k = kernel_cfg(c, k_ring<OPG>, nt, smem, budget, &per_sm); if (rc_k != FEDDB200_OK) return rc_k; }
-                const int waves = std::max(1, FB_ENV_INT("FEDDB200_RING_WAVES", 1)); // tuning aid
-                const int64_t blocks = std::min<int64_t>(tiles, (int64_t)std::max(per_sm, 1) * c->sm_count * waves);
-                k_ring<OPG><<<(unsigned)blocks, nt, smem, st>>>(G);
-                c->launches++;
-                FB_CUDA(cudaGetLastError());
-                rc = FEDDB200_OK;
+                auto launch_ring = [&](auto kernel) -> int {
+                    int per_sm = 1;
+                    { const int rc_k = kernel_cfg(c, kernel, nt, smem, budget, &per_sm); if (rc_k != FEDDB200_OK) return rc_k; }
+                    const int waves = std::max(1, FB_ENV_INT("FEDDB200_RING_WAVES", 1)); // tuning aid
+                    const int64_t blocks = std::min<int64_t>(tiles, (int64_t)std::max(per_sm, 1) * c->sm_count * waves);
+                    kernel<<<(unsigned)blocks, nt, smem, st>>>(G);
+                    c->launches++;
+                    FB_CUDA(cudaGetLastError());
+                    return FEDDB200_OK;
+                };
+                if constexpr (OPG == 0) rc = use_pts ? launch_ring(k_ring<0, true>) : launch_ring(k_ring<0, false>);
+                else rc = launch_ring(k_ring<OPG, false>);
             } else { set_error("ring rows exist for 3D P2 patterns only"); rc = FEDDB200_ELOGIC; }
         } else {
             if constexpr (DIM == 3 && NL == 10) {
@@ -641,6 +669,10 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
                 FB_CUDA(cudaGetLastError());
                 return FEDDB200_OK;
             };
+            if constexpr (OPG == 0 && DIM == 3 && NL == 10) {
+                if (use_pts) rc = b.type == 0 ? launch(k_gather<0, 3, 10, 0, true>) : launch(k_gather<0, 3, 10, 1, true>);
+                else rc = b.type == 0 ? launch(k_gather<0, 3, 10, 0>) : launch(k_gather<0, 3, 10, 1>);
+            } else
             if (b.type == 0) rc = launch(k_gather<OPG, DIM, NL, 0>);
             else {
                 if constexpr (NL > DIM + 1) rc = launch(k_gather<OPG, DIM, NL, 1>);
@@ -978,7 +1010,7 @@ int run_op(feddb200_ctx *c, const feddb200_pat *pc, int op, const double *u_d, d
         rc = ensure_gather(p);
         if (rc != FEDDB200_OK) return rc;
         GatherArgs G;
-        G.rowinfo = (const RowInfo *)p->rowinfo_d; G.rec = p->rec_d; G.geom = p->geom_d; G.ahead = p->ahead_d; G.frag = nullptr;
+        G.rowinfo = (const RowInfo *)p->rowinfo_d; G.rec = p->rec_d; G.geom = p->geom_d; G.ahead = p->ahead_d; G.frag = nullptr; G.vtx = nullptr; G.coords4 = nullptr;
         G.c0 = c0; G.c1 = c1; G.values = values_d; G.vec_dim = (op == OP_LAP && vec_field) ? dim : 0;
         canon_table(tab_h, dim, nr, G.R);
         return op == OP_LAP ? launch_gather<0>(c, p, G) : launch_gather<1>(c, p, G);

@@ -129,6 +129,10 @@ struct feddb200_pat {
     // boundary-sector fragments of the row-gather path (kernels.cuh: "fragment protocol"): two 32-byte slots per node row
     // (head, tail); null if some node row is too short for the protocol
     double *frag_d = nullptr;
+    // points path of the scalar Laplace rows (3D P2, kernels.cuh: geo_from_points): canonical vertex ids per incidence (built
+    // at the first Laplace assembly of the pattern) and the padded coordinates (rewritten by every such assembly)
+    void *vtx_d = nullptr;         // uint4 [n_inc]
+    double *coords4_d = nullptr;   // [rm->nn][4]
     double *sloc_d = nullptr;      // [ne][nloc][nloc] scalar local matrices of N(u) / the fused Navier-Stokes block (k_sloc)
     double *sloc_tab_d = nullptr;  // coefficient tensors of k_sloc (uploaded once per pattern)
     double *dt_d = nullptr;        // [ne][dim][dim][4] |det| * grad u at the element's vertices

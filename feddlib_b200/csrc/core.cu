@@ -536,7 +536,7 @@ extern "C" void feddb200_pat_free(feddb200_pat *p)
     cudaSetDevice(p->ctx->device);
     cudaFree(p->rowptr_d); cudaFree(p->colind_d); cudaFree(p->row_lid_d); cudaFree(p->pos_d);
     cudaFree(p->inc_ptr_d); cudaFree(p->inc_d); cudaFree(p->row_perm_d); cudaFree(p->colour_perm_d);
-    cudaFree(p->rec_d); cudaFree(p->geom_d); cudaFree(p->frag_d); cudaFree(p->rowinfo_d); cudaFree(p->ahead_d); cudaFree(p->task_tiles_d); cudaFree(p->tasks_d); cudaFree(p->tiletet_d); cudaFree(p->fanrec_d); cudaFree(p->star_tiles_d[0]); cudaFree(p->star_tiles_d[1]); cudaFree(p->sloc_d); cudaFree(p->sloc_tab_d); cudaFree(p->dt_d);
+    cudaFree(p->rec_d); cudaFree(p->geom_d); cudaFree(p->frag_d); cudaFree(p->vtx_d); cudaFree(p->coords4_d); cudaFree(p->rowinfo_d); cudaFree(p->ahead_d); cudaFree(p->task_tiles_d); cudaFree(p->tasks_d); cudaFree(p->tiletet_d); cudaFree(p->fanrec_d); cudaFree(p->star_tiles_d[0]); cudaFree(p->star_tiles_d[1]); cudaFree(p->sloc_d); cudaFree(p->sloc_tab_d); cudaFree(p->dt_d);
     delete p;
 }
 

@@ -769,6 +769,10 @@ struct GatherArgs {
     double *seg_ptr[kMaxGhostSeg];
     const uint32_t *ahead;    // k_gather_s: element of the incidence kRsAhead places further along the same row
     double *frag;             // fragment protocol (below): two 32-byte slots per node row; null: plain stores
+    // points path of the scalar Laplace rows (3D P2): canonical vertex ids of every incidence + padded coordinates; the
+    // geometry is recomputed per incidence instead of read as a 128-byte line (see geo_from_points)
+    const uint4 *vtx;         // [n_inc] canonical vertices (node ids of the geometry mesh)
+    const double *coords4;    // [nn][4] (x, y, z, 0)
     CanonR R;
 };
 
@@ -944,6 +948,61 @@ __device__ __forceinline__ void load_geo(const GatherArgs &A, const IncRec<NL> &
     }
 }
 
+// Points path (scalar Laplace rows of 3D P2 meshes).  A Laplace row moves 160 bytes of input (32-byte record + 128-byte
+// geometry line, re-read from DRAM about 1.7 times per element because the output stream evicts it from L2) for every
+// 80 bytes it writes; the launches run at the DRAM traffic ceiling of this access pattern (ncu: 2.3 GB read + 0.9 GB
+// written in 1.02 ms for the largest bucket of config 2).  Here an incidence carries the node ids of its four canonical
+// vertices (16 bytes, k_make_vtx) and the kernel recomputes (grad lambda_v, |det|) from the padded coordinates, which
+// stay in L2 (33 MB for a million vertices): 48 instead of 160 bytes of DRAM reads per incidence, no k_geom pass, ~55 more
+// FP64 instructions per incidence on a pipe that was 8 % busy.  The gradients are those of k_geom up to rounding (the
+// origin of the affine map is the canonical instead of the natural first vertex).
+__global__ void k_make_vtx(int64_t n_inc, const uint32_t *__restrict__ rec, const int32_t *__restrict__ conn, uint4 *__restrict__ vtx)
+{
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n_inc; k += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t e = rec[k * 8 + 5], perm = rec[k * 8 + 6];
+        const int32_t *el = conn + (int64_t)e * 10;
+        vtx[k] = make_uint4((uint32_t)el[perm & 3], (uint32_t)el[(perm >> 2) & 3], (uint32_t)el[(perm >> 4) & 3], (uint32_t)el[(perm >> 6) & 3]);
+    }
+}
+__global__ void k_coords4(int64_t nn, const double *__restrict__ coords, double *__restrict__ coords4)
+{
+    for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < nn; n += (int64_t)gridDim.x * blockDim.x)
+        st_v4(coords4 + 4 * n, coords[3 * n], coords[3 * n + 1], coords[3 * n + 2], 0.0);
+}
+// issue the four coordinate loads of an incidence into the geometry buffer (converted in place by geo_from_points)
+__device__ __forceinline__ void load_points(const GatherArgs &A, const uint4 v, IncGeo<3> &D, int dep = 0)
+{
+    ld_v4g(A.coords4 + 4 * (int64_t)v.x + dep, D.G[0]);
+    ld_v4g(A.coords4 + 4 * (int64_t)v.y + dep, D.G[1]);
+    ld_v4g(A.coords4 + 4 * (int64_t)v.z + dep, D.G[2]);
+    ld_v4g(A.coords4 + 4 * (int64_t)v.w + dep, D.G[3]);
+}
+__device__ __forceinline__ void geo_from_points(IncGeo<3> &D)
+{
+    double B[3][3];   // B[i][j] = x_{j+1}[i] - x_0[i]
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+        for (int i = 0; i < 3; i++) B[i][j] = D.G[j + 1][i] - D.G[0][i];
+    const double det = B[0][0] * B[1][1] * B[2][2] + B[0][1] * B[1][2] * B[2][0] + B[0][2] * B[1][0] * B[2][1] -
+                       B[2][0] * B[1][1] * B[0][2] - B[2][1] * B[1][2] * B[0][0] - B[2][2] * B[1][0] * B[0][1];
+    const double r = 1.0 / det, ad = fabs(det);
+    // grad lambda_k = row k-1 of B^-1 (k >= 1), grad lambda_0 = -(sum of the others)
+    D.G[1][0] = (B[1][1] * B[2][2] - B[1][2] * B[2][1]) * r;
+    D.G[1][1] = (B[0][2] * B[2][1] - B[0][1] * B[2][2]) * r;
+    D.G[1][2] = (B[0][1] * B[1][2] - B[0][2] * B[1][1]) * r;
+    D.G[2][0] = (B[1][2] * B[2][0] - B[1][0] * B[2][2]) * r;
+    D.G[2][1] = (B[0][0] * B[2][2] - B[0][2] * B[2][0]) * r;
+    D.G[2][2] = (B[0][2] * B[1][0] - B[0][0] * B[1][2]) * r;
+    D.G[3][0] = (B[1][0] * B[2][1] - B[1][1] * B[2][0]) * r;
+    D.G[3][1] = (B[0][1] * B[2][0] - B[0][0] * B[2][1]) * r;
+    D.G[3][2] = (B[0][0] * B[1][1] - B[0][1] * B[1][0]) * r;
+#pragma unroll
+    for (int d = 0; d < 3; d++) D.G[0][d] = -(D.G[1][d] + D.G[2][d] + D.G[3][d]);
+#pragma unroll
+    for (int v = 0; v < 4; v++) D.G[v][3] = ad;
+}
+
 // Row-gather kernel (output-stationary): every CSR value is written exactly once, no atomics, no memset,
 // bitwise reproducible.
 //
@@ -973,9 +1032,10 @@ template <int OPG, int DIM> struct GatherShape {
     static constexpr int NT = 32 * NBL;                   // threads per block: 32 accumulator rows
 };
 
-template <int OPG, int DIM, int NL, int TYPE>
+template <int OPG, int DIM, int NL, int TYPE, bool PTS = false>
 __global__ void __launch_bounds__(GatherShape<OPG, DIM>::NT, FB_GATHER_MINBLOCKS) k_gather(const GatherArgs A)
 {
+    static_assert(!PTS || (OPG == 0 && DIM == 3), "points path: scalar Laplace rows of 3D meshes");
     using S = GatherShape<OPG, DIM>;
     constexpr int NBL = S::NBL, CPR = S::CPR, NT = S::NT;
     constexpr int NVTX = DIM + 1;
@@ -1008,11 +1068,16 @@ __global__ void __launch_bounds__(GatherShape<OPG, DIM>::NT, FB_GATHER_MINBLOCKS
     const int64_t k1 = k0 + ninc, kl = k1 - 1;
     IncRec<NL> rc, rn, r2;
     IncGeo<DIM> g;
+    uint4 vn = make_uint4(0u, 0u, 0u, 0u);   // points path: canonical vertices of the next incidence
     if (ninc > 0) {
         load_rec<NL>(A, k0, rc);
         load_rec<NL>(A, k0 + 1 < kl ? k0 + 1 : kl, rn);
         load_rec<NL>(A, k0 + 2 < kl ? k0 + 2 : kl, r2);
-        load_geo<DIM, NL>(A, rc, g);
+        if constexpr (PTS) {
+            const uint4 vc = __ldg(A.vtx + k0);
+            vn = __ldg(A.vtx + (k0 + 1 < kl ? k0 + 1 : kl));
+            load_points(A, vc, g);
+        } else load_geo<DIM, NL>(A, rc, g);
     }
     // zero the block's accumulators while the first loads are in flight; publish the row table
     for (int x = tid; x < ROWS * pitch; x += NT) acc[x] = 0.0;
@@ -1038,6 +1103,7 @@ __global__ void __launch_bounds__(GatherShape<OPG, DIM>::NT, FB_GATHER_MINBLOCKS
         double dacc = 0.0;
         const int pdiag = (int)((rc.w[JD >> 1] >> (16 * (JD & 1))) & 0xffffu) * NBL;
         for (int64_t k = k0; k < k1; k++) {
+            if constexpr (PTS) geo_from_points(g);
             // e[s][w] from the current geometry buffer
             double e[NS][NVTX];
             const double adet = g.G[0][3];
@@ -1070,6 +1136,10 @@ __global__ void __launch_bounds__(GatherShape<OPG, DIM>::NT, FB_GATHER_MINBLOCKS
                 GatherArgs const &AA = A;
                 const uint32_t perm = rec_perm<NL>(rn.w);
                 const double *gp = AA.geom + (int64_t)rec_elem<NL>(rn.w) * GeomStride<DIM>::value + dep;
+                if constexpr (PTS) {
+                    load_points(A, vn, g, dep);
+                    vn = __ldg(A.vtx + (k + 2 < kl ? k + 2 : kl));
+                } else
                 if constexpr (DIM == 3) {
 #pragma unroll
                     for (int v = 0; v < 4; v++) ld_v4g(gp + 4 * ((perm >> (2 * v)) & 3), g.G[v]);
@@ -1180,9 +1250,10 @@ constexpr int kRingUnroll = FB_RING_UNROLL;
 __device__ __forceinline__ void cp_async16(void *sdst, const void *gsrc);
 __device__ __forceinline__ void cp_async_commit();
 template <int N> __device__ __forceinline__ void cp_async_wait();
-template <int OPG>
+template <int OPG, bool PTS = false>
 __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
 {
+    static_assert(!PTS || OPG == 0, "points path: scalar Laplace rows");
 #if FB_RING_PF_MODE >= 2
     __shared__ uint4 s_en[2][64];   // elements of the next tile's rows (second half of their row records), per lane
 #endif
@@ -1216,6 +1287,7 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
     double raw[4] = {0.0, 0.0, 0.0, 0.0};
     IncRec<NL> rc, rn, r2;
     IncGeo<DIM> g;
+    uint4 vc = make_uint4(0u, 0u, 0u, 0u), vn = vc;   // points path: canonical vertices of this / the next incidence
     {
         const int64_t node = tile * NPT + slot;
         if (lane_used && node < A.count) {
@@ -1227,7 +1299,11 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
                 load_rec<NL>(A, k0, rc);
                 load_rec<NL>(A, k0 + 1 < kl ? k0 + 1 : kl, rn);
                 load_rec<NL>(A, k0 + 2 < kl ? k0 + 2 : kl, r2);
-                load_geo<DIM, NL>(A, rc, g);
+                if constexpr (PTS) {
+                    vc = __ldg(A.vtx + k0);
+                    vn = __ldg(A.vtx + (k0 + 1 < kl ? k0 + 1 : kl));
+                    load_points(A, vc, g);
+                } else load_geo<DIM, NL>(A, rc, g);
             }
         }
     }
@@ -1299,6 +1375,7 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
             constexpr int JE[3] = {0, 1, 4}, JIN[3] = {2, 6, 5}, JOUT[3] = {3, 7, 8};
 #pragma unroll(kRingUnroll)
             for (int64_t k = k0; k < k1; k++) {
+                if constexpr (PTS) geo_from_points(g);
                 // E[s][w][b] for the two row-support vertices s = v0, v1 and the four canonical vertices w
                 double E[2][NVTX][NB];
                 {
@@ -1345,15 +1422,20 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
 #else
                     const double *gp = A.geom + (int64_t)rec_elem<NL>(rn.w) * GeomStride<DIM>::value + dep;
 #endif
+                    if constexpr (PTS) {
+                        load_points(A, vn, g, dep);
+                        vn = __ldg(A.vtx + (k + 2 < kl ? k + 2 : kl));
+                    } else {
 #pragma unroll
-                    for (int v = 0; v < 4; v++) ld_v4g(gp + 4 * ((perm >> (2 * v)) & 3), g.G[v]);
+                        for (int v = 0; v < 4; v++) ld_v4g(gp + 4 * ((perm >> (2 * v)) & 3), g.G[v]);
+                    }
 #ifdef FB_WHATIF_REC0    // timing experiment only (wrong values): every record load hits L1
                     load_rec<NL>(A, k0 + ((k + 3 - k0) & 1), r3);
 #else
                     load_rec<NL>(A, k + 3 < kl ? k + 3 : kl, r3);
 #endif
 #if FB_RING_PF_MODE == 0
-                    prefetch_l2(A.geom + (int64_t)rec_elem<NL>(r2.w) * GeomStride<DIM>::value);
+                    if constexpr (!PTS) prefetch_l2(A.geom + (int64_t)rec_elem<NL>(r2.w) * GeomStride<DIM>::value);
 #elif FB_RING_PF_MODE == 1 || FB_RING_PF_MODE == 3
                     // the whole geometry line of the incidence two places on (one request per node)
                     if (lane == slot * TPR) prefetch_l2_bulk(A.geom + (int64_t)rec_elem<NL>(r2.w) * GeomStride<DIM>::value, GeomStride<DIM>::value * 8);
@@ -1419,6 +1501,10 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
             load_rec<NL>(A, k0n, rc);
             load_rec<NL>(A, k0n + 1 < kln ? k0n + 1 : kln, rn);
             load_rec<NL>(A, k0n + 2 < kln ? k0n + 2 : kln, r2);
+            if constexpr (PTS) {
+                vc = __ldg(A.vtx + k0n);
+                vn = __ldg(A.vtx + (k0n + 1 < kln ? k0n + 1 : kln));
+            }
         }
 
         // write-out: the node's TPR dof rows are one contiguous run of the values array and of shared memory: ONE TMA
@@ -1463,7 +1549,10 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
                 }
             }
         }
-        if (nincn > 0) load_geo<DIM, NL>(A, rc, g); // next tile's first geometry line lands while the stores drain
+        if (nincn > 0) {   // next tile's first geometry line lands while the stores drain
+            if constexpr (PTS) load_points(A, vc, g);
+            else load_geo<DIM, NL>(A, rc, g);
+        }
         bulk_commit_wait_read(); // the bulk stores read this warp's shared memory: wait before it is reused
         __syncwarp();
         if (tile_n >= ntiles) break;
@@ -1474,13 +1563,13 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
 }
 
 
-template <int OPG>
+template <int OPG, bool PTS = false>
 __global__ void __launch_bounds__(64, FB_RING_MINBLOCKS) k_ring(const GatherArgs A)
 {
     extern __shared__ double acc[];          // [blockDim.x][pitch]
     // (a warp-uniform, compile-time row dof -- 32 row nodes per 96-thread block -- removes the
     // delta_ab selects but makes every geometry load touch 32 lines instead of 11: measured 3.49 ms vs 3.08 ms)
-    ring_tiles<OPG>(A, acc);
+    ring_tiles<OPG, PTS>(A, acc);
 }
 
 // -----------------------------------------------------------------------------------------

@@ -224,11 +224,13 @@ __global__ void __launch_bounds__(64, 8) k_task(const TaskArgs A)
                     }
                 }
             }
-            // positions with more than four pairs: the partial sums of the group's lanes, fixed order
+            // positions with more than four pairs: the partial sums of the group's lanes, fixed order; only the levels the
+            // largest group of the pass needs (a ring-of-6 column split in two needs one, the row node's own column three)
             const int rem = (int)((task >> 50) & 7);
-            if (__any_sync(FULL, rem != 0)) {
+            const int maxrem = __reduce_max_sync(FULL, rem);
 #pragma unroll
-                for (int d = 1; d <= 4; d <<= 1) {
+            for (int d = 1; d <= 4; d <<= 1) {
+                if (d <= maxrem) {
 #pragma unroll
                     for (int i = 0; i < NV; i++) {
                         const double t = __shfl_down_sync(FULL, X[i], d);
