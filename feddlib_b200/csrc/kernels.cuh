@@ -1310,6 +1310,9 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
     for (;;) {
         const bool live = lane_used && tile * NPT + slot < A.count;
         const int a = lane - slot * TPR;
+#ifdef FB_RING_UNITVEC_DOF
+        const double ea[3] = {a == 0 ? 1.0 : 0.0, a == 1 ? 1.0 : 0.0, a == 2 ? 1.0 : 0.0};   // unit vector of the row dof
+#endif
         const int64_t base = __double_as_longlong(raw[0]);
         const int64_t k0 = __double_as_longlong(raw[1]);
         const int L = live ? (int)(__double_as_longlong(raw[2]) & 0xffffffff) : 0;
@@ -1392,9 +1395,18 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
                             }
                     } else {
                         const double mud = mu * adet, lamd = lam * adet;
+                        // the row dof a differs from lane to lane: register selects (42 FSEL + predicated moves per incidence).
+                        // FB_RING_UNITVEC_DOF replaces them by products with the unit vector e_a (36 more FP64 instructions, 70
+                        // fewer others): measured SLOWER, 2.54 against 2.47 ms -- an FP64 instruction holds the issue port of its
+                        // sub-partition for two cycles (16 lanes), so the loop costs 2 x 200 FP64 + 210 other slots and moving
+                        // work onto the FP64 pipe is the wrong direction
                         double Ga[NVTX];
 #pragma unroll
+#ifndef FB_RING_UNITVEC_DOF
                         for (int w = 0; w < NVTX; w++) Ga[w] = a == 0 ? g.G[w][0] : (a == 1 ? g.G[w][1] : g.G[w][2]);
+#else
+                        for (int w = 0; w < NVTX; w++) Ga[w] = fma(ea[2], g.G[w][2], fma(ea[1], g.G[w][1], ea[0] * g.G[w][0]));
+#endif
 #pragma unroll
                         for (int s = 0; s < 2; s++) {
                             const double ls = lamd * Ga[s];
@@ -1406,7 +1418,11 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
                                 const double mdot = mud * dot, mga = mud * Ga[w];
                                 // E^{ab}_{sw} = mu (delta_ab G_s.G_w + G_s[b] G_w[a]) + lambda G_s[a] G_w[b]
 #pragma unroll
+#ifndef FB_RING_UNITVEC_DOF
                                 for (int b = 0; b < DIM; b++) E[s][w][b] = (a == b ? mdot : 0.0) + mga * g.G[s][b] + ls * g.G[w][b];
+#else
+                                for (int b = 0; b < DIM; b++) E[s][w][b] = ea[b] * mdot + mga * g.G[s][b] + ls * g.G[w][b];
+#endif
                             }
                         }
                     }
