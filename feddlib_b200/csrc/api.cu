@@ -79,11 +79,15 @@ template <int OP>
 int launch_elem(feddb200_ctx *c, int dim, int nr, int nc, ElemArgs &A, bool atomic)
 {
     if constexpr (OP == OP_B) {
+        if (dim == 2 && nr == 1 && nc == 3) return launch_elem_t<OP, 2, 1, 3>(c, A, atomic);   // P0 pressure: rows on the element map
+        if (dim == 2 && nr == 1 && nc == 6) return launch_elem_t<OP, 2, 1, 6>(c, A, atomic);
         if (dim == 2 && nr == 3 && nc == 3) return launch_elem_t<OP, 2, 3, 3>(c, A, atomic);
         if (dim == 2 && nr == 3 && nc == 6) return launch_elem_t<OP, 2, 3, 6>(c, A, atomic);
         if (dim == 3 && nr == 4 && nc == 4) return launch_elem_t<OP, 3, 4, 4>(c, A, atomic);
         if (dim == 3 && nr == 4 && nc == 10) return launch_elem_t<OP, 3, 4, 10>(c, A, atomic);
     } else if constexpr (OP == OP_BT) {
+        if (dim == 2 && nr == 3 && nc == 1) return launch_elem_t<OP, 2, 3, 1>(c, A, atomic);   // P0 pressure: columns on the element map
+        if (dim == 2 && nr == 6 && nc == 1) return launch_elem_t<OP, 2, 6, 1>(c, A, atomic);
         if (dim == 2 && nr == 3 && nc == 3) return launch_elem_t<OP, 2, 3, 3>(c, A, atomic);
         if (dim == 2 && nr == 6 && nc == 3) return launch_elem_t<OP, 2, 6, 3>(c, A, atomic);
         if (dim == 3 && nr == 4 && nc == 4) return launch_elem_t<OP, 3, 4, 4>(c, A, atomic);

@@ -215,7 +215,9 @@ extern "C" int feddb200_copy_d2h(feddb200_ctx *c, void *dst, const void *src, in
 // ---------------------------------------------------------------------------------------
 static bool valid_elem(int dim, int nloc)
 {
-    return (dim == 2 && (nloc == 3 || nloc == 6)) || (dim == 3 && (nloc == 4 || nloc == 10));
+    // nloc == 1: the P0 pressure space of assemblyDivAndDivT (one pseudo-node per element; its ids are the element map,
+    // FE_def.hpp:1954-1957).  2D only: FE::phi has no P0 case for dim 3 (FE_def.hpp:5037 ff.)
+    return (dim == 2 && (nloc == 1 || nloc == 3 || nloc == 6)) || (dim == 3 && (nloc == 4 || nloc == 10));
 }
 
 extern "C" int feddb200_mesh_upload(feddb200_ctx *c, feddb200_mesh **out, int dim, int nloc, int64_t ne,
@@ -223,7 +225,7 @@ extern "C" int feddb200_mesh_upload(feddb200_ctx *c, feddb200_mesh **out, int di
 {
     FB_LOGIC(!c || !out, "feddb200_mesh_upload: null context/output");
     FB_LOGIC(!valid_elem(dim, nloc),
-             "feddb200_mesh_upload: only P1/P2 triangles (3/6 nodes) and tetrahedra (4/10 nodes) are implemented");
+             "feddb200_mesh_upload: only P1/P2 triangles (3/6 nodes), tetrahedra (4/10 nodes) and the 2D P0 pseudo-mesh (1 node per element) are implemented");
     FB_LOGIC(ne < 0 || nn < 0 || (ne > 0 && !conn) || (nn > 0 && !coords), "feddb200_mesh_upload: bad sizes/pointers");
     FB_LOGIC(ne >= (int64_t(1) << 27), "feddb200_mesh_upload: more than 2^27 elements per GPU are not supported");
     for (int64_t k = 0; k < ne * nloc; k++)

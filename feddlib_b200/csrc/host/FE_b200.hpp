@@ -213,6 +213,19 @@ class FE_b200 {
         auto elements = domain->getElementsC();
         auto points = domain->getPointsRepeated();
         s.ne = elements->numberElements();
+        if (s.FEType == "P0") {
+            // pressure space of assemblyDivAndDivT (FE_def.hpp:1954-1957): one pseudo-node per element, numbered by the
+            // element map; the node lists and points of the domain are not read
+            s.nloc = 1;
+            s.nn = s.ne;
+            s.p0 = true;
+            std::vector<std::int32_t> conn0((std::size_t)s.ne);
+            for (std::int64_t T = 0; T < s.ne; T++) conn0[(std::size_t)T] = (std::int32_t)T;
+            std::vector<double> zeros((std::size_t)std::max<std::int64_t>(s.ne, 1) * s.dim, 0.0);
+            b200::check(feddb200_mesh_upload(ctx_, &s.mesh, s.dim, 1, s.ne, conn0.data(), s.nn, zeros.data()));
+            slots_.push_back(s);
+            return;
+        }
         s.nloc = s.ne > 0 ? (int)elements->getElement(0).getVectorNodeList().size() : nloc_of(s.dim, s.FEType);
         s.nn = (std::int64_t)points->size();
         std::vector<std::int32_t> conn((std::size_t)s.ne * s.nloc);
@@ -422,8 +435,10 @@ class FE_b200 {
     void assemblyDivAndDivT(int dim, std::string FEType1, std::string FEType2, int /*degree*/, MatrixPtr_Type &Bmat,
                             MatrixPtr_Type &BTmat, MapConstPtr_Type map1, MapConstPtr_Type map2, bool callFillComplete = true)
     {
-        if (FEType2 == "P0" || FEType2 == "P1-disc" || FEType2 == "P1-disc-global")
-            throw std::logic_error("assemblyDivAndDivT: discontinuous pressure spaces are not implemented in the B200 engine");
+        if (FEType2 == "P1-disc" || FEType2 == "P1-disc-global")
+            throw std::logic_error("assemblyDivAndDivT: P1-disc pressure is not implemented in the B200 engine (the reference pairs it with Q2 meshes)");
+        // FE::phi has a P0 case for dim 1 and 2 only (FE_def.hpp:4955, 4993): in 3D the reference reads an uninitialised value
+        if (FEType2 == "P0" && dim != 2) throw std::logic_error("assemblyDivAndDivT: P0 pressure is implemented for dim == 2 only (as in the reference)");
         const int loc1 = checkFE(dim, FEType1), loc2 = checkFE(dim, FEType2);
         feddb200_pat *pB = pattern(loc2, loc1), *pBT = pattern(loc1, loc2);
         b200::LocalCsr<SC, LO, GO> cB, cBT;
@@ -477,6 +492,7 @@ class FE_b200 {
         std::int64_t ne = 0, nn = 0;
         std::string FEType;
         std::vector<std::int32_t> owner;   // multi-rank: owning rank of every repeated node
+        bool p0 = false;                   // P0 space: "nodes" are the elements, numbered by Domain::getElementMap
     };
 
     // multi-rank plan of one pattern + the state of its node-pattern callback
@@ -560,7 +576,7 @@ class FE_b200 {
             st->colind.resize((std::size_t)nnz);
             b200::check(feddb200_pattern_expand(ctx_, p, rowDofs, colDofs, mode, st->rowptr.data(), st->colind.data()));
             if (pl == plans_.end()) {
-                MapConstPtr_Type mapRep = slots_[colLoc].domain->getMapRepeated();
+                MapConstPtr_Type mapRep = slots_[colLoc].p0 ? slots_[colLoc].domain->getElementMap() : slots_[colLoc].domain->getMapRepeated();
                 st->colmap.resize((std::size_t)nCols * colDofs);
                 for (std::int64_t j = 0; j < nCols; j++)
                     for (int d = 0; d < colDofs; d++)

@@ -87,11 +87,12 @@ class Domain {
     Teuchos::RCP<Elements> getElementsC() const { return elementsC_; }
     Teuchos::RCP<std::vector<std::vector<double> > > getPointsRepeated() const { return pointsRep_; }
     MapConstPtr_Type getMapRepeated() const { return mapRepeated_; }
+    MapConstPtr_Type getElementMap() const { return elementMap_; }   // P0 spaces: numbering of the elements (Domain_decl.hpp)
     int dim_;
     std::string FEType_;
     Teuchos::RCP<Elements> elementsC_;
     Teuchos::RCP<std::vector<std::vector<double> > > pointsRep_;
-    MapConstPtr_Type mapRepeated_;
+    MapConstPtr_Type mapRepeated_, elementMap_;
 };
 
 template <class SC, class LO, class GO, class NO>

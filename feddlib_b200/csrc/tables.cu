@@ -22,6 +22,7 @@ static const int kEdges3[6][2] = {{0, 1}, {1, 2}, {0, 2}, {0, 3}, {1, 3}, {2, 3}
 
 static int fe_order(int dim, int nloc)
 {
+    if (dim == 2 && nloc == 1) return 0;   // P0 (pressure of assemblyDivAndDivT, 2D)
     if (nloc == dim + 1) return 1;
     if ((dim == 2 && nloc == 6) || (dim == 3 && nloc == 10)) return 2;
     return -1;
@@ -93,6 +94,7 @@ static double basis(int dim, int order, int i, const double *x)
 {
     double lam[4];
     bary(dim, x, lam);
+    if (order == 0) return 1.0;             // FE::phi `case 0: //P0` (FE_def.hpp:4993)
     if (order == 1) return lam[i];
     if (i <= dim) return lam[i] * (2.0 * lam[i] - 1.0);
     const int *e = dim == 2 ? kEdges2[i - 3] : kEdges3[i - 4];
@@ -106,7 +108,8 @@ static void basis_grad(int dim, int order, int i, const double *x, double *g)
     // d lambda_v / d x_c
     auto dl = [&](int v, int c) { return v == 0 ? -1.0 : (v == c + 1 ? 1.0 : 0.0); };
     for (int c = 0; c < dim; c++) {
-        if (order == 1) g[c] = dl(i, c);
+        if (order == 0) g[c] = 0.0;
+        else if (order == 1) g[c] = dl(i, c);
         else if (i <= dim) g[c] = (4.0 * lam[i] - 1.0) * dl(i, c);
         else {
             const int *e = dim == 2 ? kEdges2[i - 3] : kEdges3[i - 4];

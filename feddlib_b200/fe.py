@@ -76,6 +76,18 @@ class Domain:
         self.mapUnique_ = mapUnique
 
     @classmethod
+    def p0_of(cls, domain: "Domain", elementMap: Map | None = None):
+        """The P0 space on the elements of `domain` (pressure of assemblyDivAndDivT, FE_def.hpp:1954-1957): one pseudo-node
+        per element whose global ids are the ELEMENT map (Domain::getElementMap; default: the local element numbers)."""
+        ne = domain.getElementsC().shape[0]
+        emap = elementMap if elementMap is not None else Map(np.arange(ne, dtype=np.int64), domain.getMapRepeated().rank,
+                                                              domain.getMapRepeated().nranks)
+        d = cls(domain.getDimension(), "P0", np.arange(ne, dtype=np.int32)[:, None], np.zeros((ne, domain.getDimension())), emap)
+        return d
+
+    def getElementMap(self): return self.mapRepeated_ if self.FEType_ == "P0" else None
+
+    @classmethod
     def buildMesh(cls, dim: int, FEType: str, N: int, M: int, rank: int = 0, nranks: int = 1):
         """Built-in structured square/cube (Domain::buildMesh -> MeshStructured::buildMesh2D/3D)."""
         conn, coords, gid = _mesh.build_structured(dim, FEType, N, M, rank)
@@ -327,8 +339,11 @@ class FE:
     # ---- FE_def.hpp:1932-2057 (and the "Fast" variant :2061-2148, same result) ----
     def assemblyDivAndDivT(self, dim, FEType1, FEType2, degree, Bmat: Matrix, BTmat: Matrix, map1: Map, map2: Map,
                            callFillComplete=True):
-        if FEType2 in ("P0", "P1-disc", "P1-disc-global"):
-            raise LogicError("Not implemented for P0 / P1-disc pressure on the B200 path")
+        if FEType2 in ("P1-disc", "P1-disc-global"):
+            raise LogicError("Not implemented for P1-disc pressure on the B200 path (the reference pairs it with Q2 meshes)")
+        if FEType2 == "P0" and dim != 2:
+            # FE::phi has a P0 case for dim 1 and 2 only (FE_def.hpp:4955, 4993): in 3D the reference reads an uninitialised value
+            raise LogicError("P0 pressure is implemented for dim == 2 only (as in the reference)")
         dv = self.domainVec_[self.checkFE(dim, FEType1)]
         dp = self.domainVec_[self.checkFE(dim, FEType2)]
         if dv.getElementsC().shape[0] != dp.getElementsC().shape[0]:

@@ -180,11 +180,12 @@ static int fo_is(const char *a, const char *b) { return strcmp(a, b) == 0; }
 /* nodes per element; -1 if unsupported on this path */
 int fo_nloc(int dim, const char *fe)
 {
+    if (fo_is(fe, "P0")) return dim == 2 ? 1 : -1;   /* FE_def.hpp:6766-6769: one local "point", intFE = 0 (2D; see fo_phi) */
     if (fo_is(fe, "P1")) return dim + 1;
     if (fo_is(fe, "P2")) return dim == 2 ? 6 : (dim == 3 ? 10 : -1);
     return -1;
 }
-static int fo_intfe(const char *fe) { return fo_is(fe, "P1") ? 1 : (fo_is(fe, "P2") ? 2 : -1); }
+static int fo_intfe(const char *fe) { return fo_is(fe, "P0") ? 0 : (fo_is(fe, "P1") ? 1 : (fo_is(fe, "P2") ? 2 : -1)); }
 
 /* FE_def.hpp:5431-5512 */
 int fo_determine_degree2(int dim, const char *fe1, const char *fe2, int t1, int t2, int extra)
@@ -293,6 +294,9 @@ int fo_quadrature(int dim, int deg, double *pts, double *w)
 /* FE_def.hpp:4991-5088 (P1/P2 cases) */
 double fo_phi(int dim, int intFE, int i, const double *p)
 {
+    /* P0: `case 0: //P0` of FE::phi exists for dim 1 and 2 only (FE_def.hpp:4955, 4993); in 3D the reference leaves *value
+     * uninitialised (no case 0 below :5037), so P0 is a 2D feature -- the callers reject it for dim 3 */
+    if (intFE == 0 && i == 0 && dim == 2) return 1.;
     if (dim == 2) {
         if (intFE == 1) {
             switch (i) {

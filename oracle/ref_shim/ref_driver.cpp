@@ -30,6 +30,8 @@ static Teuchos::RCP<Domain_t> make_domain(int dim, const char *fe, int64_t ne, c
             for (int c = 0; c < dim; c++) (*d->pointsRep_)[k][c] = coords[k * dim + c];
     std::vector<GOx> g(gid, gid + nn);
     d->mapRepeated_ = Teuchos::RCP<const Map_t>(new Map_t(g.data(), g.size()));
+    // a "P0" domain is described by one pseudo-node per element: its ids are the element map (rows of B, FE_def.hpp:1954, 2012)
+    if (std::string(fe) == "P0") d->elementMap_ = d->mapRepeated_;
     return d;
 }
 

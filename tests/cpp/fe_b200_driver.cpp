@@ -194,6 +194,24 @@ int main(int argc, char **argv)
             all = compare("assemblyDivAndDivT: B", g_seated[B.get()], refB, gid2, 1) && all;
             all = compare("assemblyDivAndDivT: BT", g_seated[BT.get()], refBT, gid1, dim) && all;
         }
+        if (dim == 2) { // B and B^T with P0 pressure: rows / columns on the element map (FE_def.hpp:1954-1957, 2012-2013, 2039-2040)
+            std::vector<int32_t> conn0((std::size_t)ne);
+            std::vector<int64_t> egid((std::size_t)ne);
+            for (int64_t e = 0; e < ne; e++) { conn0[(std::size_t)e] = (int32_t)e; egid[(std::size_t)e] = (e * 7919) % ne; }   // a permuted element map
+            if (ne % 7919 == 0) for (int64_t e = 0; e < ne; e++) egid[(std::size_t)e] = e;
+            Teuchos::RCP<Domain_t> d0 = make_domain(dim, "P0", ne, conn0.data(), 1, nullptr, ne, egid.data());
+            d0->elementMap_ = d0->mapRepeated_;
+            fe.addFE(d0);
+            fo_matrix *rB = fo_matrix_new(ne, 64), *rBT = fo_matrix_new(dim * nglob1, 64);
+            if (ref_assemble(5, dim, fe1, "P0", ne, conn1.data(), nloc1, xyz.data(), nn1, gid1.data(), conn0.data(), 1, ne, egid.data(),
+                             nullptr, 0, 0, rB, rBT) != 0) { std::printf("reference failed: %s\n", ref_last_error()); return 1; }
+            RefCsr refB = ref_csr(rB, ne), refBT = ref_csr(rBT, dim * nglob1);
+            fo_matrix_free(rB); fo_matrix_free(rBT);
+            Teuchos::RCP<Matrix_t> B(new Matrix_t(nullptr)), BT(new Matrix_t(nullptr));
+            fe.assemblyDivAndDivT(dim, fe1, "P0", 2, B, BT, Teuchos::RCP<const Map_t>(), Teuchos::RCP<const Map_t>(), true);
+            all = compare("assemblyDivAndDivT (P0 pressure): B", g_seated[B.get()], refB, egid, 1) && all;
+            all = compare("assemblyDivAndDivT (P0 pressure): BT", g_seated[BT.get()], refBT, gid1, dim) && all;
+        }
         // assemblyRHS (constant source), "Scalar" and "Vector"
         for (int vec = 0; vec < 2; vec++) {
             const double f[3] = {1.5, -2.0, 0.25};

@@ -25,6 +25,11 @@ def inputs(dim, fe, M, warp):
     return conn, coords, conn_p, random_u(dim, coords.shape[0])
 
 
+def p0_inputs(ne):
+    """One pseudo-node per element and a permuted element map."""
+    return np.arange(ne, dtype=np.int32)[:, None], np.random.default_rng(11).permutation(ne).astype(np.int64)
+
+
 if __name__ == "__main__":
     assert R.available(), "build oracle/_ref first (make -C oracle ref)"
     out = {}
@@ -42,6 +47,11 @@ if __name__ == "__main__":
         (B, BT) = R.assemble("div", dim, fe, conn, coords, fe2="P1", conn2=conn_p)
         for tag, (rp, ci, v) in (("B", B), ("BT", BT)):
             out[f"{name}/div{tag}/rowptr"], out[f"{name}/div{tag}/col"], out[f"{name}/div{tag}/val"] = rp, ci, v
+        if dim == 2:  # P0 pressure: rows of B / columns of B^T on the element map (FE_def.hpp:1954-1957; 2D only, see fo_phi)
+            conn0, egid = p0_inputs(conn.shape[0])
+            (B, BT) = R.assemble("div", dim, fe, conn, coords, fe2="P0", conn2=conn0, gid2=egid)
+            for tag, (rp, ci, v) in (("B", B), ("BT", BT)):
+                out[f"{name}/divP0{tag}/rowptr"], out[f"{name}/divP0{tag}/col"], out[f"{name}/divP0{tag}/val"] = rp, ci, v
         f = np.array([1.5, -2.0, 0.25])[:dim]
         out[f"{name}/rhs_scalar"] = R.assemble_rhs(dim, fe, conn, coords, f, 1, False)
         out[f"{name}/rhs_vector"] = R.assemble_rhs(dim, fe, conn, coords, f, 1, True)

@@ -72,6 +72,37 @@ def test_fe_interface_all_entry_points(engine_ctx):
     assert rel_frobenius(B.numpy_values(), -ro[2]) <= TOL
 
 
+def test_fe_interface_p0_pressure(engine_ctx):
+    """assemblyDivAndDivT with FEType2 = "P0" through the reference-interface mirror: rows of B on the element map
+    (FE_def.hpp:1954-1957); 3D raises like any combination the reference cannot evaluate (FE::phi has no P0 case there)."""
+    from feddlib_b200 import FE, Domain, LogicError, Map, Matrix
+    dim = 2
+    dv = Domain.buildMesh(dim, "P2", 1, 5)
+    ne = dv.getElementsC().shape[0]
+    egid = np.random.default_rng(3).permutation(ne).astype(np.int64)
+    d0 = Domain.p0_of(dv, Map(egid))
+    fe = FE(ctx=engine_ctx)
+    fe.addFE(dv); fe.addFE(d0)
+    B = Matrix(d0.getMapUnique(), dim * dv.getApproxEntriesPerRow())
+    BT = Matrix(dv.getMapVecFieldUnique(), 8)
+    fe.assemblyDivAndDivT(dim, "P2", "P0", 2, B, BT, dv.getMapVecFieldUnique(), d0.getMapUnique(), True)
+    conn, co = dv.getElementsC(), dv.getPointsRepeated()
+    n = co.shape[0]
+    from oracle import oracle as O
+    Bo, BTo = O.Matrix(ne, 64), O.Matrix(dim * n)
+    conn0 = np.arange(ne, dtype=np.int32)[:, None]
+    O.assembly_div_divT(dim, "P2", "P0", conn, co, np.arange(n), conn0, np.arange(ne), Bo, BTo)   # local numbering: gid == lid
+    for M_, ref in ((B, Bo.csr()), (BT, BTo.csr())):
+        assert np.array_equal(M_.rowptr, ref[0]) and np.array_equal(M_.colind, ref[1])
+        assert rel_frobenius(M_.numpy_values(), ref[2]) <= TOL
+    assert B.getMap().isSameAs(d0.getMapUnique()) and d0.getElementMap().isSameAs(Map(egid))
+    d3 = Domain.buildMesh(3, "P2", 1, 2)
+    fe3 = FE(ctx=engine_ctx)
+    fe3.addFE(d3)
+    with pytest.raises(LogicError):
+        fe3.assemblyDivAndDivT(3, "P2", "P0", 2, B, BT, None, None, True)
+
+
 def test_error_behaviour_matches_reference(engine_ctx):
     from feddlib_b200 import FE, Domain, LogicError, Matrix
     d = Domain.buildMesh(2, "P1", 1, 3)

@@ -167,6 +167,42 @@ def test_div_and_divT(case, mode):
 
 
 @pytest.mark.parametrize("mode", MODES)
+def test_div_and_divT_p0_pressure(case, mode):
+    """P0 pressure (FE_def.hpp:1954-1957, 2012-2013, 2039-2040): rows of B / columns of B^T on the element map, described to the
+    engine as one pseudo-node per element.  2D only (FE::phi has no P0 case for dim 3); gather mode falls back to the
+    coloured element-row kernels for this pair of spaces."""
+    from feddlib_b200 import BLOCK_FULL, LogicError, Mesh, Pattern, assemble_div_divT
+    ctx = case["ctx"]
+    ctx.set_scatter_mode(mode)
+    d, conn, coords = case["dim"], case["conn"], case["coords"]
+    ne = conn.shape[0]
+    conn0 = np.arange(ne, dtype=np.int32)[:, None]
+    if d == 3:
+        with pytest.raises(LogicError):
+            Mesh(ctx, d, conn0, np.zeros((ne, d)))
+        return
+    mesh0 = Mesh(ctx, d, conn0, np.zeros((ne, d)))
+    patB, patBT = Pattern(ctx, mesh0, case["mesh"]), Pattern(ctx, case["mesh"], mesh0)
+    vB, vBT = assemble_div_divT(ctx, patB, patBT)
+    for op, pat, vals, rd, cd in (("div", patB, vB, 1, d), ("divT", patBT, vBT, d, 1)):
+        rp_o, ci_o, v_o = oracle_csr(op, d, case["fe"], conn, coords, fe2="P0", conn2=conn0)
+        rp, ci = pat.expand(rd, cd, BLOCK_FULL)
+        assert np.array_equal(rp, rp_o) and np.array_equal(ci, ci_o)
+        assert rel_frobenius(vals, v_o) <= TOL
+    import scipy.sparse as sp
+    rpB, ciB = patB.expand(1, d, BLOCK_FULL)
+    rpT, ciT = patBT.expand(d, 1, BLOCK_FULL)
+    B = sp.csr_matrix((vB, ciB, rpB), shape=(ne, d * coords.shape[0]))
+    BT = sp.csr_matrix((vBT, ciT, rpT), shape=(d * coords.shape[0], ne))
+    assert abs(B - BT.T).max() <= 1e-15 * abs(B).max()
+    # divergence theorem per element: sum_j B_{e,(j,d)} x_j[d] summed over d = dim * |e| for u = x  (a KAT that needs no oracle)
+    if case["fe"] == "P1":
+        from feddlib_b200.mesh import element_volumes
+        vol = np.abs(element_volumes(conn[:, : d + 1], coords))
+        assert np.allclose(B @ coords.reshape(-1), d * vol, rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("mode", MODES)
 def test_ns_jacobian_fused_equals_sum_of_parts(case, mode):
     """rho*nu*A + rho*N + rho*W on the union pattern (NavierStokes_def.hpp:140-152, 297-313); gather mode is the
     fused row-gather kernel k_gatherx<X_NSJ> that bench.py times."""

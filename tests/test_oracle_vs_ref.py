@@ -52,6 +52,25 @@ def test_div_restatement_matches_reference(dim, fe1):
             assert all(np.array_equal(x, y) for x, y in zip(got, ref)), op
 
 
+@pytest.mark.parametrize("dim,fe1", [(2, "P2"), (2, "P1")])
+def test_div_p0_pressure_restatement_matches_reference(dim, fe1):
+    """P0 pressure (FE_def.hpp:1954-1957, 2012-2013, 2039-2040): the rows of B / columns of B^T live on the ELEMENT map;
+    described to both sides as one pseudo-node per element whose global ids are the element map.  2D only: FE::phi has
+    no P0 case for dim 3 (the reference returns uninitialised values there)."""
+    conn, coords = mesh_structured(dim, fe1, 3, warp=True)
+    ne, n = conn.shape[0], coords.shape[0]
+    conn0 = np.arange(ne, dtype=np.int32)[:, None]
+    egid = np.random.default_rng(7).permutation(ne).astype(np.int64)      # element map with permuted global ids
+    for op, fast in (("div", False), ("div_fast", True)):
+        (B, BT) = R.assemble(op, dim, fe1, conn, coords, fe2="P0", conn2=conn0, gid2=egid)
+        Bo, BTo = O.Matrix(ne, 64), O.Matrix(dim * n)
+        O.assembly_div_divT(dim, fe1, "P0", conn, coords, np.arange(n), conn0, egid, Bo, BTo, fast=fast)
+        for got, ref in ((Bo.csr(), B), (BTo.csr(), BT)):
+            assert all(np.array_equal(x, y) for x, y in zip(got, ref)), op
+        assert B[0][-1] == ne * conn.shape[1] * dim                         # every element row holds dim * nloc entries
+    assert O.determine_degree(dim, fe1, "P0", 1, 0, 0) == R.determine_degree(dim, fe1, "P0", 1, 0, 0)
+
+
 def test_tables_and_degrees_match_reference():
     for dim in (2, 3):
         for fe in ("P1", "P2"):
