@@ -282,6 +282,11 @@ int build_star_tiles(feddb200_pat *p, const std::vector<RowInfo> &info)
 int ensure_gather(feddb200_pat *p)
 {
     if (p->gather_ready) return FEDDB200_OK;
+    {   // a previous attempt may have failed half-way (out of memory): drop what it left before building again
+        auto drop = [](auto *&q) { if (q) { cudaFree(q); q = nullptr; } };
+        drop(p->rec_d); drop(p->rowinfo_d); drop(p->row_perm_d); drop(p->ahead_d); drop(p->task_tiles_d); drop(p->tasks_d);
+        drop(p->tiletet_d); drop(p->fanrec_d); drop(p->star_tiles_d[0]); drop(p->star_tiles_d[1]); drop(p->geom_d); drop(p->frag_d);
+    }
     feddb200_ctx *c = p->ctx;
     const int dim = p->rm->dim, nl = p->rm->nloc;
     const int64_t n_rows = p->n_rows;

@@ -93,6 +93,7 @@ struct feddb200_ctx {
 
 struct feddb200_mesh {
     feddb200_ctx *ctx = nullptr;
+    int device = 0;              // device ordinal (copied: the mesh may be freed after its context)
     int dim = 0, nloc = 0;
     int64_t ne = 0, nn = 0;
     int32_t *conn_d = nullptr;
@@ -102,6 +103,7 @@ struct feddb200_mesh {
 
 struct feddb200_pat {
     feddb200_ctx *ctx = nullptr;
+    int device = 0;              // device ordinal (copied: the pattern may be freed after its context)
     const feddb200_mesh *rm = nullptr, *cm = nullptr;
     int64_t n_rows = 0, n_owned = 0, n_cols = 0, nnz = 0, nnz_owned = 0;
     int max_len = 0;

@@ -232,7 +232,7 @@ extern "C" int feddb200_mesh_upload(feddb200_ctx *c, feddb200_mesh **out, int di
         FB_LOGIC(conn[k] < 0 || conn[k] >= nn, "feddb200_mesh_upload: connectivity entry out of range");
     FB_CUDA(cudaSetDevice(c->device));
     auto *m = new feddb200_mesh();
-    m->ctx = c; m->dim = dim; m->nloc = nloc; m->ne = ne; m->nn = nn;
+    m->ctx = c; m->device = c->device; m->dim = dim; m->nloc = nloc; m->ne = ne; m->nn = nn;
     m->conn_h.assign(conn, conn + ne * nloc);
     FB_CUDA(cudaMalloc(&m->conn_d, std::max<size_t>(8, sizeof(int32_t) * ne * nloc)));
     FB_CUDA(cudaMalloc(&m->coords_d, std::max<size_t>(8, sizeof(double) * nn * dim)));
@@ -254,7 +254,7 @@ extern "C" int feddb200_mesh_update_coords(feddb200_ctx *c, feddb200_mesh *m, co
 extern "C" void feddb200_mesh_free(feddb200_mesh *m)
 {
     if (!m) return;
-    cudaSetDevice(m->ctx->device);
+    cudaSetDevice(m->device);   // not m->ctx->device: bindings may free a mesh after feddb200_destroy
     cudaFree(m->conn_d);
     cudaFree(m->coords_d);
     delete m;
@@ -402,11 +402,24 @@ extern "C" int feddb200_pattern_build(feddb200_ctx *c, feddb200_pat **out, const
     const int64_t ne = rm->ne;
 
     auto *p = new feddb200_pat();
-    p->ctx = c; p->rm = rm; p->cm = cm;
+    p->ctx = c; p->device = c->device; p->rm = rm; p->cm = cm;
     p->n_rows = n_rows; p->n_owned = n_owned; p->n_cols = n_cols;
     p->pos_stride = (nc + 1) & ~1;
+    // every early return below (FB_CUDA / FB_LOGIC) frees the half-built pattern and the device temporaries
+    struct Guard {
+        feddb200_pat *pat;
+        std::vector<void **> tmps;
+        ~Guard() { for (void **t : tmps) if (*t) { cudaFree(*t); *t = nullptr; } if (pat) feddb200_pat_free(pat); }
+    } guard{p, {}};
+    auto tmp_of = [&guard](auto **pp) { guard.tmps.push_back(reinterpret_cast<void **>(pp)); };
 
     int32_t *row_lid_d = nullptr, *col_lid_d = nullptr, *er_d = nullptr, *ec_d = nullptr;
+    tmp_of(&col_lid_d); tmp_of(&er_d); tmp_of(&ec_d);   // row_lid_d belongs to the pattern
+    // temporaries of the sort / unique / incidence steps (function scope: the guard outlives the blocks that use them)
+    void *sort_tmp = nullptr, *uniq_tmp = nullptr, *inc_tmp = nullptr;
+    int64_t *count_d = nullptr;
+    int32_t *k_a = nullptr, *k_b = nullptr, *v_a = nullptr, *v_b = nullptr;
+    tmp_of(&sort_tmp); tmp_of(&uniq_tmp); tmp_of(&inc_tmp); tmp_of(&count_d); tmp_of(&k_a); tmp_of(&k_b); tmp_of(&v_a); tmp_of(&v_b);
     if (row_lid) {
         FB_CUDA(cudaMalloc(&row_lid_d, sizeof(int32_t) * std::max<int64_t>(rm->nn, 1)));
         FB_CUDA(cudaMemcpyAsync(row_lid_d, row_lid, sizeof(int32_t) * rm->nn, cudaMemcpyHostToDevice, st));
@@ -420,6 +433,7 @@ extern "C" int feddb200_pattern_build(feddb200_ctx *c, feddb200_pat **out, const
     // 1. keys
     const int64_t nkeys = ne * nr * nc + n_extra;
     uint64_t *keys_a = nullptr, *keys_b = nullptr;
+    tmp_of(&keys_a); tmp_of(&keys_b);
     FB_CUDA(cudaMalloc(&keys_a, sizeof(uint64_t) * std::max<int64_t>(nkeys, 1)));
     FB_CUDA(cudaMalloc(&keys_b, sizeof(uint64_t) * std::max<int64_t>(nkeys, 1)));
     if (ne > 0) {
@@ -439,27 +453,24 @@ extern "C" int feddb200_pattern_build(feddb200_ctx *c, feddb200_pat **out, const
         cub::DoubleBuffer<uint64_t> db(keys_a, keys_b);
         size_t tmp_bytes = 0;
         FB_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, db, nkeys, 0, 64, st));
-        void *tmp = nullptr;
-        FB_CUDA(cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 8)));
-        FB_CUDA(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, db, nkeys, 0, 64, st));
+        FB_CUDA(cudaMalloc(&sort_tmp, std::max<size_t>(tmp_bytes, 8)));
+        FB_CUDA(cub::DeviceRadixSort::SortKeys(sort_tmp, tmp_bytes, db, nkeys, 0, 64, st));
         FB_CUDA(cudaStreamSynchronize(st));
-        cudaFree(tmp);
+        cudaFree(sort_tmp); sort_tmp = nullptr;
         if (db.Current() != keys_a) std::swap(keys_a, keys_b);
     }
     // 3. unique
     int64_t nuniq = 0;
     {
-        int64_t *count_d = nullptr;
         FB_CUDA(cudaMalloc(&count_d, sizeof(int64_t)));
         size_t tmp_bytes = 0;
         FB_CUDA(cub::DeviceSelect::Unique(nullptr, tmp_bytes, keys_a, keys_b, count_d, nkeys, st));
-        void *tmp = nullptr;
-        FB_CUDA(cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 8)));
-        FB_CUDA(cub::DeviceSelect::Unique(tmp, tmp_bytes, keys_a, keys_b, count_d, nkeys, st));
+        FB_CUDA(cudaMalloc(&uniq_tmp, std::max<size_t>(tmp_bytes, 8)));
+        FB_CUDA(cub::DeviceSelect::Unique(uniq_tmp, tmp_bytes, keys_a, keys_b, count_d, nkeys, st));
         FB_CUDA(cudaMemcpyAsync(&nuniq, count_d, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
         FB_CUDA(cudaStreamSynchronize(st));
-        cudaFree(tmp);
-        cudaFree(count_d);
+        cudaFree(uniq_tmp); uniq_tmp = nullptr;
+        cudaFree(count_d); count_d = nullptr;
         if (nuniq > 0) { // the drop key, if present, is the last unique key
             uint64_t last = 0;
             FB_CUDA(cudaMemcpy(&last, keys_b + (nuniq - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost));
@@ -467,7 +478,7 @@ extern "C" int feddb200_pattern_build(feddb200_ctx *c, feddb200_pat **out, const
         }
     }
     p->nnz = nuniq;
-    cudaFree(keys_a);
+    cudaFree(keys_a); keys_a = nullptr;
     // 4. colind, rowptr
     FB_CUDA(cudaMalloc(&p->colind_d, sizeof(int32_t) * std::max<int64_t>(nuniq, 1)));
     FB_CUDA(cudaMalloc(&p->rowptr_d, sizeof(int64_t) * (n_rows + 1)));
@@ -477,15 +488,14 @@ extern "C" int feddb200_pattern_build(feddb200_ctx *c, feddb200_pat **out, const
     p->rowptr_h.resize(n_rows + 1);
     FB_CUDA(cudaMemcpyAsync(p->rowptr_h.data(), p->rowptr_d, sizeof(int64_t) * (n_rows + 1), cudaMemcpyDeviceToHost, st));
     FB_CUDA(cudaStreamSynchronize(st));
-    cudaFree(keys_b);
+    cudaFree(keys_b); keys_b = nullptr;
     p->nnz_owned = p->rowptr_h[n_owned];
     int max_len = 0;
     for (int64_t r = 0; r < n_rows; r++) max_len = std::max<int>(max_len, (int)(p->rowptr_h[r + 1] - p->rowptr_h[r]));
     p->max_len = max_len;
     if (max_len >= 0xffff) {
         fb::set_error("feddb200_pattern_build: a node row has >= 65535 entries (position map is 16 bit)");
-        feddb200_pat_free(p);
-        return FEDDB200_ELOGIC;
+        return FEDDB200_ELOGIC;   // the guard frees the pattern
     }
     // 5. position map
     FB_CUDA(cudaMalloc(&p->pos_d, sizeof(uint16_t) * std::max<int64_t>(ne * nr * p->pos_stride, 1)));
@@ -498,7 +508,6 @@ extern "C" int feddb200_pattern_build(feddb200_ctx *c, feddb200_pat **out, const
     // 6. incidences (row -> (element, local index)), stable sort keeps elements ascending
     {
         const int64_t n = ne * nr;
-        int32_t *k_a = nullptr, *k_b = nullptr, *v_a = nullptr, *v_b = nullptr;
         FB_CUDA(cudaMalloc(&k_a, sizeof(int32_t) * std::max<int64_t>(n, 1)));
         FB_CUDA(cudaMalloc(&k_b, sizeof(int32_t) * std::max<int64_t>(n, 1)));
         FB_CUDA(cudaMalloc(&v_a, sizeof(int32_t) * std::max<int64_t>(n, 1)));
@@ -510,9 +519,8 @@ extern "C" int feddb200_pattern_build(feddb200_ctx *c, feddb200_pat **out, const
         cub::DoubleBuffer<int32_t> dk(k_a, k_b), dv(v_a, v_b);
         size_t tmp_bytes = 0;
         FB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, n, 0, bits_for(n_rows), st));
-        void *tmp = nullptr;
-        FB_CUDA(cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 8)));
-        FB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dv, n, 0, bits_for(n_rows), st));
+        FB_CUDA(cudaMalloc(&inc_tmp, std::max<size_t>(tmp_bytes, 8)));
+        FB_CUDA(cub::DeviceRadixSort::SortPairs(inc_tmp, tmp_bytes, dk, dv, n, 0, bits_for(n_rows), st));
         FB_CUDA(cudaMalloc(&p->inc_ptr_d, sizeof(int64_t) * (n_rows + 1)));
         k_lower_bound32<<<grid_for(n_rows + 1), 256, 0, st>>>(n_rows, n, dk.Current(), p->inc_ptr_d);
         c->launches++;
@@ -523,11 +531,8 @@ extern "C" int feddb200_pattern_build(feddb200_ctx *c, feddb200_pat **out, const
         FB_CUDA(cudaMalloc(&p->inc_d, sizeof(int32_t) * std::max<int64_t>(n_inc, 1)));
         FB_CUDA(cudaMemcpyAsync(p->inc_d, dv.Current(), sizeof(int32_t) * n_inc, cudaMemcpyDeviceToDevice, st));
         FB_CUDA(cudaStreamSynchronize(st));
-        cudaFree(tmp); cudaFree(k_a); cudaFree(k_b); cudaFree(v_a); cudaFree(v_b);
     }
-    cudaFree(col_lid_d);
-    cudaFree(er_d);
-    cudaFree(ec_d);
+    guard.pat = nullptr;   // success: the caller owns the pattern; the guard frees what is left of the temporaries
     *out = p;
     return FEDDB200_OK;
 }
@@ -535,7 +540,7 @@ extern "C" int feddb200_pattern_build(feddb200_ctx *c, feddb200_pat **out, const
 extern "C" void feddb200_pat_free(feddb200_pat *p)
 {
     if (!p) return;
-    cudaSetDevice(p->ctx->device);
+    cudaSetDevice(p->device);   // not p->ctx->device: bindings may free a pattern after feddb200_destroy
     cudaFree(p->rowptr_d); cudaFree(p->colind_d); cudaFree(p->row_lid_d); cudaFree(p->pos_d);
     cudaFree(p->inc_ptr_d); cudaFree(p->inc_d); cudaFree(p->row_perm_d); cudaFree(p->colour_perm_d);
     cudaFree(p->rec_d); cudaFree(p->geom_d); cudaFree(p->frag_d); cudaFree(p->vtx_d); cudaFree(p->coords4_d); cudaFree(p->rowinfo_d); cudaFree(p->ahead_d); cudaFree(p->task_tiles_d); cudaFree(p->tasks_d); cudaFree(p->tiletet_d); cudaFree(p->fanrec_d); cudaFree(p->star_tiles_d[0]); cudaFree(p->star_tiles_d[1]); cudaFree(p->sloc_d); cudaFree(p->sloc_tab_d); cudaFree(p->dt_d);
