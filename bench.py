@@ -380,6 +380,7 @@ def main():
                          "ghost-row kernels; 'nccl' = all-to-all-v of the ghost values on a side stream")
     ap.add_argument("--no-parity", dest="no_parity", action="store_true", help="skip the sampled-row parity check of the full-size matrix")
     ap.add_argument("--no-ns", action="store_true", help="skip the secondary Navier-Stokes block timings")
+    ap.add_argument("--no-ns-mgpu", dest="no_ns_mgpu", action="store_true", help="several GPUs: skip the Navier-Stokes block on the partition")
     ap.add_argument("--ns-M", dest="ns_M", type=int, default=50, help="H/h of the P2-P1 cube of the secondary timings")
     ap.add_argument("--cfg4-levels", dest="cfg4_levels", type=int, default=2, help="regular refinements of DFG3DCylinder_6k (config 4)")
     ap.add_argument("--all-modes", action="store_true", help="also time the other scatter modes (extra keys)")
@@ -516,6 +517,24 @@ def main():
         phases = {k: float(v) for k, v in zip(keys, t.tolist())}
         phases["what"] = "device ms per phase of one step, max over ranks; the barrier runs under the owned rows"
 
+    # several GPUs: the fused Navier-Stokes (0,0) block on the same partition (same node pattern and value layout as the
+    # elasticity matrix): velocity on the unique map -> repeated map on the device (MultiVector::importFromVector,
+    # NavierStokes_def.hpp:294), assembly with the NCCL ghost-row exchange under the owned rows, unpack-add
+    ns_mgpu = None
+    if runner is not None and args.mode == "gather" and not args.no_ns_mgpu:
+        u_unique = torch.from_numpy(np.random.default_rng(1234 + rank).uniform(-1, 1, dim * runner.plan.n_owned)).cuda()
+
+        def ns_step():
+            u_rep = runner.import_vector(u_unique, dim)
+            runner.assemble_overlapped(values, dim, dim, BLOCK_FULL, lambda: pat.assemble_ns_jacobian_d(values, u_rep, 1.0, 1.0e-3, True))
+
+        ns_ms, ns_launches = timed(ns_step, max(3, args.steps // 2), 3)
+        ns_mgpu = {"workload": f"fused (0,0) block rho*nu*A + rho*N(u) + rho*W(u), P2 cube H/h={M} per GPU, {ne * world} tets on {world} GPUs, "
+                               "velocity import + NCCL ghost-row exchange inside the step",
+                   "ms_per_step": ns_ms, "elements_per_s": ne * world / (ns_ms * 1e-3), "launches_per_step": ns_launches,
+                   "hbm_frac_per_gpu": (ne * conn.shape[1] * 4 + (M + 1) ** 3 * dim * 8 + nnz * 8) / (ns_ms * 1e-3) / 1e9 / peaks()[0]}
+        step(); ctx.synchronize()   # leave the elasticity matrix in `values` for the checksum / e2e below
+
     ne_total = ne * world
     value = ne_total / (ms * 1e-3)
 
@@ -636,6 +655,8 @@ def main():
                 "clocks": clocks, "checksum_first_1Mi_values": checksum, "parity_check": parity}
         if phases:
             line["multi_gpu_phase_ms"] = phases
+        if ns_mgpu:
+            line["navier_stokes_block_multi_gpu"] = ns_mgpu
         if extra:
             line["other_scatter_modes"] = extra
         if ns_extra:
