@@ -826,7 +826,7 @@ int launch_gatherx_t(feddb200_ctx *c, feddb200_pat *p, const feddb200_mesh *vm, 
                     FB_CUDA(cudaMalloc(&p->sloc_tab_d, sizeof(double) * tab.size()));
                     FB_CUDA(cudaMemcpy(p->sloc_tab_d, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
                 }
-                const int nts = 128;
+                const int nts = std::max(32, std::min(128, FB_ENV_INT("FEDDB200_SLOC_NT", 128) & ~31)); // tuning aid
                 const size_t smem_s = sizeof(double) * ((size_t)NLV * NLV * NLV * 2 + (size_t)NLV * NLV * 4 + (size_t)16 * nts);
                 k_sloc<DIM, NLV><<<(unsigned)((ne + nts - 1) / nts), nts, smem_s, c->stream>>>(
                     ne, vm->conn_d, p->geom_d, u_d, p->sloc_tab_d, OPX == X_NSJ ? C.c0 : 0.0, OPX == X_NSJ ? C.c1 : 1.0, p->sloc_d);

@@ -2049,7 +2049,11 @@ __global__ void __launch_bounds__(128) k_sloc(int64_t ne, const int32_t *__restr
         }
     }
     double *out = sloc + e * (int64_t)(NL * NL);
-#pragma unroll 1
+#ifndef FB_SLOC_UNROLL
+#define FB_SLOC_UNROLL 1
+#endif
+    constexpr int kSlocUnroll = FB_SLOC_UNROLL;
+#pragma unroll(kSlocUnroll)
     for (int i = 0; i < NL; i++) {
         double acc[NL];
 #pragma unroll
