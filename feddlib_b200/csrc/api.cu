@@ -593,7 +593,7 @@ int launch_gather_t(feddb200_ctx *c, const feddb200_pat *p, GatherArgs &G)
                     }
                 }
                 const int nt = std::max(32, std::min(64, FB_ENV_INT("FEDDB200_RING_NT", 64) & ~31)); // tuning aid
-                const int npt = 32 / TPR;                       // row nodes per warp tile
+                const int npt = TPR == 3 ? FB_RING_NPT3 : 32 / TPR;   // row nodes per warp tile
                 // node pitch: room for the TPR dof rows + the phase shift; among the next candidates the one with the fewest
                 // bank conflicts when the threads of a half-warp store to the same position of their rows
                 const int n_row = NBr * std::max(1, b.lcap - 1), need = TPR * NBr * b.lcap + 1; // typical row: lcap rounds L up to a multiple of 4

@@ -1267,7 +1267,11 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
     // a tile = the NPT row nodes of ONE WARP; lane < NPT * TPR owns dof a = lane % TPR of the tile's node lane / TPR, so
     // the TPR dof rows of a node are always in the same warp (they are contiguous in the values array and leave in ONE
     // bulk store) and warps never wait for one another
-    constexpr int NPT = 32 / TPR;
+#ifndef FB_RING_NPT3
+#define FB_RING_NPT3 10     // row nodes per warp tile of the elasticity ring rows (3 lanes each); must be even (16-byte aligned
+                            // warp areas).  8 nodes = 12 instead of 10 resident warps at L = 27, 24 active lanes: measured 2.51 vs 2.47 ms
+#endif
+    constexpr int NPT = TPR == 3 ? FB_RING_NPT3 : 32 / TPR;
     const int slot = lane / TPR;
     const bool lane_used = lane < NPT * TPR;
     const int64_t ntiles = (A.count + NPT - 1) / NPT;
