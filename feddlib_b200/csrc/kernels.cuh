@@ -2166,10 +2166,25 @@ __global__ void __launch_bounds__(64, 4) k_gatherx(const GatherXArgs A)
 #pragma unroll
     for (int b = 0; b < NB; b++) dacc[b] = 0.0;
     int pdiag = 0;
-    IncRec<NL> rc, rn;
-    if (ninc > 0) load_rec<NL>(RA, k0, rc);
+    // N(u) / fused block: records two incidences ahead and the next incidence's row of S_e requested into L2 one iteration
+    // early (the dependent chain record -> natural indices -> ten 8-byte loads was fully exposed; see k_gatherw)
+    constexpr bool AHEAD = OPX == X_ADV || OPX == X_NSJ;
+    IncRec<NL> rc, rn, r2;
+    if (ninc > 0) {
+        load_rec<NL>(RA, k0, rc);
+        if constexpr (AHEAD) load_rec<NL>(RA, k0 + (ninc > 1 ? 1 : 0), rn);
+    }
     for (int k = 0; k < ninc; k++) {
-        if (k + 1 < ninc) load_rec<NL>(RA, k0 + k + 1, rn);
+        if constexpr (AHEAD) {
+            load_rec<NL>(RA, k0 + (k + 2 < ninc ? k + 2 : ninc - 1), r2);
+#ifndef FB_GATHERW_NO_PREFETCH
+            if (k + 1 < ninc) {
+                const double *sn = A.sloc + ((int64_t)rec_elem<NL>(rn.w) * NL + rec_natidx<NL>(rn.w, JD < 0 ? 0 : JD)) * NL;
+#pragma unroll
+                for (int x = 0; x < NL; x += 4) prefetch_l2(sn + x);
+            }
+#endif
+        } else if (k + 1 < ninc) load_rec<NL>(RA, k0 + k + 1, rn);
         const uint32_t perm = rec_perm<NL>(rc.w);
         const int64_t e = rec_elem<NL>(rc.w);
         IncGeo<DIM> g;
@@ -2260,6 +2275,7 @@ __global__ void __launch_bounds__(64, 4) k_gatherx(const GatherXArgs A)
             }
         }
         rc = rn;
+        if constexpr (AHEAD) rn = r2;
     }
     if (JD >= 0 && ninc > 0) {
 #pragma unroll
@@ -2306,8 +2322,16 @@ __global__ void __launch_bounds__(32 * DIM, 4) k_gatherw(const GatherXArgs A)
     }
     GatherArgs RA; // only .rec is used by the shared load helper
     RA.rec = A.rec;
-    IncRec<NL> rc, rn;
-    if (ninc > 0) load_rec<NL>(RA, k0, rc);
+    // records two incidences ahead; the element data of the NEXT incidence (its sector of |det| grad u, its row of S_e) is
+    // requested into L2 one iteration early -- no registers held across the latency (ncu before: 60 % of the main loop's
+    // stall samples sat on the first uses of these two loads)
+    // (Navier-Stokes block only: W(u) alone has one load per incidence and measured 5 % slower with the look-ahead)
+    constexpr bool AHEAD = OPX == X_NSJ;
+    IncRec<NL> rc, rn, r2;
+    if (ninc > 0) {
+        load_rec<NL>(RA, k0, rc);
+        if constexpr (AHEAD) load_rec<NL>(RA, k0 + (ninc > 1 ? 1 : 0), rn);
+    }
     for (int x = tid; x < ROWS * pitch; x += NT) acc[x] = 0.0;
     const int row = tid / NB;
     if (b == 0) {
@@ -2320,7 +2344,18 @@ __global__ void __launch_bounds__(32 * DIM, 4) k_gatherw(const GatherXArgs A)
     double dacc = 0.0;
     int pdiag = 0;
     for (int k = 0; k < ninc; k++) {
-        if (k + 1 < ninc) load_rec<NL>(RA, k0 + k + 1, rn);
+        if constexpr (AHEAD) load_rec<NL>(RA, k0 + (k + 2 < ninc ? k + 2 : ninc - 1), r2);
+        else if (k + 1 < ninc) load_rec<NL>(RA, k0 + k + 1, rn);
+#ifndef FB_GATHERW_NO_PREFETCH
+        if (AHEAD && k + 1 < ninc) {
+            const int64_t en = rec_elem<NL>(rn.w);
+            prefetch_l2(A.dt + ((en * DIM + a) * DIM + b) * 4);
+            if (OPX == X_NSJ && a == b) {
+                const double *sn = A.sloc + (en * NL + rec_natidx<NL>(rn.w, JD)) * NL;
+                prefetch_l2(sn); prefetch_l2(sn + 4); prefetch_l2(sn + 8);
+            }
+        }
+#endif
         const uint32_t perm = rec_perm<NL>(rc.w);
         const int64_t e = rec_elem<NL>(rc.w);
         // |det| grad u (component a, b) at the canonical vertices: four 8-byte loads of one sector, addressed through the
@@ -2328,8 +2363,18 @@ __global__ void __launch_bounds__(32 * DIM, 4) k_gatherw(const GatherXArgs A)
         double dv[NVTX];
         {
             const double *dp = A.dt + ((e * DIM + a) * DIM + b) * 4;
+#ifdef FB_GATHERW_V4   // A/B: one 32-byte load + register selects
+            double dn[4];
+            ld_v4(dp, dn);
+#pragma unroll
+            for (int v = 0; v < NVTX; v++) {
+                const int pv = (perm >> (2 * v)) & 3;
+                dv[v] = cw * (pv == 0 ? dn[0] : (pv == 1 ? dn[1] : (pv == 2 ? dn[2] : dn[3])));
+            }
+#else
 #pragma unroll
             for (int v = 0; v < NVTX; v++) dv[v] = cw * __ldg(dp + ((perm >> (2 * v)) & 3));
+#endif
         }
         double val[NL];
         if (OPX == X_NSJ && a == b) {   // scalar part (k_sloc): the diagonal components only
@@ -2365,6 +2410,7 @@ __global__ void __launch_bounds__(32 * DIM, 4) k_gatherw(const GatherXArgs A)
             *ptr[jj] = old[jj] + val[jc];
         }
         rc = rn;
+        if constexpr (AHEAD) rn = r2;
     }
     if (ninc > 0) my[pdiag] = dacc;
     __syncthreads();
