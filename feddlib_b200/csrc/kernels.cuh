@@ -872,6 +872,12 @@ __device__ __forceinline__ void bulk_commit_wait_read()
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#ifdef FB_GATHERW_PF_L1
+#define FB_PF_ELEM prefetch_l1
+#else
+#define FB_PF_ELEM prefetch_l2
+#endif
 // prefetch.global.L2 brings in ONE 32-byte sector (ncu: 12 sectors per warp-wide prefetch of ten 128-byte lines); whole
 // lines / spans go through the bulk (TMA) prefetch: address 16-byte aligned, size a multiple of 16
 __device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes)
@@ -2181,7 +2187,7 @@ __global__ void __launch_bounds__(64, 4) k_gatherx(const GatherXArgs A)
             if (k + 1 < ninc) {
                 const double *sn = A.sloc + ((int64_t)rec_elem<NL>(rn.w) * NL + rec_natidx<NL>(rn.w, JD < 0 ? 0 : JD)) * NL;
 #pragma unroll
-                for (int x = 0; x < NL; x += 4) prefetch_l2(sn + x);
+                for (int x = 0; x < NL; x += 4) FB_PF_ELEM(sn + x);
             }
 #endif
         } else if (k + 1 < ninc) load_rec<NL>(RA, k0 + k + 1, rn);
@@ -2349,10 +2355,10 @@ __global__ void __launch_bounds__(32 * DIM, 4) k_gatherw(const GatherXArgs A)
 #ifndef FB_GATHERW_NO_PREFETCH
         if (AHEAD && k + 1 < ninc) {
             const int64_t en = rec_elem<NL>(rn.w);
-            prefetch_l2(A.dt + ((en * DIM + a) * DIM + b) * 4);
+            FB_PF_ELEM(A.dt + ((en * DIM + a) * DIM + b) * 4);
             if (OPX == X_NSJ && a == b) {
                 const double *sn = A.sloc + (en * NL + rec_natidx<NL>(rn.w, JD)) * NL;
-                prefetch_l2(sn); prefetch_l2(sn + 4); prefetch_l2(sn + 8);
+                FB_PF_ELEM(sn); FB_PF_ELEM(sn + 4); FB_PF_ELEM(sn + 8);
             }
         }
 #endif
