@@ -1245,7 +1245,8 @@ __global__ void __launch_bounds__(GatherShape<OPG, DIM>::NT, FB_GATHER_MINBLOCKS
 #define FB_RING_PF_AT 1      // main-loop iteration after which the next tile's lines are requested into L2
 #endif
 // L2 prefetch of k_ring (tuning aid).  0: one sector of the geometry line two incidences ahead (default), 1: that whole line
-// (bulk prefetch), 2: everything the next tile reads, a tile ahead (bulk prefetches), 3: 1 + 2.  Measured on B200, config 3:
+// (bulk prefetch), 2: everything the next tile reads, a tile ahead (bulk prefetches), 3: 1 + 2, 4: all four sectors of that line
+// by plain prefetches (config 3 2.57 ms, config 2 3.78 instead of 3.08 ms).  Measured on B200, config 3:
 // 2.49 / 2.71 / 2.65 / 2.91 ms per assembly -- every additional prefetched byte makes the step SLOWER: the ring launches move
 // 3.5-3.8 TB/s of DRAM traffic (writes + reads), the ceiling of this write pattern (tools/microbench_window.cu), so they are
 // bound by DRAM traffic, not by the latency their long-scoreboard stalls suggest.
@@ -1460,7 +1461,15 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
 #else
                     load_rec<NL>(A, k + 3 < kl ? k + 3 : kl, r3);
 #endif
-#if FB_RING_PF_MODE == 0
+#if FB_RING_PF_MODE == 4
+                    // all four sectors of the geometry line two incidences ahead, plain (LSU) prefetches: the dof lanes of a node
+                    // share them (a = 0: sectors 0 and 3, a = 1: 1, a = 2: 2); a scalar row requests all four itself
+                    if constexpr (!PTS) {
+                        const double *pg = A.geom + (int64_t)rec_elem<NL>(r2.w) * GeomStride<DIM>::value;
+                        if constexpr (TPR == 1) { prefetch_l2(pg); prefetch_l2(pg + 4); prefetch_l2(pg + 8); prefetch_l2(pg + 12); }
+                        else { prefetch_l2(pg + 4 * a); if (a == 0) prefetch_l2(pg + 12); }
+                    }
+#elif FB_RING_PF_MODE == 0
                     if constexpr (!PTS) prefetch_l2(A.geom + (int64_t)rec_elem<NL>(r2.w) * GeomStride<DIM>::value);
 #elif FB_RING_PF_MODE == 1 || FB_RING_PF_MODE == 3
                     // the whole geometry line of the incidence two places on (one request per node)
