@@ -1246,7 +1246,8 @@ __global__ void __launch_bounds__(GatherShape<OPG, DIM>::NT, FB_GATHER_MINBLOCKS
 #endif
 // L2 prefetch of k_ring (tuning aid).  0: one sector of the geometry line two incidences ahead (default), 1: that whole line
 // (bulk prefetch), 2: everything the next tile reads, a tile ahead (bulk prefetches), 3: 1 + 2, 4: all four sectors of that line
-// by plain prefetches (config 3 2.57 ms, config 2 3.78 instead of 3.08 ms).  Measured on B200, config 3:
+// by plain prefetches (config 3 2.57 ms, config 2 3.78 instead of 3.08 ms), 5: none (2.68 / 3.37 ms), 6: sectors 0 and 2
+// (2.57 / 3.49 ms) -- exactly one sector is the optimum.  Measured on B200, config 3:
 // 2.49 / 2.71 / 2.65 / 2.91 ms per assembly -- every additional prefetched byte makes the step SLOWER: the ring launches move
 // 3.5-3.8 TB/s of DRAM traffic (writes + reads), the ceiling of this write pattern (tools/microbench_window.cu), so they are
 // bound by DRAM traffic, not by the latency their long-scoreboard stalls suggest.
@@ -1468,6 +1469,13 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
                         const double *pg = A.geom + (int64_t)rec_elem<NL>(r2.w) * GeomStride<DIM>::value;
                         if constexpr (TPR == 1) { prefetch_l2(pg); prefetch_l2(pg + 4); prefetch_l2(pg + 8); prefetch_l2(pg + 12); }
                         else { prefetch_l2(pg + 4 * a); if (a == 0) prefetch_l2(pg + 12); }
+                    }
+#elif FB_RING_PF_MODE == 6
+                    // both 64-byte halves of the line (sectors 0 and 2)
+                    if constexpr (!PTS) {
+                        const double *pg = A.geom + (int64_t)rec_elem<NL>(r2.w) * GeomStride<DIM>::value;
+                        if constexpr (TPR == 1) { prefetch_l2(pg); prefetch_l2(pg + 8); }
+                        else if (a < 2) prefetch_l2(pg + 8 * a);
                     }
 #elif FB_RING_PF_MODE == 0
                     if constexpr (!PTS) prefetch_l2(A.geom + (int64_t)rec_elem<NL>(r2.w) * GeomStride<DIM>::value);
