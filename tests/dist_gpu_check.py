@@ -124,6 +124,18 @@ def main():
             diff = got - J[rows]
             relJ = float(np.sqrt(diff.multiply(diff).sum() / J[rows].multiply(J[rows]).sum()))
             assert relJ <= 1e-12, f"rank {rank}: multi-GPU Navier-Stokes block, relative Frobenius error {relJ:.3e}"
+            # ghost rows NEXT TO the owned rows (row phases ROWS_GEOM / ROWS_GHOST_ONLY, side stream): same matrix, bitwise
+            if world > 1:
+                vA = ctx.empty_values(pat.nnz(dim, dim, BLOCK_FULL)); vB = ctx.empty_values(pat.nnz(dim, dim, BLOCK_FULL))
+                run.concurrent_ghost = False
+                run.assemble_linelas_fused(vA, lam, mu)
+                ctx.synchronize(); dist.barrier()
+                run.concurrent_ghost = True
+                run.assemble_linelas_fused(vB, lam, mu)
+                ctx.synchronize(); dist.barrier()
+                run.concurrent_ghost = False
+                nown = pat.nnz_owned(dim, dim, BLOCK_FULL)
+                assert torch.equal(vA[:nown], vB[:nown]), f"rank {rank}: concurrent ghost rows differ from the serial phases"
             # the peer-memory path must refuse operators whose kernels do not store ghost rows through it
             from feddlib_b200 import LogicError
             try:

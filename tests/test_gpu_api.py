@@ -233,7 +233,8 @@ def test_multi_gpu_exchange_if_available():
 
 def test_alternative_star_kernels_in_a_subprocess():
     """k_fan (FEDDB200_FAN=1) and k_star (FEDDB200_STAR=1) are alternative row kernels of 3D P2 that are off by default (their
-    knobs are read once per process): the same parity check as the default path, in a child process per setting."""
+    knobs are read once per process): the same parity check as the default path, in a child process per setting.  The same
+    goes for the measured-but-off protocols (fragments, Laplace points path)."""
     import os
     import subprocess
     import sys
@@ -258,6 +259,9 @@ for name, make in (("cube", lambda: mesh_structured(3, "P2", 4)), ("warp", lambd
         assert err <= TOL, (name, op, err)
 print("ok")
 ''' % (root, os.path.join(root, "tests"))
-    for env in ({"FEDDB200_FAN": "1"}, {"FEDDB200_STAR": "1"}, {"FEDDB200_TASK": "0"}):
+    # ... and the optional write / input protocols of the default kernels: boundary-sector fragments + k_stitch
+    # (FEDDB200_FRAG=1), Laplace geometry from the vertex coordinates (FEDDB200_LAPLACE_POINTS=1)
+    for env in ({"FEDDB200_FAN": "1"}, {"FEDDB200_STAR": "1"}, {"FEDDB200_TASK": "0"}, {"FEDDB200_FRAG": "1"},
+                {"FEDDB200_LAPLACE_POINTS": "1"}, {"FEDDB200_FRAG": "1", "FEDDB200_LAPLACE_POINTS": "1"}):
         r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
         assert r.returncode == 0 and "ok" in r.stdout, (env, r.stdout[-500:], r.stderr[-1500:])
