@@ -609,10 +609,12 @@ def main():
                 r = subprocess.run([exe, str(M), str(max(2, args.e2e_steps)), str(local_rank)], capture_output=True, text=True, timeout=600)
                 cpp = json.loads(r.stdout.strip().splitlines()[-1])
                 e2e["cpp_host"] = {"value": ne / (cpp["ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": cpp["ms_per_step"],
-                                   "ms_best": cpp["ms_best"], "first_call_s": cpp["first_call_s"], "addFE_s": cpp["addFE_s"],
+                                   "ms_best": cpp["ms_best"], "update_points_ms": cpp.get("update_points_ms"),
+                                   "first_call_s": cpp["first_call_s"], "addFE_s": cpp["addFE_s"],
                                    "checksum_first_1Mi_values": cpp["checksum_first_1Mi_values"],
-                                   "what": "FEDD::FE_b200::assemblyLinElasXDim (C++), points H2D from pageable host memory + "
-                                           "assembly + CSR values D2H into a pooled page-locked buffer owned by the returned matrix"}
+                                   "what": "FEDD::FE_b200::updatePoints + assemblyLinElasXDim (C++): the reference's vector-of-vectors points "
+                                           "flattened into a page-locked staging buffer + H2D, assembly, CSR values D2H into a pooled "
+                                           "page-locked buffer owned by the returned matrix"}
             except Exception as exc:  # noqa: BLE001
                 e2e["cpp_host"] = {"error": str(exc)[:200]}
     else:

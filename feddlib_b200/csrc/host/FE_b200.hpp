@@ -157,11 +157,10 @@ namespace b200 {
 // vec2D_dbl_Type (one std::vector per point) -> flat array; the pointer chase over millions of small vectors is the slowest
 // host step of a re-upload of the mesh points, so it runs on a few threads
 template <class Points>
-inline void flatten_points(const Points &points, std::int64_t nn, int dim, std::vector<double> &xyz)
+inline void flatten_points(const Points &points, std::int64_t nn, int dim, double *xyz)
 {
-    xyz.resize((std::size_t)nn * dim);
     const unsigned hw = std::thread::hardware_concurrency();
-    const int nt = nn < (1 << 16) ? 1 : (int)std::max(1u, std::min(8u, hw ? hw : 1u));
+    const int nt = nn < (1 << 16) ? 1 : (int)std::max(1u, std::min(16u, hw ? hw : 1u));
     auto part = [&](int t) {
         const std::int64_t k0 = nn * t / nt, k1 = nn * (t + 1) / nt;
         for (std::int64_t k = k0; k < k1; k++)
@@ -171,6 +170,12 @@ inline void flatten_points(const Points &points, std::int64_t nn, int dim, std::
     std::vector<std::thread> th;
     for (int t = 0; t < nt; t++) th.emplace_back(part, t);
     for (std::thread &t : th) t.join();
+}
+template <class Points>
+inline void flatten_points(const Points &points, std::int64_t nn, int dim, std::vector<double> &xyz)
+{
+    xyz.resize((std::size_t)nn * dim);
+    flatten_points(points, nn, dim, xyz.data());
 }
 } // namespace b200
 
@@ -197,7 +202,7 @@ class FE_b200 {
         pool_->retire();
         for (auto &kv : plans_) feddb200_halo_free(kv.second->halo);
         for (auto &kv : pats_) feddb200_pat_free(kv.second);
-        for (auto &s : slots_) feddb200_mesh_free(s.mesh);
+        for (auto &s : slots_) { feddb200_mesh_free(s.mesh); if (s.xyz_pinned) feddb200_host_free(ctx_, s.xyz_pinned); }
         feddb200_destroy(ctx_);
     }
     FE_b200(const FE_b200 &) = delete;
@@ -261,9 +266,16 @@ class FE_b200 {
     {
         Slot &s = slots_.at((std::size_t)loc);
         auto points = s.domain->getPointsRepeated();
-        std::vector<double> xyz;
-        b200::flatten_points(*points, s.nn, s.dim, xyz);
-        b200::check(feddb200_mesh_update_coords(ctx_, s.mesh, xyz.data()));
+        // flat page-locked staging buffer, kept with the slot: no 67 MB allocation + page faults per call (config 3) and the
+        // upload runs at PCIe speed instead of through the driver's bounce buffer (measured 37 ms -> see bench `cpp_host`)
+        if (!s.xyz_pinned) {
+            void *q = nullptr;
+            b200::check(feddb200_host_alloc(ctx_, &q, (std::int64_t)sizeof(double) * std::max<std::int64_t>(s.nn * s.dim, 1)));
+            s.xyz_pinned = static_cast<double *>(q);
+        }
+        else b200::check(feddb200_synchronize(ctx_));   // the previous upload from this buffer has left the host
+        b200::flatten_points(*points, s.nn, s.dim, s.xyz_pinned);
+        b200::check(feddb200_mesh_update_coords(ctx_, s.mesh, s.xyz_pinned));
     }
 
     void setScatterMode(int mode) { b200::check(feddb200_set_scatter_mode(ctx_, mode)); }
@@ -493,6 +505,7 @@ class FE_b200 {
         std::string FEType;
         std::vector<std::int32_t> owner;   // multi-rank: owning rank of every repeated node
         bool p0 = false;                   // P0 space: "nodes" are the elements, numbered by Domain::getElementMap
+        double *xyz_pinned = nullptr;      // page-locked staging of the flat points (updatePoints)
     };
 
     // multi-rank plan of one pattern + the state of its node-pattern callback
