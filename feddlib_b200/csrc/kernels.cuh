@@ -2189,9 +2189,14 @@ __global__ void __launch_bounds__(64, 4) k_gatherx(const GatherXArgs A)
 #pragma unroll
     for (int b = 0; b < NB; b++) dacc[b] = 0.0;
     int pdiag = 0;
-    // N(u) / fused block: records two incidences ahead and the next incidence's row of S_e requested into L2 one iteration
-    // early (the dependent chain record -> natural indices -> ten 8-byte loads was fully exposed; see k_gatherw)
+    // fused block (where it runs through this kernel): records two incidences ahead and the next incidence's row of S_e
+    // requested into L2 one iteration early (see k_gatherw).  Not for N(u) alone: 1.65 -> 1.53 ms on the structured cube
+    // (M = 50) but 4.03 -> 4.75 ms on config 4's unstructured mesh (FB_GATHERX_ADV_AHEAD switches it on)
+#ifdef FB_GATHERX_ADV_AHEAD
     constexpr bool AHEAD = OPX == X_ADV || OPX == X_NSJ;
+#else
+    constexpr bool AHEAD = OPX == X_NSJ;
+#endif
     IncRec<NL> rc, rn, r2;
     if (ninc > 0) {
         load_rec<NL>(RA, k0, rc);
