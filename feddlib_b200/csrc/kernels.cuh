@@ -1246,13 +1246,17 @@ __global__ void __launch_bounds__(GatherShape<OPG, DIM>::NT, FB_GATHER_MINBLOCKS
 #endif
 // L2 prefetch of k_ring (tuning aid).  0: one sector of the geometry line two incidences ahead (default), 1: that whole line
 // (bulk prefetch), 2: everything the next tile reads, a tile ahead (bulk prefetches), 3: 1 + 2, 4: all four sectors of that line
-// by plain prefetches (config 3 2.57 ms, config 2 3.78 instead of 3.08 ms), 5: none (2.68 / 3.37 ms), 6: sectors 0 and 2
-// (2.57 / 3.49 ms) -- exactly one sector is the optimum.  Measured on B200, config 3:
+// by plain prefetches (config 3 2.484 ms against 2.465, config 2 3.24 against 3.10 ms), 5: none (2.60 / 3.07 ms), 6: sectors
+// 0 and 2 (2.48 / 3.16 ms) -- one sector two incidences ahead is the optimum inside a row.  Measured on B200, config 3:
 // 2.49 / 2.71 / 2.65 / 2.91 ms per assembly -- every additional prefetched byte makes the step SLOWER: the ring launches move
 // 3.5-3.8 TB/s of DRAM traffic (writes + reads), the ceiling of this write pattern (tools/microbench_window.cu), so they are
 // bound by DRAM traffic, not by the latency their long-scoreboard stalls suggest.
+// 7: mode 0 + the incidence records of the NEXT tile's rows by plain prefetches from inside the main loop: config 3
+// 2.465 -> 2.379 ms, config 2 3.10 -> 3.02 ms (same box).  8 (default): 7 + the first geometry sector of the next tile's
+// first two incidences: config 3 2.470 (mode 0) / 2.387 (7) / 2.346 ms (8) on one box.  What helps is taking the DRAM misses
+// out of the dependent chain row record -> incidence records -> geometry at every tile start -- with few, plain requests.
 #ifndef FB_RING_PF_MODE
-#define FB_RING_PF_MODE 0
+#define FB_RING_PF_MODE 8
 #endif
 constexpr int kRingUnroll = FB_RING_UNROLL;
 __device__ __forceinline__ void cp_async16(void *sdst, const void *gsrc);
@@ -1262,7 +1266,7 @@ template <int OPG, bool PTS = false>
 __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
 {
     static_assert(!PTS || OPG == 0, "points path: scalar Laplace rows");
-#if FB_RING_PF_MODE >= 2
+#if FB_RING_PF_MODE == 2 || FB_RING_PF_MODE == 3
     __shared__ uint4 s_en[2][64];   // elements of the next tile's rows (second half of their row records), per lane
 #endif
     constexpr int DIM = 3, NL = 10, NVTX = 4;
@@ -1336,7 +1340,11 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
         const bool live_n = lane_used && tile_n < ntiles && node_n < A.count;
         double rawn[4] = {0.0, 0.0, 0.0, 0.0};
         if (live_n) ld_v4(reinterpret_cast<const double *>(A.rowinfo + A.start + node_n), rawn);
-#if FB_RING_PF_MODE >= 2
+#if FB_RING_PF_MODE == 8
+        uint2 en01 = make_uint2(0u, 0u);   // elements of the next row's first two incidences
+        if (live_n) en01 = __ldg(reinterpret_cast<const uint2 *>(A.rowinfo + A.start + node_n) + 4);
+#endif
+#if FB_RING_PF_MODE == 2 || FB_RING_PF_MODE == 3
         // ... and the elements of its rows (second half of the row record): their geometry lines, the rows' incidence
         // records and the row records of the tile after the next are requested into L2 a whole tile ahead (do_prefetch
         // below, issued by the node's first lane from inside the main loop, once this load has landed).  These lines are
@@ -1477,7 +1485,7 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
                         if constexpr (TPR == 1) { prefetch_l2(pg); prefetch_l2(pg + 8); }
                         else if (a < 2) prefetch_l2(pg + 8 * a);
                     }
-#elif FB_RING_PF_MODE == 0
+#elif FB_RING_PF_MODE == 0 || FB_RING_PF_MODE == 7 || FB_RING_PF_MODE == 8
                     if constexpr (!PTS) prefetch_l2(A.geom + (int64_t)rec_elem<NL>(r2.w) * GeomStride<DIM>::value);
 #elif FB_RING_PF_MODE == 1 || FB_RING_PF_MODE == 3
                     // the whole geometry line of the incidence two places on (one request per node)
@@ -1525,14 +1533,27 @@ __device__ __forceinline__ void ring_tiles(const GatherArgs &A, double *acc)
                     }
                 }
                 rc = rn; rn = r2; r2 = r3;
-#if FB_RING_PF_MODE >= 2
+#if FB_RING_PF_MODE == 2 || FB_RING_PF_MODE == 3
                 if (!pf_done && k >= k0 + FB_RING_PF_AT) do_prefetch();
+#elif FB_RING_PF_MODE == 7 || FB_RING_PF_MODE == 8
+                // the incidence records of the NEXT tile's row (one 32-byte sector each, plain prefetches shared by the dof lanes
+                // of the node), once its row record has landed: every tile otherwise starts with a DRAM miss on them
+                if (k == k0 + FB_RING_PF_AT && live_n) {
+                    const int64_t k0p = __double_as_longlong(rawn[1]);
+                    const int nincp = (int)(__double_as_longlong(rawn[2]) >> 32);
+                    for (int j = lane - slot * TPR; j < nincp; j += TPR) prefetch_l2(A.rec + (k0p + j) * RecWords<NL>::value);
+#if FB_RING_PF_MODE == 8
+                    // ... and the first sector of the geometry lines of its first two incidences (RowInfo::e)
+                    if (lane - slot * TPR < 2 && lane - slot * TPR < nincp)
+                        prefetch_l2(A.geom + (int64_t)(lane - slot * TPR == 0 ? en01.x : en01.y) * GeomStride<DIM>::value);
+#endif
+                }
 #endif
             }
 #pragma unroll
             for (int b = 0; b < NB; b++) { my[p_v0 + b] = accE[0][b]; my[p_v1 + b] = accE[1][b]; my[p_self + b] = accE[2][b]; }
         }
-#if FB_RING_PF_MODE >= 2
+#if FB_RING_PF_MODE == 2 || FB_RING_PF_MODE == 3
         if (!pf_done) do_prefetch();
 #endif
 
